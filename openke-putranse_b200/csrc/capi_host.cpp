@@ -1,0 +1,290 @@
+// Host half of the C-ABI: the Base.so-compatible process-global surface and the pk_* exports of
+// graph state.  See include/putranse.h for the map to the reference's symbols.
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <ctime>
+#include <thread>
+
+#include "common.hpp"
+#include "graph_host.hpp"
+#include "global_state.hpp"
+#include <mutex>
+
+namespace pk {
+
+std::string& last_error() {
+    thread_local std::string e;
+    return e;
+}
+int& launch_counter() {
+    thread_local int n = 0;
+    return n;
+}
+
+Global& G() {
+    static Global g;
+    return g;
+}
+
+const TripleIndex& current_index() {
+    Global& g = G();
+    return g.swapped ? g.universe.local : g.graph.train;
+}
+
+uint64_t index_epoch() { return G().index_epoch; }
+
+}  // namespace pk
+
+using pk::G;
+
+extern "C" {
+
+int pk_last_error(char* buf, int n) {
+    const std::string& e = pk::last_error();
+    if (buf && n > 0) {
+        const int m = (int)std::min<size_t>(e.size(), (size_t)n - 1);
+        std::memcpy(buf, e.data(), (size_t)m);
+        buf[m] = 0;
+    }
+    return (int)e.size();
+}
+
+const char* pk_version(void) { return "putranse-b200 0.1 (sm_100a)"; }
+
+int pk_last_launch_count(void) { return pk::launch_counter(); }
+
+// ---------------------------------------------------------------- settings
+void setInPath(char* path) { G().graph.in_path = path ? path : ""; }
+void setOutPath(char*) {}
+void setWorkThreads(PK_INT threads) { G().graph.work_threads = threads < 1 ? 1 : (threads > 64 ? 64 : threads); }
+PK_INT getWorkThreads(void) { return G().graph.work_threads; }
+void setBern(PK_INT con) { G().graph.bern = con; }
+
+PK_INT getEntityTotal(void) { return G().swapped ? G().universe.local.n_ent : G().graph.n_ent; }
+PK_INT getRelationTotal(void) { return G().swapped ? G().universe.local.n_rel : G().graph.n_rel; }
+PK_INT getTrainTotal(void) { return pk::current_index().n_tri(); }
+PK_INT getTestTotal(void) { return (PK_INT)G().graph.test.size(); }
+PK_INT getValidTotal(void) { return (PK_INT)G().graph.valid.size(); }
+PK_INT getTripleTotal(void) { return (PK_INT)G().graph.all_hrt.size(); }
+
+void setRandomSeed(PK_INT seed) {
+    if (seed == -1) seed = (PK_INT)time(nullptr);
+    G().seed = seed;
+    G().rng.reseed((uint32_t)seed);
+}
+PK_INT getRandomSeed(void) { return G().seed; }
+void randReset(void) {
+    for (int64_t i = 0; i < G().graph.work_threads; ++i) G().lcg[i] = (uint64_t)(int64_t)G().rng.next();
+}
+
+void importTrainFiles(void) {
+    std::string err;
+    if (!G().graph.import_train(&err)) {
+        pk::fail(PK_ERR_IO, err);
+        fprintf(stderr, "putranse: importTrainFiles failed: %s\n", err.c_str());
+        return;
+    }
+    G().index_epoch++;
+}
+
+void importTestFiles(void) {
+    std::string err;
+    if (!G().graph.import_test(&err)) {
+        pk::fail(PK_ERR_IO, err);
+        fprintf(stderr, "putranse: importTestFiles failed: %s\n", err.c_str());
+    }
+}
+
+int pk_import_count(void) { return (int)G().graph.import_count; }
+
+// ---------------------------------------------------------------- universes (global, reference order of calls)
+void getParallelUniverse(PK_INT tc, PK_REAL balance) {
+    std::string err;
+    pk::Universe& u = G().universe;
+    u = pk::Universe();
+    if (G().swapped) {
+        pk::fail(PK_ERR_STATE, "getParallelUniverse: helpers are swapped; call resetUniverse first");
+        return;
+    }
+    G().have_universe = G().graph.walk_universe(G().rng, tc, balance, &u, &err);
+    if (!G().have_universe) {
+        pk::fail(PK_ERR_STATE, err);
+        fprintf(stderr, "putranse: getParallelUniverse failed: %s\n", err.c_str());
+    }
+    std::memcpy(u.lcg, G().lcg, sizeof u.lcg);
+}
+PK_INT getEntityTotalUniverse(void) { return G().swapped ? G().graph.n_ent : (G().have_universe ? G().universe.local.n_ent : 0); }
+PK_INT getRelationTotalUniverse(void) { return G().swapped ? G().graph.n_rel : (G().have_universe ? G().universe.local.n_rel : 0); }
+PK_INT getTrainTotalUniverse(void) { return G().swapped ? G().graph.train.n_tri() : (G().have_universe ? G().universe.local.n_tri() : 0); }
+void getEntityRemapping(PK_INT* out) {
+    if (!G().have_universe) return;
+    for (size_t i = 0; i < G().universe.ent_remap.size(); ++i) out[i] = G().universe.ent_remap[i];
+}
+void getRelationRemapping(PK_INT* out) {
+    if (!G().have_universe) return;
+    for (size_t i = 0; i < G().universe.rel_remap.size(); ++i) out[i] = G().universe.rel_remap[i];
+}
+void swapHelpers(void) {
+    if (!G().have_universe) {
+        pk::fail(PK_ERR_STATE, "swapHelpers: no universe has been built");
+        return;
+    }
+    G().swapped = !G().swapped;
+    G().index_epoch++;
+}
+void resetUniverse(void) {
+    if (G().swapped) swapHelpers();
+    G().universe = pk::Universe();
+    G().have_universe = false;
+}
+
+int pk_universe_triples(int32_t* out) {
+    if (!G().have_universe) return pk::fail(PK_ERR_STATE, "pk_universe_triples: no universe");
+    std::memcpy(out, G().universe.collected.data(), G().universe.collected.size() * sizeof(pk::Tri));
+    return PK_OK;
+}
+
+int pk_train_index(int32_t* by_head, int32_t* by_tail, float* left_mean, float* right_mean) {
+    const pk::TripleIndex& ix = pk::current_index();
+    if (ix.n_tri() == 0) return pk::fail(PK_ERR_STATE, "pk_train_index: nothing imported");
+    if (by_head) std::memcpy(by_head, ix.by_head.data(), ix.by_head.size() * sizeof(pk::Tri));
+    if (by_tail) std::memcpy(by_tail, ix.by_tail.data(), ix.by_tail.size() * sizeof(pk::Tri));
+    if (left_mean) std::memcpy(left_mean, ix.left_mean.data(), ix.left_mean.size() * sizeof(float));
+    if (right_mean) std::memcpy(right_mean, ix.right_mean.data(), ix.right_mean.size() * sizeof(float));
+    return PK_OK;
+}
+
+int pk_get_lcg(uint64_t* s) {
+    std::memcpy(s, G().lcg, (size_t)G().graph.work_threads * 8);
+    return PK_OK;
+}
+int pk_set_lcg(const uint64_t* s) {
+    std::memcpy(G().lcg, s, (size_t)G().graph.work_threads * 8);
+    return PK_OK;
+}
+
+// ---------------------------------------------------------------- evaluation lists
+int pk_eval_triples(int which, int32_t* hrt) {
+    const std::vector<pk::Tri>& q = which == 0 ? G().graph.test : G().graph.valid;
+    if (q.empty()) return pk::fail(PK_ERR_STATE, "pk_eval_triples: importTestFiles has not run");
+    std::memcpy(hrt, q.data(), q.size() * sizeof(pk::Tri));
+    return PK_OK;
+}
+
+int pk_filter_csr(int which, int side, int64_t* offsets, int32_t* cand, int64_t* n_cand) {
+    if (G().graph.all_hrt.empty()) return pk::fail(PK_ERR_STATE, "pk_filter_csr: importTestFiles has not run");
+    if (which < 0 || which > 1 || side < 0 || side > 1) return pk::fail(PK_ERR_ARG, "pk_filter_csr: bad selector");
+    std::vector<int64_t> off;
+    std::vector<int32_t> c;
+    G().graph.filter_candidates(which, side, off, c);
+    if (n_cand) *n_cand = (int64_t)c.size();
+    if (offsets) std::memcpy(offsets, off.data(), off.size() * 8);
+    if (cand && !c.empty()) std::memcpy(cand, c.data(), c.size() * 4);
+    return PK_OK;
+}
+
+// candidate batches in the reference's order: slot 0 = the true triple, then every other entity
+// ascending (Test.h:61-68, Valid.h:58-67)
+static void fill_batch(const pk::Tri& x, bool head, PK_INT* ph, PK_INT* pt, PK_INT* pr) {
+    const int64_t E = G().graph.n_ent;
+    ph[0] = x.h; pt[0] = x.t; pr[0] = x.r;
+    const int64_t truth = head ? x.h : x.t;
+    for (int64_t i = 1; i < E; ++i) {
+        const int64_t e = i - 1 < truth ? i - 1 : i;
+        ph[i] = head ? e : x.h;
+        pt[i] = head ? x.t : e;
+        pr[i] = x.r;
+    }
+}
+void initTest(void) { G().last_head = G().last_tail = 0; pk::test_metrics_reset(); }
+void validInit(void) { G().last_valid_head = G().last_valid_tail = 0; pk::valid_metrics_reset(); }
+void getHeadBatch(PK_INT* ph, PK_INT* pt, PK_INT* pr) { fill_batch(G().graph.test[(size_t)G().last_head++], true, ph, pt, pr); }
+void getTailBatch(PK_INT* ph, PK_INT* pt, PK_INT* pr) { fill_batch(G().graph.test[(size_t)G().last_tail++], false, ph, pt, pr); }
+void getValidHeadBatch(PK_INT* ph, PK_INT* pt, PK_INT* pr) { fill_batch(G().graph.valid[(size_t)G().last_valid_head++], true, ph, pt, pr); }
+void getValidTailBatch(PK_INT* ph, PK_INT* pt, PK_INT* pr) { fill_batch(G().graph.valid[(size_t)G().last_valid_tail++], false, ph, pt, pr); }
+
+// ---------------------------------------------------------------- many universes, many threads
+struct pk_universe_set {
+    std::vector<pk::Universe> u;
+    int work_threads = 1;
+};
+
+pk_universe_set* pk_universes_build(int n, const int64_t* seeds, const int64_t* tcs, const float* balances, int nthreads) {
+    if (n < 0 || !seeds || !tcs || !balances) {
+        pk::fail(PK_ERR_ARG, "pk_universes_build: null argument");
+        return nullptr;
+    }
+    if (G().graph.train.n_tri() == 0) {
+        pk::fail(PK_ERR_STATE, "pk_universes_build: importTrainFiles has not run");
+        return nullptr;
+    }
+    pk_universe_set* s = new pk_universe_set();
+    s->u.resize((size_t)n);
+    s->work_threads = (int)G().graph.work_threads;
+    if (nthreads < 1) nthreads = (int)std::max(1u, std::thread::hardware_concurrency());
+    nthreads = std::min(nthreads, std::max(n, 1));
+    std::atomic<int> next{0};
+    std::atomic<bool> failed{false};
+    std::string first_err;
+    std::mutex* mu = new std::mutex();
+    const pk::Graph& g = G().graph;
+    auto work = [&]() {
+        for (;;) {
+            const int i = next.fetch_add(1);
+            if (i >= n) break;
+            std::string err;
+            if (!g.build_universe(seeds[i], tcs[i], balances[i], &s->u[(size_t)i], &err)) {
+                std::lock_guard<std::mutex> lk(*mu);
+                if (!failed.exchange(true)) first_err = "universe " + std::to_string(i) + ": " + err;
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nthreads; ++t) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+    delete mu;
+    if (failed) {
+        pk::fail(PK_ERR_STATE, first_err);
+        delete s;
+        return nullptr;
+    }
+    return s;
+}
+
+void pk_universes_free(pk_universe_set* s) { delete s; }
+int pk_universes_count(const pk_universe_set* s) { return s ? (int)s->u.size() : 0; }
+
+int pk_universes_sizes(const pk_universe_set* s, int64_t* n_tri, int64_t* n_ent, int64_t* n_rel, int64_t* focus) {
+    if (!s) return pk::fail(PK_ERR_ARG, "pk_universes_sizes: null set");
+    for (size_t i = 0; i < s->u.size(); ++i) {
+        if (n_tri) n_tri[i] = s->u[i].local.n_tri();
+        if (n_ent) n_ent[i] = s->u[i].local.n_ent;
+        if (n_rel) n_rel[i] = s->u[i].local.n_rel;
+        if (focus) focus[i] = s->u[i].focus;
+    }
+    return PK_OK;
+}
+
+int pk_universes_export(const pk_universe_set* s, int32_t* tri_by_head, int32_t* tri_by_tail, int32_t* tri_collected,
+                        int32_t* ent_remap, int32_t* rel_remap, float* left_mean, float* right_mean, uint64_t* lcg) {
+    if (!s) return pk::fail(PK_ERR_ARG, "pk_universes_export: null set");
+    size_t to = 0, eo = 0, ro = 0;
+    for (size_t i = 0; i < s->u.size(); ++i) {
+        const pk::Universe& u = s->u[i];
+        const size_t nt = (size_t)u.local.n_tri(), ne = (size_t)u.local.n_ent, nr = (size_t)u.local.n_rel;
+        if (tri_by_head) std::memcpy(tri_by_head + to * 3, u.local.by_head.data(), nt * sizeof(pk::Tri));
+        if (tri_by_tail) std::memcpy(tri_by_tail + to * 3, u.local.by_tail.data(), nt * sizeof(pk::Tri));
+        if (tri_collected) std::memcpy(tri_collected + to * 3, u.collected.data(), nt * sizeof(pk::Tri));
+        if (ent_remap) std::memcpy(ent_remap + eo, u.ent_remap.data(), ne * 4);
+        if (rel_remap) std::memcpy(rel_remap + ro, u.rel_remap.data(), nr * 4);
+        if (left_mean) std::memcpy(left_mean + ro, u.local.left_mean.data(), nr * 4);
+        if (right_mean) std::memcpy(right_mean + ro, u.local.right_mean.data(), nr * 4);
+        if (lcg) std::memcpy(lcg + i * (size_t)s->work_threads, u.lcg, (size_t)s->work_threads * 8);
+        to += nt; eo += ne; ro += nr;
+    }
+    return PK_OK;
+}
+
+}  // extern "C"

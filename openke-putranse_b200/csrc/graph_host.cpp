@@ -1,0 +1,445 @@
+// Host-side graph state for the PuTransE hot path.  See graph_host.hpp for the map to the
+// reference files.  Nothing here is a numerical fallback for the CUDA path: this is the integer
+// work the reference also does on the host (file parsing, index building, subgraph sampling).
+#include "graph_host.hpp"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <unordered_set>
+
+namespace pk {
+
+// ------------------------------------------------------------------------------------------------
+// glibc rand(): srandom_r seeds 31 words with the Park-Miller LCG (Schrage form), then discards
+// 310 outputs of x[i] = x[i-3] + x[i-31]; rand() returns the sum shifted right by one.
+void GlibcRand::reseed(uint32_t seed) {
+    if (seed == 0) seed = 1;
+    int32_t word = (int32_t)seed;
+    r_[0] = (uint32_t)word;
+    for (int i = 1; i < 31; ++i) {
+        long hi = word / 127773, lo = word % 127773;
+        long w = 16807 * lo - 2836 * hi;
+        if (w < 0) w += 2147483647;
+        word = (int32_t)w;
+        r_[i] = (uint32_t)word;
+    }
+    f_ = 3;
+    b_ = 0;
+    for (int i = 0; i < 310; ++i) (void)next();
+}
+
+int32_t GlibcRand::next() {
+    uint32_t v = (r_[f_] += r_[b_]);
+    if (++f_ >= 31) f_ = 0;
+    if (++b_ >= 31) b_ = 0;
+    return (int32_t)(v >> 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+static bool read_triples(const std::string& path, std::vector<Tri>* out, int64_t* lines, std::string* err) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) {
+        *err = "cannot open " + path;
+        return false;
+    }
+    fseek(f, 0, SEEK_END);
+    long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    std::string buf((size_t)sz, '\0');
+    if (sz > 0 && fread(&buf[0], 1, (size_t)sz, f) != (size_t)sz) {
+        fclose(f);
+        *err = "short read on " + path;
+        return false;
+    }
+    fclose(f);
+    // The reference takes the record count from the number of '\n' (openke/base/Utilities.h:47-57)
+    // and then reads that many "h t r" records with fscanf (openke/base/Reader.h:188-197).
+    int64_t n = 0;
+    for (char c : buf) n += (c == '\n');
+    *lines = n;
+    out->clear();
+    out->reserve((size_t)n);
+    const char* p = buf.c_str();
+    auto next_int = [&](int64_t* v) -> bool {
+        while (*p && (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r')) ++p;
+        if (!*p) return false;
+        bool neg = false;
+        if (*p == '-') { neg = true; ++p; }
+        if (*p < '0' || *p > '9') return false;
+        int64_t x = 0;
+        while (*p >= '0' && *p <= '9') x = x * 10 + (*p++ - '0');
+        *v = neg ? -x : x;
+        return true;
+    };
+    for (int64_t i = 0; i < n; ++i) {
+        int64_t h, t, r;
+        if (!next_int(&h) || !next_int(&t) || !next_int(&r)) {
+            *err = "malformed triple record in " + path;
+            return false;
+        }
+        out->push_back(Tri{(int32_t)h, (int32_t)r, (int32_t)t});
+    }
+    return true;
+}
+
+static bool count_lines(const std::string& path, int64_t* n, std::string* err) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) {
+        *err = "cannot open " + path;
+        return false;
+    }
+    char buf[1 << 16];
+    int64_t c = 0;
+    size_t got;
+    while ((got = fread(buf, 1, sizeof buf, f)) > 0)
+        for (size_t i = 0; i < got; ++i) c += (buf[i] == '\n');
+    fclose(f);
+    *n = c;
+    return true;
+}
+
+static void sort_unique(std::vector<Tri>& v, bool (*less)(const Tri&, const Tri&)) {
+    std::sort(v.begin(), v.end(), less);
+    v.erase(std::unique(v.begin(), v.end()), v.end());
+}
+
+void TripleIndex::build_ranges() {
+    // reference Reader.h:106-146: lef defaults to 0 (calloc), rig to -1
+    lef_head.assign((size_t)n_ent, 0);
+    rig_head.assign((size_t)n_ent, -1);
+    lef_tail.assign((size_t)n_ent, 0);
+    rig_tail.assign((size_t)n_ent, -1);
+    const int64_t n = n_tri();
+    for (int64_t i = 0; i < n; ++i) {
+        const int32_t h = by_head[(size_t)i].h, t = by_tail[(size_t)i].t;
+        if (i == 0 || by_head[(size_t)i - 1].h != h) lef_head[(size_t)h] = i;
+        rig_head[(size_t)h] = i;
+        if (i == 0 || by_tail[(size_t)i - 1].t != t) lef_tail[(size_t)t] = i;
+        rig_tail[(size_t)t] = i;
+    }
+}
+
+void TripleIndex::count_distinct(std::vector<int64_t>& heads, std::vector<int64_t>& tails) const {
+    heads.assign((size_t)n_rel, 0);
+    tails.assign((size_t)n_rel, 0);
+    const int64_t n = n_tri();
+    for (int64_t i = 0; i < n; ++i) {
+        const Tri& a = by_head[(size_t)i];
+        if (i == 0 || by_head[(size_t)i - 1].h != a.h || by_head[(size_t)i - 1].r != a.r) heads[(size_t)a.r]++;
+        const Tri& b = by_tail[(size_t)i];
+        if (i == 0 || by_tail[(size_t)i - 1].t != b.t || by_tail[(size_t)i - 1].r != b.r) tails[(size_t)b.r]++;
+    }
+}
+
+// The reference adds 1.0 once per distinct (entity, relation) pair to a float that — on a repeated
+// import in the same process — still holds the previous import's mean, and divides an un-zeroed,
+// therefore n-times-accumulated, frequency by it (Reader.h:148-166 with Utilities.h:60-96).  The
+// chain of float additions is reproduced literally so the resulting probabilities are bit-equal.
+static float bump(float start, int64_t times) {
+    float v = start;
+    for (int64_t i = 0; i < times; ++i) v = (float)((double)v + 1.0);
+    return v;
+}
+
+bool Graph::import_train(std::string* err) {
+    int64_t nr, ne;
+    if (!count_lines(in_path + "relation2id.txt", &nr, err)) return false;
+    if (!count_lines(in_path + "entity2id.txt", &ne, err)) return false;
+    std::vector<Tri> raw;
+    if (!read_triples(in_path + "train2id.txt", &raw, &train_lines, err)) return false;
+    if (raw.empty()) {
+        *err = "empty training set in " + in_path;
+        return false;
+    }
+    for (const Tri& x : raw)
+        if (x.h < 0 || x.t < 0 || x.r < 0 || x.h >= ne || x.t >= ne || x.r >= nr) {
+            *err = "triple id out of range in " + in_path + "train2id.txt";
+            return false;
+        }
+    const bool same_shape = (nr == n_rel && (int64_t)train.left_mean.size() == nr);
+    n_rel = nr;
+    n_ent = ne;
+    train.n_ent = ne;
+    train.n_rel = nr;
+    train.by_head = raw;
+    sort_unique(train.by_head, less_hrt);
+    train.by_tail = train.by_head;
+    std::sort(train.by_tail.begin(), train.by_tail.end(), less_trh);
+    train.build_ranges();
+    by_rel = train.by_head;
+    std::sort(by_rel.begin(), by_rel.end(), less_rht);
+    lef_rel.assign((size_t)nr, 0);
+    rig_rel.assign((size_t)nr, -1);
+    for (int64_t i = 0; i < (int64_t)by_rel.size(); ++i) {
+        const int32_t r = by_rel[(size_t)i].r;
+        if (i == 0 || by_rel[(size_t)i - 1].r != r) lef_rel[(size_t)r] = i;
+        rig_rel[(size_t)r] = i;
+    }
+    // Bernoulli statistics with the reference's import-count drift.
+    import_count = same_shape ? import_count + 1 : 1;
+    if (!same_shape) {
+        train.left_mean.assign((size_t)nr, 0.f);
+        train.right_mean.assign((size_t)nr, 0.f);
+    }
+    std::vector<int64_t> freq((size_t)nr, 0), dh, dt;
+    for (const Tri& x : train.by_head) freq[(size_t)x.r]++;
+    train.count_distinct(dh, dt);
+    for (int64_t r = 0; r < nr; ++r) {
+        const int64_t f = freq[(size_t)r] * import_count;  // INT accumulated over imports
+        train.left_mean[(size_t)r] = (float)f / bump(train.left_mean[(size_t)r], dh[(size_t)r]);
+        train.right_mean[(size_t)r] = (float)f / bump(train.right_mean[(size_t)r], dt[(size_t)r]);
+    }
+    return true;
+}
+
+bool Graph::import_test(std::string* err) {
+    int64_t nr, ne, lines;
+    if (!count_lines(in_path + "relation2id.txt", &nr, err)) return false;
+    if (!count_lines(in_path + "entity2id.txt", &ne, err)) return false;
+    n_rel = nr;
+    n_ent = ne;
+    std::vector<Tri> tr;
+    if (!read_triples(in_path + "test2id.txt", &test, &lines, err)) return false;
+    if (!read_triples(in_path + "train2id.txt", &tr, &lines, err)) return false;
+    if (!read_triples(in_path + "valid2id.txt", &valid, &lines, err)) return false;
+    all_hrt.clear();
+    all_hrt.reserve(test.size() + tr.size() + valid.size());
+    all_hrt.insert(all_hrt.end(), test.begin(), test.end());
+    all_hrt.insert(all_hrt.end(), tr.begin(), tr.end());
+    all_hrt.insert(all_hrt.end(), valid.begin(), valid.end());
+    for (const Tri& x : all_hrt)
+        if (x.h < 0 || x.t < 0 || x.r < 0 || x.h >= ne || x.t >= ne || x.r >= nr) {
+            *err = "triple id out of range under " + in_path;
+            return false;
+        }
+    // The reference keeps duplicates in tripleList; membership (_find) is all that is ever asked.
+    sort_unique(all_hrt, less_hrt);
+    all_trh = all_hrt;
+    std::sort(all_trh.begin(), all_trh.end(), less_trh);
+    std::sort(test.begin(), test.end(), less_rht);    // Reader.h:311
+    std::sort(valid.begin(), valid.end(), less_rht);  // Reader.h:312
+    return true;
+}
+
+void Graph::filter_candidates(int which, int side, std::vector<int64_t>& off, std::vector<int32_t>& cand) const {
+    const std::vector<Tri>& q = which == 0 ? test : valid;
+    off.assign(q.size() + 1, 0);
+    cand.clear();
+    for (size_t i = 0; i < q.size(); ++i) {
+        const Tri& x = q[i];
+        if (side == 0) {  // head prediction: all j with (j, r, t) known, j != h
+            Tri lo{INT32_MIN, x.r, x.t};
+            auto it = std::lower_bound(all_trh.begin(), all_trh.end(), lo, less_trh);
+            for (; it != all_trh.end() && it->t == x.t && it->r == x.r; ++it)
+                if (it->h != x.h) cand.push_back(it->h);
+        } else {  // tail prediction: all j with (h, r, j) known, j != t
+            Tri lo{x.h, x.r, INT32_MIN};
+            auto it = std::lower_bound(all_hrt.begin(), all_hrt.end(), lo, less_hrt);
+            for (; it != all_hrt.end() && it->h == x.h && it->r == x.r; ++it)
+                if (it->t != x.t) cand.push_back(it->t);
+        }
+        off[i + 1] = (int64_t)cand.size();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Universe construction.  Draw order of the libc generator is the contract (SURVEY.md appendix A,
+// reference UniverseConstructor.h:39-67,92-191,327-397); the containers are not.
+namespace {
+
+// k-th remaining element of a sorted array under deletions (replaces std::advance over std::set).
+struct Fenwick {
+    std::vector<int32_t> t;
+    int n, top;
+    explicit Fenwick(int n_) : t((size_t)n_ + 1, 0), n(n_) {
+        for (int i = 1; i <= n; ++i) {
+            t[(size_t)i] += 1;
+            int j = i + (i & -i);
+            if (j <= n) t[(size_t)j] += t[(size_t)i];
+        }
+        top = 1;
+        while (top * 2 <= n) top *= 2;
+    }
+    int kth(int k) const {  // 0-based rank -> 0-based position
+        int pos = 0, rem = k + 1;
+        for (int s = top; s > 0; s >>= 1)
+            if (pos + s <= n && t[(size_t)(pos + s)] < rem) {
+                pos += s;
+                rem -= t[(size_t)pos];
+            }
+        return pos;
+    }
+    void remove(int p) {
+        for (int i = p + 1; i <= n; i += i & -i) t[(size_t)i] -= 1;
+    }
+};
+
+struct TriHash {
+    size_t operator()(const Tri& x) const {
+        uint64_t k = ((uint64_t)(uint32_t)x.h * 0x9E3779B97F4A7C15ULL) ^ ((uint64_t)(uint32_t)x.t * 0xC2B2AE3D27D4EB4FULL) ^
+                     ((uint64_t)(uint32_t)x.r * 0x165667B19E3779F9ULL);
+        return (size_t)(k ^ (k >> 29));
+    }
+};
+
+}  // namespace
+
+bool Graph::build_universe(int64_t seed, int64_t tc, float balance, Universe* u, std::string* err) const {
+    GlibcRand rng((uint32_t)seed);                       // setRandomSeed -> srand   (Random.h:38-45)
+    std::memset(u->lcg, 0, sizeof u->lcg);
+    const int64_t wt = std::min<int64_t>(work_threads, 64);
+    for (int64_t i = 0; i < wt; ++i) u->lcg[i] = (uint64_t)(int64_t)rng.next();  // randReset (Random.h:11-15)
+    u->seed = seed;
+    const bool ok = walk_universe(rng, tc, balance, u, err);
+    u->draws += wt;
+    return ok;
+}
+
+bool Graph::walk_universe(GlibcRand& rng, int64_t tc, float balance, Universe* u, std::string* err) const {
+    if (train.n_tri() == 0) {
+        *err = "build_universe: no training graph imported";
+        return false;
+    }
+    if (tc <= 0) {
+        *err = "build_universe: triple_constraint must be positive";
+        return false;
+    }
+    u->tc = tc;
+    u->balance = balance;
+    int64_t draws = 0;
+
+    const int64_t focus = rng.range(0, n_rel);           // UniverseConstructor.h:341
+    ++draws;
+    u->focus = focus;
+    const int64_t threshold = (int64_t)(balance * (float)tc);  // :345-346 (float product, truncated)
+
+    // entities that occur with the focus relation, ascending (:69-80)
+    std::vector<int32_t> frontier;
+    if (rig_rel[(size_t)focus] >= 0) {
+        for (int64_t i = lef_rel[(size_t)focus]; i <= rig_rel[(size_t)focus]; ++i) {
+            frontier.push_back(by_rel[(size_t)i].h);
+            frontier.push_back(by_rel[(size_t)i].t);
+        }
+        std::sort(frontier.begin(), frontier.end());
+        frontier.erase(std::unique(frontier.begin(), frontier.end()), frontier.end());
+    }
+    if (threshold >= 0 && (int64_t)frontier.size() > threshold) {  // :352-354, :55-67
+        Fenwick fw((int)frontier.size());
+        std::vector<int32_t> subset;
+        int64_t remaining = (int64_t)frontier.size();
+        while ((int64_t)subset.size() < threshold) {
+            const int k = (int)((int64_t)rng.next() % remaining);
+            ++draws;
+            const int pos = fw.kth(k);
+            subset.push_back(frontier[(size_t)pos]);
+            fw.remove(pos);
+            --remaining;
+        }
+        std::sort(subset.begin(), subset.end());
+        frontier.swap(subset);
+    }
+
+    // bidirectional random walk (:92-191)
+    const TripleIndex& g = train;
+    std::vector<Tri>& got = u->collected;
+    got.clear();
+    got.reserve((size_t)tc);
+    std::unordered_set<Tri, TriHash> seen;
+    seen.reserve((size_t)tc * 2);
+    std::set<int32_t> next_points;  // survives rounds: skipped entities resurface one round later
+    int64_t target = tc;
+    int32_t last_dup_entity = -1;
+    int dup_tol = 5, stall_tol = 20;
+    int64_t last_size = 0;
+    std::vector<int32_t> leftover;
+    while ((int64_t)got.size() < target) {
+        leftover.clear();
+        size_t i = 0;
+        while (i < frontier.size() && (int64_t)got.size() < target) {
+            const int32_t e = frontier[i];
+            const bool head_first = (rng.next() % 1000) < 500;  // :122 (prob is the float 500)
+            ++draws;
+            const bool has_h = g.rig_head[(size_t)e] != -1, has_t = g.rig_tail[(size_t)e] != -1;
+            int side;  // 0 head, 1 tail
+            if (head_first) side = has_h ? 0 : (has_t ? 1 : -1);
+            else            side = has_t ? 1 : (has_h ? 0 : -1);
+            Tri x{0, 0, 0};
+            int32_t nxt = -1;
+            if (side == 0) {
+                const int64_t idx = rng.range(g.lef_head[(size_t)e], g.rig_head[(size_t)e] + 1);  // :40
+                ++draws;
+                x = g.by_head[(size_t)idx];
+                nxt = x.t;
+            } else if (side == 1) {
+                const int64_t idx = rng.range(g.lef_tail[(size_t)e], g.rig_tail[(size_t)e] + 1);  // :48
+                ++draws;
+                x = g.by_tail[(size_t)idx];
+                nxt = x.h;
+            }
+            if (seen.count(x)) {  // :141-154
+                if (last_dup_entity == e) --dup_tol;
+                else last_dup_entity = e;
+                if (dup_tol == 0) {
+                    dup_tol = 5;
+                    leftover.push_back(e);
+                    ++i;
+                }
+                continue;
+            }
+            got.push_back(x);
+            seen.insert(x);
+            next_points.insert(nxt);
+            ++i;  // erase(it++)
+        }
+        for (; i < frontier.size(); ++i) leftover.push_back(frontier[i]);
+        // entity_set.swap(new_starting_points) (:170)
+        frontier.assign(next_points.begin(), next_points.end());
+        next_points.clear();
+        next_points.insert(leftover.begin(), leftover.end());
+        if ((int64_t)got.size() == last_size) --stall_tol;
+        else { last_size = (int64_t)got.size(); stall_tol = 20; }
+        if (stall_tol == 0) {  // :181-186
+            target = (int64_t)got.size();
+            break;
+        }
+    }
+    u->draws = draws;
+    if (got.empty()) {
+        *err = "build_universe: random walk collected no triples";
+        return false;
+    }
+
+    // local ids by first appearance: h, then t, then r (:193-233)
+    std::vector<int32_t> emap((size_t)n_ent, -1), rmap((size_t)n_rel, -1);
+    u->ent_remap.clear();
+    u->rel_remap.clear();
+    TripleIndex& L = u->local;
+    L.by_head.resize(got.size());
+    for (size_t k = 0; k < got.size(); ++k) {
+        const Tri& x = got[k];
+        if (emap[(size_t)x.h] < 0) { emap[(size_t)x.h] = (int32_t)u->ent_remap.size(); u->ent_remap.push_back(x.h); }
+        if (emap[(size_t)x.t] < 0) { emap[(size_t)x.t] = (int32_t)u->ent_remap.size(); u->ent_remap.push_back(x.t); }
+        if (rmap[(size_t)x.r] < 0) { rmap[(size_t)x.r] = (int32_t)u->rel_remap.size(); u->rel_remap.push_back(x.r); }
+        L.by_head[k] = Tri{emap[(size_t)x.h], rmap[(size_t)x.r], emap[(size_t)x.t]};
+    }
+    L.n_ent = (int64_t)u->ent_remap.size();
+    L.n_rel = (int64_t)u->rel_remap.size();
+    std::sort(L.by_head.begin(), L.by_head.end(), less_hrt);  // :236
+    L.by_tail = L.by_head;
+    std::sort(L.by_tail.begin(), L.by_tail.end(), less_trh);
+    L.build_ranges();
+    // universe-local Bernoulli statistics (:294-324); freshly allocated per universe, no drift
+    std::vector<int64_t> freq((size_t)L.n_rel, 0), dh, dt;
+    for (const Tri& x : L.by_head) freq[(size_t)x.r]++;
+    L.count_distinct(dh, dt);
+    L.left_mean.resize((size_t)L.n_rel);
+    L.right_mean.resize((size_t)L.n_rel);
+    for (int64_t r = 0; r < L.n_rel; ++r) {
+        L.left_mean[(size_t)r] = (float)freq[(size_t)r] / bump(0.f, dh[(size_t)r]);
+        L.right_mean[(size_t)r] = (float)freq[(size_t)r] / bump(0.f, dt[(size_t)r]);
+    }
+    return true;
+}
+
+}  // namespace pk
