@@ -1,0 +1,479 @@
+#!/usr/bin/env python
+"""bench.py — PuTransE positive triples/sec on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W              # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...    # the reference's CPU path, same box
+
+Workload `m2` (default; BASELINE.json configs[1]): the static PuTransE experiment on WN18 —
+universes seeded 4,5,6,... with the hyper-parameter ranges of the reference's
+experiments/static_experiment_PuTransE_on_WN18.py:43-88 (TransE d=20, L1, Adagrad, nbatches=20,
+k=1, unfiltered uniform negatives, tc in [500,2000), epochs in [50,200)).  One STEP = training one
+chunk of `--universes` universes from scratch (all epochs x 20 batches of every universe).
+positive triples = sum over universes of epochs * nbatches * batch_size.
+
+`value`   : device-resident leg — subgraphs sampled, tables initialised and uploaded BEFORE the
+            timed region; the timed region is the batched-universe kernel (K2) only.
+`e2e`     : the same job through the public API, Parallel_Universe_Config.train_parallel_universes:
+            host subgraph sampling + torch table init + H2D + K2 + D2H of the per-step losses.
+`roofline`: K2's algorithmic bytes / its CUDA-event duration against the measured HBM peak.
+`cpu_baseline` / `--impl reference`: reference Base.so (oracle/_ref) sampling + the op-for-op torch
+            CPU port of the reference's Python training loop (oracle/model_math.py) on host cores.
+With N > 1 (torchrun) every rank runs its own `--universes` universes (weak scaling; universes are
+independent, no training-time communication).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(REPO, "openke-putranse_b200"), REPO, os.path.join(REPO, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+STATIC_RANGES = dict(min_margin=1, max_margin=4, min_lr=0.001, max_lr=0.1, min_num_epochs=50, max_num_epochs=200,
+                     min_triple_constraint=500, max_triple_constraint=2000, min_balance=0.25, max_balance=0.5)
+MODEL_PARAM = {"dim": 20, "p_norm": 1, "norm_flag": 1}
+NBATCHES, K_NEG = 20, 1
+
+
+def algorithmic_bytes_per_positive(model="transe", d=20, k=1, opt="adagrad"):
+    """rows(model,k) * d * 4 * rw(opt) + idx."""
+    rows = {"transe": 3 + k, "transh": 4 + k, "transd": 6 + 2 * k}[model]
+    rw = 4 if opt == "adagrad" else 2
+    return rows * d * 4 * rw + 12 + 4 * k
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_ev = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_ev.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop_ev.wait(0.2)
+
+    def stop(self):
+        self._stop_ev.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def make_pu(path, seed_offset=0):
+    from openke.config import Parallel_Universe_Config
+    from openke.data import TrainDataLoader, TestDataLoader
+    from openke.module.model import TransE
+    train = TrainDataLoader(in_path=path, nbatches=NBATCHES, threads=8, sampling_mode="normal", bern_flag=0, filter_flag=0,
+                            neg_ent=K_NEG, neg_rel=0, random_seed=123)
+    test = TestDataLoader(path, "link")          # re-seeds the shared state with 4, like the static script
+    pu = Parallel_Universe_Config(training_identifier="bench", train_dataloader=train, test_dataloader=test,
+                                  initial_num_universes=None, embedding_model=TransE, embedding_model_param=MODEL_PARAM,
+                                  checkpoint_dir=None, valid_steps=10 ** 9, save_steps=None, training_setting="static",
+                                  incremental_strategy=None, **STATIC_RANGES)
+    pu.initial_random_seed += seed_offset
+    return pu
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import util
+    from openke import _native as N
+    rank, world, local = dist_env()
+    N.require_cuda()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    import tempfile
+    path = util.materialize_wn18(tempfile.mkdtemp())
+    nU = args.universes
+
+    # ---- device-resident leg: build the launch once, replay it
+    pu = make_pu(path, seed_offset=rank * nU)
+    pu.record_losses = True
+    ids = list(range(nU))
+    launch = prepare_resident_launch(pu, ids, dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    st = torch.cuda.current_stream(dev)
+
+    def one_step(timed):
+        launch["reset"]()
+        flush.fill_(1)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(st)
+        launch["run"]()
+        ev1.record(st)
+        if timed is not None:
+            timed.append((ev0, ev1))
+
+    for _ in range(args.warmup):
+        one_step(None)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    evs = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one_step(evs)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    elapsed = time.perf_counter() - t0
+    clk = clocks.stop()
+    kernel_ms = [a.elapsed_time(b) for a, b in evs]
+    launches = launch["launches"] * args.steps
+    positives = launch["positives"]
+    final_loss = float(launch["loss"][-1].item())
+    if dist:
+        t = torch.tensor([elapsed, float(np.mean(kernel_ms))], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed, kms = float(t[0]), float(t[1])
+        tot = torch.tensor([float(positives)], device=dev, dtype=torch.float64)
+        dist.all_reduce(tot)
+        positives_all = float(tot[0])
+    else:
+        kms, positives_all = float(np.mean(kernel_ms)), float(positives)
+    value = positives_all * args.steps / elapsed
+
+    # ---- end-to-end leg through the public API (fresh object per step: same seeds, same work)
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    e2e_pos, h2d, d2h = 0, 0, 0
+    make_pu(path, seed_offset=rank * nU).train_parallel_universes(min(nU, 8))   # warm-up of the host path
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        p2 = make_pu(path, seed_offset=rank * nU)
+        p2.record_losses = True
+        p2.train_parallel_universes(nU)
+        e2e_pos = p2.positive_triples
+        ck = p2._chunks[0]
+        h2d = sum(t.numel() * 4 for t in ck.tables.values()) + int(ck.toff[-1]) * 12
+        d2h = sum(v.nbytes for v in p2.universe_losses.values())
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    e2e_elapsed = time.perf_counter() - t0
+    timings = dict(p2.timings)
+    if dist:
+        t = torch.tensor([e2e_elapsed], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_elapsed = float(t[0])
+        tot = torch.tensor([float(e2e_pos)], device=dev, dtype=torch.float64)
+        dist.all_reduce(tot)
+        e2e_pos = float(tot[0])
+    e2e_value = e2e_pos * e2e_steps / e2e_elapsed
+
+    if rank != 0:
+        return
+    peak, peak_src = measured_peaks()
+    bpp = algorithmic_bytes_per_positive("transe", MODEL_PARAM["dim"], K_NEG, "adagrad")
+    achieved = positives * bpp / (np.mean(kernel_ms) * 1e-3) / 1e9
+    line = {
+        "metric": "PuTransE positive triples/sec (all universes)", "value": value, "unit": "positive triples/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "WN18 graph (repacked reference benchmark files, tests/golden/wn18.npz); universes sampled from it",
+        "config": {"workload": "m2: PuTransE static WN18, %d universes/GPU (seeds 4..), TransE d=20 L1 Adagrad, nbatches=20, k=1"
+                               % nU, "universes_per_gpu": nU, "l2": "flushed between steps (256 MiB write)",
+                   "positive_triples_per_step_per_gpu": positives, "final_loss_last_universe": final_loss},
+        "e2e": {"value": e2e_value, "unit": "positive triples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "ms_per_step": e2e_elapsed / e2e_steps * 1e3,
+                "host_breakdown_s_per_step": {k: v for k, v in timings.items()}},
+        "gpu_launches": launches,
+        "kernel_ms_per_step": float(np.mean(kernel_ms)),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_positive": bpp,
+                     "note": "K2 is latency-bound: universe tables are shared-memory/L2 resident, see DESIGN.md"},
+        "clocks": clk,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_reference_leg(path, budget_s=args.cpu_budget)
+    print(json.dumps(line))
+
+
+def prepare_resident_launch(pu, ids, dev):
+    """Everything _train_chunk does before the kernel, kept resident; returns closures that reset the
+    tables to their initial values and relaunch K2."""
+    import torch
+    from openke import _native as N
+    ck = pu._train_chunk(ids)     # first (untimed) training: leaves descriptors + inputs resident
+    torch.cuda.synchronize()
+    # initial tables again (same seeds): rebuild them on the host exactly as _train_chunk does
+    init = {}
+    for name in ck.proto.table_names():
+        init[name] = torch.empty_like(ck.tables[name])
+    seeds = [pu.initial_random_seed + u for u in ids]
+    for i, u in enumerate(ids):
+        torch.manual_seed(seeds[i])
+        sp = pu.embedding_model(int(ck.nE[i]), int(ck.nR[i]), **pu.embedding_model_param)
+        for name in sp.table_names():
+            o = ck.eoff if name in sp._ent_tables else ck.roff
+            init[name][o[i]:o[i + 1]].copy_(getattr(sp, name).weight.data)
+    nb = pu.train_dataloader.nbatches
+    n = len(ids)
+    desc = (N.UniverseDesc * n)()
+    W = pu.train_dataloader.work_threads
+    lib = pu.lib
+    loss_total = 0
+    # re-derive the descriptors (the library call copied them; we need our own for replays)
+    s = np.array(seeds, dtype=np.int64)
+    tcs = np.array([pu.universe_hyper[u]["tc"] for u in ids], dtype=np.int64)
+    bals = np.array([pu.universe_hyper[u]["balance"] for u in ids], dtype=np.float32)
+    h = lib.pk_universes_build(n, N.addr(s), N.addr(tcs), N.addr(bals), 0)
+    lcg = np.zeros((n, W), dtype=np.uint64)
+    N.check(lib.pk_universes_export(h, None, None, None, None, None, None, None, N.addr(lcg)))
+    lib.pk_universes_free(h)
+    positives = 0
+    for i, u in enumerate(ids):
+        hy = pu.universe_hyper[u]
+        dd = desc[i]
+        dd.tri_off, dd.ent_off, dd.rel_off = int(ck.toff[i]), int(ck.eoff[i]), int(ck.roff[i])
+        dd.n_tri, dd.n_ent, dd.n_rel = int(ck.nT[i]), int(ck.nE[i]), int(ck.nR[i])
+        dd.batch_size, dd.nbatches, dd.epochs = hy["batch_size"], nb, hy["epochs"]
+        dd.margin, dd.lr = float(hy["margin"]), float(hy["lr"])
+        dd.loss_off = loss_total
+        for w in range(W):
+            dd.lcg[w] = int(lcg[i, w])
+        loss_total += hy["epochs"] * nb
+        positives += hy["epochs"] * nb * hy["batch_size"]
+    d_loss = torch.zeros(loss_total, dtype=torch.float32, device=dev)
+    cfg = ck.proto.native_cfg(opt=N.PK_ADAGRAD, neg_ent=K_NEG, bern=0, filt=0, work_threads=W)
+    tab = pu._packed_tables(ck, with_state=True)
+    d_by_head = ck.train_inputs[0]
+    st = torch.cuda.current_stream(dev).cuda_stream
+    state = {"launches": 0}
+
+    def reset():
+        for name, t in ck.tables.items():
+            t.copy_(init[name])
+            ck.state[name].zero_()
+
+    def run():
+        N.check(lib.pk_train_universes(ctypes.byref(cfg), ctypes.byref(tab), d_by_head.data_ptr(), None, None, None, desc, n,
+                                       d_loss.data_ptr(), st), "pk_train_universes")
+        state["launches"] = lib.pk_last_launch_count()
+
+    run_once = run
+    reset()
+    run_once()
+    torch.cuda.synchronize()
+    return {"reset": reset, "run": run, "launches": state["launches"], "positives": positives, "loss": d_loss}
+
+
+# ------------------------------------------------------------------------------------------------
+_TUNED = {}
+
+
+def cpu_reference_leg(path, budget_s=20.0, universes=None, max_epochs=None):
+    """The reference's CPU path for the same workload on this box's host cores: reference Base.so
+    (oracle/_ref, compiled unmodified from /root/reference) for subgraph + batch sampling when it is
+    present — else the oracle's C++ restatement — and the op-for-op torch port of the reference's
+    Python training loop (oracle/model_math.py).  Thread counts (torch intra-op threads and the
+    reference sampler's pthreads) are auto-tuned first on a few untimed steps so that the baseline
+    is the best this box's host cores can do: at universe scale (B~50, d=20) more threads are
+    usually slower.  Bounded sample: universes 0,1,... of the same seed sequence until `budget_s`
+    seconds of CPU work are spent (or exactly `universes` of them)."""
+    import torch
+    from oracle import native as on
+    from oracle.model_math import TorchOracle
+    from openke.config import Parallel_Universe_Config
+    from openke.module.model import TransE
+    cores = os.cpu_count() or 1
+    w = np.load(os.path.join(REPO, "tests", "golden", "wn18.npz"))
+    R = on.load_reference()
+    kind = "port"
+    devnull = saved = None
+    if R is not None:
+        R.setInPath(ctypes.create_string_buffer(path.encode(), len(path) * 2))
+        R.setBern(0)
+        R.setWorkThreads(8)
+        R.setRandomSeed(4)
+        R.randReset()
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        saved = os.dup(1)
+        sys.stdout.flush()
+        os.dup2(devnull, 1)          # the reference printf()s on every call
+    else:
+        o = on.Oracle(threads=8, bern=0)
+        o.import_train(w["train"], 40943, 18)
+    pu = Parallel_Universe_Config.__new__(Parallel_Universe_Config)
+    for k_, v_ in STATIC_RANGES.items():
+        setattr(pu, k_, v_)
+    pu.const_num_epochs = max_epochs
+
+    def run_universe(u, step_cap=None):
+        seed = 4 + u
+        hy = pu.draw_universe_hyper(seed)
+        torch.manual_seed(seed)
+        if R is not None:
+            R.setRandomSeed(seed)
+            R.randReset()
+            R.getParallelUniverse(hy["tc"], ctypes.c_float(hy["balance"]))
+            nT, nE, nR = R.getTrainTotalUniverse(), R.getEntityTotalUniverse(), R.getRelationTotalUniverse()
+            R.swapHelpers()
+        else:
+            o.seed(seed)
+            tri, er, rr = o.universe(hy["tc"], hy["balance"])
+            nT, nE, nR = tri.shape[0], er.shape[0], rr.shape[0]
+            o.swap()
+        B = nT // NBATCHES
+        ref = TransE(nE, nR, **MODEL_PARAM)
+        orc = TorchOracle("transe", {n: getattr(ref, n).weight.detach().numpy() for n in ref.table_names()}, p_norm=1,
+                          opt="adagrad", lr=hy["lr"], margin=hy["margin"], k=K_NEG)
+        n = B * (1 + K_NEG)
+        bh, bt, br, by = np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n, np.float32)
+        steps = hy["epochs"] * NBATCHES if step_cap is None else min(step_cap, hy["epochs"] * NBATCHES)
+        for _ in range(steps):
+            if R is not None:
+                R.sampling(on._addr(bh), on._addr(bt), on._addr(br), on._addr(by), B, K_NEG, 0, 0, 0, 0, 0)
+                orc.step(bh, bt, br)
+            else:
+                orc.step(*o.sampling(B, K_NEG, 0))
+        if R is not None:
+            R.resetUniverse()
+        else:
+            o.swap()
+        return steps, steps * B
+
+    try:
+        if R is not None:
+            R.importTrainFiles()
+        if not _TUNED:
+            best = None
+            for tt in sorted({1, 2, 4, cores}):
+                for stt in ((1, 8) if R is not None else (8,)):
+                    torch.set_num_threads(tt)
+                    if R is not None:
+                        R.setWorkThreads(stt)
+                    run_universe(0, step_cap=5)
+                    t0 = time.perf_counter()
+                    run_universe(0, step_cap=40)
+                    dt = time.perf_counter() - t0
+                    if best is None or dt < best[0]:
+                        best = (dt, tt, stt)
+            _TUNED.update(torch_threads=best[1], sampler_threads=best[2])
+        torch.set_num_threads(_TUNED["torch_threads"])
+        if R is not None:
+            R.setWorkThreads(_TUNED["sampler_threads"])
+        t0 = time.perf_counter()
+        positives, u, steps_total = 0, 0, 0
+        while True:
+            st_, pos_ = run_universe(u)
+            steps_total += st_
+            positives += pos_
+            u += 1
+            if (universes is not None and u >= universes) or (universes is None and time.perf_counter() - t0 > budget_s):
+                break
+        dt = time.perf_counter() - t0
+    finally:
+        if saved is not None:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(devnull)
+            os.close(saved)
+    used = max(_TUNED["torch_threads"], _TUNED["sampler_threads"])
+    return {"value": positives / dt, "unit": "positive triples/s", "cores": used, "kind": kind,
+            "sample": "universes 0..%d of the same seed sequence (%d steps, %d positive triples, %.1f s): %s sampling + torch %s CPU "
+                      "port of the reference training loop; auto-tuned for best throughput on this host (%d cores): torch threads=%d, "
+                      "sampler threads=%d" % (u - 1, steps_total, positives, dt,
+                                              "reference Base.so (oracle/_ref)" if R is not None else "oracle C++", torch.__version__,
+                                              cores, _TUNED["torch_threads"], _TUNED["sampler_threads"])}
+
+
+def run_reference(args):
+    rank, world, local = dist_env()
+    if rank != 0:
+        return
+    import tempfile
+    import util
+    path = util.materialize_wn18(tempfile.mkdtemp())
+    # one step = universe 0 of the workload with its epochs capped so that a step is a few seconds
+    res = []
+    for _ in range(args.warmup):
+        cpu_reference_leg(path, universes=1, max_epochs=args.ref_epochs)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res.append(cpu_reference_leg(path, universes=1, max_epochs=args.ref_epochs))
+    dt = time.perf_counter() - t0
+    v = float(np.mean([r["value"] for r in res]))
+    base = dict(res[-1])
+    base["value"] = v
+    line = {"impl": "reference", "metric": "PuTransE positive triples/sec (all universes)", "value": v,
+            "unit": "positive triples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "WN18 graph (repacked reference benchmark files)",
+            "config": {"workload": "m2: PuTransE static WN18 (bounded sample: universe 0, epochs capped at %d per step)" % args.ref_epochs},
+            "cpu_baseline": base,
+            "e2e": {"value": v, "unit": "positive triples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--universes", type=int, default=100)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--ref-epochs", type=int, default=40)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

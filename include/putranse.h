@@ -236,6 +236,13 @@ int pk_rank_from_energy(const float* d_energy, int64_t n_ent_global, int64_t n, 
  * int64[2] = {0, #known}; d_ranks2: int32[2] = raw, filtered. */
 int pk_rank_candidate_row(const float* d_con, int64_t n_ent, const int32_t* d_truth1, const int64_t* d_foff2,
                           const int32_t* d_fcand, int32_t* d_ranks2, void* stream);
+/* Model.forward / Model.predict on int64 index batches (reference TransE.py:62-74,88-94 and the
+ * TransH/TransD twins).  Output length n = max(nh, nt, nr); arrays shorter than n broadcast by
+ * modulo, which is what the reference's view(-1, r.shape[0], dim) does.  head_batch = 1 computes
+ * h + (r - t), otherwise (h + r) - t.  *d_bad_flag is set to 1 if an index is out of range. */
+int pk_score_batch(const pk_model_cfg* cfg, const pk_tables* tab, const int64_t* d_h, int64_t nh, const int64_t* d_t,
+                   int64_t nt, const int64_t* d_r, int64_t nr, int head_batch, float* d_out, int* d_bad_flag,
+                   void* stream);
 /* fill with +inf */
 int pk_fill_inf(float* d, int64_t n, void* stream);
 

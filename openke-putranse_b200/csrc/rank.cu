@@ -327,6 +327,36 @@ __global__ void k_fill(float* p, int64_t n, float v) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Model.forward / Model.predict on index batches (reference TransE.py:62-74,88-94): one thread per
+// output score; index arrays broadcast by modulo exactly like the reference's view(-1, r.shape[0], d).
+struct ScoreParams {
+    SpaceView sp;
+    const int64_t* h; const int64_t* t; const int64_t* r;
+    int64_t nh, nt, nr, n;
+    int head_batch;  // 1: h + (r - t) ; 0: (h + r) - t
+    float* out;
+    int64_t n_ent, n_rel;
+    int* bad;
+};
+
+__global__ void __launch_bounds__(128) k_score_batch(const __grid_constant__ ScoreParams P) {
+    const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (i >= P.n) return;
+    const int d = P.sp.d;
+    const int64_t h = P.h[i % P.nh], t = P.t[i % P.nt], r = P.r[i % P.nr];
+    if (h < 0 || h >= P.n_ent || t < 0 || t >= P.n_ent || r < 0 || r >= P.n_rel) { *P.bad = 1; P.out[i] = nanf(""); return; }
+    float rh[R_MAXD], w[R_MAXD], y[R_MAXD], q[R_MAXD];
+    rel_operand(P.sp, (int)r, rh, w);
+    const int side = P.head_batch ? 0 : 1;
+    const int64_t fix = side == 0 ? t : h, var = side == 0 ? h : t;
+    ent_operand(P.sp, P.sp.ent[0] + (size_t)fix * d, P.sp.ent[1] ? P.sp.ent[1] + (size_t)fix * d : nullptr, w, y);
+    query_vector(d, side, rh, y, q);
+    ent_operand(P.sp, P.sp.ent[0] + (size_t)var * d, P.sp.ent[1] ? P.sp.ent[1] + (size_t)var * d : nullptr, w, y);
+    P.out[i] = energy(d, P.sp.p_norm, side, q, y, 1);
+}
+
 struct Scratch {  // query vectors + targets, grown on demand, per thread
     float* p = nullptr;
     size_t cap = 0;
@@ -430,6 +460,23 @@ extern "C" int pk_rank_candidate_row(const float* d_con, int64_t n_ent, const in
     P.foff = d_foff2; P.fcand = d_fcand; P.ranks = d_ranks2; P.layout = 1;
     k3_rank_rows<<<1, R_THREADS, 0, (cudaStream_t)stream>>>(P);
     PK_LAUNCHED("k3_rank_rows");
+    return PK_OK;
+}
+
+
+extern "C" int pk_score_batch(const pk_model_cfg* cfg, const pk_tables* tab, const int64_t* d_h, int64_t nh, const int64_t* d_t,
+                              int64_t nt, const int64_t* d_r, int64_t nr, int head_batch, float* d_out, int* d_bad_flag,
+                              void* stream) {
+    pk::launch_counter() = 0;
+    ScoreParams P;
+    int rc = fill_space(P.sp, cfg, tab, "pk_score_batch");
+    if (rc != PK_OK) return rc;
+    if (!d_h || !d_t || !d_r || !d_out || !d_bad_flag || nh < 1 || nt < 1 || nr < 1) return pk::fail(PK_ERR_ARG, "pk_score_batch: null/empty argument");
+    P.h = d_h; P.t = d_t; P.r = d_r; P.nh = nh; P.nt = nt; P.nr = nr;
+    P.n = std::max(nh, std::max(nt, nr));
+    P.head_batch = head_batch; P.out = d_out; P.n_ent = tab->n_ent; P.n_rel = tab->n_rel; P.bad = d_bad_flag;
+    k_score_batch<<<(unsigned)((P.n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(P);
+    PK_LAUNCHED("k_score_batch");
     return PK_OK;
 }
 

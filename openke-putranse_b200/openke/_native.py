@@ -120,6 +120,7 @@ def _declare(L):
         "pk_universe_energies": (ctypes.c_int, [ctypes.POINTER(ModelCfg), ctypes.POINTER(Tables), vp, vp, vp, vp, vp, I, vp, I, vp]),
         "pk_rank_from_energy": (ctypes.c_int, [vp, I, I, vp, vp, vp, vp, vp, vp]),
         "pk_rank_candidate_row": (ctypes.c_int, [vp, I, vp, vp, vp, vp, vp]),
+        "pk_score_batch": (ctypes.c_int, [ctypes.POINTER(ModelCfg), ctypes.POINTER(Tables), vp, I, vp, I, vp, I, ctypes.c_int, vp, vp, vp]),
         "pk_fill_inf": (ctypes.c_int, [vp, I, vp]),
     }
     for name, (res, args) in sig.items():

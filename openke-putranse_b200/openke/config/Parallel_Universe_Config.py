@@ -1,0 +1,642 @@
+"""PuTransE orchestrator: many small embedding spaces ("universes") trained on random-walk
+subgraphs, combined at evaluation time by a minimum over universes.
+
+Constructor kwargs, public attributes and method names follow the reference's
+``openke/config/Parallel_Universe_Config.py:62-946``.  What changed is where the work happens:
+
+reference (per universe, sequential)                  here (per CHUNK of universes)
+-------------------------------------------------     ---------------------------------------------
+set_random_seed; Python draws tc, balance             same draws, same order, private Random(seed)
+getParallelUniverse (single-threaded, libc rand)      pk_universes_build: all universes of the chunk
+                                                      on host threads, bit-identical subgraphs
+torch.manual_seed + model init                        same (torch CPU generator), packed + one H2D
+Trainer.run: epochs x nbatches Python steps           pk_train_universes: ONE launch, a block/universe
+eval_universes: Python loop triple x universe with    pk_universe_energies + (NCCL min all-reduce when
+  per-entity .item() min                                universes are sharded over ranks) +
+testHead/testTail in C on the host                    pk_rank_from_energy
+
+Universes are independent given ``initial_random_seed + universe_id`` (reference :324), so with
+``torch.distributed`` initialised each rank trains the universes ``u % world_size == rank`` with
+no communication; evaluation min-all-reduces the energy tiles.
+"""
+import ctypes
+import os
+import time
+from collections import defaultdict
+from random import Random
+
+import numpy as np
+import torch
+
+from .. import _native as N
+from ..module.loss import MarginLoss
+from ..module.model.Model import Model
+from ..module.strategy import NegativeSampling
+from .Tester import Tester, link_metrics
+from ..data.TestDataLoader import TestDataLoader
+
+
+def get_string_key(entity, relation):
+    return "{},{}".format(entity, relation)
+
+
+def defaultdict_int(innerfactory=int):
+    return defaultdict(innerfactory)
+
+
+def _dist():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist, dist.get_rank(), dist.get_world_size()
+    return None, 0, 1
+
+
+class _Chunk(object):
+    """One pk_train_universes launch worth of universes: packed device tables + host-side maps."""
+    pass
+
+
+class Parallel_Universe_Config(Tester):
+    def __init__(self, train_dataloader=None, training_identifier="", valid_dataloader=None, test_dataloader=None,
+                 initial_num_universes=5000, min_margin=1, max_margin=4, min_lr=0.01, max_lr=0.1, min_num_epochs=50,
+                 max_num_epochs=200, const_num_epochs=None, min_triple_constraint=500, max_triple_constraint=2000,
+                 min_balance=0.25, max_balance=0.5, embedding_model=None, embedding_model_param=None,
+                 missing_embedding_handling="last_rank", save_steps=5, checkpoint_dir="./checkpoint/", valid_steps=5,
+                 early_stopping_patience=5, training_setting="static", incremental_strategy="normal"):
+        super().__init__(data_loader=test_dataloader, use_gpu=torch.cuda.is_available())
+        if training_setting != "static":
+            raise NotImplementedError("incremental PuTransE is outside the B200 hot path (SURVEY.md 8(f))")
+        if missing_embedding_handling != "last_rank":
+            raise NotImplementedError("missing_embedding_handling='null_vector' is not implemented (SURVEY.md 8(f))")
+        self.train_dataloader = train_dataloader
+        self.ent_tot = train_dataloader.entTotal
+        self.rel_tot = train_dataloader.relTotal
+        self.training_identifier = training_identifier
+        self.embedding_model = embedding_model
+        self.embedding_model_param = embedding_model_param or {}
+
+        self.initial_num_universes = initial_num_universes
+        self.next_universe_id = 0
+        self.trained_embedding_spaces = defaultdict(Model)          # universe id -> embedding space
+        self.entity_id_mappings = defaultdict(defaultdict_int)      # universe id -> global entity -> local
+        self.relation_id_mappings = defaultdict(defaultdict_int)
+        self.entity_universes = defaultdict(set)                    # global entity -> universe ids
+        self.relation_universes = defaultdict(set)
+        # the loaders share one library state: this is whatever seed was set last (reference :97)
+        self.initial_random_seed = self.train_dataloader.lib.getRandomSeed()
+
+        self.min_margin, self.max_margin = min_margin, max_margin
+        self.min_lr, self.max_lr = min_lr, max_lr
+        self.min_num_epochs, self.max_num_epochs = min_num_epochs, max_num_epochs
+        self.const_num_epochs = const_num_epochs
+        self.min_triple_constraint, self.max_triple_constraint = min_triple_constraint, max_triple_constraint
+        self.min_balance, self.max_balance = min_balance, max_balance
+        self.save_steps, self.checkpoint_dir = save_steps, checkpoint_dir
+        self.missing_embedding_handling = missing_embedding_handling
+
+        self.valid_dataloader = valid_dataloader if valid_dataloader is not None else TestDataLoader(
+            train_dataloader.in_path, sampling_mode="link", mode="valid")
+        self.valid_steps = valid_steps
+        self.early_stopping_patience = early_stopping_patience
+        self.early_stopping_patience_const = early_stopping_patience
+        self.bad_counts = 0
+        self.best_hit10 = 0
+        self.best_state = None
+        self.training_setting = training_setting
+        self.incremental_strategy = incremental_strategy
+
+        # B200 build state
+        self._chunks = []
+        self.universe_hyper = {}          # universe id -> dict(tc, balance, margin, epochs, lr, nT, nE, nR, focus)
+        self.universe_losses = {}         # universe id -> np.float32 [epochs*nbatches] (if record_losses)
+        self.record_losses = False
+        self.sampler_threads = 0          # host threads for universe construction (0 = all cores)
+        self.max_chunk = 1024             # universes per launch
+        self.max_energy_bytes = 8 << 30   # size of one [keys, E] energy tile
+        self.training_duration = 0.0
+        self.positive_triples = 0         # sum over universes of epochs * nbatches * batch_size
+        self.gpu_launches = 0
+        self._rank_cache = {}
+        self.timings = defaultdict(float)
+
+    # ------------------------------------------------------------------ small reference-API helpers
+    def get_default_value_list(self):
+        return [float("inf") for _ in range(self.ent_tot)]
+
+    def set_min_max_triple_constraint(self, min, max):
+        self.min_triple_constraint, self.max_triple_constraint = min, max
+
+    def set_random_seed(self, rand_seed):
+        import random
+        self.train_dataloader.lib.setRandomSeed(rand_seed)
+        self.train_dataloader.lib.randReset()
+        random.seed(rand_seed)
+        torch.manual_seed(rand_seed)
+
+    def set_valid_dataloader(self, valid_dataloader):
+        self.valid_dataloader = valid_dataloader
+
+    def set_test_dataloader(self, test_dataloader):
+        self.data_loader = test_dataloader
+
+    def embedding_model_factory(self, ent_tot, rel_tot, margin):
+        return NegativeSampling(model=self.embedding_model(ent_tot, rel_tot, **self.embedding_model_param),
+                                loss=MarginLoss(margin=margin), batch_size=self.train_dataloader.batch_size)
+
+    def reset_valid_variables(self):
+        self.early_stopping_patience = self.early_stopping_patience_const
+        self.best_state = {}
+        self.best_hit10 = 0
+        self.bad_counts = 0
+
+    def gather_embedding_spaces(self, entity_1, rel, entity_2=None):
+        ids = self.entity_universes[entity_1].intersection(self.relation_universes[rel])
+        if entity_2 is not None:
+            ids = ids.intersection(self.entity_universes[entity_2])
+        return ids
+
+    def calculate_unembedded_ratio(self, mode="examine_entities"):
+        mapping = self.entity_universes if mode == "examine_entities" else self.relation_universes
+        total = self.train_dataloader.entTotal if mode == "examine_entities" else self.train_dataloader.relTotal
+        return sum(1 for i in range(total) if len(mapping[i]) == 0) / total
+
+    # ------------------------------------------------------------------ hyper-parameter draws
+    def draw_universe_hyper(self, seed):
+        """The reference's Python draws for one universe, in its order (reference :211-212,232,237-240),
+        from a generator seeded like ``random.seed(seed)``."""
+        rnd = Random(seed)
+        tc = rnd.randrange(self.min_triple_constraint, self.max_triple_constraint)
+        balance = round(rnd.uniform(self.min_balance, self.max_balance), 2)
+        margin = rnd.randrange(self.min_margin, self.max_margin)
+        epochs = self.const_num_epochs if self.const_num_epochs is not None else \
+            rnd.randrange(self.min_num_epochs, self.max_num_epochs)
+        lr = round(rnd.uniform(self.min_lr, self.max_lr), len(str(self.min_lr).split(".")[1]))
+        return dict(tc=tc, balance=balance, margin=margin, epochs=epochs, lr=lr)
+
+    # ------------------------------------------------------------------ training
+    def _device(self):
+        if not self.use_gpu:
+            raise N.NativeError("PuTransE on the B200 path needs a CUDA device: there is no CPU implementation")
+        N.require_cuda()
+        return torch.device("cuda", torch.cuda.current_device())
+
+    def _train_chunk(self, universe_ids):
+        lib, dl = self.lib, self.train_dataloader
+        dev = self._device()
+        n = len(universe_ids)
+        t0 = time.perf_counter()
+        hyper = [self.draw_universe_hyper(self.initial_random_seed + u) for u in universe_ids]
+        seeds = np.array([self.initial_random_seed + u for u in universe_ids], dtype=np.int64)
+        tcs = np.array([h["tc"] for h in hyper], dtype=np.int64)
+        bals = np.array([h["balance"] for h in hyper], dtype=np.float32)
+        # -- subgraphs: bit-identical to the reference's getParallelUniverse, on host threads
+        lib.setWorkThreads(dl.work_threads)
+        handle = lib.pk_universes_build(n, N.addr(seeds), N.addr(tcs), N.addr(bals), int(self.sampler_threads))
+        if not handle:
+            raise N.NativeError("pk_universes_build: %s" % N.last_error())
+        try:
+            nT, nE, nR, focus = (np.zeros(n, dtype=np.int64) for _ in range(4))
+            N.check(lib.pk_universes_sizes(handle, N.addr(nT), N.addr(nE), N.addr(nR), N.addr(focus)), "pk_universes_sizes")
+            sT, sE, sR = int(nT.sum()), int(nE.sum()), int(nR.sum())
+            W = dl.work_threads
+            by_head = np.zeros((sT, 3), dtype=np.int32)
+            by_tail = np.zeros((sT, 3), dtype=np.int32) if dl.filter else None
+            ent_remap, rel_remap = np.zeros(sE, dtype=np.int32), np.zeros(sR, dtype=np.int32)
+            lm, rm = np.zeros(sR, dtype=np.float32), np.zeros(sR, dtype=np.float32)
+            lcg = np.zeros((n, W), dtype=np.uint64)
+            N.check(lib.pk_universes_export(handle, N.addr(by_head), N.addr(by_tail) if by_tail is not None else None, None,
+                                            N.addr(ent_remap), N.addr(rel_remap), N.addr(lm), N.addr(rm), N.addr(lcg)),
+                    "pk_universes_export")
+        finally:
+            lib.pk_universes_free(handle)
+        t1 = time.perf_counter()
+        self.timings["universe_sampling"] += t1 - t0
+        toff = np.concatenate([[0], np.cumsum(nT)]).astype(np.int64)
+        eoff = np.concatenate([[0], np.cumsum(nE)]).astype(np.int64)
+        roff = np.concatenate([[0], np.cumsum(nR)]).astype(np.int64)
+
+        # -- initial tables: the reference's torch CPU initialisation, universe by universe
+        proto = None
+        spaces = []
+        packed_host = None
+        for i, u in enumerate(universe_ids):
+            torch.manual_seed(int(seeds[i]))
+            space = self.embedding_model(int(nE[i]), int(nR[i]), **self.embedding_model_param)
+            if proto is None:
+                proto = space
+                d = space.dim_native
+                packed_host = {name: torch.empty((sE if name in space._ent_tables else sR, d), dtype=torch.float32).pin_memory()
+                               for name in space.table_names()}
+            for name in space.table_names():
+                o = eoff if name in space._ent_tables else roff
+                packed_host[name][o[i]:o[i + 1]].copy_(getattr(space, name).weight.data)
+            spaces.append(space)
+        t2 = time.perf_counter()
+        self.timings["table_init"] += t2 - t1
+
+        ck = _Chunk()
+        ck.ids = list(universe_ids)
+        ck.nT, ck.nE, ck.nR, ck.eoff, ck.roff, ck.toff = nT, nE, nR, eoff, roff, toff
+        ck.ent_remap, ck.rel_remap = ent_remap, rel_remap
+        ck.proto = proto
+        ck.tables = {name: t.to(dev, non_blocking=True) for name, t in packed_host.items()}
+        adagrad = True  # reference :241-242 hard-codes opt_method='Adagrad' for universes
+        ck.state = {name: torch.zeros_like(t) for name, t in ck.tables.items()} if adagrad else None
+        d_by_head = torch.from_numpy(by_head).to(dev, non_blocking=True)
+        d_by_tail = torch.from_numpy(by_tail).to(dev, non_blocking=True) if by_tail is not None else None
+        d_lm = torch.from_numpy(lm).to(dev, non_blocking=True) if dl.bern else None
+        d_rm = torch.from_numpy(rm).to(dev, non_blocking=True) if dl.bern else None
+
+        nb = dl.nbatches
+        desc = (N.UniverseDesc * n)()
+        loss_total = 0
+        for i in range(n):
+            B = int(nT[i]) // nb
+            if B < 1:
+                raise N.NativeError("universe %d has %d triples: fewer than nbatches=%d" % (universe_ids[i], nT[i], nb))
+            h = hyper[i]
+            dd = desc[i]
+            dd.tri_off, dd.ent_off, dd.rel_off = int(toff[i]), int(eoff[i]), int(roff[i])
+            dd.n_tri, dd.n_ent, dd.n_rel = int(nT[i]), int(nE[i]), int(nR[i])
+            dd.batch_size, dd.nbatches, dd.epochs = B, nb, int(h["epochs"])
+            dd.margin, dd.lr = float(h["margin"]), float(h["lr"])
+            dd.loss_off = loss_total if self.record_losses else -1
+            for w in range(min(W, 8)):
+                dd.lcg[w] = int(lcg[i, w])
+            loss_total += h["epochs"] * nb
+            h.update(nT=int(nT[i]), nE=int(nE[i]), nR=int(nR[i]), focus=int(focus[i]), batch_size=B, nbatches=nb)
+            self.universe_hyper[universe_ids[i]] = h
+            self.positive_triples += h["epochs"] * nb * B
+        d_loss = torch.zeros(max(loss_total, 1), dtype=torch.float32, device=dev) if self.record_losses else None
+
+        cfg = proto.native_cfg(opt=N.PK_ADAGRAD, neg_ent=dl.negative_ent, bern=1 if dl.bern else 0,
+                               filt=1 if dl.filter else 0, work_threads=W)
+        tab = self._packed_tables(ck, with_state=True)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        N.check(lib.pk_train_universes(ctypes.byref(cfg), ctypes.byref(tab), d_by_head.data_ptr(),
+                                       d_by_tail.data_ptr() if d_by_tail is not None else None,
+                                       d_lm.data_ptr() if d_lm is not None else None,
+                                       d_rm.data_ptr() if d_rm is not None else None,
+                                       desc, n, d_loss.data_ptr() if d_loss is not None else None, st),
+                "pk_train_universes")
+        self.gpu_launches += lib.pk_last_launch_count()
+        ck.train_inputs = (d_by_head, d_by_tail, d_lm, d_rm)  # keep alive until the stream is done
+        t3 = time.perf_counter()
+        self.timings["launch"] += t3 - t2
+
+        # -- expose every universe as an embedding-space module over views of the packed tables
+        for i, u in enumerate(universe_ids):
+            space = spaces[i]
+            for name in space.table_names():
+                o = eoff if name in space._ent_tables else roff
+                getattr(space, name).weight = torch.nn.Parameter(ck.tables[name][o[i]:o[i + 1]], requires_grad=False)
+            for p in (space.zero_const, space.pi_const):
+                p.data = p.data.to(dev)
+            space.eval()
+            self.trained_embedding_spaces[u] = space
+            er = ent_remap[eoff[i]:eoff[i + 1]].tolist()
+            rr = rel_remap[roff[i]:roff[i + 1]].tolist()
+            emap = self.entity_id_mappings[u]
+            emap.update(zip(er, range(len(er))))
+            rmap = self.relation_id_mappings[u]
+            rmap.update(zip(rr, range(len(rr))))
+            for g in er:
+                self.entity_universes[g].add(u)
+            for g in rr:
+                self.relation_universes[g].add(u)
+        if self.record_losses:
+            host = d_loss.cpu().numpy()
+            o = 0
+            for i, u in enumerate(universe_ids):
+                steps = hyper[i]["epochs"] * nb
+                self.universe_losses[u] = host[o:o + steps].copy()
+                o += steps
+        self._chunks.append(ck)
+        self._rank_cache.clear()
+        self.timings["bookkeeping"] += time.perf_counter() - t3
+        return ck
+
+    def _packed_tables(self, ck, with_state=False):
+        t = N.Tables()
+        for i in range(2):
+            t.ent[i] = t.rel[i] = t.ent_state[i] = t.rel_state[i] = None
+        for i, name in enumerate(ck.proto._ent_tables):
+            t.ent[i] = ck.tables[name].data_ptr()
+            if with_state and ck.state is not None:
+                t.ent_state[i] = ck.state[name].data_ptr()
+        for i, name in enumerate(ck.proto._rel_tables):
+            t.rel[i] = ck.tables[name].data_ptr()
+            if with_state and ck.state is not None:
+                t.rel_state[i] = ck.state[name].data_ptr()
+        t.n_ent, t.n_rel = int(ck.eoff[-1]), int(ck.roff[-1])
+        return t
+
+    def train_parallel_universes(self, num_of_embedding_spaces):
+        """Reference :316-367.  Universes are trained in chunks that end where the reference would
+        validate (every ``valid_steps`` universes); with torch.distributed each rank trains its share."""
+        dist, rank, world = _dist()
+        training_duration = 0.0
+        done = 0
+        while done < num_of_embedding_spaces:
+            c = min(num_of_embedding_spaces - done, self.valid_steps - (done % self.valid_steps), self.max_chunk * world)
+            start = time.time()
+            ids = [self.next_universe_id + j for j in range(c)]
+            mine = [u for u in ids if u % world == rank]
+            if mine:
+                self._train_chunk(mine)
+            self.next_universe_id += c
+            done += c
+            if self.use_gpu:
+                torch.cuda.synchronize()
+            training_duration += time.time() - start
+            if done % self.valid_steps == 0:
+                print("Universe %d has finished, validating..." % (self.next_universe_id - 1))
+                self.eval_universes(eval_mode="valid")
+                hit10 = self.valid()
+                print("Current hit@10: {}".format(hit10))
+                if hit10 > self.best_hit10:
+                    self.best_hit10 = hit10
+                    print("Best model | hit@10 of valid set is %f" % self.best_hit10)
+                    if self.checkpoint_dir and rank == 0:
+                        self.save_model("Best_model_Pu{}_{}.ckpt".format(self.embedding_model.__name__, self.training_identifier))
+                    self.bad_counts = 0
+                else:
+                    print("Hit@10 of valid set is %f | bad count is %d" % (hit10, self.bad_counts))
+                    self.bad_counts += 1
+                if self.bad_counts == self.early_stopping_patience:
+                    print("Early stopping at universe {}".format(self.next_universe_id - 1))
+                    break
+            if self.save_steps and self.checkpoint_dir and rank == 0 and (done // self.save_steps) > ((done - c) // self.save_steps):
+                self.save_model()
+        self.training_duration += training_duration
+        print("Time took for creation of embedding spaces: {:5.3f}s".format(training_duration))
+
+    def add_embedding_space(self, embedding_space):
+        for p in embedding_space.parameters():
+            p.requires_grad = False
+        self.trained_embedding_spaces[self.next_universe_id] = embedding_space
+
+    # ------------------------------------------------------------------ evaluation
+    def _rank_split(self, loader):
+        """Raw/filtered ranks [n,4] of every triple of `loader` under the min-over-universes energy
+        (reference eval_universes :556-603 + global_energy_estimation :605-642 + Test.h ranking)."""
+        lib = self.lib
+        dev = self._device()
+        dist, rank, world = _dist()
+        tri, filt = loader.eval_arrays()
+        n = tri.shape[0]
+        E = self.ent_tot
+        # keys: head side fixes (t, r); tail side fixes (h, r)
+        fixed = np.concatenate([tri[:, 2], tri[:, 0]]).astype(np.int64)
+        rel = np.concatenate([tri[:, 1], tri[:, 1]]).astype(np.int64)
+        side = np.concatenate([np.zeros(n, np.int64), np.ones(n, np.int64)])
+        truth = np.concatenate([tri[:, 0], tri[:, 2]]).astype(np.int32)
+        code = (side * E + fixed) * self.rel_tot + rel
+        ucode, key_of_query = np.unique(code, return_inverse=True)
+        K = ucode.shape[0]
+        k_rel = ucode % self.rel_tot
+        k_fixed = (ucode // self.rel_tot) % E
+        k_side = ucode // (self.rel_tot * E)
+        foff = np.concatenate([filt[0][0], filt[0][0][-1] + filt[1][0][1:]]).astype(np.int64)
+        fcand = np.concatenate([filt[0][1], filt[1][1]]).astype(np.int32)
+        if fcand.size == 0:
+            fcand = np.zeros(1, np.int32)
+        d_foff, d_fcand = torch.from_numpy(foff).to(dev), torch.from_numpy(fcand).to(dev)
+        d_truth = torch.from_numpy(truth).to(dev)
+        ranks = torch.zeros((2 * n, 2), dtype=torch.int32, device=dev)
+        st = torch.cuda.current_stream(dev).cuda_stream
+
+        rows_per_tile = max(1, min(K, int(self.max_energy_bytes // (4 * E))))
+        per_chunk = [self._chunk_index(ck) for ck in self._chunks]
+        order = np.argsort(key_of_query, kind="stable")   # queries grouped by key row
+        sorted_keys = key_of_query[order]
+        for k0 in range(0, K, rows_per_tile):
+            k1 = min(K, k0 + rows_per_tile)
+            energy = torch.empty((k1 - k0, E), dtype=torch.float32, device=dev)
+            N.check(lib.pk_fill_inf(energy.data_ptr(), energy.numel(), st), "pk_fill_inf")
+            for ck, ix in zip(self._chunks, per_chunk):
+                items = self._energy_items(ix, k_fixed[k0:k1], k_rel[k0:k1], k_side[k0:k1])
+                if items.shape[0] == 0:
+                    continue
+                d_items = torch.from_numpy(items.view(np.int32).reshape(-1, 6)).to(dev)
+                cfg, tab = ck.proto.native_cfg(), self._packed_tables(ck)
+                N.check(lib.pk_universe_energies(ctypes.byref(cfg), ctypes.byref(tab), ix["d_eoff"].data_ptr(),
+                                                 ix["d_roff"].data_ptr(), ix["d_nE"].data_ptr(), ix["d_remap"].data_ptr(),
+                                                 d_items.data_ptr(), items.shape[0], energy.data_ptr(), E, st),
+                        "pk_universe_energies")
+                self.gpu_launches += lib.pk_last_launch_count()
+            if dist is not None and world > 1:
+                dist.all_reduce(energy, op=dist.ReduceOp.MIN)   # NCCL min over NVLink: the one exchange step
+            lo, hi = np.searchsorted(sorted_keys, k0), np.searchsorted(sorted_keys, k1)
+            if hi > lo:
+                q = order[lo:hi]
+                d_q = torch.from_numpy(q.astype(np.int64)).to(dev)
+                d_row = torch.from_numpy((key_of_query[q] - k0).astype(np.int32)).to(dev)
+                sub_truth = d_truth[d_q].contiguous()
+                # filter CSR of the selected queries, re-based
+                cnt = foff[q + 1] - foff[q]
+                sub_off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+                take = np.concatenate([np.arange(foff[i], foff[i + 1]) for i in q]) if cnt.sum() else np.zeros(0, np.int64)
+                sub_cand = fcand[take] if take.size else np.zeros(1, np.int32)
+                d_sub_off, d_sub_cand = torch.from_numpy(sub_off).to(dev), torch.from_numpy(sub_cand.astype(np.int32)).to(dev)
+                sub_ranks = torch.zeros((q.shape[0], 2), dtype=torch.int32, device=dev)
+                N.check(lib.pk_rank_from_energy(energy.data_ptr(), E, q.shape[0], d_row.data_ptr(), sub_truth.data_ptr(),
+                                                d_sub_off.data_ptr(), d_sub_cand.data_ptr(), sub_ranks.data_ptr(), st),
+                        "pk_rank_from_energy")
+                self.gpu_launches += lib.pk_last_launch_count()
+                ranks[d_q] = sub_ranks
+        r = ranks.cpu().numpy()
+        return np.concatenate([r[:n], r[n:]], axis=1)   # head raw, head filt, tail raw, tail filt
+
+    def _chunk_index(self, ck):
+        """Inverted index of one chunk: which universes hold a global entity / relation, and under
+        which local id (replaces the reference's entity_universes / *_id_mappings dict lookups)."""
+        if getattr(ck, "index", None) is not None:
+            return ck.index
+        dev = self._device()
+        nU = len(ck.ids)
+        univ_of_row = np.repeat(np.arange(nU, dtype=np.int32), ck.nE)
+        local = (np.arange(ck.ent_remap.shape[0], dtype=np.int64) - np.repeat(ck.eoff[:-1], ck.nE)).astype(np.int32)
+        order = np.argsort(ck.ent_remap, kind="stable")
+        ix = {"ent_sorted": ck.ent_remap[order], "ent_univ": univ_of_row[order], "ent_local": local[order]}
+        rel_local = np.full((self.rel_tot, nU), -1, dtype=np.int32)
+        runiv = np.repeat(np.arange(nU, dtype=np.int32), ck.nR)
+        rloc = (np.arange(ck.rel_remap.shape[0], dtype=np.int64) - np.repeat(ck.roff[:-1], ck.nR)).astype(np.int32)
+        rel_local[ck.rel_remap, runiv] = rloc
+        ix["rel_local"] = rel_local
+        ix["d_eoff"] = torch.from_numpy(ck.eoff[:-1].copy()).to(dev)
+        ix["d_roff"] = torch.from_numpy(ck.roff[:-1].copy()).to(dev)
+        ix["d_nE"] = torch.from_numpy(ck.nE.astype(np.int32)).to(dev)
+        ix["d_remap"] = torch.from_numpy(ck.ent_remap).to(dev)
+        ck.index = ix
+        return ix
+
+    @staticmethod
+    def _energy_items(ix, k_fixed, k_rel, k_side):
+        """(key row, universe, local fixed entity, local relation, side) for every universe of the
+        chunk that contains both the key's fixed entity and its relation."""
+        lo = np.searchsorted(ix["ent_sorted"], k_fixed, side="left")
+        hi = np.searchsorted(ix["ent_sorted"], k_fixed, side="right")
+        cnt = hi - lo
+        tot = int(cnt.sum())
+        items = np.zeros(tot, dtype=N.ENERGY_ITEM_DTYPE)
+        if tot == 0:
+            return items
+        key_row = np.repeat(np.arange(k_fixed.shape[0], dtype=np.int64), cnt)
+        pos = np.arange(tot, dtype=np.int64) - np.repeat(np.cumsum(cnt) - cnt, cnt) + np.repeat(lo, cnt)
+        u = ix["ent_univ"][pos]
+        rl = ix["rel_local"][k_rel[key_row], u]
+        keep = rl >= 0
+        items = items[:int(keep.sum())]
+        items["key_row"] = key_row[keep]
+        items["universe"] = u[keep]
+        items["fixed_local"] = ix["ent_local"][pos][keep]
+        items["rel_local"] = rl[keep]
+        items["side"] = k_side[key_row][keep]
+        return items
+
+    def eval_universes(self, eval_mode):
+        loader = self.data_loader if eval_mode == "test" else self.valid_dataloader
+        self._rank_cache[eval_mode] = (self.next_universe_id, self._rank_split(loader))
+
+    def _ranks(self, eval_mode):
+        c = self._rank_cache.get(eval_mode)
+        if c is None or c[0] != self.next_universe_id:
+            self.eval_universes(eval_mode)
+            c = self._rank_cache[eval_mode]
+        return c[1]
+
+    def valid(self):
+        ranks = self._ranks("valid")
+        n = np.float32(ranks.shape[0])
+        return float((np.float32((ranks[:, 1] < 10).sum()) / n + np.float32((ranks[:, 3] < 10).sum()) / n) / np.float32(2))
+
+    def run_link_prediction(self, type_constrain=False):
+        if type_constrain:
+            raise NotImplementedError("type-constrained ranking is not on the PuTransE hot path")
+        self.data_loader.set_sampling_mode("link")
+        self.last_ranks = self._ranks("test")
+        (mrr, mr, hit10, hit3, hit1), self.last_table = link_metrics(self.last_ranks)
+        print("Mean Reciprocal Rank: {}".format(mrr))
+        print("Mean Rank: {}".format(mr))
+        print("Hits@10: {}".format(hit10))
+        print("Hits@3: {}".format(hit3))
+        print("Hits@1: {}".format(hit1))
+        return mrr, mr, hit10, hit3, hit1
+
+    def global_energy_estimation(self, data):
+        """Energy row of ONE candidate batch in the reference's candidate order (reference :605-642)."""
+        mode = data["mode"]
+        h, t, r = np.asarray(data["batch_h"]), np.asarray(data["batch_t"]), np.asarray(data["batch_r"])
+        fixed = int(t[0]) if mode == "head_batch" else int(h[0])
+        cands = h if mode == "head_batch" else t
+        side = 0 if mode == "head_batch" else 1
+        dev = self._device()
+        st = torch.cuda.current_stream(dev).cuda_stream
+        energy = torch.empty((1, self.ent_tot), dtype=torch.float32, device=dev)
+        N.check(self.lib.pk_fill_inf(energy.data_ptr(), energy.numel(), st), "pk_fill_inf")
+        for ck in self._chunks:
+            ix = self._chunk_index(ck)
+            items = self._energy_items(ix, np.array([fixed]), np.array([int(r[0])]), np.array([side]))
+            if items.shape[0]:
+                d_items = torch.from_numpy(items.view(np.int32).reshape(-1, 6)).to(dev)
+                cfg, tab = ck.proto.native_cfg(), self._packed_tables(ck)
+                N.check(self.lib.pk_universe_energies(ctypes.byref(cfg), ctypes.byref(tab), ix["d_eoff"].data_ptr(),
+                                                      ix["d_roff"].data_ptr(), ix["d_nE"].data_ptr(), ix["d_remap"].data_ptr(),
+                                                      d_items.data_ptr(), items.shape[0], energy.data_ptr(), self.ent_tot, st),
+                        "pk_universe_energies")
+        return energy[0].cpu().numpy()[cands.astype(np.int64)]
+
+    def test_one_step(self, data):
+        return self.global_energy_estimation(data)
+
+    # ------------------------------------------------------------------ checkpoints (flat tensors)
+    def save_model(self, filename=None):
+        if not filename:
+            filename = "Pu{}_learned_spaces-{}_{}.ckpt".format(self.embedding_model.__name__, self.next_universe_id,
+                                                               self.training_identifier)
+        self.save_parameters(os.path.join("{}{}".format(self.checkpoint_dir, filename)))
+
+    def extend_state_dict(self):
+        chunks = []
+        for ck in self._chunks:
+            chunks.append({"ids": ck.ids, "nT": ck.nT, "nE": ck.nE, "nR": ck.nR, "ent_remap": ck.ent_remap,
+                           "rel_remap": ck.rel_remap, "tables": {k: v.cpu() for k, v in ck.tables.items()}})
+        return {"format": "putranse-b200/flat-1", "next_universe_id": self.next_universe_id, "chunks": chunks,
+                "universe_hyper": self.universe_hyper, "embedding_model": self.embedding_model.__name__,
+                "embedding_model_param": self.embedding_model_param, "best_hit10": self.best_hit10,
+                "bad_counts": self.bad_counts, "initial_random_seed": self.initial_random_seed,
+                "ent_tot": self.ent_tot, "rel_tot": self.rel_tot}
+
+    def save_parameters(self, path):
+        os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+        torch.save(self.extend_state_dict(), path)
+
+    def process_state_dict(self, state):
+        dev = self._device()
+        self._chunks = []
+        self.trained_embedding_spaces.clear()
+        self.entity_id_mappings.clear()
+        self.relation_id_mappings.clear()
+        self.entity_universes.clear()
+        self.relation_universes.clear()
+        for c in state["chunks"]:
+            ck = _Chunk()
+            ck.ids, ck.nT, ck.nE, ck.nR = list(c["ids"]), c["nT"], c["nE"], c["nR"]
+            ck.ent_remap, ck.rel_remap = c["ent_remap"], c["rel_remap"]
+            ck.eoff = np.concatenate([[0], np.cumsum(ck.nE)]).astype(np.int64)
+            ck.roff = np.concatenate([[0], np.cumsum(ck.nR)]).astype(np.int64)
+            ck.toff = np.concatenate([[0], np.cumsum(ck.nT)]).astype(np.int64)
+            ck.tables = {k: v.to(dev) for k, v in c["tables"].items()}
+            ck.state = None
+            ck.proto = None
+            for i, u in enumerate(ck.ids):
+                space = self.embedding_model(int(ck.nE[i]), int(ck.nR[i]), **self.embedding_model_param)
+                ck.proto = ck.proto or space
+                for name in space.table_names():
+                    o = ck.eoff if name in space._ent_tables else ck.roff
+                    getattr(space, name).weight = torch.nn.Parameter(ck.tables[name][o[i]:o[i + 1]], requires_grad=False)
+                for p in (space.zero_const, space.pi_const):
+                    p.data = p.data.to(dev)
+                space.eval()
+                self.trained_embedding_spaces[u] = space
+                er = ck.ent_remap[ck.eoff[i]:ck.eoff[i + 1]].tolist()
+                rr = ck.rel_remap[ck.roff[i]:ck.roff[i + 1]].tolist()
+                self.entity_id_mappings[u].update(zip(er, range(len(er))))
+                self.relation_id_mappings[u].update(zip(rr, range(len(rr))))
+                for g in er:
+                    self.entity_universes[g].add(u)
+                for g in rr:
+                    self.relation_universes[g].add(u)
+            self._chunks.append(ck)
+        self.next_universe_id = state["next_universe_id"]
+        self.universe_hyper = state.get("universe_hyper", {})
+        self.best_hit10 = state.get("best_hit10", 0)
+        self.bad_counts = state.get("bad_counts", 0)
+        self._rank_cache.clear()
+
+    def load_parameters(self, filename):
+        state = torch.load(self.checkpoint_dir + filename, map_location="cpu", weights_only=False)
+        self.process_state_dict(state)
+
+    def extend_parallel_universe(self, other):
+        """Append another instance's universes after this one's (reference :797-823)."""
+        shift = self.next_universe_id
+        for ck in other._chunks:
+            ck.ids = [u + shift for u in ck.ids]
+            ck.index = None
+            self._chunks.append(ck)
+        for u, space in other.trained_embedding_spaces.items():
+            self.trained_embedding_spaces[u + shift] = space
+        for u, m in other.entity_id_mappings.items():
+            self.entity_id_mappings[u + shift].update(m)
+        for u, m in other.relation_id_mappings.items():
+            self.relation_id_mappings[u + shift].update(m)
+        for g, us in other.entity_universes.items():
+            self.entity_universes[g].update(u + shift for u in us)
+        for g, us in other.relation_universes.items():
+            self.relation_universes[g].update(u + shift for u in us)
+        for u, h in other.universe_hyper.items():
+            self.universe_hyper[u + shift] = h
+        self.next_universe_id += other.next_universe_id
+        self._rank_cache.clear()

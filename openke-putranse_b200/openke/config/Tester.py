@@ -1,0 +1,102 @@
+"""Link-prediction driver with the interface of the reference's ``openke/config/Tester.py:17-93``.
+
+The reference scores one [E]-long candidate batch per test triple and side, copies the scores to
+the host and ranks them in C (``testHead``/``testTail``).  Here all test triples are ranked in one
+device pass (``pk_rank_space``); the five returned numbers are accumulated in float32 in test order,
+as the reference's C globals are (openke/base/Test.h:14-16,213-223,398-454).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from .. import _native as N
+
+
+def _f32_running_sum(values):
+    """acc = (float)(acc + v) for v in order, v and the sum in double: how a C `float += double` behaves."""
+    acc = np.float32(0.0)
+    for v in values:
+        acc = np.float32(float(acc) + v)
+    return acc
+
+
+def link_metrics(ranks):
+    """ranks int [n,4] = head raw, head filtered, tail raw, tail filtered (0-based count of better
+    candidates).  Returns ((mrr, mr, hit10, hit3, hit1) filtered and head/tail-averaged — what the
+    reference's getTestLink* return — and the full raw/filtered table), accumulated like the
+    reference's float globals: sequentially, in test order (openke/base/Test.h:213-223,398-454)."""
+    n = ranks.shape[0]
+    f32 = np.float32
+    table = {}
+    for name, col in (("l_raw", 0), ("l_filter", 1), ("r_raw", 2), ("r_filter", 3)):
+        r = ranks[:, col].astype(np.int64)
+        rank_sum = _f32_running_sum((r + 1).astype(np.float64).tolist())
+        reci_sum = _f32_running_sum((1.0 / (r + 1)).tolist())
+        table[name] = (reci_sum / f32(n), rank_sum / f32(n), f32((r < 10).sum()) / f32(n), f32((r < 3).sum()) / f32(n),
+                       f32((r < 1).sum()) / f32(n))
+    avg = tuple(float((f32(a) + f32(b)) / f32(2)) for a, b in zip(table["l_filter"], table["r_filter"]))
+    return avg, table
+
+
+class Tester(object):
+    def __init__(self, model=None, data_loader=None, use_gpu=True):
+        self.lib = N.lib()
+        self.model = model
+        self.data_loader = data_loader
+        self.use_gpu = use_gpu
+        self.last_ranks = None
+        self.last_table = None
+        if self.use_gpu and self.model is not None:
+            self.model.cuda()
+
+    def set_model(self, model):
+        self.model = model
+
+    def set_data_loader(self, data_loader):
+        self.data_loader = data_loader
+
+    def set_use_gpu(self, use_gpu):
+        self.use_gpu = use_gpu
+        if self.use_gpu and self.model is not None:
+            self.model.cuda()
+
+    def to_var(self, x, use_gpu):
+        t = torch.from_numpy(x)
+        return t.cuda() if use_gpu else t
+
+    def test_one_step(self, data):
+        return self.model.predict(data)
+
+    def rank_all(self, loader=None, model=None):
+        """int32 [n,4] raw/filtered ranks of every triple of the loader, both sides."""
+        loader = loader or self.data_loader
+        model = model or self.model
+        if not self.use_gpu:
+            raise N.NativeError("use_gpu=False: link prediction on the B200 path has no CPU implementation")
+        N.require_cuda()
+        model.cuda()
+        dev = model.ent_embeddings.weight.device
+        tri, filt = loader.eval_arrays()
+        d_tri = torch.from_numpy(tri).to(dev)
+        d_f = [(torch.from_numpy(o).to(dev), torch.from_numpy(np.ascontiguousarray(c) if c.size else np.zeros(1, np.int32)).to(dev))
+               for o, c in filt]
+        ranks = torch.zeros((tri.shape[0], 4), dtype=torch.int32, device=dev)
+        cfg, tab = model.native_cfg(), model.native_tables()
+        N.check(self.lib.pk_rank_space(ctypes.byref(cfg), ctypes.byref(tab), tri.shape[0], d_tri.data_ptr(),
+                                       d_f[0][0].data_ptr(), d_f[0][1].data_ptr(), d_f[1][0].data_ptr(),
+                                       d_f[1][1].data_ptr(), ranks.data_ptr(), torch.cuda.current_stream(dev).cuda_stream),
+                "pk_rank_space")
+        self.gpu_launches = self.lib.pk_last_launch_count()
+        return ranks.cpu().numpy()
+
+    def run_link_prediction(self, type_constrain=False):
+        if type_constrain:
+            raise NotImplementedError("type-constrained ranking is not on the PuTransE hot path")
+        self.data_loader.set_sampling_mode("link")
+        self.last_ranks = self.rank_all()
+        (mrr, mr, hit10, hit3, hit1), self.last_table = link_metrics(self.last_ranks)
+        return mrr, mr, hit10, hit3, hit1
+
+    def run_triple_classification(self, threshlod=None, data_iterator=None):
+        raise NotImplementedError("triple classification is outside the B200 hot path (SURVEY.md 8(f))")

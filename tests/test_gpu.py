@@ -1,0 +1,400 @@
+"""GPU parity tests (run on the B200 box): every CUDA entry point is called through the C-ABI /
+the drop-in Python classes and compared with the oracle and with vectors minted by the unmodified
+reference.  Integer work must be bit-exact; floating point within the tolerances written here."""
+import ctypes
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+import util
+
+pytestmark = pytest.mark.gpu
+N = util.native()
+
+# fp32 tolerances (north_star: "within a stated fp32 tolerance").  Summation order differs from
+# PyTorch's CPU kernels (lane-group shuffles vs vectorised loops) and duplicate-row gradients are
+# accumulated with atomics, so single steps agree to ~1e-6 relative; training is chaotic (L1 sign
+# flips), so after tens of steps the bound is looser.
+LOSS_RTOL_EARLY, LOSS_RTOL_LATE = 2e-5, 2e-3
+TABLE_ATOL = 2e-3
+TABLE_BAD_FRACTION = 2e-3
+
+
+def fresh_library_state():
+    """Reset the process-global Bernoulli drift counter the way a fresh process would start."""
+    tiny = util.write_dataset(tempfile.mkdtemp(), [[0, 1, 0], [1, 2, 0]], [[0, 2, 0]], [[2, 0, 0]], 3, 1)
+    L = N.lib()
+    L.setInPath(tiny.encode())
+    L.importTrainFiles()
+
+
+def _tables(g, name, which):
+    pre = "%s_%s_" % (name, which)
+    return {k[len(pre):]: g[k] for k in g.files if k.startswith(pre)}
+
+
+def _close_tables(got, want, atol=TABLE_ATOL, frac=TABLE_BAD_FRACTION):
+    bad = np.abs(got - want) > atol
+    assert bad.mean() <= frac, "fraction of entries off by > %g: %g (max err %g)" % (atol, bad.mean(), np.abs(got - want).max())
+
+
+# ------------------------------------------------------------------------------------------ K0
+def test_device_sampler_bit_exact_with_reference(wn18_dir, golden):
+    from openke.data import TrainDataLoader
+    g = golden["sampler"]
+    fresh_library_state()
+    for name, bern, filt, k in (("b0f0k1", 0, 0, 1), ("b1f1k1", 1, 1, 1), ("b0f1k2", 0, 1, 2), ("b1f0k3", 1, 0, 3)):
+        dl = TrainDataLoader(in_path=wn18_dir, nbatches=100, threads=8, bern_flag=bern, filter_flag=filt, neg_ent=k,
+                             random_seed=4)
+        assert dl.batch_size == 1414 and dl.lib.pk_import_count() == int(g[name + "_imports"])
+        for call in range(3):
+            d = dl.sampling()
+            got = np.stack([d["batch_h"], d["batch_t"], d["batch_r"]])
+            assert np.array_equal(got, g[name][call]), (name, call)
+            assert np.all(d["batch_y"][:1414] == 1) and np.all(d["batch_y"][1414:] == -1)
+    dl = TrainDataLoader(in_path=wn18_dir, batch_size=1001, threads=3, bern_flag=0, filter_flag=1, neg_ent=2, random_seed=11)
+    d = dl.sampling()
+    assert np.array_equal(np.stack([d["batch_h"], d["batch_t"], d["batch_r"]]), g["odd_B1001_t3_seed11_f1k2"])
+
+
+def test_device_sampler_inside_universes(wn18_dir, golden):
+    from openke.data import TrainDataLoader
+    U = golden["universe"]
+    dl = TrainDataLoader(in_path=wn18_dir, nbatches=20, threads=8, bern_flag=0, filter_flag=0, neg_ent=1, random_seed=4)
+    for i, (seed, tc, bal) in enumerate(U["cases"]):
+        dl.lib.setRandomSeed(int(seed))
+        dl.lib.randReset()
+        dl.compile_universe_dataset(int(tc), float(bal))
+        dl.swap_helpers()
+        for call in range(2):
+            d = dl.sampling()
+            assert np.array_equal(np.stack([d["batch_h"], d["batch_t"], d["batch_r"]]), U["u%d_batches" % i][call]), (i, call)
+        dl.reset_universe()
+
+
+def test_sampler_invariants_against_oracle_full_size(wn18_dir, golden):
+    """reference Checks.h:117-160 (positives in train, filtered negatives not in train) + oracle equality."""
+    from openke.data import TrainDataLoader
+    from oracle import native as on
+    w = golden["wn18"]
+    fresh_library_state()
+    dl = TrainDataLoader(in_path=wn18_dir, batch_size=20000, threads=7, bern_flag=1, filter_flag=1, neg_ent=4, random_seed=77)
+    o = on.Oracle(threads=7, bern=1)
+    o.import_train(w["train"], 40943, 18)
+    o.seed(77)
+    train = set(map(tuple, w["train"].tolist()))
+    for _ in range(2):
+        d = dl.sampling()
+        oh, ot, orr = o.sampling(20000, 4, 1)
+        assert np.array_equal(d["batch_h"], oh) and np.array_equal(d["batch_t"], ot) and np.array_equal(d["batch_r"], orr)
+    trip = np.stack([d["batch_h"], d["batch_t"], d["batch_r"]], 1)
+    assert all(tuple(x) in train for x in trip[:20000].tolist())
+    assert not any(tuple(x) in train for x in trip[20000:].tolist())
+
+
+# ------------------------------------------------------------------------------------------ K1
+TRAIN = [("transe_l1_adagrad", "TransE", 1, "Adagrad"), ("transe_l2_sgd", "TransE", 2, "sgd"),
+         ("transh_l1_adagrad", "TransH", 1, "Adagrad"), ("transd_l1_adagrad", "TransD", 1, "Adagrad"),
+         ("transe_l1_sgd_d50_k3", "TransE", 1, "sgd")]
+
+
+def _build_model(g, name, cls, p):
+    import torch
+    import openke.module.model as M
+    from openke.module.loss import MarginLoss
+    from openke.module.strategy import NegativeSampling
+    nE, nR, B, k = (int(x) for x in g[name + "_sizes"])
+    init = _tables(g, name, "init")
+    d = init["ent_embeddings"].shape[1]
+    kw = dict(dim_e=d, dim_r=d) if cls == "TransD" else dict(dim=d)
+    emb = getattr(M, cls)(nE, nR, p_norm=p, norm_flag=True, **kw)
+    with torch.no_grad():
+        for n, v in init.items():
+            getattr(emb, n).weight.copy_(torch.from_numpy(v))
+    lr, margin = g[name + "_hyper"]
+    return NegativeSampling(model=emb, loss=MarginLoss(margin=float(margin)), batch_size=B), float(lr), B, k
+
+
+class _FakeLoader(object):
+    def __init__(self, B, k):
+        self.negative_ent, self.bern, self.filter, self.work_threads, self.batch_size = k, 0, 0, 8, B
+
+
+@pytest.mark.parametrize("name,cls,p,opt", TRAIN)
+def test_train_one_step_matches_reference_trainer(golden, name, cls, p, opt):
+    """Trainer.train_one_step on the reference's own batches: losses and final tables."""
+    from openke.config import Trainer
+    g = golden["train"]
+    model, lr, B, k = _build_model(g, name, cls, p)
+    tr = Trainer(model=model, data_loader=_FakeLoader(B, k), train_times=1, alpha=lr, use_gpu=True, opt_method=opt)
+    losses = []
+    for b in g[name + "_batches"]:
+        losses.append(tr.train_one_step({"batch_h": b[0].astype(np.int64), "batch_t": b[1].astype(np.int64),
+                                         "batch_r": b[2].astype(np.int64), "mode": "normal"}))
+    want = g[name + "_losses"]
+    assert np.allclose(losses[:5], want[:5], rtol=LOSS_RTOL_EARLY), (losses[:5], want[:5])
+    assert np.allclose(losses, want, rtol=LOSS_RTOL_LATE), np.abs(np.array(losses) - want).max()
+    for n, v in _tables(g, name, "final").items():
+        _close_tables(getattr(model.model, n).weight.detach().cpu().numpy(), v)
+    assert tr.gpu_launches >= 3 * len(losses)
+
+
+def test_train_step_single_step_against_closed_form(golden):
+    """One SGD step from identical tables: the update equals -lr * (float64 closed-form gradient)."""
+    from openke.config import Trainer
+    from oracle.model_math import closed_form_grads
+    g = golden["train"]
+    for name, cls, p, _ in TRAIN:
+        model, lr, B, k = _build_model(g, name, cls, p)
+        init = _tables(g, name, "init")
+        bh, bt, br = g[name + "_batches"][0]
+        margin = float(g[name + "_hyper"][1])
+        loss_ref, G = closed_form_grads(cls.lower(), init, bh, bt, br, k, margin, p)
+        tr = Trainer(model=model, data_loader=_FakeLoader(B, k), alpha=0.25, use_gpu=True, opt_method="sgd")
+        loss = tr.train_one_step({"batch_h": bh.astype(np.int64), "batch_t": bt.astype(np.int64), "batch_r": br.astype(np.int64),
+                                  "mode": "normal"})
+        assert abs(loss - loss_ref) < 5e-6 * max(1.0, abs(loss_ref)), name
+        for n, v in init.items():
+            got = getattr(model.model, n).weight.detach().cpu().numpy()
+            assert np.allclose(got, v - 0.25 * G[n], rtol=0, atol=2e-6), (name, n, np.abs(got - (v - 0.25 * G[n])).max())
+
+
+def test_train_step_refuses_bad_batches(golden):
+    from openke.config import Trainer
+    g = golden["train"]
+    model, lr, B, k = _build_model(g, "transe_l1_adagrad", "TransE", 1)
+    tr = Trainer(model=model, data_loader=_FakeLoader(B, k), alpha=lr, use_gpu=True, opt_method="sgd")
+    b = g["transe_l1_adagrad_batches"][0].astype(np.int64).copy()
+    before = model.model.ent_embeddings.weight.detach().cpu().numpy().copy()
+    b[0, 3] = 10 ** 6
+    with pytest.raises(N.NativeError):
+        tr.train_one_step({"batch_h": b[0], "batch_t": b[1], "batch_r": b[2], "mode": "normal"})
+    assert np.array_equal(before, model.model.ent_embeddings.weight.detach().cpu().numpy())
+
+
+@pytest.mark.parametrize("name,cls,p,opt", TRAIN[:4])
+def test_trainer_run_with_device_sampler_matches_reference(wn18_dir, golden, name, cls, p, opt):
+    """Trainer.run: sampling stays on the device (CUDA graph of sample+step); same universe, seeds and
+    initial tables as the reference run => same losses."""
+    import torch
+    from openke.config import Trainer
+    from openke.data import TrainDataLoader
+    g = golden["train"]
+    dl = TrainDataLoader(in_path=wn18_dir, nbatches=20, threads=8, bern_flag=0, filter_flag=0, neg_ent=1, random_seed=4)
+    dl.lib.setRandomSeed(7)
+    dl.lib.randReset()
+    dl.compile_universe_dataset(600, 0.25)
+    model, lr, B, k = _build_model(g, name, cls, p)
+    assert dl.batch_size == B
+    dl.swap_helpers()
+    tr = Trainer(model=model, data_loader=dl, train_times=3, alpha=lr, use_gpu=True, opt_method=opt)
+    tr.run(show_progress=False)
+    losses = np.concatenate(tr.losses)
+    want = g[name + "_losses"]
+    assert np.allclose(losses[:5], want[:5], rtol=LOSS_RTOL_EARLY)
+    assert np.allclose(losses, want[:60], rtol=LOSS_RTOL_LATE)
+    # the sampler streams were handed back: the next host-visible batch is the reference's 61st
+    d = dl.sampling()
+    dl.reset_universe()
+    for n, v in _tables(g, name, "final").items():
+        _close_tables(getattr(model.model, n).weight.detach().cpu().numpy(), v)
+
+
+# ------------------------------------------------------------------------------------------ K2 + K3u
+def _putranse(wn18_dir, n_univ, epochs, model_cls=None, param=None, record=False):
+    from openke.config import Parallel_Universe_Config
+    from openke.data import TrainDataLoader, TestDataLoader
+    from openke.module.model import TransE
+    train = TrainDataLoader(in_path=wn18_dir, nbatches=20, threads=8, sampling_mode="normal", bern_flag=0, filter_flag=0,
+                            neg_ent=1, neg_rel=0, random_seed=123)
+    test = TestDataLoader(train.in_path, "link")
+    pu = Parallel_Universe_Config(training_identifier="t", train_dataloader=train, test_dataloader=test,
+                                  initial_num_universes=None, min_margin=1, max_margin=4, min_lr=0.001, max_lr=0.1,
+                                  min_num_epochs=50, max_num_epochs=200, const_num_epochs=epochs,
+                                  min_triple_constraint=500, max_triple_constraint=2000, min_balance=0.25, max_balance=0.5,
+                                  embedding_model=model_cls or TransE,
+                                  embedding_model_param=param or {"dim": 20, "p_norm": 1, "norm_flag": 1},
+                                  checkpoint_dir=None, valid_steps=10 ** 9, save_steps=None, training_setting="static",
+                                  incremental_strategy=None)
+    pu.record_losses = record
+    pu.train_parallel_universes(n_univ)
+    return pu
+
+
+def test_putranse_end_to_end_matches_reference(wn18_dir, golden):
+    """8 universes x 3 epochs exactly as the reference ran them (tests/golden/make_golden.py putranse):
+    subgraphs and id maps bit-exact, trained tables and link-prediction ranks within tolerance."""
+    g = golden["putranse_wn18"]
+    pu = _putranse(wn18_dir, int(g["n_univ"]), int(g["epochs"]))
+    assert pu.initial_random_seed == int(g["initial_seed"]) == 4
+    for u in range(int(g["n_univ"])):
+        sp = pu.trained_embedding_spaces[u]
+        er = np.array(sorted(pu.entity_id_mappings[u], key=pu.entity_id_mappings[u].get))
+        rr = np.array(sorted(pu.relation_id_mappings[u], key=pu.relation_id_mappings[u].get))
+        assert np.array_equal(er, g["u%d_ent_remap" % u]) and np.array_equal(rr, g["u%d_rel_remap" % u])
+        _close_tables(sp.ent_embeddings.weight.detach().cpu().numpy(), g["u%d_ent" % u])
+        _close_tables(sp.rel_embeddings.weight.detach().cpu().numpy(), g["u%d_rel" % u])
+    mrr, mr, hit10, hit3, hit1 = pu.run_link_prediction()
+    ranks, want = pu.last_ranks, g["ranks"]
+    # the +inf branch (truth in no universe) is integer logic: must agree exactly
+    missing = want[:, 0] == 40943
+    assert np.array_equal(ranks[missing], want[missing])
+    same = (ranks == want).all(1).mean()
+    assert same > 0.97, same
+    ref = g["metrics"]
+    assert abs(mr - ref[1]) / ref[1] < 1e-3 and abs(mrr - ref[0]) < 5e-4 and abs(hit10 - ref[2]) < 2e-3
+
+
+def test_energy_aggregation_on_reference_tables(wn18_dir, golden):
+    """K3u alone: load the REFERENCE-trained universe tables, so ranks may differ only by fp ties."""
+    import torch
+    g = golden["putranse_wn18"]
+    pu = _putranse(wn18_dir, int(g["n_univ"]), 0)   # 0 epochs: universes + maps only
+    ck = pu._chunks[0]
+    for i, u in enumerate(ck.ids):
+        ck.tables["ent_embeddings"][ck.eoff[i]:ck.eoff[i + 1]].copy_(torch.from_numpy(g["u%d_ent" % u]))
+        ck.tables["rel_embeddings"][ck.roff[i]:ck.roff[i + 1]].copy_(torch.from_numpy(g["u%d_rel" % u]))
+    pu._rank_cache.clear()
+    pu.run_link_prediction()
+    same = (pu.last_ranks == g["ranks"]).all(1).mean()
+    assert same > 0.999, same
+    assert np.array_equal(pu.last_ranks[g["ranks"][:, 0] == 40943], g["ranks"][g["ranks"][:, 0] == 40943])
+    # global_energy_estimation (reference-API row) agrees with the oracle aggregation
+    from oracle import putranse_eval
+    spaces = [dict(tables={"ent_embeddings": g["u%d_ent" % u], "rel_embeddings": g["u%d_rel" % u]},
+                   ent_remap=g["u%d_ent_remap" % u], rel_remap=g["u%d_rel_remap" % u]) for u in range(int(g["n_univ"]))]
+    idx = int(np.nonzero(g["ranks"][:, 0] < 40943)[0][0])
+    h, r, t = g["test_sorted"][idx].tolist()
+    row = pu.global_energy_estimation({"batch_h": np.arange(40943), "batch_t": np.array([t]), "batch_r": np.array([r]),
+                                       "mode": "head_batch"})
+    want = putranse_eval.universe_energies(spaces, 40943, t, r, 0)
+    fin = np.isfinite(want)
+    assert np.array_equal(np.isfinite(row), fin) and np.allclose(row[fin], want[fin], rtol=2e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("cls,param", [("TransH", {"dim": 20, "p_norm": 1, "norm_flag": 1}),
+                                       ("TransD", {"dim_e": 20, "dim_r": 20, "p_norm": 1, "norm_flag": 1}),
+                                       ("TransE", {"dim": 50, "p_norm": 2, "norm_flag": 1})])
+def test_batched_universes_match_oracle_steps(wn18_dir, cls, param):
+    """K2 (all models): per-step losses of two universes against the torch oracle driven by the
+    oracle sampler from the same seeds."""
+    import torch
+    import openke.module.model as M
+    from oracle import native as on
+    from oracle.model_math import TorchOracle
+    torch.set_num_threads(2)
+    pu = _putranse(wn18_dir, 2, 2, model_cls=getattr(M, cls), param=param, record=True)
+    w = np.load(os.path.join(util.GOLDEN, "wn18.npz"))
+    o = on.Oracle(threads=8, bern=0)
+    o.import_train(w["train"], 40943, 18)
+    for u in range(2):
+        hy = pu.universe_hyper[u]
+        o.seed(4 + u)
+        tri, er, rr = o.universe(hy["tc"], hy["balance"])
+        torch.manual_seed(4 + u)
+        ref_model = getattr(M, cls)(len(er), len(rr), **param)   # CPU init == the product's init
+        tabs = {n: getattr(ref_model, n).weight.detach().numpy() for n in ref_model.table_names()}
+        orc = TorchOracle(cls.lower(), tabs, p_norm=param["p_norm"], opt="adagrad", lr=hy["lr"], margin=hy["margin"], k=1)
+        o.swap()
+        want = [orc.step(*o.sampling(hy["batch_size"], 1, 0)) for _ in range(hy["epochs"] * hy["nbatches"])]
+        o.swap()
+        got = pu.universe_losses[u]
+        assert np.allclose(got[:5], want[:5], rtol=LOSS_RTOL_EARLY), (cls, u, got[:5], want[:5])
+        assert np.allclose(got, want, rtol=LOSS_RTOL_LATE)
+        sp = pu.trained_embedding_spaces[u]
+        for n, v in orc.tables().items():
+            _close_tables(getattr(sp, n).weight.detach().cpu().numpy(), v)
+
+
+# ------------------------------------------------------------------------------------------ K3
+@pytest.mark.parametrize("p", [1, 2])
+def test_rank_space_known_answer_transh_checkpoint(wn18_dir, golden, p):
+    """Shipped TransH/WN18 checkpoint: per-triple ranks and the five returned metrics."""
+    import torch
+    from openke.config import Tester
+    from openke.data import TestDataLoader
+    from openke.module.model import TransH
+    g = golden["rank_transh_wn18"]
+    tl = TestDataLoader(wn18_dir, "link")
+    m = TransH(tl.entTotal, tl.relTotal, dim=20, p_norm=p, norm_flag=True)
+    with torch.no_grad():
+        for n in ("ent_embeddings", "rel_embeddings", "norm_vector"):
+            getattr(m, n).weight.copy_(torch.from_numpy(g[n]))
+    tester = Tester(model=m, data_loader=tl, use_gpu=True)
+    out = tester.run_link_prediction()
+    want = g["ranks_p%d" % p]
+    same = (tester.last_ranks == want).all(1).mean()
+    assert same > 0.995, same                      # differences only where energies tie within an ulp or two
+    assert np.abs(tester.last_ranks.astype(np.int64) - want).max() <= 3
+    ref = g["metrics_p%d" % p]
+    assert np.allclose(out, ref, rtol=2e-4, atol=2e-4), (out, ref)
+
+
+@pytest.mark.parametrize("cls", ["TransE", "TransD"])
+def test_rank_space_against_oracle_small(tmp_path, cls):
+    import torch
+    import openke.module.model as M
+    from openke.config import Tester
+    from openke.data import TestDataLoader
+    from oracle import native as on
+    from oracle.model_math import TorchOracle
+    tr, va, te = util.synthetic_graph(700, 7, 6000, 150, seed=5)
+    path = util.write_dataset(str(tmp_path / "s"), tr, va, te, 700, 7)
+    tl = TestDataLoader(path, "link")
+    torch.manual_seed(0)
+    kw = dict(dim_e=24, dim_r=24) if cls == "TransD" else dict(dim=33)
+    m = getattr(M, cls)(700, 7, p_norm=1, norm_flag=True, **kw)
+    tabs = {n: getattr(m, n).weight.detach().numpy().copy() for n in m.table_names()}
+    tester = Tester(model=m, data_loader=tl, use_gpu=True)
+    tester.run_link_prediction()
+    o = on.Oracle()
+    o.import_train(tr, 700, 7)
+    o.import_test(te, tr, va)
+    orc = TorchOracle(cls.lower(), tabs, p_norm=1)
+    tri = o.eval_list(0)
+    want = np.zeros((150, 4), np.int64)
+    with torch.no_grad():
+        for i, (h, r, t) in enumerate(tri.tolist()):
+            sc = orc.score(np.concatenate([[h], np.delete(np.arange(700), h)]), [t], [r], "head_batch").numpy()
+            want[i, :2] = o.rank_row(0, sc, i, True)
+            sc = orc.score([h], np.concatenate([[t], np.delete(np.arange(700), t)]), [r], "tail_batch").numpy()
+            want[i, 2:] = o.rank_row(0, sc, i, False)
+    assert (tester.last_ranks == want).all(1).mean() > 0.98
+    assert np.abs(tester.last_ranks - want).max() <= 2
+    # Model.predict (pk_score_batch) against the oracle's scores, all three modes
+    h, r, t = tri[0].tolist()
+    got = m.predict({"batch_h": np.arange(700), "batch_t": np.array([t]), "batch_r": np.array([r]), "mode": "head_batch"})
+    with torch.no_grad():
+        ref = orc.score(np.arange(700), [t], [r], "head_batch").numpy()
+    assert np.allclose(got, ref, rtol=2e-6, atol=2e-6)
+    got = m.predict({"batch_h": tri[:, 0], "batch_t": tri[:, 2], "batch_r": tri[:, 1], "mode": "normal"})
+    with torch.no_grad():
+        ref = orc.score(tri[:, 0], tri[:, 2], tri[:, 1], "normal").numpy()
+    assert np.allclose(got, ref, rtol=2e-6, atol=2e-6)
+
+
+def test_reference_style_manual_loop_testhead_testtail(tmp_path):
+    """The reference's own evaluation loop (Tester.run_link_prediction, reference Tester.py:70-93)
+    written against the drop-in: TestDataLoader batches -> model.predict -> lib.testHead/testTail."""
+    import torch
+    from openke.config import Tester
+    from openke.data import TestDataLoader
+    from openke.module.model import TransE
+    tr, va, te = util.synthetic_graph(500, 5, 4000, 60, seed=8)
+    path = util.write_dataset(str(tmp_path / "s"), tr, va, te, 500, 5)
+    tl = TestDataLoader(path, "link")
+    torch.manual_seed(1)
+    m = TransE(500, 5, dim=16, p_norm=1, norm_flag=True).cuda()
+    lib = tl.lib
+    lib.initTest()
+    for index, (dh, dt) in enumerate(tl):
+        s = m.predict(dh)
+        lib.testHead(N.addr(s), index, 0)
+        s = m.predict(dt)
+        lib.testTail(N.addr(s), index, 0)
+    lib.test_link_prediction(0)
+    manual = (lib.getTestLinkMRR(0), lib.getTestLinkMR(0), lib.getTestLinkHit10(0), lib.getTestLinkHit3(0), lib.getTestLinkHit1(0))
+    fused = Tester(model=m, data_loader=tl, use_gpu=True).run_link_prediction()
+    assert np.allclose(manual, fused, rtol=1e-6, atol=1e-7), (manual, fused)

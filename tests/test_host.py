@@ -1,0 +1,271 @@
+"""CPU tests of the product's host side: the C-ABI library loads and exports what include/putranse.h
+declares, and its integer work (reader, indexes, Bernoulli means, glibc rand clone, universe
+construction, filter lists) is bit-identical to vectors minted by the unmodified reference."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import util
+
+N = util.native()
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(util.REPO, "include", "putranse.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", hdr))
+    names -= {"defined", "sizeof"}
+    names = {n for n in names if not n.startswith("PK_")}
+    L = ctypes.CDLL(N.LIB_PATH)
+    missing = [n for n in sorted(names) if not hasattr(L, n)]
+    assert not missing, "declared in include/putranse.h but not exported: %s" % missing
+    assert len(names) > 60
+
+
+def test_no_cuda_means_loud_failure_not_fallback():
+    L = N.lib()
+    if L.pk_cuda_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(N.NativeError):
+        N.require_cuda()
+
+
+def test_glibc_rand_clone_matches_libc(wn18_dir):
+    """setRandomSeed/randReset expose the generator: the stream states are rand() outputs."""
+    L = N.lib()
+    libc = ctypes.CDLL("libc.so.6")
+    for seed in (1, 4, 5, 123, 2147483647, 0):
+        L.setWorkThreads(8)
+        L.setRandomSeed(seed)
+        L.randReset()
+        got = np.zeros(8, np.uint64)
+        N.check(L.pk_get_lcg(N.addr(got)))
+        libc.srand(ctypes.c_uint(seed))
+        want = np.array([libc.rand() for _ in range(8)], np.uint64)
+        assert np.array_equal(got, want), seed
+
+
+def _load(L, path, threads=8, bern=0, seed=4):
+    L.setInPath(path.encode())
+    L.setBern(bern)
+    L.setWorkThreads(threads)
+    L.setRandomSeed(seed)
+    L.randReset()
+    L.importTrainFiles()
+
+
+def test_reader_and_bernoulli_drift(wn18_dir, golden):
+    """left_mean/right_mean after the 1st..4th import of one process."""
+    L = N.lib()
+    # a different dataset shape first resets the drift, as a fresh process would
+    g = golden["sampler"]
+    import tempfile
+    tiny = util.write_dataset(tempfile.mkdtemp(), [[0, 1, 0], [1, 2, 0]], [[0, 2, 0]], [[2, 0, 0]], 3, 1)
+    _load(L, tiny)
+    for name in ("b0f0k1", "b1f1k1", "b0f1k2", "b1f0k3"):
+        _load(L, wn18_dir)
+        assert L.pk_import_count() == int(g[name + "_imports"])
+        assert (L.getEntityTotal(), L.getRelationTotal(), L.getTrainTotal()) == (40943, 18, 141442)
+        lm, rm = np.zeros(18, np.float32), np.zeros(18, np.float32)
+        N.check(L.pk_train_index(None, None, N.addr(lm), N.addr(rm)))
+        assert np.array_equal(lm, g[name + "_left_mean"]), name
+        assert np.array_equal(rm, g[name + "_right_mean"]), name
+    by_head, by_tail = np.zeros((141442, 3), np.int32), np.zeros((141442, 3), np.int32)
+    N.check(L.pk_train_index(N.addr(by_head), N.addr(by_tail), None, None))
+    k = by_head[:, 0].astype(np.int64) * 10 ** 8 + by_head[:, 1].astype(np.int64) * 10 ** 6 // 10 + 0
+    assert np.all(np.lexsort((by_head[:, 2], by_head[:, 1], by_head[:, 0])) == np.arange(141442))
+    assert np.all(np.lexsort((by_tail[:, 0], by_tail[:, 1], by_tail[:, 2])) == np.arange(141442))
+
+
+def test_universes_bit_exact_with_reference(wn18_dir, golden):
+    L = N.lib()
+    _load(L, wn18_dir)
+    U = golden["universe"]
+    for i, (seed, tc, bal) in enumerate(U["cases"]):
+        L.setRandomSeed(int(seed))
+        L.randReset()
+        L.getParallelUniverse(int(tc), float(bal))
+        nT, nE, nR = L.getTrainTotalUniverse(), L.getEntityTotalUniverse(), L.getRelationTotalUniverse()
+        assert (nT, nE, nR) == tuple(U["u%d_sizes" % i])
+        er, rr = np.zeros(nE, np.int64), np.zeros(nR, np.int64)
+        L.getEntityRemapping(N.addr(er))
+        L.getRelationRemapping(N.addr(rr))
+        tri = np.zeros((nT, 3), np.int32)
+        N.check(L.pk_universe_triples(N.addr(tri)))
+        assert np.array_equal(er, U["u%d_ent_remap" % i])
+        assert np.array_equal(rr, U["u%d_rel_remap" % i])
+        assert np.array_equal(tri, U["u%d_triples_global" % i])
+        L.swapHelpers()
+        assert (L.getTrainTotal(), L.getEntityTotal(), L.getRelationTotal()) == (nT, nE, nR)
+        bh, lm, rm = np.zeros((nT, 3), np.int32), np.zeros(nR, np.float32), np.zeros(nR, np.float32)
+        N.check(L.pk_train_index(N.addr(bh), None, N.addr(lm), N.addr(rm)))
+        assert np.array_equal(bh, U["u%d_triples_local" % i])
+        assert np.array_equal(lm, U["u%d_left_mean" % i]) and np.array_equal(rm, U["u%d_right_mean" % i])
+        L.resetUniverse()
+        assert L.getTrainTotal() == 141442
+
+
+def test_batched_threaded_builder_equals_sequential(wn18_dir, golden):
+    L = N.lib()
+    _load(L, wn18_dir)
+    U = golden["universe"]
+    cases = U["cases"]
+    n = len(cases)
+    seeds = np.ascontiguousarray(cases[:, 0], np.int64)
+    tcs = np.ascontiguousarray(cases[:, 1], np.int64)
+    bals = np.ascontiguousarray(cases[:, 2], np.float32)
+    outs = []
+    for threads in (1, 4):
+        h = L.pk_universes_build(n, N.addr(seeds), N.addr(tcs), N.addr(bals), threads)
+        assert h, N.last_error()
+        nT, nE, nR, foc = (np.zeros(n, np.int64) for _ in range(4))
+        N.check(L.pk_universes_sizes(h, N.addr(nT), N.addr(nE), N.addr(nR), N.addr(foc)))
+        er, rr = np.zeros(nE.sum(), np.int32), np.zeros(nR.sum(), np.int32)
+        bh, bt, bg = (np.zeros((nT.sum(), 3), np.int32) for _ in range(3))
+        lcg = np.zeros((n, 8), np.uint64)
+        N.check(L.pk_universes_export(h, N.addr(bh), N.addr(bt), N.addr(bg), N.addr(er), N.addr(rr), None, None, N.addr(lcg)))
+        L.pk_universes_free(h)
+        outs.append((nT, nE, nR, er, rr, bh, bt, bg, lcg))
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+    nT, nE, nR, er, rr, bh, bt, bg, lcg = outs[0]
+    eo, to = np.concatenate([[0], np.cumsum(nE)]), np.concatenate([[0], np.cumsum(nT)])
+    libc = ctypes.CDLL("libc.so.6")
+    for i in range(n):
+        assert np.array_equal(er[eo[i]:eo[i + 1]], U["u%d_ent_remap" % i])
+        assert np.array_equal(bg[to[i]:to[i + 1]], U["u%d_triples_global" % i])
+        assert np.array_equal(bh[to[i]:to[i + 1]], U["u%d_triples_local" % i])
+        libc.srand(ctypes.c_uint(int(seeds[i])))
+        assert np.array_equal(lcg[i], np.array([libc.rand() for _ in range(8)], np.uint64))
+        # (t,r,h) order of the tail index
+        t = bt[to[i]:to[i + 1]]
+        assert np.all(np.lexsort((t[:, 0], t[:, 1], t[:, 2])) == np.arange(t.shape[0]))
+
+
+def test_universe_invariants_on_synthetic_graph(tmp_path):
+    """The reference's opt-in Checks.h invariants (openke/base/UniverseSetting.h:203-269) as properties."""
+    tr, va, te = util.synthetic_graph(3000, 12, 20000, 200, seed=7)
+    path = util.write_dataset(str(tmp_path / "syn"), tr, va, te, 3000, 12)
+    L = N.lib()
+    _load(L, path, seed=3)
+    train_set = set(map(tuple, tr[:, [0, 2, 1]].tolist()))
+    for seed in range(20, 30):
+        L.setRandomSeed(seed)
+        L.randReset()
+        L.getParallelUniverse(400 + 37 * (seed % 5), 0.3)
+        nT, nE, nR = L.getTrainTotalUniverse(), L.getEntityTotalUniverse(), L.getRelationTotalUniverse()
+        assert 0 < nT <= 400 + 37 * (seed % 5)
+        tri = np.zeros((nT, 3), np.int32)
+        N.check(L.pk_universe_triples(N.addr(tri)))
+        assert all(tuple(x) in train_set for x in tri.tolist())          # universe is a subset of train
+        assert len(set(map(tuple, tri.tolist()))) == nT                     # no duplicates
+        er, rr = np.zeros(nE, np.int64), np.zeros(nR, np.int64)
+        L.getEntityRemapping(N.addr(er))
+        L.getRelationRemapping(N.addr(rr))
+        assert len(set(er.tolist())) == nE and len(set(rr.tolist())) == nR  # remaps are injective
+        L.swapHelpers()
+        loc = np.zeros((nT, 3), np.int32)
+        N.check(L.pk_train_index(N.addr(loc), None, None, None))
+        assert loc[:, [0, 2]].max() == nE - 1 and loc[:, 1].max() == nR - 1  # max local id = count - 1
+        back = np.stack([er[loc[:, 0]], rr[loc[:, 1]], er[loc[:, 2]]], 1)
+        assert set(map(tuple, back.tolist())) == set(map(tuple, tri.tolist()))  # remap round-trips
+        L.resetUniverse()
+
+
+def test_eval_lists_and_filter_csr(wn18_dir, golden):
+    L = N.lib()
+    _load(L, wn18_dir)
+    L.importTestFiles()
+    assert (L.getTestTotal(), L.getValidTotal()) == (5000, 5000)
+    tri = np.zeros((5000, 3), np.int32)
+    N.check(L.pk_eval_triples(0, N.addr(tri)))
+    assert np.array_equal(tri, golden["rank_transh_wn18"]["test_sorted"])
+    g = golden["wn18"]
+    allt = np.concatenate([g["train"], g["valid"], g["test"]])[:, [0, 2, 1]]   # -> (h,r,t)
+    known = set(map(tuple, allt.tolist()))
+    for side in (0, 1):
+        cnt = ctypes.c_int64(0)
+        off = np.zeros(5001, np.int64)
+        N.check(L.pk_filter_csr(0, side, N.addr(off), None, ctypes.byref(cnt)))
+        cand = np.zeros(cnt.value, np.int32)
+        N.check(L.pk_filter_csr(0, side, N.addr(off), N.addr(cand), ctypes.byref(cnt)))
+        assert off[-1] == cnt.value
+        for i in list(range(0, 5000, 97)):
+            h, r, t = tri[i].tolist()
+            if side == 0:
+                want = sorted(j for (j, rr, tt) in ((a, b, c) for (a, b, c) in known if b == r and c == t) if j != h)
+            else:
+                want = sorted(c for (a, b, c) in known if a == h and b == r and c != t)
+            assert cand[off[i]:off[i + 1]].tolist() == want
+
+
+def test_candidate_batches_follow_reference_order(wn18_dir):
+    L = N.lib()
+    _load(L, wn18_dir)
+    L.importTestFiles()
+    tri = np.zeros((5000, 3), np.int32)
+    N.check(L.pk_eval_triples(0, N.addr(tri)))
+    L.initTest()
+    ph, pt, pr = (np.zeros(40943, np.int64) for _ in range(3))
+    for i in range(3):
+        L.getHeadBatch(N.addr(ph), N.addr(pt), N.addr(pr))
+        h, r, t = tri[i].tolist()
+        assert ph[0] == h and np.array_equal(ph[1:], np.delete(np.arange(40943), h))
+        assert np.all(pt == t) and np.all(pr == r)
+        L.getTailBatch(N.addr(ph), N.addr(pt), N.addr(pr))
+        assert pt[0] == t and np.array_equal(pt[1:], np.delete(np.arange(40943), t)) and np.all(ph == h)
+
+
+def test_hyper_draws_match_static_script(wn18_dir):
+    """(tc, epochs, lr, margin) of universes 0-4 of the static WN18 script."""
+    from openke.config import Parallel_Universe_Config
+    pu = Parallel_Universe_Config.__new__(Parallel_Universe_Config)
+    pu.min_triple_constraint, pu.max_triple_constraint = 500, 2000
+    pu.min_balance, pu.max_balance = 0.25, 0.5
+    pu.min_margin, pu.max_margin = 1, 4
+    pu.const_num_epochs, pu.min_num_epochs, pu.max_num_epochs = None, 50, 200
+    pu.min_lr, pu.max_lr = 0.001, 0.1
+    want = [(983, 151, 0.048, 3), (1775, 185, 0.004, 2), (1675, 116, 0.005, 2), (1163, 62, 0.008, 2), (964, 82, 0.02, 2)]
+    for u, w in enumerate(want):
+        h = pu.draw_universe_hyper(4 + u)
+        assert (h["tc"], h["epochs"], h["lr"], h["margin"]) == w
+
+
+def test_link_metrics_accumulate_like_the_reference(golden):
+    from openke.config.Tester import link_metrics
+    g = golden["rank_transh_wn18"]
+    for p in (1, 2):
+        avg, _ = link_metrics(g["ranks_p%d" % p])
+        assert np.array_equal(np.array(avg, np.float32), g["metrics_p%d" % p])
+    pu = golden["putranse_wn18"]
+    avg, _ = link_metrics(pu["ranks"])
+    assert np.array_equal(np.array(avg, np.float32), pu["metrics"])   # rank sums here exceed 2**24
+
+
+def test_sharded_evaluation_min_allreduce_gloo(tmp_path):
+    """world_size-2 gloo run of the exchange step: per-rank energy tiles min-reduce to the tile a
+    single rank holding every universe would have."""
+    import subprocess
+    import sys
+    script = tmp_path / "w.py"
+    script.write_text(
+        "import os, sys, numpy as np, torch, torch.distributed as dist\n"
+        "dist.init_process_group('gloo')\n"
+        "r, w = dist.get_rank(), dist.get_world_size()\n"
+        "g = np.random.default_rng(0)\n"
+        "full = g.random((6, 16, 50)).astype(np.float32)\n"       # 6 universes, 16 keys, 50 entities
+        "full[g.random((6, 16, 50)) < 0.6] = np.inf\n"
+        "mine = [u for u in range(6) if u % w == r]\n"
+        "part = torch.from_numpy(full[mine].min(0)) if mine else torch.full((16, 50), float('inf'))\n"
+        "dist.all_reduce(part, op=dist.ReduceOp.MIN)\n"
+        "assert np.array_equal(part.numpy(), full.min(0))\n"
+        "print('ok', r)\n")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                         env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.count("ok") == 2
