@@ -113,7 +113,7 @@ __device__ __forceinline__ void apply_update(float* x_row, float* s_row, const f
 #pragma unroll
         for (int i = 0; i < L::NF; ++i) {
             s[i] = fmaf(g[i], g[i], s[i]);
-            x[i] = x[i] + (-lr * g[i]) / (sqrtf(s[i]) + 1e-10f);
+            x[i] = x[i] + div0(-lr * g[i], sqrt0(s[i]) + 1e-10f);
         }
         st_row<L>(s_row, d, lane, s);
     } else {
