@@ -243,6 +243,10 @@ int pk_rank_candidate_row(const float* d_con, int64_t n_ent, const int32_t* d_tr
 int pk_score_batch(const pk_model_cfg* cfg, const pk_tables* tab, const int64_t* d_h, int64_t nh, const int64_t* d_t,
                    int64_t nt, const int64_t* d_r, int64_t nr, int head_batch, float* d_out, int* d_bad_flag,
                    void* stream);
+/* device self-test: compares the train kernels' division / square-root helpers bit-for-bit with
+ * IEEE __fdiv_rn / __fsqrt_rn on n pseudo-random operand pairs.  mismatches3 = {division, sqrt,
+ * exact-zero cases} (HOST int64[3]); all three must be 0. */
+int pk_selftest_arith(int64_t n, uint32_t seed, int64_t* mismatches3);
 /* fill with +inf */
 int pk_fill_inf(float* d, int64_t n, void* stream);
 

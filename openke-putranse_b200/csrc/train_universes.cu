@@ -8,16 +8,29 @@
 // and the per-step ctypes call into sampling() (openke/base/Base.cpp:266-310), ~100-190 ATen
 // launches per step.
 //
+// A universe's steps are strictly sequential and one step touches < 100 KB, so the bound is the
+// LATENCY of one step on one SM, not bandwidth.  The block is therefore split into two roles that
+// run concurrently (warp specialisation, named barriers):
+//
+//   producer warps   draw batch s+1 with the reference's LCG streams (bit-exact; affine jump tables
+//                    and multiply-high modulo instead of 64-bit division), count how often every
+//                    table row occurs in that batch and give each multiply-occurring row a scratch
+//                    slot.  None of this depends on the embeddings, so it is off the critical path.
+//   consumer warps   step s: one lane group per positive sample gathers h, t, r and the corrupted
+//                    entity (shared memory), forward, margin loss, analytic backward.  A row that
+//                    occurs ONCE in the batch is updated in place by the group that read it, with
+//                    its Adagrad state prefetched from L2 at the start of the sample; a row that
+//                    occurs several times accumulates into its scratch slot and is updated after a
+//                    consumer-only barrier.  Samples whose margin term is switched off skip the
+//                    backward pass (all their gradients are exactly zero).
+//
 // Data layout.  All universes of a launch are packed: entity tables [sum nE, d], relation tables
 // [sum nR, d], sorted triple lists [sum nT, 3]; a descriptor per universe holds the offsets.  A
 // block stages its universe's tables in shared memory when they fit (local ids are dense, so the
-// staged table IS the universe's whole embedding space); the per-step gradient scratch (one row per
-// touched table row), the slot maps and the batch ids always live in shared memory.  The Adagrad
-// accumulators stay in global memory (L2-resident: touched once per step, off the critical path).
-//
-// Bound: this kernel is latency-bound by construction (a universe's steps are strictly sequential
-// and a step touches < 100 KB); the roofline that matters is "steps per second per SM".
+// staged table IS the universe's whole embedding space).  The Adagrad accumulators stay in global
+// memory (L2-resident).
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "common.hpp"
@@ -26,8 +39,6 @@
 namespace pkk2 {
 
 using namespace pkd;
-
-constexpr int K2_THREADS = 256;
 
 struct K2Params {
     const pk_universe_desc* desc;
@@ -41,75 +52,120 @@ struct K2Params {
     const float* right_mean;
     float* loss;
     int d, k, p_norm, norm_flag, opt, bern, filter, W;
-    int stage;              // tables staged in shared memory for every universe of this launch
-    int mE, mR, mB;         // launch-wide maxima: shared-memory carve-up is uniform
+    int stage;              // entity tables staged in shared memory for every universe of this launch
+    int mE, mR, mB;         // launch-wide maxima: the shared-memory carve-up is uniform
+    int np;                 // producer warps
 };
 
 __host__ __device__ inline size_t up16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 // shared-memory carve-up, identical on host (sizing) and device (pointers)
 struct K2Smem {
-    size_t ent[2], rel[2], gent[2], grel[2], lossv, slot_ent, slot_rel, touched_ent, touched_rel, ids, counters, lcg, total;
-    int slotsE, slotsR;
-    __host__ __device__ K2Smem(int model, int d, int k, int mE, int mR, int mB, int stage) {
+    size_t ent[2], rel[2], scratch, map, batch[2], lossv, lcg, total;
+    int slots;      // scratch rows: a multiply-occurring row needs >= 2 of the (3+k)B occurrences
+    int per;        // samples per LCG stream slice
+    int batch_ints; // ints in one batch buffer
+    __host__ __device__ K2Smem(int model, int d, int k, int W, int mE, int mR, int mB, int stage) {
         const int ntE = model == TRANSD ? 2 : 1, ntR = model == TRANSE ? 1 : 2;
-        slotsE = min_((long long)mE, (long long)(2 + k) * mB);
-        slotsR = min_((long long)mR, (long long)mB);
+        const int ntm = model == TRANSE ? 1 : 2;
+        const long long occ = (long long)(3 + k) * mB;
+        slots = (int)min_((long long)mE + mR, occ / 2 + 1);
+        per = (mB + W - 1) / W + 1;
         size_t o = 0;
         for (int i = 0; i < 2; ++i) { ent[i] = o; if (stage && i < ntE) o = up16(o + (size_t)mE * d * 4); }
-        for (int i = 0; i < 2; ++i) { rel[i] = o; if (stage && i < ntR) o = up16(o + (size_t)mR * d * 4); }
-        for (int i = 0; i < 2; ++i) { gent[i] = o; if (i < ntE) o = up16(o + (size_t)slotsE * d * 4); }
-        for (int i = 0; i < 2; ++i) { grel[i] = o; if (i < ntR) o = up16(o + (size_t)slotsR * d * 4); }
-        lossv = o;       o = up16(o + (size_t)mB * 4);
-        slot_ent = o;    o = up16(o + (size_t)mE * 4);
-        slot_rel = o;    o = up16(o + (size_t)mR * 4);
-        touched_ent = o; o = up16(o + (size_t)slotsE * 4);
-        touched_rel = o; o = up16(o + (size_t)slotsR * 4);
-        ids = o;         o = up16(o + (size_t)3 * mB * (1 + k) * 4);
-        counters = o;    o = up16(o + 16);
-        lcg = o;         o = up16(o + 8 * 8);
+        for (int i = 0; i < 2; ++i) { rel[i] = o; if (i < ntR) o = up16(o + (size_t)mR * d * 4); }
+        scratch = o; o = up16(o + (size_t)slots * ntm * d * 4);
+        map = o;     o = up16(o + ((size_t)mE + mR) * 4);
+        // one batch buffer: h | t | r | c[k] | code_h | code_t | code_r | code_c[k] | dup[slots] | ndup
+        batch_ints = (int)(2 * occ) + slots + 4;
+        for (int i = 0; i < 2; ++i) { batch[i] = o; o = up16(o + (size_t)batch_ints * 4); }
+        lossv = o;   o = up16(o + (size_t)mB * 4);
+        // s0[8] | Aadv[8] | Cadv[8] | A[per] | C[per]
+        lcg = o;     o = up16(o + (size_t)(24 + 2 * per) * 8);
         total = o;
     }
-    __host__ __device__ static int min_(long long a, long long b) { return (int)(a < b ? a : b); }
+    __host__ __device__ static long long min_(long long a, long long b) { return a < b ? a : b; }
 };
 
 #ifdef PK_MODEL_TU
-template <class L>
-struct K2Ctx {
-    float* ent[2];
-    float* rel[2];
-    float* gent[2];
-    float* grel[2];
-    const int* slot_ent;
-    const int* slot_rel;
-    int d;
-    __device__ __forceinline__ const float* ent_row(int tbl, int id) const { return ent[tbl] + (size_t)id * d; }
-    __device__ __forceinline__ const float* rel_row(int tbl, int id) const { return rel[tbl] + (size_t)id * d; }
-    __device__ __forceinline__ void add(float* base, int slot, const float (&g)[L::NF], int lane) const {
-        float* p = base + (size_t)slot * d;
-#pragma unroll
-        for (int i = 0; i < L::NF; ++i) {
-            const int e = elem_of<L>(lane, i);
-            if (e < d && g[i] != 0.f) atomicAdd(p + e, g[i]);
-        }
+
+// x mod n for a divisor fixed per universe: multiply-high by m = floor((2^64-1)/n), then at most two
+// conditional subtractions (q underestimates floor(x/n) by < 3).  ~12 instructions instead of the
+// ~80 of a 64-bit division.
+struct FastMod { uint64_t n, m; };
+__device__ __forceinline__ FastMod make_fastmod(uint64_t n) {
+    FastMod f;
+    f.n = n;
+    f.m = ~0ULL / n;
+    return f;
+}
+__device__ __forceinline__ uint64_t fastmod(uint64_t x, const FastMod& f) {
+    const uint64_t q = __umul64hi(x, f.m);
+    uint64_t r = x - q * f.n;
+    if (r >= f.n) r -= f.n;
+    if (r >= f.n) r -= f.n;
+    return r;
+}
+
+// coefficients of n LCG steps: x -> A x + C
+__device__ __forceinline__ void lcg_affine(uint64_t n, uint64_t& A, uint64_t& C) {
+    uint64_t a = kLcgMul, c = kLcgInc, ra = 1, rc = 0;
+    while (n) {
+        if (n & 1) { ra = ra * a; rc = rc * a + c; }
+        c = (a + 1) * c;
+        a = a * a;
+        n >>= 1;
     }
-    __device__ __forceinline__ void add_ent(int tbl, int id, const float (&g)[L::NF], int lane, bool pred) const {
-        if (pred) add(gent[tbl], slot_ent[id], g, lane);
+    A = ra;
+    C = rc;
+}
+
+__device__ __forceinline__ void named_barrier(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// one batch as the producers hand it to the consumers
+struct BatchView {
+    int32_t* h;
+    int32_t* t;
+    int32_t* r;
+    int32_t* c;        // [k][B]  corrupted entity | (side << 31); side 0: tail replaced, 1: head replaced
+    int32_t* code_h;   // -1: the row occurs once in this batch (update in place); else scratch slot
+    int32_t* code_t;
+    int32_t* code_r;
+    int32_t* code_c;
+    int32_t* dup;      // unified row id (entity e -> e, relation r -> nE + r) of every scratch slot
+    int32_t* ndup;
+    __device__ __forceinline__ BatchView(unsigned char* base, int B, int k, int slots) {
+        int32_t* p = reinterpret_cast<int32_t*>(base);
+        h = p; p += B;
+        t = p; p += B;
+        r = p; p += B;
+        c = p; p += (size_t)B * k;
+        code_h = p; p += B;
+        code_t = p; p += B;
+        code_r = p; p += B;
+        code_c = p; p += (size_t)B * k;
+        dup = p; p += slots;
+        ndup = p;
     }
-    __device__ __forceinline__ void add_rel(int tbl, int id, const float (&g)[L::NF], int lane, bool pred) const {
-        if (pred) add(grel[tbl], slot_rel[id], g, lane);
-    }
+};
+
+// a table row as the backward pass addresses it: id, duplicate-slot code, prefetched Adagrad state
+template <class L, int NTM>
+struct K2Tgt {
+    int32_t id, code;
+    float st[NTM][L::NF];
 };
 
 // x <- optimizer(x, g): SGD  x -= lr g ;  Adagrad  s += g^2, x -= lr g / (sqrt(s) + 1e-10)
 // (torch.optim.SGD / Adagrad as configured by reference Trainer.py:65-70,84-88; lr_decay = weight_decay = 0)
 template <class L>
-__device__ __forceinline__ void apply_update(float* x_row, float* s_row, const float (&g)[L::NF], int d, int lane, int opt, float lr) {
+__device__ __forceinline__ void apply_update(float* x_row, float* s_row, float (&s)[L::NF], const float (&g)[L::NF], int d, int lane,
+                                             int opt, float lr) {
     float x[L::NF];
     ld_row<L>(x_row, d, lane, x);
     if (opt == PK_ADAGRAD) {
-        float s[L::NF];
-        ld_row<L>(s_row, d, lane, s);
 #pragma unroll
         for (int i = 0; i < L::NF; ++i) {
             s[i] = fmaf(g[i], g[i], s[i]);
@@ -123,146 +179,344 @@ __device__ __forceinline__ void apply_update(float* x_row, float* s_row, const f
     st_row<L>(x_row, d, lane, x);
 }
 
-template <int MODEL, class L>
-__global__ void __launch_bounds__(K2_THREADS) k2_train_universes(const __grid_constant__ K2Params P) {
-    extern __shared__ __align__(16) unsigned char smem[];
+template <class L, int NTM_>
+struct K2Ctx {
+    static constexpr int NTM = NTM_;
+    float* ent[2];        // working tables: shared memory when staged, else global
+    float* rel[2];
+    float* ent_state[2];  // global; nullptr for SGD
+    float* rel_state[2];
+    float* scratch;       // [slots][NTM][d]
+    int d, opt;
+    float lr;
+    __device__ __forceinline__ const float* ent_row(int tbl, int id) const { return ent[tbl] + (size_t)id * d; }
+    __device__ __forceinline__ const float* rel_row(int tbl, int id) const { return rel[tbl] + (size_t)id * d; }
+    // issue the loads of a singly-occurring row's optimizer state early; they complete behind the math
+    template <int NT>
+    __device__ __forceinline__ void prefetch(K2Tgt<L, NTM>& tg, bool is_ent, int lane, bool pred) const {
+        if (opt != PK_ADAGRAD) return;
+#pragma unroll
+        for (int t = 0; t < NT; ++t)
+            ld_row<L>((is_ent ? ent_state[t] : rel_state[t]) + (size_t)tg.id * d, d, lane, tg.st[t], pred && tg.code < 0);
+    }
+    __device__ __forceinline__ void emit(float* table, float* state, int tbl, K2Tgt<L, NTM>& tg, const float (&g)[L::NF], int lane) const {
+        if (tg.code < 0) {
+            apply_update<L>(table + (size_t)tg.id * d, state ? state + (size_t)tg.id * d : nullptr, tg.st[tbl], g, d, lane, opt, lr);
+        } else {
+            float* p = scratch + ((size_t)tg.code * NTM + tbl) * d;
+#pragma unroll
+            for (int i = 0; i < L::NF; ++i) {
+                const int e = elem_of<L>(lane, i);
+                if (e < d && g[i] != 0.f) atomicAdd(p + e, g[i]);
+            }
+        }
+    }
+    __device__ __forceinline__ void add_ent(int tbl, const K2Tgt<L, NTM>& tg, const float (&g)[L::NF], int lane, bool pred) const {
+        if (pred) emit(ent[tbl], ent_state[tbl], tbl, const_cast<K2Tgt<L, NTM>&>(tg), g, lane);
+    }
+    __device__ __forceinline__ void add_rel(int tbl, const K2Tgt<L, NTM>& tg, const float (&g)[L::NF], int lane, bool pred) const {
+        if (pred) emit(rel[tbl], rel_state[tbl], tbl, const_cast<K2Tgt<L, NTM>&>(tg), g, lane);
+    }
+};
+
+// One positive sample b and its k negatives (each negative replaces exactly one side, as the
+// reference sampler does: Base.cpp:216-232).  Every lane of the warp must call this; `act` masks
+// the memory side effects of idle groups.  Returns sum_j max(p - n_j, -m).
+template <int MODEL, class L, class Ctx>
+__device__ __forceinline__ float k2_sample(Ctx& cx, const Hyper& hp, int lane, int B, int b, bool act, const BatchView& bv) {
     constexpr int ntE = MODEL == TRANSD ? 2 : 1, ntR = MODEL == TRANSE ? 1 : 2;
-    constexpr int NG = K2_THREADS / L::G;
+    using Tg = K2Tgt<L, Ctx::NTM>;
+    Tg th, tt, tr;
+    th.id = act ? bv.h[b] : 0; th.code = act ? bv.code_h[b] : 0;
+    tt.id = act ? bv.t[b] : 0; tt.code = act ? bv.code_t[b] : 0;
+    tr.id = act ? bv.r[b] : 0; tr.code = act ? bv.code_r[b] : 0;
+    cx.template prefetch<ntE>(th, true, lane, act);
+    cx.template prefetch<ntE>(tt, true, lane, act);
+    cx.template prefetch<ntR>(tr, false, lane, act);
+
+    RelOp<MODEL, L> rel;
+    ld_row<L>(cx.rel_row(0, tr.id), hp.d, lane, rel.y, act);
+    if (hp.norm_flag) {
+        rel.n = normalize_row<L>(rel.y, rel.free_);
+    } else {
+        rel.n = 1.f;
+        rel.free_ = false;
+    }
+    if constexpr (MODEL != TRANSE) {
+        ld_row<L>(cx.rel_row(1, tr.id), hp.d, lane, rel.w, act);
+        if constexpr (MODEL == TRANSH) rel.nw = normalize_row<L>(rel.w, rel.freew_);
+#pragma unroll
+        for (int i = 0; i < L::NF; ++i) rel.gw[i] = 0.f;
+    }
+    EntOp<MODEL, L> ph, pt;
+    ent_forward<MODEL, L>(cx, hp, lane, th.id, act, rel, ph);
+    ent_forward<MODEL, L>(cx, hp, lane, tt.id, act, rel, pt);
+
+    float dirp[L::NF];
+#pragma unroll
+    for (int i = 0; i < L::NF; ++i) dirp[i] = (ph.y[i] + rel.y[i]) - pt.y[i];
+    const float p = score_and_dir<L>(dirp, hp.p_norm);
+
+    float UH[L::NF], UT[L::NF], UR[L::NF];
+#pragma unroll
+    for (int i = 0; i < L::NF; ++i) UH[i] = UT[i] = UR[i] = 0.f;
+    float cp = 0.f, loss = 0.f;
+
+    for (int j = 0; j < hp.k; ++j) {
+        const int32_t cj = act ? bv.c[(size_t)j * B + b] : 0;
+        const bool head_replaced = cj < 0;
+        Tg tc;
+        tc.id = cj & 0x7fffffff;
+        tc.code = act ? bv.code_c[(size_t)j * B + b] : 0;
+        cx.template prefetch<ntE>(tc, true, lane, act);
+        EntOp<MODEL, L> pc;
+        ent_forward<MODEL, L>(cx, hp, lane, tc.id, act, rel, pc);
+        float dn[L::NF];
+#pragma unroll
+        for (int i = 0; i < L::NF; ++i)
+            dn[i] = head_replaced ? (pc.y[i] + rel.y[i]) - pt.y[i] : (ph.y[i] + rel.y[i]) - pc.y[i];
+        const float n = score_and_dir<L>(dn, hp.p_norm);
+        const float diff = p - n;
+        float g = diff > -hp.margin ? hp.inv_bk : (diff == -hp.margin ? 0.5f * hp.inv_bk : 0.f);
+        if (!act) g = 0.f;
+        loss += fmaxf(diff, -hp.margin);
+        cp += g;
+        // a switched-off margin term has exactly zero gradients everywhere: skip (warp-uniform)
+        if (__any_sync(0xffffffffu, g != 0.f)) {
+            float Uc[L::NF];
+#pragma unroll
+            for (int i = 0; i < L::NF; ++i) {
+                const float v = -g * dn[i];  // dL/dn_j = -g ; d n_j / d(h + r - t) = dn
+                UR[i] += v;
+                if (head_replaced) { Uc[i] = v; UT[i] -= v; }
+                else               { Uc[i] = -v; UH[i] += v; }
+            }
+            ent_backward<MODEL, L>(cx, hp, lane, tc, act && g != 0.f, rel, pc, Uc);
+        }
+    }
+    if (__any_sync(0xffffffffu, cp != 0.f)) {
+        const bool upd = act && cp != 0.f;
+#pragma unroll
+        for (int i = 0; i < L::NF; ++i) {
+            const float v = cp * dirp[i];
+            UH[i] += v;
+            UR[i] += v;
+            UT[i] -= v;
+        }
+        ent_backward<MODEL, L>(cx, hp, lane, th, upd, rel, ph, UH);
+        ent_backward<MODEL, L>(cx, hp, lane, tt, upd, rel, pt, UT);
+        if (hp.norm_flag) normalize_bwd<L>(rel.y, rel.n, rel.free_, UR);
+        cx.add_rel(0, tr, UR, lane, upd);
+        if constexpr (MODEL == TRANSH) {
+            normalize_bwd<L>(rel.w, rel.nw, rel.freew_, rel.gw);
+            cx.add_rel(1, tr, rel.gw, lane, upd);
+        } else if constexpr (MODEL == TRANSD) {
+            cx.add_rel(1, tr, rel.gw, lane, upd);
+        }
+    }
+    return loss;
+}
+
+template <int MODEL, class L, int NT>
+__global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__ K2Params P) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int ntE = MODEL == TRANSD ? 2 : 1, ntR = MODEL == TRANSE ? 1 : 2, NTM = MODEL == TRANSE ? 1 : 2;
     const pk_universe_desc& U = P.desc[blockIdx.x];
-    const K2Smem S(MODEL, P.d, P.k, P.mE, P.mR, P.mB, P.stage);
-    const int tid = threadIdx.x, lane = tid % L::G, grp = tid / L::G;
-    const int d = P.d, k = P.k, B = U.batch_size, nE = U.n_ent, nR = U.n_rel;
+    const K2Smem S(MODEL, P.d, P.k, P.W, P.mE, P.mR, P.mB, P.stage);
+    const int tid = threadIdx.x;
+    const int d = P.d, k = P.k, B = U.batch_size, nE = U.n_ent, nR = U.n_rel, W = P.W;
+    const int NC = NT / 32 - P.np;          // consumer warps
+    const int n_cons = NC * 32, n_prod = P.np * 32;
+    const bool producer = tid >= n_cons;
 
     float* g_ent[2];   // this universe's tables in global memory
     float* g_rel[2];
-    float* st_ent[2];
-    float* st_rel[2];
+    K2Ctx<L, NTM> cx;
+    cx.d = d; cx.opt = P.opt; cx.lr = U.lr;
     for (int i = 0; i < 2; ++i) {
         g_ent[i] = (i < ntE) ? P.ent[i] + (size_t)U.ent_off * d : nullptr;
         g_rel[i] = (i < ntR) ? P.rel[i] + (size_t)U.rel_off * d : nullptr;
-        st_ent[i] = (i < ntE && P.opt == PK_ADAGRAD) ? P.ent_state[i] + (size_t)U.ent_off * d : nullptr;
-        st_rel[i] = (i < ntR && P.opt == PK_ADAGRAD) ? P.rel_state[i] + (size_t)U.rel_off * d : nullptr;
-    }
-    K2Ctx<L> cx;
-    cx.d = d;
-    for (int i = 0; i < 2; ++i) {
+        cx.ent_state[i] = (i < ntE && P.opt == PK_ADAGRAD) ? P.ent_state[i] + (size_t)U.ent_off * d : nullptr;
+        cx.rel_state[i] = (i < ntR && P.opt == PK_ADAGRAD) ? P.rel_state[i] + (size_t)U.rel_off * d : nullptr;
         cx.ent[i] = P.stage ? reinterpret_cast<float*>(smem + S.ent[i]) : g_ent[i];
-        cx.rel[i] = P.stage ? reinterpret_cast<float*>(smem + S.rel[i]) : g_rel[i];
-        cx.gent[i] = reinterpret_cast<float*>(smem + S.gent[i]);
-        cx.grel[i] = reinterpret_cast<float*>(smem + S.grel[i]);
+        cx.rel[i] = reinterpret_cast<float*>(smem + S.rel[i]);
     }
+    cx.scratch = reinterpret_cast<float*>(smem + S.scratch);
+    int32_t* map = reinterpret_cast<int32_t*>(smem + S.map);   // per table row: count (low 16) | slot << 16
     float* lossv = reinterpret_cast<float*>(smem + S.lossv);
-    int* slot_ent = reinterpret_cast<int*>(smem + S.slot_ent);
-    int* slot_rel = reinterpret_cast<int*>(smem + S.slot_rel);
-    int* touched_ent = reinterpret_cast<int*>(smem + S.touched_ent);
-    int* touched_rel = reinterpret_cast<int*>(smem + S.touched_rel);
-    int32_t* bh = reinterpret_cast<int32_t*>(smem + S.ids);
-    int32_t* bt = bh + (size_t)B * (1 + k);
-    int32_t* br = bt + (size_t)B * (1 + k);
-    int* counters = reinterpret_cast<int*>(smem + S.counters);  // [0] touched entities, [1] touched relations
-    uint64_t* lcg = reinterpret_cast<uint64_t*>(smem + S.lcg);
-    cx.slot_ent = slot_ent;
-    cx.slot_rel = slot_rel;
+    uint64_t* s0 = reinterpret_cast<uint64_t*>(smem + S.lcg);  // stream states at the start of the next batch
+    uint64_t* Aadv = s0 + 8;
+    uint64_t* Cadv = Aadv + 8;
+    uint64_t* Aj = Cadv + 8;
+    uint64_t* Cj = Aj + S.per;
+    const int per = (B % W == 0) ? B / W : B / W + 1;   // Base.cpp:199-207
 
-    // ---- stage tables, clear scratch
-    if (P.stage) {
-        for (int t = 0; t < ntE; ++t)
-            for (int i = tid; i < nE * d; i += K2_THREADS) cx.ent[t][i] = g_ent[t][i];
+    // ---- stage tables, clear scratch, build the LCG jump tables
+    {
+        const bool vec = (d % 4 == 0);
+        for (int t = 0; t < ntE && P.stage; ++t) {
+            if (vec) {
+                const float4* src = reinterpret_cast<const float4*>(g_ent[t]);
+                float4* dst = reinterpret_cast<float4*>(cx.ent[t]);
+                for (int i = tid; i < nE * d / 4; i += NT) dst[i] = src[i];
+            } else {
+                for (int i = tid; i < nE * d; i += NT) cx.ent[t][i] = g_ent[t][i];
+            }
+        }
         for (int t = 0; t < ntR; ++t)
-            for (int i = tid; i < nR * d; i += K2_THREADS) cx.rel[t][i] = g_rel[t][i];
+            for (int i = tid; i < nR * d; i += NT) cx.rel[t][i] = g_rel[t][i];
+        for (int i = tid; i < S.slots * NTM * d; i += NT) cx.scratch[i] = 0.f;
+        for (int i = tid; i < nE + nR; i += NT) map[i] = 0;
+        if (tid < 8) s0[tid] = U.lcg[tid];
+        if (tid < W) {
+            int64_t lef, rig;
+            slice_of(B, W, tid, lef, rig);
+            lcg_affine((uint64_t)(rig - lef) * (uint64_t)(1 + 2 * k), Aadv[tid], Cadv[tid]);
+        }
+        for (int j = tid; j < per; j += NT) lcg_affine((uint64_t)j * (uint64_t)(1 + 2 * k), Aj[j], Cj[j]);
     }
-    for (int t = 0; t < ntE; ++t)
-        for (int i = tid; i < S.slotsE * d; i += K2_THREADS) cx.gent[t][i] = 0.f;
-    for (int t = 0; t < ntR; ++t)
-        for (int i = tid; i < S.slotsR * d; i += K2_THREADS) cx.grel[t][i] = 0.f;
-    for (int i = tid; i < nE; i += K2_THREADS) slot_ent[i] = -1;
-    for (int i = tid; i < nR; i += K2_THREADS) slot_rel[i] = -1;
-    if (tid < 8) lcg[tid] = U.lcg[tid];
-    if (tid < 2) counters[tid] = 0;
     __syncthreads();
 
-    SamplerView sv;
-    sv.by_head = P.by_head + (size_t)U.tri_off * 3;
-    sv.by_tail = P.by_tail ? P.by_tail + (size_t)U.tri_off * 3 : nullptr;
-    sv.left_mean = P.left_mean ? P.left_mean + U.rel_off : nullptr;
-    sv.right_mean = P.right_mean ? P.right_mean + U.rel_off : nullptr;
-    sv.n_tri = U.n_tri;
-    sv.n_ent = nE;
-    sv.n_rel = nR;
+    const long long steps = (long long)U.epochs * U.nbatches;
 
+    // ------------------------------------------------------------------------------------ producer
+    // The reference sampling() call (Base.cpp:185-310, Corrupt.h:9-105), bit-exact, one thread per
+    // positive, plus the occurrence analysis of the batch.
+    const int32_t* by_head = P.by_head + (size_t)U.tri_off * 3;
+    const int32_t* by_tail = P.by_tail ? P.by_tail + (size_t)U.tri_off * 3 : nullptr;
+    const FastMod fm_tri = make_fastmod((uint64_t)U.n_tri), fm_coin = make_fastmod(1000ULL),
+                  fm_ent = make_fastmod((uint64_t)(nE - 1));
+    auto count_row = [&](int32_t uid, const BatchView& bv) {
+        const int32_t old = atomicAdd(&map[uid], 1);
+        if ((old & 0xffff) == 1) {   // second occurrence: the row needs a scratch slot
+            const int32_t s = atomicAdd(bv.ndup, 1);
+            bv.dup[s] = uid;
+            atomicAdd(&map[uid], s << 16);
+        }
+    };
+    auto code_of = [&](int32_t uid) -> int32_t {
+        const int32_t m = map[uid];
+        return (m & 0xffff) > 1 ? (m >> 16) : -1;
+    };
+    auto produce = [&](int buf) {
+        const int ptid = tid - n_cons;
+        BatchView bv(smem + S.batch[0] + (size_t)buf * (S.batch[1] - S.batch[0]), B, k, S.slots);
+        if (ptid == 0) *bv.ndup = 0;
+        named_barrier(2, n_prod);
+        for (int b = ptid; b < B; b += n_prod) {
+            const int id = b / per, j = b - id * per;
+            uint64_t s = Aj[j] * s0[id] + Cj[j];
+            const int64_t i = (int64_t)fastmod(lcg_next(s), fm_tri);
+            const int32_t h = by_head[i * 3 + 0], r = by_head[i * 3 + 1], t = by_head[i * 3 + 2];
+            bv.h[b] = h; bv.t[b] = t; bv.r[b] = r;
+            count_row(h, bv); count_row(t, bv); count_row(nE + r, bv);
+            float prob = 500.f;
+            if (P.bern) {
+                const float rm = P.right_mean[U.rel_off + r], lm = P.left_mean[U.rel_off + r];
+                prob = __fdiv_rn(__fmul_rn(1000.f, rm), __fadd_rn(rm, lm));  // Base.cpp:220-221
+            }
+            for (int n = 0; n < k; ++n) {
+                const uint64_t coin = fastmod(lcg_next(s), fm_coin);
+                const uint64_t x = lcg_next(s);
+                int32_t c, side;
+                if ((float)coin < prob) {   // keep head, replace tail (corrupt_head, Corrupt.h:9-57)
+                    if (!P.filter) { const int64_t tmp = (int64_t)fastmod(x, fm_ent); c = (int32_t)(tmp < h ? tmp : tmp + 1); }
+                    else c = corrupt_entity(x, by_head, U.n_tri, nE, h, r, 0, 2, true);
+                    side = 0;
+                } else {                    // keep tail, replace head (corrupt_tail, Corrupt.h:59-105)
+                    if (!P.filter) { const int64_t tmp = (int64_t)fastmod(x, fm_ent); c = (int32_t)(tmp < t ? tmp : tmp + 1); }
+                    else c = corrupt_entity(x, by_tail, U.n_tri, nE, t, r, 2, 0, true);
+                    side = 1;
+                }
+                bv.c[(size_t)n * B + b] = (int32_t)((uint32_t)c | ((uint32_t)side << 31));
+                count_row(c, bv);
+            }
+        }
+        named_barrier(2, n_prod);
+        for (int b = ptid; b < B; b += n_prod) {
+            bv.code_h[b] = code_of(bv.h[b]);
+            bv.code_t[b] = code_of(bv.t[b]);
+            bv.code_r[b] = code_of(nE + bv.r[b]);
+            for (int n = 0; n < k; ++n) bv.code_c[(size_t)n * B + b] = code_of(bv.c[(size_t)n * B + b] & 0x7fffffff);
+        }
+        named_barrier(2, n_prod);
+        for (int b = ptid; b < B; b += n_prod) {
+            map[bv.h[b]] = 0; map[bv.t[b]] = 0; map[nE + bv.r[b]] = 0;
+            for (int n = 0; n < k; ++n) map[bv.c[(size_t)n * B + b] & 0x7fffffff] = 0;
+        }
+        if (ptid < W) s0[ptid] = Aadv[ptid] * s0[ptid] + Cadv[ptid];
+    };
+
+    if (producer && steps > 0) produce(0);
+    __syncthreads();
+
+    // ------------------------------------------------------------------------------------ consumers
+    constexpr int GPW = 32 / L::G;          // lane groups per warp
+    const int lane = tid % L::G, grp = tid / L::G;
+    const int NG = NC * GPW;
     Hyper hp;
     hp.d = d; hp.k = k; hp.p_norm = P.p_norm; hp.norm_flag = P.norm_flag;
     hp.margin = U.margin;
     hp.inv_bk = 1.f / (float)((long long)B * k);
-    const long long steps = (long long)U.epochs * U.nbatches;
-    const int nids = B * (1 + k);
 
     for (long long step = 0; step < steps; ++step) {
-        // ---- phase 0: the reference sampling() call, bit-exact, one thread per positive
-        for (int b = tid; b < B; b += K2_THREADS) {
-            int64_t j;
-            const int id = stream_of(B, P.W, b, j);
-            sample_one(sv, lcg[id], j, B, k, P.bern != 0, P.filter != 0, b, bh, bt, br);
-        }
-        __syncthreads();
-        // ---- phase 1a: give every touched table row a scratch slot
-        for (int i = tid; i < nids; i += K2_THREADS) {
-            const int a = bh[i], c = bt[i];
-            if (atomicCAS(&slot_ent[a], -1, -2) == -1) { const int s = atomicAdd(&counters[0], 1); touched_ent[s] = a; slot_ent[a] = s; }
-            if (atomicCAS(&slot_ent[c], -1, -2) == -1) { const int s = atomicAdd(&counters[0], 1); touched_ent[s] = c; slot_ent[c] = s; }
-            if (i < B) {
-                const int r = br[i];
-                if (atomicCAS(&slot_rel[r], -1, -2) == -1) { const int s = atomicAdd(&counters[1], 1); touched_rel[s] = r; slot_rel[r] = s; }
+        const int buf = (int)(step & 1);
+        if (producer) {
+            if (step + 1 < steps) produce(buf ^ 1);
+        } else {
+            const BatchView bv(smem + S.batch[0] + (size_t)buf * (S.batch[1] - S.batch[0]), B, k, S.slots);
+            // ---- phase A: forward + analytic backward; singly-occurring rows updated in place
+            for (int base = 0; base < B; base += NG) {
+                const int b = base + grp;
+                const bool act = b < B;
+                const float l = k2_sample<MODEL, L>(cx, hp, lane, B, b, act, bv);
+                if (act && lane == 0) lossv[b] = l;
             }
-        }
-        if (tid < P.W) lcg[tid] = lcg_advance_batch(lcg[tid], P.W, tid, B, k);
-        __syncthreads();
-        // ---- phase 1b: forward + analytic backward, gradients accumulated per touched row
-        for (int base = 0; base < B; base += NG) {
-            const int b = base + grp;
-            const bool act = b < B;
-            const float l = process_sample<MODEL, L>(cx, hp, lane, B, b, act, bh, bt, br);
-            if (act && lane == 0) lossv[b] = l;
-        }
-        __syncthreads();
-        // ---- phase 2: optimizer on the touched rows, scratch back to zero
-        const int nte = counters[0], ntr = counters[1];
-        for (int s = grp; s < nte + ntr; s += NG) {
-            const bool is_ent = s < nte;
-            const int slot = is_ent ? s : s - nte;
-            const int id = is_ent ? touched_ent[slot] : touched_rel[slot];
-            const int nt = is_ent ? ntE : ntR;
-            for (int t = 0; t < nt; ++t) {
-                float* grow = (is_ent ? cx.gent[t] : cx.grel[t]) + (size_t)slot * d;
-                float g[L::NF];
-                ld_row<L>(grow, d, lane, g);
-                float* xrow = (is_ent ? cx.ent[t] : cx.rel[t]) + (size_t)id * d;
-                float* srow = P.opt == PK_ADAGRAD ? (is_ent ? st_ent[t] : st_rel[t]) + (size_t)id * d : nullptr;
-                apply_update<L>(xrow, srow, g, d, lane, P.opt, U.lr);
+            named_barrier(1, n_cons);
+            // ---- phase B: optimizer on the multiply-occurring rows, scratch back to zero
+            const int nd = *bv.ndup;
+            for (int s = grp; s < nd; s += NG) {
+                const int uid = bv.dup[s];
+                const bool is_ent = uid < nE;
+                const int id = is_ent ? uid : uid - nE;
+                const int nt = is_ent ? ntE : ntR;
+                for (int t = 0; t < nt; ++t) {
+                    float* grow = cx.scratch + ((size_t)s * NTM + t) * d;
+                    float g[L::NF], st[L::NF];
+                    ld_row<L>(grow, d, lane, g);
+                    float* xrow = (is_ent ? cx.ent[t] : cx.rel[t]) + (size_t)id * d;
+                    float* srow = P.opt == PK_ADAGRAD ? (is_ent ? cx.ent_state[t] : cx.rel_state[t]) + (size_t)id * d : nullptr;
+                    ld_row<L>(srow, d, lane, st, P.opt == PK_ADAGRAD);
+                    apply_update<L>(xrow, srow, st, g, d, lane, P.opt, U.lr);
 #pragma unroll
-                for (int i = 0; i < L::NF; ++i) g[i] = 0.f;
-                st_row<L>(grow, d, lane, g);
+                    for (int i = 0; i < L::NF; ++i) g[i] = 0.f;
+                    st_row<L>(grow, d, lane, g);
+                }
             }
-            if (lane == 0) { if (is_ent) slot_ent[id] = -1; else slot_rel[id] = -1; }
-        }
-        if (tid < 32 && U.loss_off >= 0) {  // deterministic loss reduction: mean + margin (MarginLoss.py:28)
-            float acc = 0.f;
-            for (int b = tid; b < B; b += 32) acc += lossv[b];
-            acc = gsum<32>(acc);
-            if (tid == 0) P.loss[U.loss_off + step] = acc / (float)((long long)B * k) + U.margin;
+            if (tid < 32 && U.loss_off >= 0) {  // deterministic loss reduction: mean + margin (MarginLoss.py:28)
+                float acc = 0.f;
+                for (int b = tid; b < B; b += 32) acc += lossv[b];
+                acc = gsum<32>(acc);
+                if (tid == 0) P.loss[U.loss_off + step] = acc / (float)((long long)B * k) + U.margin;
+            }
         }
         __syncthreads();
-        if (tid < 2) counters[tid] = 0;
-        // (next phase 0 does not touch counters; phase 1a runs after the next barrier)
     }
 
     // ---- write staged tables back
-    if (P.stage) {
-        __syncthreads();
-        for (int t = 0; t < ntE; ++t)
-            for (int i = tid; i < nE * d; i += K2_THREADS) g_ent[t][i] = cx.ent[t][i];
+    {
+        const bool vec = (d % 4 == 0);
+        for (int t = 0; t < ntE && P.stage; ++t) {
+            if (vec) {
+                const float4* src = reinterpret_cast<const float4*>(cx.ent[t]);
+                float4* dst = reinterpret_cast<float4*>(g_ent[t]);
+                for (int i = tid; i < nE * d / 4; i += NT) dst[i] = src[i];
+            } else {
+                for (int i = tid; i < nE * d; i += NT) g_ent[t][i] = cx.ent[t][i];
+            }
+        }
         for (int t = 0; t < ntR; ++t)
-            for (int i = tid; i < nR * d; i += K2_THREADS) g_rel[t][i] = cx.rel[t][i];
+            for (int i = tid; i < nR * d; i += NT) g_rel[t][i] = cx.rel[t][i];
     }
 }
 
@@ -284,12 +538,16 @@ inline LaySel pick_layout(int model, int d) {
     return LaySel{V, 32, 1};
 }
 
+// threads per block: as many consumer warps as the register budget allows
+constexpr int k2_threads(int model, int nf) { return (model != 2 && nf <= 4) ? 512 : 256; }
+
 #ifdef PK_MODEL_TU
 template <int MODEL, int V, int G, int CPL>
 int launch_k2(const K2Params& P, int n, size_t smem, cudaStream_t st) {
-    auto kern = k2_train_universes<MODEL, Lay<V, G, CPL>>;
+    constexpr int NT = k2_threads(MODEL, V * CPL);
+    auto kern = k2_train_universes<MODEL, Lay<V, G, CPL>, NT>;
     PK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<n, K2_THREADS, smem, st>>>(P);
+    kern<<<n, NT, smem, st>>>(P);
     PK_LAUNCHED("k2_train_universes");
     return PK_OK;
 }
@@ -339,21 +597,24 @@ extern "C" int pk_train_universes(const pk_model_cfg* cfg, const pk_tables* pack
     if (cfg->work_threads < 1 || cfg->work_threads > 8) return pk::fail(PK_ERR_UNSUPPORTED, "pk_train_universes: work_threads must be in [1,8]");
     if (cfg->filter && !d_by_tail) return pk::fail(PK_ERR_ARG, "pk_train_universes: filter needs the (t,r,h) index");
     if (cfg->bern && (!d_left_mean || !d_right_mean)) return pk::fail(PK_ERR_ARG, "pk_train_universes: bern needs the relation means");
+    if (!d_by_head) return pk::fail(PK_ERR_ARG, "pk_train_universes: null triple index");
     cudaStream_t st = (cudaStream_t)stream;
-    const int d = cfg->dim, k = cfg->neg_ent;
+    const int d = cfg->dim, k = cfg->neg_ent, W = cfg->work_threads;
 
     int dev = 0, max_smem = 0;
     PK_CUDA(cudaGetDevice(&dev));
     PK_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
 
-    // split into a staged launch (tables fit in shared memory) and an unstaged one
+    // split into a staged launch (entity tables fit in shared memory) and an unstaged one
     std::vector<pk_universe_desc> cls[2];
     int mE[2] = {1, 1}, mR[2] = {1, 1}, mB[2] = {1, 1};
     for (int i = 0; i < n; ++i) {
         const pk_universe_desc& u = h_desc[i];
         if (u.n_ent < 2 || u.n_rel < 1 || u.n_tri < 1 || u.batch_size < 1 || u.nbatches < 0 || u.epochs < 0)
             return pk::fail(PK_ERR_ARG, "pk_train_universes: degenerate universe descriptor");
-        K2Smem own(cfg->model, d, k, u.n_ent, u.n_rel, u.batch_size, 1);
+        if ((long long)(3 + k) * u.batch_size >= 65536)
+            return pk::fail(PK_ERR_UNSUPPORTED, "pk_train_universes: batch too large for the universe kernel ((3+k)B < 65536); use pk_train_steps");
+        K2Smem own(cfg->model, d, k, W, u.n_ent, u.n_rel, u.batch_size, 1);
         const int c = own.total <= (size_t)max_smem ? 0 : 1;
         cls[c].push_back(u);
         mE[c] = std::max(mE[c], u.n_ent);
@@ -363,7 +624,7 @@ extern "C" int pk_train_universes(const pk_model_cfg* cfg, const pk_tables* pack
     // the uniform carve-up uses the class maxima; if that overflows, demote the largest universes
     for (;;) {
         if (cls[0].empty()) break;
-        K2Smem s(cfg->model, d, k, mE[0], mR[0], mB[0], 1);
+        K2Smem s(cfg->model, d, k, W, mE[0], mR[0], mB[0], 1);
         if (s.total <= (size_t)max_smem) break;
         size_t worst = 0;
         for (size_t i = 1; i < cls[0].size(); ++i)
@@ -382,11 +643,16 @@ extern "C" int pk_train_universes(const pk_model_cfg* cfg, const pk_tables* pack
     }
 
     const LaySel lay = pick_layout(cfg->model, d);
+    const int threads = k2_threads(cfg->model, lay.V * lay.CPL);
+    int np = threads == 512 ? 3 : 2;
+    if (const char* e = getenv("PK_K2_PRODUCERS")) np = std::max(1, std::min(threads / 32 - 1, atoi(e)));
     for (int c = 0; c < 2; ++c) {
         if (cls[c].empty()) continue;
         const size_t bytes = cls[c].size() * sizeof(pk_universe_desc);
         if (g_desc[c].cap < bytes) {
             if (g_desc[c].d) cudaFree(g_desc[c].d);
+            g_desc[c].d = nullptr;
+            g_desc[c].cap = 0;
             PK_CUDA(cudaMalloc(&g_desc[c].d, bytes));
             g_desc[c].cap = bytes;
         }
@@ -404,10 +670,11 @@ extern "C" int pk_train_universes(const pk_model_cfg* cfg, const pk_tables* pack
         P.by_head = d_by_head; P.by_tail = d_by_tail; P.left_mean = d_left_mean; P.right_mean = d_right_mean;
         P.loss = d_loss;
         P.d = d; P.k = k; P.p_norm = cfg->p_norm; P.norm_flag = cfg->norm_flag; P.opt = cfg->opt;
-        P.bern = cfg->bern; P.filter = cfg->filter; P.W = cfg->work_threads;
+        P.bern = cfg->bern; P.filter = cfg->filter; P.W = W;
         P.stage = c == 0;
         P.mE = mE[c]; P.mR = mR[c]; P.mB = mB[c];
-        K2Smem s(cfg->model, d, k, mE[c], mR[c], mB[c], P.stage);
+        P.np = np;
+        K2Smem s(cfg->model, d, k, W, mE[c], mR[c], mB[c], P.stage);
         if (s.total > (size_t)max_smem)
             return pk::fail(PK_ERR_UNSUPPORTED, "pk_train_universes: a universe's batch scratch exceeds shared memory; use pk_train_steps");
         // descriptors were copied from pageable host memory owned by this call: the copy has

@@ -40,6 +40,16 @@ def _close_tables(got, want, atol=TABLE_ATOL, frac=TABLE_BAD_FRACTION):
     assert bad.mean() <= frac, "fraction of entries off by > %g: %g (max err %g)" % (atol, bad.mean(), np.abs(got - want).max())
 
 
+# ------------------------------------------------------------------------------------------ arithmetic
+def test_fast_division_and_sqrt_are_correctly_rounded():
+    """The train kernels divide with a refined reciprocal and take square roots with rsqrt + an FMA
+    correction (kge_device.cuh); both must round exactly like the IEEE operations the reference's
+    PyTorch kernels use.  2^28 random operand pairs spanning 2^-40..2^40, plus the exact-zero cases."""
+    bad = np.zeros(3, dtype=np.int64)
+    N.check(N.lib().pk_selftest_arith(1 << 28, 12345, N.addr(bad)), "pk_selftest_arith")
+    assert bad.tolist() == [0, 0, 0], "mismatches (division, sqrt, zero cases): %s" % bad.tolist()
+
+
 # ------------------------------------------------------------------------------------------ K0
 def test_device_sampler_bit_exact_with_reference(wn18_dir, golden):
     from openke.data import TrainDataLoader
