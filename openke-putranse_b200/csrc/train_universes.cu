@@ -526,6 +526,12 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
 struct LaySel { int V, G, CPL; };
 
 inline LaySel pick_layout(int model, int d) {
+    if (const char* e = getenv("PK_K2_G")) {   // experiment: few lanes per sample, whole row in registers
+        const int G = atoi(e);
+        if (d == 20 && G == 1) return LaySel{4, 1, 5};
+        if (d == 20 && G == 2) return LaySel{4, 2, 3};
+        if (d == 20 && G == 4) return LaySel{4, 4, 2};
+    }
     const int V = d % 4 == 0 ? 4 : (d % 2 == 0 ? 2 : 1);
     const int chunks = d / V;
     const int nf_cap = model == TRANSD ? 4 : 8;  // registers per row per lane
@@ -539,7 +545,7 @@ inline LaySel pick_layout(int model, int d) {
 }
 
 // threads per block: as many consumer warps as the register budget allows
-constexpr int k2_threads(int model, int nf) { return (model != 2 && nf <= 4) ? 512 : 256; }
+constexpr int k2_threads(int model, int nf) { return (model != 2 && nf <= 4) ? 512 : 256; }  // TODO tune
 
 #ifdef PK_MODEL_TU
 template <int MODEL, int V, int G, int CPL>
@@ -555,6 +561,7 @@ int launch_k2(const K2Params& P, int n, size_t smem, cudaStream_t st) {
 template <int MODEL>
 int dispatch_layout(const LaySel& l, const K2Params& P, int n, size_t smem, cudaStream_t st) {
 #define PK_CASE(v, g, c) if (l.V == v && l.G == g && l.CPL == c) return launch_k2<MODEL, v, g, c>(P, n, smem, st);
+    PK_CASE(4, 1, 5) PK_CASE(4, 2, 3) PK_CASE(4, 4, 2)
     PK_CASE(4, 8, 1) PK_CASE(4, 8, 2) PK_CASE(4, 32, 1) PK_CASE(4, 32, 2)
     PK_CASE(2, 8, 1) PK_CASE(2, 8, 2) PK_CASE(2, 8, 4) PK_CASE(2, 32, 1) PK_CASE(2, 32, 2) PK_CASE(2, 32, 4)
     PK_CASE(1, 8, 1) PK_CASE(1, 8, 2) PK_CASE(1, 8, 4) PK_CASE(1, 8, 8) PK_CASE(1, 32, 1) PK_CASE(1, 32, 2) PK_CASE(1, 32, 4) PK_CASE(1, 32, 8)

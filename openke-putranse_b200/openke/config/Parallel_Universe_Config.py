@@ -33,6 +33,7 @@ from ..module.loss import MarginLoss
 from ..module.model.Model import Model
 from ..module.strategy import NegativeSampling
 from .Tester import Tester, link_metrics
+from ._universe_maps import SpaceMap, LocalIdMaps, MembershipMap
 from ..data.TestDataLoader import TestDataLoader
 
 
@@ -77,11 +78,15 @@ class Parallel_Universe_Config(Tester):
 
         self.initial_num_universes = initial_num_universes
         self.next_universe_id = 0
-        self.trained_embedding_spaces = defaultdict(Model)          # universe id -> embedding space
-        self.entity_id_mappings = defaultdict(defaultdict_int)      # universe id -> global entity -> local
-        self.relation_id_mappings = defaultdict(defaultdict_int)
-        self.entity_universes = defaultdict(set)                    # global entity -> universe ids
-        self.relation_universes = defaultdict(set)
+        # the reference's containers (reference :80-90), materialised lazily from the packed chunks
+        self._chunks = []
+        self._where = {}                                            # universe id -> (chunk, index in chunk)
+        self._maps_version = 0
+        self.trained_embedding_spaces = SpaceMap(self)              # universe id -> embedding space
+        self.entity_id_mappings = LocalIdMaps(self, "ent")          # universe id -> global entity -> local
+        self.relation_id_mappings = LocalIdMaps(self, "rel")
+        self.entity_universes = MembershipMap(self, "ent")          # global entity -> universe ids
+        self.relation_universes = MembershipMap(self, "rel")
         # the loaders share one library state: this is whatever seed was set last (reference :97)
         self.initial_random_seed = self.train_dataloader.lib.getRandomSeed()
 
@@ -106,7 +111,6 @@ class Parallel_Universe_Config(Tester):
         self.incremental_strategy = incremental_strategy
 
         # B200 build state
-        self._chunks = []
         self.universe_hyper = {}          # universe id -> dict(tc, balance, margin, epochs, lr, nT, nE, nR, focus)
         self.universe_losses = {}         # universe id -> np.float32 [epochs*nbatches] (if record_losses)
         self.record_losses = False
@@ -215,22 +219,21 @@ class Parallel_Universe_Config(Tester):
         eoff = np.concatenate([[0], np.cumsum(nE)]).astype(np.int64)
         roff = np.concatenate([[0], np.cumsum(nR)]).astype(np.int64)
 
-        # -- initial tables: the reference's torch CPU initialisation, universe by universe
-        proto = None
-        spaces = []
-        packed_host = None
+        # -- initial tables: the reference's torch CPU initialisation (same generator, same draws,
+        #    same order: torch.manual_seed(seed + u) then the model constructor's init), written
+        #    straight into one packed pinned buffer per table
+        model_cls, param = self.embedding_model, self.embedding_model_param
+        specs0 = model_cls.table_specs(2, 1, **param)
+        ent_names = set(model_cls._ent_tables)
+        d = specs0[0][2]
+        packed_host = {attr: torch.empty((sE if attr in ent_names else sR, dim), dtype=torch.float32).pin_memory()
+                       for attr, _, dim in specs0}
         for i, u in enumerate(universe_ids):
             torch.manual_seed(int(seeds[i]))
-            space = self.embedding_model(int(nE[i]), int(nR[i]), **self.embedding_model_param)
-            if proto is None:
-                proto = space
-                d = space.dim_native
-                packed_host = {name: torch.empty((sE if name in space._ent_tables else sR, d), dtype=torch.float32).pin_memory()
-                               for name in space.table_names()}
-            for name in space.table_names():
-                o = eoff if name in space._ent_tables else roff
-                packed_host[name][o[i]:o[i + 1]].copy_(getattr(space, name).weight.data)
-            spaces.append(space)
+            views = {attr: packed_host[attr][(eoff if attr in ent_names else roff)[i]:(eoff if attr in ent_names else roff)[i + 1]]
+                     for attr in packed_host}
+            model_cls.initial_tables_into(int(nE[i]), int(nR[i]), views, **param)
+        proto = self._proto()
         t2 = time.perf_counter()
         self.timings["table_init"] += t2 - t1
 
@@ -284,26 +287,10 @@ class Parallel_Universe_Config(Tester):
         t3 = time.perf_counter()
         self.timings["launch"] += t3 - t2
 
-        # -- expose every universe as an embedding-space module over views of the packed tables
+        # -- the reference's per-universe containers are views of this chunk, built on first use
         for i, u in enumerate(universe_ids):
-            space = spaces[i]
-            for name in space.table_names():
-                o = eoff if name in space._ent_tables else roff
-                getattr(space, name).weight = torch.nn.Parameter(ck.tables[name][o[i]:o[i + 1]], requires_grad=False)
-            for p in (space.zero_const, space.pi_const):
-                p.data = p.data.to(dev)
-            space.eval()
-            self.trained_embedding_spaces[u] = space
-            er = ent_remap[eoff[i]:eoff[i + 1]].tolist()
-            rr = rel_remap[roff[i]:roff[i + 1]].tolist()
-            emap = self.entity_id_mappings[u]
-            emap.update(zip(er, range(len(er))))
-            rmap = self.relation_id_mappings[u]
-            rmap.update(zip(rr, range(len(rr))))
-            for g in er:
-                self.entity_universes[g].add(u)
-            for g in rr:
-                self.relation_universes[g].add(u)
+            self._where[u] = (ck, i)
+        self._maps_version += 1
         if self.record_losses:
             host = d_loss.cpu().numpy()
             o = 0
@@ -315,6 +302,13 @@ class Parallel_Universe_Config(Tester):
         self._rank_cache.clear()
         self.timings["bookkeeping"] += time.perf_counter() - t3
         return ck
+
+    def _proto(self):
+        """A 2-entity instance of the embedding model: carries dim / p_norm / norm_flag / table names."""
+        if getattr(self, "_proto_space", None) is None:
+            with torch.random.fork_rng(devices=[]):
+                self._proto_space = self.embedding_model(2, 1, **self.embedding_model_param)
+        return self._proto_space
 
     def _packed_tables(self, ck, with_state=False):
         t = N.Tables()
@@ -372,6 +366,8 @@ class Parallel_Universe_Config(Tester):
         print("Time took for creation of embedding spaces: {:5.3f}s".format(training_duration))
 
     def add_embedding_space(self, embedding_space):
+        """Reference :260-264.  Externally trained spaces are kept for inspection only: evaluation on
+        this path reads the packed chunks that train_parallel_universes produces."""
         for p in embedding_space.parameters():
             p.requires_grad = False
         self.trained_embedding_spaces[self.next_universe_id] = embedding_space
@@ -575,11 +571,10 @@ class Parallel_Universe_Config(Tester):
     def process_state_dict(self, state):
         dev = self._device()
         self._chunks = []
-        self.trained_embedding_spaces.clear()
-        self.entity_id_mappings.clear()
-        self.relation_id_mappings.clear()
-        self.entity_universes.clear()
-        self.relation_universes.clear()
+        self._where = {}
+        for m in (self.trained_embedding_spaces, self.entity_id_mappings, self.relation_id_mappings,
+                  self.entity_universes, self.relation_universes):
+            m.clear()
         for c in state["chunks"]:
             ck = _Chunk()
             ck.ids, ck.nT, ck.nE, ck.nR = list(c["ids"]), c["nT"], c["nE"], c["nR"]
@@ -589,26 +584,11 @@ class Parallel_Universe_Config(Tester):
             ck.toff = np.concatenate([[0], np.cumsum(ck.nT)]).astype(np.int64)
             ck.tables = {k: v.to(dev) for k, v in c["tables"].items()}
             ck.state = None
-            ck.proto = None
+            ck.proto = self._proto()
             for i, u in enumerate(ck.ids):
-                space = self.embedding_model(int(ck.nE[i]), int(ck.nR[i]), **self.embedding_model_param)
-                ck.proto = ck.proto or space
-                for name in space.table_names():
-                    o = ck.eoff if name in space._ent_tables else ck.roff
-                    getattr(space, name).weight = torch.nn.Parameter(ck.tables[name][o[i]:o[i + 1]], requires_grad=False)
-                for p in (space.zero_const, space.pi_const):
-                    p.data = p.data.to(dev)
-                space.eval()
-                self.trained_embedding_spaces[u] = space
-                er = ck.ent_remap[ck.eoff[i]:ck.eoff[i + 1]].tolist()
-                rr = ck.rel_remap[ck.roff[i]:ck.roff[i + 1]].tolist()
-                self.entity_id_mappings[u].update(zip(er, range(len(er))))
-                self.relation_id_mappings[u].update(zip(rr, range(len(rr))))
-                for g in er:
-                    self.entity_universes[g].add(u)
-                for g in rr:
-                    self.relation_universes[g].add(u)
+                self._where[u] = (ck, i)
             self._chunks.append(ck)
+        self._maps_version += 1
         self.next_universe_id = state["next_universe_id"]
         self.universe_hyper = state.get("universe_hyper", {})
         self.best_hit10 = state.get("best_hit10", 0)
@@ -625,18 +605,13 @@ class Parallel_Universe_Config(Tester):
         for ck in other._chunks:
             ck.ids = [u + shift for u in ck.ids]
             ck.index = None
+            for i, u in enumerate(ck.ids):
+                self._where[u] = (ck, i)
             self._chunks.append(ck)
-        for u, space in other.trained_embedding_spaces.items():
+        for u, space in other.trained_embedding_spaces._extra.items():
             self.trained_embedding_spaces[u + shift] = space
-        for u, m in other.entity_id_mappings.items():
-            self.entity_id_mappings[u + shift].update(m)
-        for u, m in other.relation_id_mappings.items():
-            self.relation_id_mappings[u + shift].update(m)
-        for g, us in other.entity_universes.items():
-            self.entity_universes[g].update(u + shift for u in us)
-        for g, us in other.relation_universes.items():
-            self.relation_universes[g].update(u + shift for u in us)
         for u, h in other.universe_hyper.items():
             self.universe_hyper[u + shift] = h
         self.next_universe_id += other.next_universe_id
+        self._maps_version += 1
         self._rank_cache.clear()

@@ -26,19 +26,41 @@ class Model(BaseModule):
         self.rel_tot = rel_tot
 
     # ---- shared construction (reference TransE.py:17-43 and twins)
+    @staticmethod
+    def _fill_tables(specs, margin, epsilon, views):
+        """Initial values of the tables in `specs` order, written into the [rows, dim] float32 CPU
+        tensors `views[attr]`, consuming the torch CPU generator exactly like the reference's
+        constructor: every nn.Embedding draws a normal_() at creation (torch's default init), then
+        all tables are re-drawn with xavier_uniform_ (or uniform_(+-(margin+epsilon)/dim))."""
+        for attr, _, _ in specs:
+            views[attr].normal_()
+        for attr, _, dim in specs:
+            if margin is None or epsilon is None:
+                nn.init.xavier_uniform_(views[attr])
+            else:
+                rng = (margin + epsilon) / dim
+                nn.init.uniform_(tensor=views[attr], a=-rng, b=rng)
+
+    @classmethod
+    def table_specs(cls, ent_tot, rel_tot, **param):
+        """[(attr, rows, dim)] in the reference's creation order (it fixes the RNG stream of the init)."""
+        raise NotImplementedError
+
+    @classmethod
+    def initial_tables_into(cls, ent_tot, rel_tot, views, **param):
+        """What ``cls(ent_tot, rel_tot, **param)`` would hold right after construction, written
+        straight into `views` (e.g. slices of one packed pinned buffer) without building a module."""
+        cls._fill_tables(cls.table_specs(ent_tot, rel_tot, **param), param.get("margin"), param.get("epsilon"), views)
+
     def _init_tables(self, specs, margin, epsilon, ranges):
         """specs: [(attr, rows, dim)] in the reference's creation order; xavier unless margin+epsilon."""
         for attr, rows, dim in specs:
-            setattr(self, attr, nn.Embedding(rows, dim))
-        if margin is None or epsilon is None:
-            for attr, _, _ in specs:
-                nn.init.xavier_uniform_(getattr(self, attr).weight.data)
-        else:
+            emb = nn.Embedding(rows, dim, _weight=torch.empty(rows, dim))   # no draw here: _fill_tables replays it
+            setattr(self, attr, emb)
+        self._fill_tables(specs, margin, epsilon, {attr: getattr(self, attr).weight.data for attr, _, _ in specs})
+        if not (margin is None or epsilon is None):
             for name, value in ranges.items():
                 setattr(self, name, nn.Parameter(torch.Tensor([value]), requires_grad=False))
-            for attr, _, dim in specs:
-                rng = (margin + epsilon) / dim
-                nn.init.uniform_(tensor=getattr(self, attr).weight.data, a=-rng, b=rng)
         if margin is not None:
             self.margin = nn.Parameter(torch.Tensor([margin]), requires_grad=False)
             self.margin_flag = True

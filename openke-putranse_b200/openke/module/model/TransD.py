@@ -19,6 +19,10 @@ class TransD(Model):
         self.norm_flag, self.p_norm = norm_flag, p_norm
         rng = None if margin is None or epsilon is None else (margin + epsilon) / dim_e
         # creation order = reference TransD.py:18-21 (it fixes the torch RNG stream of the init)
-        self._init_tables([("ent_embeddings", ent_tot, dim_e), ("rel_embeddings", rel_tot, dim_r),
-                           ("ent_transfer", ent_tot, dim_e), ("rel_transfer", rel_tot, dim_r)], margin, epsilon,
+        self._init_tables(self.table_specs(ent_tot, rel_tot, dim_e=dim_e, dim_r=dim_r), margin, epsilon,
                           {"ent_embedding_range": rng, "rel_embedding_range": rng})
+
+    @classmethod
+    def table_specs(cls, ent_tot, rel_tot, dim_e=100, dim_r=100, **_):
+        return [("ent_embeddings", ent_tot, dim_e), ("rel_embeddings", rel_tot, dim_r),
+                ("ent_transfer", ent_tot, dim_e), ("rel_transfer", rel_tot, dim_r)]

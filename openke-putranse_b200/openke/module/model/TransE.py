@@ -11,5 +11,8 @@ class TransE(Model):
         self.dim, self.margin, self.epsilon = dim, margin, epsilon
         self.norm_flag, self.p_norm = norm_flag, p_norm
         rng = None if margin is None or epsilon is None else (margin + epsilon) / dim
-        self._init_tables([("ent_embeddings", ent_tot, dim), ("rel_embeddings", rel_tot, dim)], margin, epsilon,
-                          {"embedding_range": rng})
+        self._init_tables(self.table_specs(ent_tot, rel_tot, dim=dim), margin, epsilon, {"embedding_range": rng})
+
+    @classmethod
+    def table_specs(cls, ent_tot, rel_tot, dim=100, **_):
+        return [("ent_embeddings", ent_tot, dim), ("rel_embeddings", rel_tot, dim)]
