@@ -193,12 +193,14 @@ def run_ours(args):
         dist.barrier()
     p2.timings.clear()
     pos0 = p2.positive_triples
+    n_chunks = len(p2._chunks)
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         p2.train_parallel_universes(nU)
-        ck = p2._chunks[-1]
-        h2d += sum(t.numel() * 4 for t in ck.tables.values()) + int(ck.toff[-1]) * 12
-        d2h += sum(p2.universe_losses[u].nbytes for u in ck.ids)
+        for ck in p2._chunks[n_chunks:]:
+            h2d += sum(t.numel() * 4 for t in ck.tables.values()) + int(ck.toff[-1]) * 12
+            d2h += sum(p2.universe_losses[u].nbytes for u in ck.ids)
+        n_chunks = len(p2._chunks)
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
@@ -249,7 +251,8 @@ def prepare_resident_launch(pu, ids, dev):
     tables to their initial values and relaunch K2."""
     import torch
     from openke import _native as N
-    ck = pu._train_chunk(ids)     # first (untimed) training: leaves descriptors + inputs resident
+    ck = pu._train_piece(ids, None)     # first (untimed) training: leaves descriptors + inputs resident
+    pu._finish_piece(ck)
     torch.cuda.synchronize()
     # initial tables again (same seeds): rebuild them on the host exactly as _train_chunk does
     init = {}

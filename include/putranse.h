@@ -119,6 +119,17 @@ int  pk_universes_export(const pk_universe_set* s, int32_t* tri_by_head, int32_t
                          int32_t* tri_collected_global, int32_t* ent_remap, int32_t* rel_remap,
                          float* left_mean, float* right_mean, uint64_t* lcg /*[n*workThreads]*/);
 
+/* Initial tables of n embedding spaces on host threads, bit-identical to the reference's model
+ * constructors after torch.manual_seed(seeds[i]) (reference openke/module/model/TransE.py:17-22,
+ * TransH.py:17-24, TransD.py:18-27; Parallel_Universe_Config.py:157-161): every table first
+ * consumes torch's default nn.Embedding normal_() draw, then all tables are drawn
+ * uniform(-bounds, +bounds) from the same mt19937 stream, in table order.
+ * rows/row_off/bounds are [n * n_tables] (space-major); out[t] is the packed [sum rows, dims[t]]
+ * HOST buffer of table t.  fused = 1 evaluates x*(to-from)+from with one rounding (how torch's
+ * AVX2/AVX-512 builds contract it), 0 with two. */
+int pk_torch_init_tables(int n, const int64_t* seeds, int n_tables, const int64_t* rows, const int32_t* dims,
+                         float* const* out, const int64_t* row_off, const double* bounds, int fused, int nthreads);
+
 /* ===================================================================================== (C)
  * CUDA entry points.  Pointers named d_* are device pointers; `stream` is a cudaStream_t.
  * ------------------------------------------------------------------------------------------- */

@@ -581,12 +581,6 @@ int launch_model0(const LaySel& l, const K2Params& P, int n, size_t smem, cudaSt
 int launch_model1(const LaySel& l, const K2Params& P, int n, size_t smem, cudaStream_t st);
 int launch_model2(const LaySel& l, const K2Params& P, int n, size_t smem, cudaStream_t st);
 
-struct DescBuf {  // device copy of the descriptors, grown on demand, one per thread
-    pk_universe_desc* d = nullptr;
-    size_t cap = 0;
-};
-thread_local DescBuf g_desc[2];
-
 }  // namespace pkk2
 
 using namespace pkk2;
@@ -655,21 +649,21 @@ extern "C" int pk_train_universes(const pk_model_cfg* cfg, const pk_tables* pack
     if (const char* e = getenv("PK_K2_PRODUCERS")) np = std::max(1, std::min(threads / 32 - 1, atoi(e)));
     for (int c = 0; c < 2; ++c) {
         if (cls[c].empty()) continue;
-        const size_t bytes = cls[c].size() * sizeof(pk_universe_desc);
-        if (g_desc[c].cap < bytes) {
-            if (g_desc[c].d) cudaFree(g_desc[c].d);
-            g_desc[c].d = nullptr;
-            g_desc[c].cap = 0;
-            PK_CUDA(cudaMalloc(&g_desc[c].d, bytes));
-            g_desc[c].cap = bytes;
-        }
+        K2Smem s(cfg->model, d, k, W, mE[c], mR[c], mB[c], c == 0);
+        if (s.total > (size_t)max_smem)
+            return pk::fail(PK_ERR_UNSUPPORTED, "pk_train_universes: a universe's batch scratch exceeds shared memory; use pk_train_steps");
         // the longest universes first: blocks are scheduled in index order
         std::stable_sort(cls[c].begin(), cls[c].end(), [](const pk_universe_desc& a, const pk_universe_desc& b) {
             return (long long)a.epochs * a.nbatches * a.batch_size > (long long)b.epochs * b.nbatches * b.batch_size;
         });
-        PK_CUDA(cudaMemcpyAsync(g_desc[c].d, cls[c].data(), bytes, cudaMemcpyHostToDevice, st));
+        // device copy of the descriptors: stream-ordered allocation, so that calls on different
+        // streams (pieces of one chunk run concurrently) never share a buffer
+        const size_t bytes = cls[c].size() * sizeof(pk_universe_desc);
+        pk_universe_desc* d_desc = nullptr;
+        PK_CUDA(cudaMallocAsync((void**)&d_desc, bytes, st));
+        PK_CUDA(cudaMemcpyAsync(d_desc, cls[c].data(), bytes, cudaMemcpyHostToDevice, st));
         K2Params P;
-        P.desc = g_desc[c].d;
+        P.desc = d_desc;
         for (int i = 0; i < 2; ++i) {
             P.ent[i] = packed->ent[i]; P.rel[i] = packed->rel[i];
             P.ent_state[i] = packed->ent_state[i]; P.rel_state[i] = packed->rel_state[i];
@@ -681,9 +675,6 @@ extern "C" int pk_train_universes(const pk_model_cfg* cfg, const pk_tables* pack
         P.stage = c == 0;
         P.mE = mE[c]; P.mR = mR[c]; P.mB = mB[c];
         P.np = np;
-        K2Smem s(cfg->model, d, k, W, mE[c], mR[c], mB[c], P.stage);
-        if (s.total > (size_t)max_smem)
-            return pk::fail(PK_ERR_UNSUPPORTED, "pk_train_universes: a universe's batch scratch exceeds shared memory; use pk_train_steps");
         // descriptors were copied from pageable host memory owned by this call: the copy has
         // completed (or been staged) when cudaMemcpyAsync returns, so cls[c] may go out of scope
         int rc = PK_OK;
@@ -691,6 +682,7 @@ extern "C" int pk_train_universes(const pk_model_cfg* cfg, const pk_tables* pack
         if (cfg->model == PK_TRANSE) rc = launch_model0(lay, P, nblk, s.total, st);
         else if (cfg->model == PK_TRANSH) rc = launch_model1(lay, P, nblk, s.total, st);
         else rc = launch_model2(lay, P, nblk, s.total, st);
+        cudaFreeAsync(d_desc, st);
         if (rc != PK_OK) return rc;
     }
     return PK_OK;

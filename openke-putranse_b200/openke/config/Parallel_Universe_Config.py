@@ -115,7 +115,9 @@ class Parallel_Universe_Config(Tester):
         self.universe_losses = {}         # universe id -> np.float32 [epochs*nbatches] (if record_losses)
         self.record_losses = False
         self.sampler_threads = 0          # host threads for universe construction (0 = all cores)
-        self.max_chunk = 1024             # universes per launch
+        self.max_chunk = 1024             # universes per train_parallel_universes chunk
+        self.piece_size = 1 << 30         # universes per launch inside a chunk (set smaller to pipeline host prep and GPU)
+        self._streams = None
         self.max_energy_bytes = 8 << 30   # size of one [keys, E] energy tile
         self.training_duration = 0.0
         self.positive_triples = 0         # sum over universes of epochs * nbatches * batch_size
@@ -185,6 +187,43 @@ class Parallel_Universe_Config(Tester):
         return torch.device("cuda", torch.cuda.current_device())
 
     def _train_chunk(self, universe_ids):
+        """Train `universe_ids` as a pipeline of pieces: while the GPU trains piece i (its own
+        stream), the host samples and initialises piece i+1.  Pieces of one call run concurrently
+        on the device (one thread block per universe, 148 SMs)."""
+        dev = self._device()
+        piece = max(1, int(self.piece_size))
+        pieces = [universe_ids[i:i + piece] for i in range(0, len(universe_ids), piece)]
+        if len(pieces) == 1:
+            cks = [self._train_piece(pieces[0], None)]
+        else:
+            if self._streams is None:
+                self._streams = [torch.cuda.Stream(device=dev) for _ in range(4)]
+            cur = torch.cuda.current_stream(dev)
+            cks = []
+            for i, ids in enumerate(pieces):
+                st = self._streams[i % len(self._streams)]
+                st.wait_stream(cur)
+                with torch.cuda.stream(st):
+                    cks.append(self._train_piece(ids, st))
+            for st in self._streams:
+                cur.wait_stream(st)
+        t0 = time.perf_counter()
+        for ck in cks:
+            self._finish_piece(ck)
+        self.timings["bookkeeping"] += time.perf_counter() - t0
+        return cks[0] if len(cks) == 1 else cks
+
+    def _finish_piece(self, ck):
+        if ck.d_loss is not None:
+            host = ck.d_loss.cpu().numpy()
+            o = 0
+            for u in ck.ids:
+                steps = self.universe_hyper[u]["epochs"] * self.universe_hyper[u]["nbatches"]
+                self.universe_losses[u] = host[o:o + steps].copy()
+                o += steps
+            ck.d_loss = None
+
+    def _train_piece(self, universe_ids, stream):
         lib, dl = self.lib, self.train_dataloader
         dev = self._device()
         n = len(universe_ids)
@@ -225,14 +264,18 @@ class Parallel_Universe_Config(Tester):
         model_cls, param = self.embedding_model, self.embedding_model_param
         specs0 = model_cls.table_specs(2, 1, **param)
         ent_names = set(model_cls._ent_tables)
-        d = specs0[0][2]
-        packed_host = {attr: torch.empty((sE if attr in ent_names else sR, dim), dtype=torch.float32).pin_memory()
+        packed_host = {attr: torch.empty((sE if attr in ent_names else sR, dim), dtype=torch.float32, pin_memory=True)
                        for attr, _, dim in specs0}
-        for i, u in enumerate(universe_ids):
-            torch.manual_seed(int(seeds[i]))
-            views = {attr: packed_host[attr][(eoff if attr in ent_names else roff)[i]:(eoff if attr in ent_names else roff)[i + 1]]
-                     for attr in packed_host}
-            model_cls.initial_tables_into(int(nE[i]), int(nR[i]), views, **param)
+        offs = {attr: (eoff if attr in ent_names else roff) for attr in packed_host}
+        fused = self._native_init_mode()
+        if fused is not None and param.get("margin") is None and min(int(nR.min()), int(nE.min())) * min(s_[2] for s_ in specs0) >= 16:
+            # host threads, bit-identical to torch's generator (verified once per process in _native_init_mode)
+            self._native_init(model_cls, param, seeds, nE, nR, packed_host, offs, fused)
+        else:
+            for i, u in enumerate(universe_ids):
+                torch.manual_seed(int(seeds[i]))
+                views = {attr: packed_host[attr][offs[attr][i]:offs[attr][i + 1]] for attr in packed_host}
+                model_cls.initial_tables_into(int(nE[i]), int(nR[i]), views, **param)
         proto = self._proto()
         t2 = time.perf_counter()
         self.timings["table_init"] += t2 - t1
@@ -275,7 +318,7 @@ class Parallel_Universe_Config(Tester):
         cfg = proto.native_cfg(opt=N.PK_ADAGRAD, neg_ent=dl.negative_ent, bern=1 if dl.bern else 0,
                                filt=1 if dl.filter else 0, work_threads=W)
         tab = self._packed_tables(ck, with_state=True)
-        st = torch.cuda.current_stream(dev).cuda_stream
+        st = (stream if stream is not None else torch.cuda.current_stream(dev)).cuda_stream
         N.check(lib.pk_train_universes(ctypes.byref(cfg), ctypes.byref(tab), d_by_head.data_ptr(),
                                        d_by_tail.data_ptr() if d_by_tail is not None else None,
                                        d_lm.data_ptr() if d_lm is not None else None,
@@ -283,7 +326,8 @@ class Parallel_Universe_Config(Tester):
                                        desc, n, d_loss.data_ptr() if d_loss is not None else None, st),
                 "pk_train_universes")
         self.gpu_launches += lib.pk_last_launch_count()
-        ck.train_inputs = (d_by_head, d_by_tail, d_lm, d_rm)  # keep alive until the stream is done
+        ck.train_inputs = (d_by_head, d_by_tail, d_lm, d_rm, packed_host)  # keep alive until the stream is done
+        ck.d_loss = d_loss
         t3 = time.perf_counter()
         self.timings["launch"] += t3 - t2
 
@@ -291,17 +335,58 @@ class Parallel_Universe_Config(Tester):
         for i, u in enumerate(universe_ids):
             self._where[u] = (ck, i)
         self._maps_version += 1
-        if self.record_losses:
-            host = d_loss.cpu().numpy()
-            o = 0
-            for i, u in enumerate(universe_ids):
-                steps = hyper[i]["epochs"] * nb
-                self.universe_losses[u] = host[o:o + steps].copy()
-                o += steps
         self._chunks.append(ck)
         self._rank_cache.clear()
-        self.timings["bookkeeping"] += time.perf_counter() - t3
         return ck
+
+    def _native_init(self, model_cls, param, seeds, nE, nR, packed_host, offs, fused):
+        import math
+        specs0 = model_cls.table_specs(2, 1, **param)
+        ent_names = set(model_cls._ent_tables)
+        n, T = len(seeds), len(specs0)
+        rows = np.stack([(nE if attr in ent_names else nR) for attr, _, _ in specs0], axis=1).astype(np.int64)
+        dims = np.array([dim for _, _, dim in specs0], dtype=np.int32)
+        row_off = np.stack([offs[attr][:-1] for attr, _, _ in specs0], axis=1).astype(np.int64)
+        # nn.init.xavier_uniform_: a = sqrt(3) * gain * sqrt(2 / (fan_in + fan_out)), in Python doubles
+        bounds = np.array([[math.sqrt(3.0) * (1.0 * math.sqrt(2.0 / float(int(rows[i, t]) + int(dims[t])))) for t in range(T)]
+                           for i in range(n)], dtype=np.float64)
+        ptrs = (ctypes.c_void_p * T)(*[packed_host[attr].data_ptr() for attr, _, _ in specs0])
+        N.check(self.lib.pk_torch_init_tables(n, N.addr(np.ascontiguousarray(seeds, dtype=np.int64)), T, N.addr(np.ascontiguousarray(rows)),
+                                              N.addr(dims), ptrs, N.addr(np.ascontiguousarray(row_off)), N.addr(bounds), int(fused),
+                                              int(self.sampler_threads)), "pk_torch_init_tables")
+
+    _INIT_MODE = {}
+
+    def _native_init_mode(self):
+        """Which rounding variant of pk_torch_init_tables reproduces THIS torch build's CPU generator
+        bit-for-bit for this model (1 fused, 0 unfused), or None if neither does (then torch itself
+        initialises every universe).  Checked once per process on two small spaces."""
+        key = (self.embedding_model, tuple(sorted((k, str(v)) for k, v in self.embedding_model_param.items())))
+        if key not in Parallel_Universe_Config._INIT_MODE:
+            model_cls, param = self.embedding_model, self.embedding_model_param
+            mode = None
+            try:
+                specs0 = model_cls.table_specs(2, 1, **param)
+                ent_names = set(model_cls._ent_tables)
+                nE, nR, seeds = np.array([37, 64]), np.array([5, 16]), np.array([12345, (1 << 33) + 7])
+                want = []
+                with torch.random.fork_rng(devices=[]):
+                    for i in range(2):
+                        torch.manual_seed(int(seeds[i]))
+                        m = model_cls(int(nE[i]), int(nR[i]), **param)
+                        want.append({a: getattr(m, a).weight.data.clone() for a, _, _ in specs0})
+                eo, ro = np.array([0, 37, 101]), np.array([0, 5, 21])
+                for fused in (1, 0):
+                    host = {a: torch.empty((101 if a in ent_names else 21, dim)) for a, _, dim in specs0}
+                    offs = {a: (eo if a in ent_names else ro) for a in host}
+                    self._native_init(model_cls, param, seeds, nE, nR, host, offs, fused)
+                    if all(torch.equal(host[a][offs[a][i]:offs[a][i + 1]], want[i][a]) for i in range(2) for a in host):
+                        mode = fused
+                        break
+            except Exception:
+                mode = None
+            Parallel_Universe_Config._INIT_MODE[key] = mode
+        return Parallel_Universe_Config._INIT_MODE[key]
 
     def _proto(self):
         """A 2-entity instance of the embedding model: carries dim / p_norm / norm_flag / table names."""

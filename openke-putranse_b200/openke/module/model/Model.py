@@ -27,19 +27,21 @@ class Model(BaseModule):
 
     # ---- shared construction (reference TransE.py:17-43 and twins)
     @staticmethod
-    def _fill_tables(specs, margin, epsilon, views):
+    def _fill_tables(specs, margin, epsilon, views, generator=None):
         """Initial values of the tables in `specs` order, written into the [rows, dim] float32 CPU
         tensors `views[attr]`, consuming the torch CPU generator exactly like the reference's
         constructor: every nn.Embedding draws a normal_() at creation (torch's default init), then
-        all tables are re-drawn with xavier_uniform_ (or uniform_(+-(margin+epsilon)/dim))."""
+        all tables are re-drawn with xavier_uniform_ (or uniform_(+-(margin+epsilon)/dim)).
+        `generator`: a torch.Generator seeded like torch.manual_seed(seed) yields the same stream as
+        the global one, which lets several universes be initialised on different threads."""
         for attr, _, _ in specs:
-            views[attr].normal_()
+            views[attr].normal_(generator=generator)
         for attr, _, dim in specs:
             if margin is None or epsilon is None:
-                nn.init.xavier_uniform_(views[attr])
+                nn.init.xavier_uniform_(views[attr], generator=generator)
             else:
                 rng = (margin + epsilon) / dim
-                nn.init.uniform_(tensor=views[attr], a=-rng, b=rng)
+                nn.init.uniform_(tensor=views[attr], a=-rng, b=rng, generator=generator)
 
     @classmethod
     def table_specs(cls, ent_tot, rel_tot, **param):
@@ -47,10 +49,11 @@ class Model(BaseModule):
         raise NotImplementedError
 
     @classmethod
-    def initial_tables_into(cls, ent_tot, rel_tot, views, **param):
+    def initial_tables_into(cls, ent_tot, rel_tot, views, generator=None, **param):
         """What ``cls(ent_tot, rel_tot, **param)`` would hold right after construction, written
         straight into `views` (e.g. slices of one packed pinned buffer) without building a module."""
-        cls._fill_tables(cls.table_specs(ent_tot, rel_tot, **param), param.get("margin"), param.get("epsilon"), views)
+        cls._fill_tables(cls.table_specs(ent_tot, rel_tot, **param), param.get("margin"), param.get("epsilon"), views,
+                         generator=generator)
 
     def _init_tables(self, specs, margin, epsilon, ranges):
         """specs: [(attr, rows, dim)] in the reference's creation order; xavier unless margin+epsilon."""

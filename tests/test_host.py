@@ -269,3 +269,34 @@ def test_sharded_evaluation_min_allreduce_gloo(tmp_path):
                          env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert out.stdout.count("ok") == 2
+
+
+@pytest.mark.parametrize("cls_name,param", [("TransE", {"dim": 20, "p_norm": 1, "norm_flag": True}),
+                                            ("TransH", {"dim": 20, "p_norm": 1, "norm_flag": True}),
+                                            ("TransD", {"dim_e": 20, "dim_r": 20})])
+def test_native_table_init_replays_torch_generator(cls_name, param):
+    """pk_torch_init_tables must leave exactly what ``torch.manual_seed(seed); Model(nE, nR, ...)`` leaves
+    (reference openke/module/model/TransE.py:17-22 + torch's nn.Embedding default init), for seeds beyond
+    32 bits and table sizes on both sides of a multiple of 16."""
+    import torch
+    import openke.module.model as M
+    from openke.config.Parallel_Universe_Config import Parallel_Universe_Config as PU
+    cls = getattr(M, cls_name)
+    pu = PU.__new__(PU)
+    pu.embedding_model, pu.embedding_model_param, pu.sampler_threads = cls, param, 3
+    pu.lib = N.lib()
+    fused = pu._native_init_mode()
+    assert fused in (0, 1), "neither rounding variant reproduces this torch build"
+    nE, nR = np.array([583, 2632, 1084, 800]), np.array([11, 17, 13, 4])
+    seeds = np.array([4, 5, (1 << 40) + 6, 7])
+    specs = cls.table_specs(2, 1, **param)
+    ent = set(cls._ent_tables)
+    eo, ro = np.concatenate([[0], np.cumsum(nE)]), np.concatenate([[0], np.cumsum(nR)])
+    host = {a: torch.full((int(eo[-1]) if a in ent else int(ro[-1]), d), float("nan")) for a, _, d in specs}
+    offs = {a: (eo if a in ent else ro) for a in host}
+    pu._native_init(cls, param, seeds, nE, nR, host, offs, fused)
+    for i in range(4):
+        torch.manual_seed(int(seeds[i]))
+        m = cls(int(nE[i]), int(nR[i]), **param)
+        for a in host:
+            assert torch.equal(host[a][offs[a][i]:offs[a][i + 1]], getattr(m, a).weight.data), (cls_name, i, a)
