@@ -86,7 +86,7 @@ __device__ __forceinline__ void k1_apply_update(float* x_row, float* s_row, cons
 #pragma unroll
         for (int i = 0; i < L::NF; ++i) {
             s[i] = fmaf(g[i], g[i], s[i]);
-            x[i] = x[i] + div0(-lr * g[i], sqrt0(s[i]) + 1e-10f);
+            x[i] = fmaf(-lr * g[i], rcp_nr(sqrt0(s[i]) + 1e-10f), x[i]);
         }
         st_row<L>(s_row, d, lane, s);
     } else {

@@ -52,7 +52,6 @@ struct K2Params {
     const float* right_mean;
     float* loss;
     int d, k, p_norm, norm_flag, opt, bern, filter, W;
-    int stage;              // entity tables staged in shared memory for every universe of this launch
     int mE, mR, mB;         // launch-wide maxima: the shared-memory carve-up is uniform
     int np;                 // producer warps
 };
@@ -61,23 +60,29 @@ __host__ __device__ inline size_t up16(size_t x) { return (x + 15) & ~(size_t)15
 
 // shared-memory carve-up, identical on host (sizing) and device (pointers)
 struct K2Smem {
-    size_t ent[2], rel[2], scratch, map, batch[2], lossv, lcg, total;
-    int slots;      // scratch rows: a multiply-occurring row needs >= 2 of the (3+k)B occurrences
+    size_t ent[2], rel[2], rel_state[2], relc[2], reln, relacc, scratch, map, batch[2], lossv, lcg, total;
+    int slots;      // entity scratch rows: a multiply-occurring entity needs >= 2 of the (2+k)B occurrences
+    int nrelcap;    // distinct relations a batch can hold
     int per;        // samples per LCG stream slice
     int batch_ints; // ints in one batch buffer
     __host__ __device__ K2Smem(int model, int d, int k, int W, int mE, int mR, int mB, int stage) {
         const int ntE = model == TRANSD ? 2 : 1, ntR = model == TRANSE ? 1 : 2;
-        const int ntm = model == TRANSE ? 1 : 2;
-        const long long occ = (long long)(3 + k) * mB;
-        slots = (int)min_((long long)mE + mR, occ / 2 + 1);
+        const int nrc = model == TRANSH ? 2 : 1;   // cached relation operands: r^ (all), w^ (TransH)
+        const long long occ = (long long)(2 + k) * mB;
+        slots = (int)min_((long long)mE, occ / 2 + 1);
+        nrelcap = (int)min_(mR, mB);
         per = (mB + W - 1) / W + 1;
         size_t o = 0;
         for (int i = 0; i < 2; ++i) { ent[i] = o; if (stage && i < ntE) o = up16(o + (size_t)mE * d * 4); }
         for (int i = 0; i < 2; ++i) { rel[i] = o; if (i < ntR) o = up16(o + (size_t)mR * d * 4); }
-        scratch = o; o = up16(o + (size_t)slots * ntm * d * 4);
+        for (int i = 0; i < 2; ++i) { rel_state[i] = o; if (i < ntR) o = up16(o + (size_t)mR * d * 4); }
+        for (int i = 0; i < 2; ++i) { relc[i] = o; if (i < nrc) o = up16(o + (size_t)mR * d * 4); }
+        reln = o;    o = up16(o + (size_t)2 * mR * 4);
+        relacc = o;  o = up16(o + (size_t)mR * ntR * d * 12);  // fixed-point relation gradient sums, three int32 limbs
+        scratch = o; o = up16(o + (size_t)slots * ntE * d * 4);
         map = o;     o = up16(o + ((size_t)mE + mR) * 4);
-        // one batch buffer: h | t | r | c[k] | code_h | code_t | code_r | code_c[k] | dup[slots] | ndup
-        batch_ints = (int)(2 * occ) + slots + 4;
+        // one batch buffer: h | t | r | c[k] | code_h | code_t | code_c[k] | dup[slots] | rel_ids | ndup | nrel
+        batch_ints = (int)((3 + k) * (long long)mB + occ) + slots + nrelcap + 4;
         for (int i = 0; i < 2; ++i) { batch[i] = o; o = up16(o + (size_t)batch_ints * 4); }
         lossv = o;   o = up16(o + (size_t)mB * 4);
         // s0[8] | Aadv[8] | Cadv[8] | A[per] | C[per]
@@ -129,14 +134,15 @@ struct BatchView {
     int32_t* h;
     int32_t* t;
     int32_t* r;
-    int32_t* c;        // [k][B]  corrupted entity | (side << 31); side 0: tail replaced, 1: head replaced
-    int32_t* code_h;   // -1: the row occurs once in this batch (update in place); else scratch slot
+    int32_t* c;            // [k][B]  corrupted entity | (side << 31); side 0: tail replaced, 1: head replaced
+    int32_t* code_h;       // -1: the entity row occurs once in this batch (update in place); else scratch slot
     int32_t* code_t;
-    int32_t* code_r;
     int32_t* code_c;
-    int32_t* dup;      // unified row id (entity e -> e, relation r -> nE + r) of every scratch slot
+    int32_t* dup;          // entity id of every scratch slot
+    int32_t* rel_ids;      // distinct relations of the batch
     int32_t* ndup;
-    __device__ __forceinline__ BatchView(unsigned char* base, int B, int k, int slots) {
+    int32_t* nrel;
+    __device__ __forceinline__ BatchView(unsigned char* base, int B, int k, int slots, int nrelcap) {
         int32_t* p = reinterpret_cast<int32_t*>(base);
         h = p; p += B;
         t = p; p += B;
@@ -144,18 +150,19 @@ struct BatchView {
         c = p; p += (size_t)B * k;
         code_h = p; p += B;
         code_t = p; p += B;
-        code_r = p; p += B;
         code_c = p; p += (size_t)B * k;
         dup = p; p += slots;
+        rel_ids = p; p += nrelcap;
         ndup = p;
+        nrel = p + 1;
     }
 };
 
-// a table row as the backward pass addresses it: id, duplicate-slot code, prefetched Adagrad state
-template <class L, int NTM>
+// an entity row as the backward pass addresses it: id, duplicate-slot code, prefetched Adagrad state
+template <class L, int NTE>
 struct K2Tgt {
     int32_t id, code;
-    float st[NTM][L::NF];
+    float st[NTE][L::NF];
 };
 
 // x <- optimizer(x, g): SGD  x -= lr g ;  Adagrad  s += g^2, x -= lr g / (sqrt(s) + 1e-10)
@@ -169,7 +176,7 @@ __device__ __forceinline__ void apply_update(float* x_row, float* s_row, float (
 #pragma unroll
         for (int i = 0; i < L::NF; ++i) {
             s[i] = fmaf(g[i], g[i], s[i]);
-            x[i] = x[i] + div0(-lr * g[i], sqrt0(s[i]) + 1e-10f);
+            x[i] = fmaf(-lr * g[i], rcp_nr(sqrt0(s[i]) + 1e-10f), x[i]);
         }
         st_row<L>(s_row, d, lane, s);
     } else {
@@ -179,31 +186,29 @@ __device__ __forceinline__ void apply_update(float* x_row, float* s_row, float (
     st_row<L>(x_row, d, lane, x);
 }
 
-template <class L, int NTM_>
+template <class L, int NTE_>
 struct K2Ctx {
-    static constexpr int NTM = NTM_;
-    float* ent[2];        // working tables: shared memory when staged, else global
-    float* rel[2];
+    static constexpr int NTE = NTE_;
+    float* ent[2];        // working entity tables: shared memory when staged, else global
     float* ent_state[2];  // global; nullptr for SGD
-    float* rel_state[2];
-    float* scratch;       // [slots][NTM][d]
+    float* scratch;       // [slots][NTE][d]
     int d, opt;
     float lr;
     __device__ __forceinline__ const float* ent_row(int tbl, int id) const { return ent[tbl] + (size_t)id * d; }
-    __device__ __forceinline__ const float* rel_row(int tbl, int id) const { return rel[tbl] + (size_t)id * d; }
     // issue the loads of a singly-occurring row's optimizer state early; they complete behind the math
-    template <int NT>
-    __device__ __forceinline__ void prefetch(K2Tgt<L, NTM>& tg, bool is_ent, int lane, bool pred) const {
+    __device__ __forceinline__ void prefetch(K2Tgt<L, NTE>& tg, int lane, bool pred) const {
         if (opt != PK_ADAGRAD) return;
 #pragma unroll
-        for (int t = 0; t < NT; ++t)
-            ld_row<L>((is_ent ? ent_state[t] : rel_state[t]) + (size_t)tg.id * d, d, lane, tg.st[t], pred && tg.code < 0);
+        for (int t = 0; t < NTE; ++t) ld_row<L>(ent_state[t] + (size_t)tg.id * d, d, lane, tg.st[t], pred && tg.code < 0);
     }
-    __device__ __forceinline__ void emit(float* table, float* state, int tbl, K2Tgt<L, NTM>& tg, const float (&g)[L::NF], int lane) const {
+    __device__ __forceinline__ void add_ent(int tbl, const K2Tgt<L, NTE>& tgc, const float (&g)[L::NF], int lane, bool pred) const {
+        if (!pred) return;
+        K2Tgt<L, NTE>& tg = const_cast<K2Tgt<L, NTE>&>(tgc);
         if (tg.code < 0) {
-            apply_update<L>(table + (size_t)tg.id * d, state ? state + (size_t)tg.id * d : nullptr, tg.st[tbl], g, d, lane, opt, lr);
+            apply_update<L>(ent[tbl] + (size_t)tg.id * d, ent_state[tbl] ? ent_state[tbl] + (size_t)tg.id * d : nullptr, tg.st[tbl], g, d,
+                            lane, opt, lr);
         } else {
-            float* p = scratch + ((size_t)tg.code * NTM + tbl) * d;
+            float* p = scratch + ((size_t)tg.code * NTE + tbl) * d;
 #pragma unroll
             for (int i = 0; i < L::NF; ++i) {
                 const int e = elem_of<L>(lane, i);
@@ -211,46 +216,96 @@ struct K2Ctx {
             }
         }
     }
-    __device__ __forceinline__ void add_ent(int tbl, const K2Tgt<L, NTM>& tg, const float (&g)[L::NF], int lane, bool pred) const {
-        if (pred) emit(ent[tbl], ent_state[tbl], tbl, const_cast<K2Tgt<L, NTM>&>(tg), g, lane);
-    }
-    __device__ __forceinline__ void add_rel(int tbl, const K2Tgt<L, NTM>& tg, const float (&g)[L::NF], int lane, bool pred) const {
-        if (pred) emit(rel[tbl], rel_state[tbl], tbl, const_cast<K2Tgt<L, NTM>&>(tg), g, lane);
-    }
 };
+
+// Relation-side operands, cached per step: r^ = normalize(r) (or r when !norm_flag), for TransH also
+// w^ = normalize(norm_vector[r]); their norms; and the accumulator of the raw relation gradients
+// (w.r.t. r^ and w^ / r_p).  A relation occurs in many samples of a batch (the universe's focus
+// relation in half of them), and shared memory has native atomic adds only for 32-bit integers
+// (fp32 and 64-bit adds are compare-and-swap loops that collapse under that contention).  The sums
+// are therefore kept in 2^-44 fixed point split into three int32 limbs of 20 bits (room for 2047
+// addends): exact for every term >= 2^-21, order-independent, hence deterministic, and each add is
+// three fire-and-forget ATOMS.ADD.  The normalisation backward and the optimizer run once per
+// relation after the consumer barrier.
+struct RelCache {
+    float* rel[2];     // working relation tables (shared memory)
+    float* state[2];   // their Adagrad state (shared memory)
+    float* c[2];       // cached operands
+    float* n;          // [2][mR] clamped norms
+    int32_t* acc;      // [mR][ntR][3 limbs][d]
+    int mR;
+};
+constexpr float kFixScale = 17592186044416.f;          // 2^44
+constexpr float kFixInv = 1.f / 17592186044416.f;
+constexpr float kFixClamp = 262144.f;                   // |g| <= 2^18 keeps the top limb far from overflow
+
+template <class L>
+__device__ __forceinline__ void fix_add_row(int32_t* row, int d, int lane, const float (&g)[L::NF]) {
+#pragma unroll
+    for (int i = 0; i < L::NF; ++i) {
+        const int e = elem_of<L>(lane, i);
+        if (e < d && g[i] != 0.f) {
+            const long long v = __float2ll_rn(fminf(fmaxf(g[i], -kFixClamp), kFixClamp) * kFixScale);
+            atomicAdd(row + e, (int32_t)(v & 0xfffff));
+            atomicAdd(row + d + e, (int32_t)((v >> 20) & 0xfffff));
+            atomicAdd(row + 2 * d + e, (int32_t)(v >> 40));
+        }
+    }
+}
+// read a fixed-point row as fp32 and reset it; returns whether this lane saw a non-zero sum
+template <class L>
+__device__ __forceinline__ bool fix_take_row(int32_t* row, int d, int lane, float (&g)[L::NF]) {
+    bool nz = false;
+#pragma unroll
+    for (int i = 0; i < L::NF; ++i) {
+        const int e = elem_of<L>(lane, i);
+        long long v = 0;
+        if (e < d) {
+            const int32_t a0 = row[e], a1 = row[d + e], a2 = row[2 * d + e];
+            if ((a0 | a1 | a2) != 0) { row[e] = 0; row[d + e] = 0; row[2 * d + e] = 0; }
+            v = ((long long)a2 << 40) + ((long long)a1 << 20) + (long long)a0;
+        }
+        nz |= v != 0;
+        g[i] = (float)v * kFixInv;
+    }
+    return nz;
+}
 
 // One positive sample b and its k negatives (each negative replaces exactly one side, as the
 // reference sampler does: Base.cpp:216-232).  Every lane of the warp must call this; `act` masks
 // the memory side effects of idle groups.  Returns sum_j max(p - n_j, -m).
 template <int MODEL, class L, class Ctx>
-__device__ __forceinline__ float k2_sample(Ctx& cx, const Hyper& hp, int lane, int B, int b, bool act, const BatchView& bv) {
-    constexpr int ntE = MODEL == TRANSD ? 2 : 1, ntR = MODEL == TRANSE ? 1 : 2;
-    using Tg = K2Tgt<L, Ctx::NTM>;
-    Tg th, tt, tr;
+__device__ __forceinline__ float k2_sample(Ctx& cx, const RelCache& rc, const Hyper& hp, int lane, int B, int b, bool act,
+                                           const BatchView& bv) {
+    constexpr int ntR = MODEL == TRANSE ? 1 : 2;
+    using Tg = K2Tgt<L, Ctx::NTE>;
+    Tg th, tt;
     th.id = act ? bv.h[b] : 0; th.code = act ? bv.code_h[b] : 0;
     tt.id = act ? bv.t[b] : 0; tt.code = act ? bv.code_t[b] : 0;
-    tr.id = act ? bv.r[b] : 0; tr.code = act ? bv.code_r[b] : 0;
-    cx.template prefetch<ntE>(th, true, lane, act);
-    cx.template prefetch<ntE>(tt, true, lane, act);
-    cx.template prefetch<ntR>(tr, false, lane, act);
+    const int32_t r = act ? bv.r[b] : 0;
+    cx.prefetch(th, lane, act);
+    cx.prefetch(tt, lane, act);
 
     RelOp<MODEL, L> rel;
-    ld_row<L>(cx.rel_row(0, tr.id), hp.d, lane, rel.y, act);
-    if (hp.norm_flag) {
-        rel.n = normalize_row<L>(rel.y, rel.free_);
-    } else {
-        rel.n = 1.f;
-        rel.free_ = false;
-    }
+    ld_row<L>(rc.c[0] + (size_t)r * hp.d, hp.d, lane, rel.y, act);
+    if constexpr (MODEL == TRANSH) ld_row<L>(rc.c[1] + (size_t)r * hp.d, hp.d, lane, rel.w, act);
+    if constexpr (MODEL == TRANSD) ld_row<L>(rc.rel[1] + (size_t)r * hp.d, hp.d, lane, rel.w, act);
     if constexpr (MODEL != TRANSE) {
-        ld_row<L>(cx.rel_row(1, tr.id), hp.d, lane, rel.w, act);
-        if constexpr (MODEL == TRANSH) rel.nw = normalize_row<L>(rel.w, rel.freew_);
 #pragma unroll
         for (int i = 0; i < L::NF; ++i) rel.gw[i] = 0.f;
     }
-    EntOp<MODEL, L> ph, pt;
-    ent_forward<MODEL, L>(cx, hp, lane, th.id, act, rel, ph);
-    ent_forward<MODEL, L>(cx, hp, lane, tt.id, act, rel, pt);
+    // all table rows of the sample are requested before any arithmetic (the first negative too)
+    EntOp<MODEL, L> ph, pt, pc;
+    Tg tc;
+    int32_t cj = act ? bv.c[b] : 0;
+    tc.id = cj & 0x7fffffff;
+    tc.code = act ? bv.code_c[b] : 0;
+    ent_load<MODEL, L>(cx, hp, lane, th.id, act, ph);
+    ent_load<MODEL, L>(cx, hp, lane, tt.id, act, pt);
+    ent_load<MODEL, L>(cx, hp, lane, tc.id, act, pc);
+    cx.prefetch(tc, lane, act);
+    ent_project<MODEL, L>(hp, rel, ph);
+    ent_project<MODEL, L>(hp, rel, pt);
 
     float dirp[L::NF];
 #pragma unroll
@@ -263,14 +318,15 @@ __device__ __forceinline__ float k2_sample(Ctx& cx, const Hyper& hp, int lane, i
     float cp = 0.f, loss = 0.f;
 
     for (int j = 0; j < hp.k; ++j) {
-        const int32_t cj = act ? bv.c[(size_t)j * B + b] : 0;
+        if (j > 0) {
+            cj = act ? bv.c[(size_t)j * B + b] : 0;
+            tc.id = cj & 0x7fffffff;
+            tc.code = act ? bv.code_c[(size_t)j * B + b] : 0;
+            cx.prefetch(tc, lane, act);
+            ent_load<MODEL, L>(cx, hp, lane, tc.id, act, pc);
+        }
         const bool head_replaced = cj < 0;
-        Tg tc;
-        tc.id = cj & 0x7fffffff;
-        tc.code = act ? bv.code_c[(size_t)j * B + b] : 0;
-        cx.template prefetch<ntE>(tc, true, lane, act);
-        EntOp<MODEL, L> pc;
-        ent_forward<MODEL, L>(cx, hp, lane, tc.id, act, rel, pc);
+        ent_project<MODEL, L>(hp, rel, pc);
         float dn[L::NF];
 #pragma unroll
         for (int i = 0; i < L::NF; ++i)
@@ -294,8 +350,8 @@ __device__ __forceinline__ float k2_sample(Ctx& cx, const Hyper& hp, int lane, i
             ent_backward<MODEL, L>(cx, hp, lane, tc, act && g != 0.f, rel, pc, Uc);
         }
     }
+    const bool upd = act && cp != 0.f;
     if (__any_sync(0xffffffffu, cp != 0.f)) {
-        const bool upd = act && cp != 0.f;
 #pragma unroll
         for (int i = 0; i < L::NF; ++i) {
             const float v = cp * dirp[i];
@@ -305,42 +361,51 @@ __device__ __forceinline__ float k2_sample(Ctx& cx, const Hyper& hp, int lane, i
         }
         ent_backward<MODEL, L>(cx, hp, lane, th, upd, rel, ph, UH);
         ent_backward<MODEL, L>(cx, hp, lane, tt, upd, rel, pt, UT);
-        if (hp.norm_flag) normalize_bwd<L>(rel.y, rel.n, rel.free_, UR);
-        cx.add_rel(0, tr, UR, lane, upd);
-        if constexpr (MODEL == TRANSH) {
-            normalize_bwd<L>(rel.w, rel.nw, rel.freew_, rel.gw);
-            cx.add_rel(1, tr, rel.gw, lane, upd);
-        } else if constexpr (MODEL == TRANSD) {
-            cx.add_rel(1, tr, rel.gw, lane, upd);
+        // raw relation gradients (w.r.t. r^ and w^ / r_p): summed per relation in fixed point; the
+        // normalisation backward and the update happen once per relation after the barrier
+        if (upd) {
+            int32_t* pr = rc.acc + (size_t)r * ntR * 3 * hp.d;
+            fix_add_row<L>(pr, hp.d, lane, UR);
+            if constexpr (MODEL != TRANSE) fix_add_row<L>(pr + 3 * hp.d, hp.d, lane, rel.gw);
         }
     }
     return loss;
 }
 
-template <int MODEL, class L, int NT>
+template <int MODEL, class L, int NT, int STAGE>
 __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__ K2Params P) {
     extern __shared__ __align__(16) unsigned char smem[];
-    constexpr int ntE = MODEL == TRANSD ? 2 : 1, ntR = MODEL == TRANSE ? 1 : 2, NTM = MODEL == TRANSE ? 1 : 2;
+    constexpr int ntE = MODEL == TRANSD ? 2 : 1, ntR = MODEL == TRANSE ? 1 : 2;
     const pk_universe_desc& U = P.desc[blockIdx.x];
-    const K2Smem S(MODEL, P.d, P.k, P.W, P.mE, P.mR, P.mB, P.stage);
+    const K2Smem S(MODEL, P.d, P.k, P.W, P.mE, P.mR, P.mB, STAGE);
     const int tid = threadIdx.x;
     const int d = P.d, k = P.k, B = U.batch_size, nE = U.n_ent, nR = U.n_rel, W = P.W;
     const int NC = NT / 32 - P.np;          // consumer warps
     const int n_cons = NC * 32, n_prod = P.np * 32;
     const bool producer = tid >= n_cons;
+    constexpr int GPW = 32 / L::G;          // lane groups per warp
+    const int lane = tid % L::G, grp = tid / L::G;
+    const unsigned gmask = group_mask<L::G>(tid);
 
     float* g_ent[2];   // this universe's tables in global memory
     float* g_rel[2];
-    K2Ctx<L, NTM> cx;
+    float* g_rel_state[2];
+    K2Ctx<L, ntE> cx;
+    RelCache rc;
     cx.d = d; cx.opt = P.opt; cx.lr = U.lr;
+    rc.mR = P.mR;
     for (int i = 0; i < 2; ++i) {
         g_ent[i] = (i < ntE) ? P.ent[i] + (size_t)U.ent_off * d : nullptr;
         g_rel[i] = (i < ntR) ? P.rel[i] + (size_t)U.rel_off * d : nullptr;
+        g_rel_state[i] = (i < ntR && P.opt == PK_ADAGRAD) ? P.rel_state[i] + (size_t)U.rel_off * d : nullptr;
         cx.ent_state[i] = (i < ntE && P.opt == PK_ADAGRAD) ? P.ent_state[i] + (size_t)U.ent_off * d : nullptr;
-        cx.rel_state[i] = (i < ntR && P.opt == PK_ADAGRAD) ? P.rel_state[i] + (size_t)U.rel_off * d : nullptr;
-        cx.ent[i] = P.stage ? reinterpret_cast<float*>(smem + S.ent[i]) : g_ent[i];
-        cx.rel[i] = reinterpret_cast<float*>(smem + S.rel[i]);
+        cx.ent[i] = STAGE ? reinterpret_cast<float*>(smem + S.ent[i]) : g_ent[i];
+        rc.rel[i] = reinterpret_cast<float*>(smem + S.rel[i]);
+        rc.state[i] = reinterpret_cast<float*>(smem + S.rel_state[i]);
+        rc.c[i] = reinterpret_cast<float*>(smem + S.relc[i]);
     }
+    rc.n = reinterpret_cast<float*>(smem + S.reln);
+    rc.acc = reinterpret_cast<int32_t*>(smem + S.relacc);
     cx.scratch = reinterpret_cast<float*>(smem + S.scratch);
     int32_t* map = reinterpret_cast<int32_t*>(smem + S.map);   // per table row: count (low 16) | slot << 16
     float* lossv = reinterpret_cast<float*>(smem + S.lossv);
@@ -350,11 +415,30 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
     uint64_t* Aj = Cadv + 8;
     uint64_t* Cj = Aj + S.per;
     const int per = (B % W == 0) ? B / W : B / W + 1;   // Base.cpp:199-207
+    const size_t batch_stride = S.batch[1] - S.batch[0];
+
+    // refresh the cached operands of relation r from the working tables (group-masked shuffles:
+    // groups of one warp work on different relations)
+    auto recache = [&](int r) {
+        float x[L::NF];
+        ld_row<L>(rc.rel[0] + (size_t)r * d, d, lane, x);
+        float n = 1.f;
+        bool fr = false;
+        if (P.norm_flag) n = normalize_row<L>(x, fr, gmask);
+        st_row<L>(rc.c[0] + (size_t)r * d, d, lane, x);
+        if (lane == 0) rc.n[r] = n;
+        if constexpr (MODEL == TRANSH) {
+            ld_row<L>(rc.rel[1] + (size_t)r * d, d, lane, x);
+            n = normalize_row<L>(x, fr, gmask);
+            st_row<L>(rc.c[1] + (size_t)r * d, d, lane, x);
+            if (lane == 0) rc.n[rc.mR + r] = n;
+        }
+    };
 
     // ---- stage tables, clear scratch, build the LCG jump tables
     {
         const bool vec = (d % 4 == 0);
-        for (int t = 0; t < ntE && P.stage; ++t) {
+        for (int t = 0; t < ntE && STAGE; ++t) {
             if (vec) {
                 const float4* src = reinterpret_cast<const float4*>(g_ent[t]);
                 float4* dst = reinterpret_cast<float4*>(cx.ent[t]);
@@ -364,8 +448,12 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
             }
         }
         for (int t = 0; t < ntR; ++t)
-            for (int i = tid; i < nR * d; i += NT) cx.rel[t][i] = g_rel[t][i];
-        for (int i = tid; i < S.slots * NTM * d; i += NT) cx.scratch[i] = 0.f;
+            for (int i = tid; i < nR * d; i += NT) {
+                rc.rel[t][i] = g_rel[t][i];
+                rc.state[t][i] = g_rel_state[t] ? g_rel_state[t][i] : 0.f;
+            }
+        for (int i = tid; i < S.slots * ntE * d; i += NT) cx.scratch[i] = 0.f;
+        for (int i = tid; i < nR * ntR * 3 * d; i += NT) rc.acc[i] = 0;
         for (int i = tid; i < nE + nR; i += NT) map[i] = 0;
         if (tid < 8) s0[tid] = U.lcg[tid];
         if (tid < W) {
@@ -376,6 +464,7 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
         for (int j = tid; j < per; j += NT) lcg_affine((uint64_t)j * (uint64_t)(1 + 2 * k), Aj[j], Cj[j]);
     }
     __syncthreads();
+    for (int r = grp; r < nR; r += NT / L::G) recache(r);
 
     const long long steps = (long long)U.epochs * U.nbatches;
 
@@ -386,22 +475,22 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
     const int32_t* by_tail = P.by_tail ? P.by_tail + (size_t)U.tri_off * 3 : nullptr;
     const FastMod fm_tri = make_fastmod((uint64_t)U.n_tri), fm_coin = make_fastmod(1000ULL),
                   fm_ent = make_fastmod((uint64_t)(nE - 1));
-    auto count_row = [&](int32_t uid, const BatchView& bv) {
-        const int32_t old = atomicAdd(&map[uid], 1);
+    auto count_ent = [&](int32_t e, const BatchView& bv) {
+        const int32_t old = atomicAdd(&map[e], 1);
         if ((old & 0xffff) == 1) {   // second occurrence: the row needs a scratch slot
             const int32_t s = atomicAdd(bv.ndup, 1);
-            bv.dup[s] = uid;
-            atomicAdd(&map[uid], s << 16);
+            bv.dup[s] = e;
+            atomicAdd(&map[e], s << 16);
         }
     };
-    auto code_of = [&](int32_t uid) -> int32_t {
-        const int32_t m = map[uid];
+    auto code_of = [&](int32_t e) -> int32_t {
+        const int32_t m = map[e];
         return (m & 0xffff) > 1 ? (m >> 16) : -1;
     };
     auto produce = [&](int buf) {
         const int ptid = tid - n_cons;
-        BatchView bv(smem + S.batch[0] + (size_t)buf * (S.batch[1] - S.batch[0]), B, k, S.slots);
-        if (ptid == 0) *bv.ndup = 0;
+        BatchView bv(smem + S.batch[0] + (size_t)buf * batch_stride, B, k, S.slots, S.nrelcap);
+        if (ptid == 0) { *bv.ndup = 0; *bv.nrel = 0; }
         named_barrier(2, n_prod);
         for (int b = ptid; b < B; b += n_prod) {
             const int id = b / per, j = b - id * per;
@@ -409,7 +498,8 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
             const int64_t i = (int64_t)fastmod(lcg_next(s), fm_tri);
             const int32_t h = by_head[i * 3 + 0], r = by_head[i * 3 + 1], t = by_head[i * 3 + 2];
             bv.h[b] = h; bv.t[b] = t; bv.r[b] = r;
-            count_row(h, bv); count_row(t, bv); count_row(nE + r, bv);
+            count_ent(h, bv); count_ent(t, bv);
+            if (atomicAdd(&map[nE + r], 1) == 0) bv.rel_ids[atomicAdd(bv.nrel, 1)] = r;   // distinct relations of the batch
             float prob = 500.f;
             if (P.bern) {
                 const float rm = P.right_mean[U.rel_off + r], lm = P.left_mean[U.rel_off + r];
@@ -429,14 +519,13 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
                     side = 1;
                 }
                 bv.c[(size_t)n * B + b] = (int32_t)((uint32_t)c | ((uint32_t)side << 31));
-                count_row(c, bv);
+                count_ent(c, bv);
             }
         }
         named_barrier(2, n_prod);
         for (int b = ptid; b < B; b += n_prod) {
             bv.code_h[b] = code_of(bv.h[b]);
             bv.code_t[b] = code_of(bv.t[b]);
-            bv.code_r[b] = code_of(nE + bv.r[b]);
             for (int n = 0; n < k; ++n) bv.code_c[(size_t)n * B + b] = code_of(bv.c[(size_t)n * B + b] & 0x7fffffff);
         }
         named_barrier(2, n_prod);
@@ -448,11 +537,9 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
     };
 
     if (producer && steps > 0) produce(0);
-    __syncthreads();
+    __syncthreads();   // also orders the initial recache() before the first step
 
     // ------------------------------------------------------------------------------------ consumers
-    constexpr int GPW = 32 / L::G;          // lane groups per warp
-    const int lane = tid % L::G, grp = tid / L::G;
     const int NG = NC * GPW;
     Hyper hp;
     hp.d = d; hp.k = k; hp.p_norm = P.p_norm; hp.norm_flag = P.norm_flag;
@@ -464,33 +551,62 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
         if (producer) {
             if (step + 1 < steps) produce(buf ^ 1);
         } else {
-            const BatchView bv(smem + S.batch[0] + (size_t)buf * (S.batch[1] - S.batch[0]), B, k, S.slots);
-            // ---- phase A: forward + analytic backward; singly-occurring rows updated in place
+            const BatchView bv(smem + S.batch[0] + (size_t)buf * batch_stride, B, k, S.slots, S.nrelcap);
+            // ---- phase A: forward + analytic backward; singly-occurring entity rows updated in place
             for (int base = 0; base < B; base += NG) {
                 const int b = base + grp;
                 const bool act = b < B;
-                const float l = k2_sample<MODEL, L>(cx, hp, lane, B, b, act, bv);
+                const float l = k2_sample<MODEL, L>(cx, rc, hp, lane, B, b, act, bv);
                 if (act && lane == 0) lossv[b] = l;
             }
             named_barrier(1, n_cons);
-            // ---- phase B: optimizer on the multiply-occurring rows, scratch back to zero
-            const int nd = *bv.ndup;
-            for (int s = grp; s < nd; s += NG) {
-                const int uid = bv.dup[s];
-                const bool is_ent = uid < nE;
-                const int id = is_ent ? uid : uid - nE;
-                const int nt = is_ent ? ntE : ntR;
-                for (int t = 0; t < nt; ++t) {
-                    float* grow = cx.scratch + ((size_t)s * NTM + t) * d;
-                    float g[L::NF], st[L::NF];
-                    ld_row<L>(grow, d, lane, g);
-                    float* xrow = (is_ent ? cx.ent[t] : cx.rel[t]) + (size_t)id * d;
-                    float* srow = P.opt == PK_ADAGRAD ? (is_ent ? cx.ent_state[t] : cx.rel_state[t]) + (size_t)id * d : nullptr;
-                    ld_row<L>(srow, d, lane, st, P.opt == PK_ADAGRAD);
-                    apply_update<L>(xrow, srow, st, g, d, lane, P.opt, U.lr);
+            // ---- phase B: one item per distinct relation (take the fixed-point gradient sums, normalisation
+            //      backward, update, refresh the cache) and per multiply-occurring entity row
+            const int nrel = *bv.nrel, nd = *bv.ndup;
+            for (int it = grp; it < nrel + nd; it += NG) {
+                if (it < nrel) {
+                    const int r = bv.rel_ids[it];
+                    int32_t* pr = rc.acc + (size_t)r * ntR * 3 * d;
+                    float g0[L::NF], g1[ntR == 2 ? L::NF : 1];
+                    bool nz = fix_take_row<L>(pr, d, lane, g0);
+                    if constexpr (ntR == 2) nz |= fix_take_row<L>(pr + 3 * d, d, lane, g1);
+                    // an all-zero sum updates nothing (SGD and Adagrad leave zero-gradient rows unchanged)
+                    if (__ballot_sync(gmask, nz) != 0u) {
+                        float y[L::NF], st[L::NF];
+                        if (P.norm_flag) {
+                            ld_row<L>(rc.c[0] + (size_t)r * d, d, lane, y);
+                            const float n = rc.n[r];
+                            normalize_bwd<L>(y, n, n > kNormEps, g0, gmask);
+                        }
+                        ld_row<L>(rc.state[0] + (size_t)r * d, d, lane, st);
+                        apply_update<L>(rc.rel[0] + (size_t)r * d, rc.state[0] + (size_t)r * d, st, g0, d, lane, P.opt, U.lr);
+                        if constexpr (MODEL == TRANSH) {
+                            ld_row<L>(rc.c[1] + (size_t)r * d, d, lane, y);
+                            const float n = rc.n[rc.mR + r];
+                            normalize_bwd<L>(y, n, n > kNormEps, g1, gmask);
+                        }
+                        if constexpr (ntR == 2) {
+                            ld_row<L>(rc.state[1] + (size_t)r * d, d, lane, st);
+                            apply_update<L>(rc.rel[1] + (size_t)r * d, rc.state[1] + (size_t)r * d, st, g1, d, lane, P.opt, U.lr);
+                        }
+                        recache(r);
+                    }
+                } else {
+                    const int s = it - nrel;
+                    const int id = bv.dup[s];
 #pragma unroll
-                    for (int i = 0; i < L::NF; ++i) g[i] = 0.f;
-                    st_row<L>(grow, d, lane, g);
+                    for (int t = 0; t < ntE; ++t) {
+                        float* grow = cx.scratch + ((size_t)s * ntE + t) * d;
+                        float g[L::NF], st[L::NF];
+                        ld_row<L>(grow, d, lane, g);
+                        float* xrow = cx.ent[t] + (size_t)id * d;
+                        float* srow = P.opt == PK_ADAGRAD ? cx.ent_state[t] + (size_t)id * d : nullptr;
+                        ld_row<L>(srow, d, lane, st, P.opt == PK_ADAGRAD);
+                        apply_update<L>(xrow, srow, st, g, d, lane, P.opt, U.lr);
+#pragma unroll
+                        for (int i = 0; i < L::NF; ++i) g[i] = 0.f;
+                        st_row<L>(grow, d, lane, g);
+                    }
                 }
             }
             if (tid < 32 && U.loss_off >= 0) {  // deterministic loss reduction: mean + margin (MarginLoss.py:28)
@@ -506,7 +622,7 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
     // ---- write staged tables back
     {
         const bool vec = (d % 4 == 0);
-        for (int t = 0; t < ntE && P.stage; ++t) {
+        for (int t = 0; t < ntE && STAGE; ++t) {
             if (vec) {
                 const float4* src = reinterpret_cast<const float4*>(cx.ent[t]);
                 float4* dst = reinterpret_cast<float4*>(g_ent[t]);
@@ -516,7 +632,10 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
             }
         }
         for (int t = 0; t < ntR; ++t)
-            for (int i = tid; i < nR * d; i += NT) g_rel[t][i] = cx.rel[t][i];
+            for (int i = tid; i < nR * d; i += NT) {
+                g_rel[t][i] = rc.rel[t][i];
+                if (g_rel_state[t]) g_rel_state[t][i] = rc.state[t][i];
+            }
     }
 }
 
@@ -526,12 +645,6 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
 struct LaySel { int V, G, CPL; };
 
 inline LaySel pick_layout(int model, int d) {
-    if (const char* e = getenv("PK_K2_G")) {   // experiment: few lanes per sample, whole row in registers
-        const int G = atoi(e);
-        if (d == 20 && G == 1) return LaySel{4, 1, 5};
-        if (d == 20 && G == 2) return LaySel{4, 2, 3};
-        if (d == 20 && G == 4) return LaySel{4, 4, 2};
-    }
     const int V = d % 4 == 0 ? 4 : (d % 2 == 0 ? 2 : 1);
     const int chunks = d / V;
     const int nf_cap = model == TRANSD ? 4 : 8;  // registers per row per lane
@@ -545,23 +658,28 @@ inline LaySel pick_layout(int model, int d) {
 }
 
 // threads per block: as many consumer warps as the register budget allows
-constexpr int k2_threads(int model, int nf) { return (model != 2 && nf <= 4) ? 512 : 256; }  // TODO tune
+constexpr int k2_threads(int model, int nf) { return (model != 2 && nf <= 4) ? 512 : 256; }
 
 #ifdef PK_MODEL_TU
 template <int MODEL, int V, int G, int CPL>
-int launch_k2(const K2Params& P, int n, size_t smem, cudaStream_t st) {
+int launch_k2(const K2Params& P, int stage, int n, size_t smem, cudaStream_t st) {
     constexpr int NT = k2_threads(MODEL, V * CPL);
-    auto kern = k2_train_universes<MODEL, Lay<V, G, CPL>, NT>;
-    PK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<n, NT, smem, st>>>(P);
+    if (stage) {
+        auto kern = k2_train_universes<MODEL, Lay<V, G, CPL>, NT, 1>;
+        PK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<n, NT, smem, st>>>(P);
+    } else {
+        auto kern = k2_train_universes<MODEL, Lay<V, G, CPL>, NT, 0>;
+        PK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<n, NT, smem, st>>>(P);
+    }
     PK_LAUNCHED("k2_train_universes");
     return PK_OK;
 }
 
 template <int MODEL>
-int dispatch_layout(const LaySel& l, const K2Params& P, int n, size_t smem, cudaStream_t st) {
-#define PK_CASE(v, g, c) if (l.V == v && l.G == g && l.CPL == c) return launch_k2<MODEL, v, g, c>(P, n, smem, st);
-    PK_CASE(4, 1, 5) PK_CASE(4, 2, 3) PK_CASE(4, 4, 2)
+int dispatch_layout(const LaySel& l, const K2Params& P, int stage, int n, size_t smem, cudaStream_t st) {
+#define PK_CASE(v, g, c) if (l.V == v && l.G == g && l.CPL == c) return launch_k2<MODEL, v, g, c>(P, stage, n, smem, st);
     PK_CASE(4, 8, 1) PK_CASE(4, 8, 2) PK_CASE(4, 32, 1) PK_CASE(4, 32, 2)
     PK_CASE(2, 8, 1) PK_CASE(2, 8, 2) PK_CASE(2, 8, 4) PK_CASE(2, 32, 1) PK_CASE(2, 32, 2) PK_CASE(2, 32, 4)
     PK_CASE(1, 8, 1) PK_CASE(1, 8, 2) PK_CASE(1, 8, 4) PK_CASE(1, 8, 8) PK_CASE(1, 32, 1) PK_CASE(1, 32, 2) PK_CASE(1, 32, 4) PK_CASE(1, 32, 8)
@@ -572,14 +690,55 @@ int dispatch_layout(const LaySel& l, const K2Params& P, int n, size_t smem, cuda
 // one translation unit per model keeps the build parallel: -DPK_MODEL_TU=0|1|2
 #define PK_CAT2(a, b) a##b
 #define PK_CAT(a, b) PK_CAT2(a, b)
-int PK_CAT(launch_model, PK_MODEL_TU)(const LaySel& l, const K2Params& P, int n, size_t smem, cudaStream_t st) {
-    return dispatch_layout<PK_MODEL_TU>(l, P, n, smem, st);
+int PK_CAT(launch_model, PK_MODEL_TU)(const LaySel& l, const K2Params& P, int stage, int n, size_t smem, cudaStream_t st) {
+    return dispatch_layout<PK_MODEL_TU>(l, P, stage, n, smem, st);
 }
 }  // namespace pkk2
 #else
-int launch_model0(const LaySel& l, const K2Params& P, int n, size_t smem, cudaStream_t st);
-int launch_model1(const LaySel& l, const K2Params& P, int n, size_t smem, cudaStream_t st);
-int launch_model2(const LaySel& l, const K2Params& P, int n, size_t smem, cudaStream_t st);
+int launch_model0(const LaySel& l, const K2Params& P, int stage, int n, size_t smem, cudaStream_t st);
+int launch_model1(const LaySel& l, const K2Params& P, int stage, int n, size_t smem, cudaStream_t st);
+int launch_model2(const LaySel& l, const K2Params& P, int stage, int n, size_t smem, cudaStream_t st);
+
+// Device copies of the universe descriptors.  Launches on different streams (pieces of one chunk run
+// concurrently) must not share a buffer, and stream-ordered cudaMallocAsync goes back to the driver on
+// every call with the default pool settings, so a small per-thread pool hands out buffers whose last
+// launch has completed (event query) and grows otherwise.
+struct DescSlot {
+    pk_universe_desc* d = nullptr;
+    size_t cap = 0;
+    cudaEvent_t done = nullptr;
+    bool busy = false;
+};
+thread_local std::vector<DescSlot> g_desc_pool;
+
+// The unstaged class (universes whose tables do not fit in shared memory) runs beside the staged one
+// on a side stream: fork from / join into the caller's stream with events.
+struct SideStream {
+    cudaStream_t st = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+thread_local SideStream g_side;
+
+DescSlot* acquire_desc(size_t bytes) {
+    for (auto& s : g_desc_pool)
+        if (!s.busy || cudaEventQuery(s.done) == cudaSuccess) {
+            s.busy = false;
+            if (s.cap < bytes) {
+                if (s.d) cudaFree(s.d);
+                s.d = nullptr;
+                s.cap = 0;
+                if (cudaMalloc(&s.d, bytes) != cudaSuccess) return nullptr;
+                s.cap = bytes;
+            }
+            return &s;
+        }
+    DescSlot s;
+    if (cudaMalloc(&s.d, bytes) != cudaSuccess) return nullptr;
+    s.cap = bytes;
+    if (cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) != cudaSuccess) { cudaFree(s.d); return nullptr; }
+    g_desc_pool.push_back(s);
+    return &g_desc_pool.back();
+}
 
 }  // namespace pkk2
 
@@ -613,8 +772,8 @@ extern "C" int pk_train_universes(const pk_model_cfg* cfg, const pk_tables* pack
         const pk_universe_desc& u = h_desc[i];
         if (u.n_ent < 2 || u.n_rel < 1 || u.n_tri < 1 || u.batch_size < 1 || u.nbatches < 0 || u.epochs < 0)
             return pk::fail(PK_ERR_ARG, "pk_train_universes: degenerate universe descriptor");
-        if ((long long)(3 + k) * u.batch_size >= 65536)
-            return pk::fail(PK_ERR_UNSUPPORTED, "pk_train_universes: batch too large for the universe kernel ((3+k)B < 65536); use pk_train_steps");
+        if ((long long)(3 + k) * u.batch_size >= 32768 || (long long)u.batch_size * k > 2047)
+            return pk::fail(PK_ERR_UNSUPPORTED, "pk_train_universes: batch too large for the universe kernel (B*k <= 2047); use pk_train_steps");
         K2Smem own(cfg->model, d, k, W, u.n_ent, u.n_rel, u.batch_size, 1);
         const int c = own.total <= (size_t)max_smem ? 0 : 1;
         cls[c].push_back(u);
@@ -647,8 +806,20 @@ extern "C" int pk_train_universes(const pk_model_cfg* cfg, const pk_tables* pack
     const int threads = k2_threads(cfg->model, lay.V * lay.CPL);
     int np = threads == 512 ? 3 : 2;
     if (const char* e = getenv("PK_K2_PRODUCERS")) np = std::max(1, std::min(threads / 32 - 1, atoi(e)));
-    for (int c = 0; c < 2; ++c) {
+    const bool both = !cls[0].empty() && !cls[1].empty();
+    cudaStream_t caller = st;
+    if (both) {
+        if (!g_side.st) {
+            PK_CUDA(cudaStreamCreateWithFlags(&g_side.st, cudaStreamNonBlocking));
+            PK_CUDA(cudaEventCreateWithFlags(&g_side.fork, cudaEventDisableTiming));
+            PK_CUDA(cudaEventCreateWithFlags(&g_side.join, cudaEventDisableTiming));
+        }
+        PK_CUDA(cudaEventRecord(g_side.fork, caller));
+        PK_CUDA(cudaStreamWaitEvent(g_side.st, g_side.fork, 0));
+    }
+    for (int c = 1; c >= 0; --c) {   // the unstaged class first: its universes are the slowest
         if (cls[c].empty()) continue;
+        st = (both && c == 1) ? g_side.st : caller;
         K2Smem s(cfg->model, d, k, W, mE[c], mR[c], mB[c], c == 0);
         if (s.total > (size_t)max_smem)
             return pk::fail(PK_ERR_UNSUPPORTED, "pk_train_universes: a universe's batch scratch exceeds shared memory; use pk_train_steps");
@@ -656,11 +827,10 @@ extern "C" int pk_train_universes(const pk_model_cfg* cfg, const pk_tables* pack
         std::stable_sort(cls[c].begin(), cls[c].end(), [](const pk_universe_desc& a, const pk_universe_desc& b) {
             return (long long)a.epochs * a.nbatches * a.batch_size > (long long)b.epochs * b.nbatches * b.batch_size;
         });
-        // device copy of the descriptors: stream-ordered allocation, so that calls on different
-        // streams (pieces of one chunk run concurrently) never share a buffer
         const size_t bytes = cls[c].size() * sizeof(pk_universe_desc);
-        pk_universe_desc* d_desc = nullptr;
-        PK_CUDA(cudaMallocAsync((void**)&d_desc, bytes, st));
+        DescSlot* slot = acquire_desc(bytes);
+        if (!slot) return pk::cuda_fail(cudaGetLastError(), "pk_train_universes: descriptor buffer");
+        pk_universe_desc* d_desc = slot->d;
         PK_CUDA(cudaMemcpyAsync(d_desc, cls[c].data(), bytes, cudaMemcpyHostToDevice, st));
         K2Params P;
         P.desc = d_desc;
@@ -672,18 +842,22 @@ extern "C" int pk_train_universes(const pk_model_cfg* cfg, const pk_tables* pack
         P.loss = d_loss;
         P.d = d; P.k = k; P.p_norm = cfg->p_norm; P.norm_flag = cfg->norm_flag; P.opt = cfg->opt;
         P.bern = cfg->bern; P.filter = cfg->filter; P.W = W;
-        P.stage = c == 0;
         P.mE = mE[c]; P.mR = mR[c]; P.mB = mB[c];
         P.np = np;
         // descriptors were copied from pageable host memory owned by this call: the copy has
         // completed (or been staged) when cudaMemcpyAsync returns, so cls[c] may go out of scope
         int rc = PK_OK;
         const int nblk = (int)cls[c].size();
-        if (cfg->model == PK_TRANSE) rc = launch_model0(lay, P, nblk, s.total, st);
-        else if (cfg->model == PK_TRANSH) rc = launch_model1(lay, P, nblk, s.total, st);
-        else rc = launch_model2(lay, P, nblk, s.total, st);
-        cudaFreeAsync(d_desc, st);
+        if (cfg->model == PK_TRANSE) rc = launch_model0(lay, P, c == 0, nblk, s.total, st);
+        else if (cfg->model == PK_TRANSH) rc = launch_model1(lay, P, c == 0, nblk, s.total, st);
+        else rc = launch_model2(lay, P, c == 0, nblk, s.total, st);
         if (rc != PK_OK) return rc;
+        slot->busy = true;
+        PK_CUDA(cudaEventRecord(slot->done, st));
+    }
+    if (both) {
+        PK_CUDA(cudaEventRecord(g_side.join, g_side.st));
+        PK_CUDA(cudaStreamWaitEvent(caller, g_side.join, 0));
     }
     return PK_OK;
 }
