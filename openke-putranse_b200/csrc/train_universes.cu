@@ -186,15 +186,46 @@ __device__ __forceinline__ void apply_update(float* x_row, float* s_row, float (
     st_row<L>(x_row, d, lane, x);
 }
 
-template <class L, int NTE_>
+struct RelCache;
+template <class L>
+__device__ __forceinline__ void fix_add_row(int32_t* row, int d, int lane, const float (&g)[L::NF]);
+
+template <class L, int NTE_, int NTR_>
 struct K2Ctx {
-    static constexpr int NTE = NTE_;
+    static constexpr int NTE = NTE_, NTR = NTR_;
+    using Tgt = K2Tgt<L, NTE_>;
     float* ent[2];        // working entity tables: shared memory when staged, else global
     float* ent_state[2];  // global; nullptr for SGD
     float* scratch;       // [slots][NTE][d]
+    const float* rel_c[2];   // cached relation operands: r^ ; w^ (TransH) or the raw r_p table (TransD)
+    int32_t* rel_acc;        // fixed-point relation gradient sums [mR][NTR][3][d]
+    const int32_t* bh;       // the current batch (BatchView of this step)
+    const int32_t* bt;
+    const int32_t* br;
+    const int32_t* bc;
+    const int32_t* code_h;
+    const int32_t* code_t;
+    const int32_t* code_c;
+    int B;
     int d, opt;
     float lr;
-    __device__ __forceinline__ const float* ent_row(int tbl, int id) const { return ent[tbl] + (size_t)id * d; }
+    __device__ __forceinline__ void load_pos(int64_t b, bool act, Tgt& th, Tgt& tt, int32_t& r) const {
+        th.id = act ? bh[b] : 0; th.code = act ? code_h[b] : 0;
+        tt.id = act ? bt[b] : 0; tt.code = act ? code_t[b] : 0;
+        r = act ? br[b] : 0;
+    }
+    __device__ __forceinline__ bool load_neg(int j, int64_t b, bool act, Tgt& tc) const {
+        const int32_t cj = act ? bc[(size_t)j * B + b] : 0;
+        tc.id = cj & 0x7fffffff;
+        tc.code = act ? code_c[(size_t)j * B + b] : 0;
+        return cj < 0;
+    }
+    __device__ __forceinline__ const float* rel_y(int r) const { return rel_c[0] + (size_t)r * d; }
+    __device__ __forceinline__ const float* rel_w(int r) const { return rel_c[1] + (size_t)r * d; }
+    __device__ __forceinline__ void rel_add(int tbl, int r, const float (&g)[L::NF], int lane) const {
+        fix_add_row<L>(rel_acc + ((size_t)r * NTR + tbl) * 3 * d, d, lane, g);
+    }
+    __device__ __forceinline__ const float* ent_row(int tbl, const Tgt& tg) const { return ent[tbl] + (size_t)tg.id * d; }
     // issue the loads of a singly-occurring row's optimizer state early; they complete behind the math
     __device__ __forceinline__ void prefetch(K2Tgt<L, NTE>& tg, int lane, bool pred) const {
         if (opt != PK_ADAGRAD) return;
@@ -271,107 +302,6 @@ __device__ __forceinline__ bool fix_take_row(int32_t* row, int d, int lane, floa
     return nz;
 }
 
-// One positive sample b and its k negatives (each negative replaces exactly one side, as the
-// reference sampler does: Base.cpp:216-232).  Every lane of the warp must call this; `act` masks
-// the memory side effects of idle groups.  Returns sum_j max(p - n_j, -m).
-template <int MODEL, class L, class Ctx>
-__device__ __forceinline__ float k2_sample(Ctx& cx, const RelCache& rc, const Hyper& hp, int lane, int B, int b, bool act,
-                                           const BatchView& bv) {
-    constexpr int ntR = MODEL == TRANSE ? 1 : 2;
-    using Tg = K2Tgt<L, Ctx::NTE>;
-    Tg th, tt;
-    th.id = act ? bv.h[b] : 0; th.code = act ? bv.code_h[b] : 0;
-    tt.id = act ? bv.t[b] : 0; tt.code = act ? bv.code_t[b] : 0;
-    const int32_t r = act ? bv.r[b] : 0;
-    cx.prefetch(th, lane, act);
-    cx.prefetch(tt, lane, act);
-
-    RelOp<MODEL, L> rel;
-    ld_row<L>(rc.c[0] + (size_t)r * hp.d, hp.d, lane, rel.y, act);
-    if constexpr (MODEL == TRANSH) ld_row<L>(rc.c[1] + (size_t)r * hp.d, hp.d, lane, rel.w, act);
-    if constexpr (MODEL == TRANSD) ld_row<L>(rc.rel[1] + (size_t)r * hp.d, hp.d, lane, rel.w, act);
-    if constexpr (MODEL != TRANSE) {
-#pragma unroll
-        for (int i = 0; i < L::NF; ++i) rel.gw[i] = 0.f;
-    }
-    // all table rows of the sample are requested before any arithmetic (the first negative too)
-    EntOp<MODEL, L> ph, pt, pc;
-    Tg tc;
-    int32_t cj = act ? bv.c[b] : 0;
-    tc.id = cj & 0x7fffffff;
-    tc.code = act ? bv.code_c[b] : 0;
-    ent_load<MODEL, L>(cx, hp, lane, th.id, act, ph);
-    ent_load<MODEL, L>(cx, hp, lane, tt.id, act, pt);
-    ent_load<MODEL, L>(cx, hp, lane, tc.id, act, pc);
-    cx.prefetch(tc, lane, act);
-    ent_project<MODEL, L>(hp, rel, ph);
-    ent_project<MODEL, L>(hp, rel, pt);
-
-    float dirp[L::NF];
-#pragma unroll
-    for (int i = 0; i < L::NF; ++i) dirp[i] = (ph.y[i] + rel.y[i]) - pt.y[i];
-    const float p = score_and_dir<L>(dirp, hp.p_norm);
-
-    float UH[L::NF], UT[L::NF], UR[L::NF];
-#pragma unroll
-    for (int i = 0; i < L::NF; ++i) UH[i] = UT[i] = UR[i] = 0.f;
-    float cp = 0.f, loss = 0.f;
-
-    for (int j = 0; j < hp.k; ++j) {
-        if (j > 0) {
-            cj = act ? bv.c[(size_t)j * B + b] : 0;
-            tc.id = cj & 0x7fffffff;
-            tc.code = act ? bv.code_c[(size_t)j * B + b] : 0;
-            cx.prefetch(tc, lane, act);
-            ent_load<MODEL, L>(cx, hp, lane, tc.id, act, pc);
-        }
-        const bool head_replaced = cj < 0;
-        ent_project<MODEL, L>(hp, rel, pc);
-        float dn[L::NF];
-#pragma unroll
-        for (int i = 0; i < L::NF; ++i)
-            dn[i] = head_replaced ? (pc.y[i] + rel.y[i]) - pt.y[i] : (ph.y[i] + rel.y[i]) - pc.y[i];
-        const float n = score_and_dir<L>(dn, hp.p_norm);
-        const float diff = p - n;
-        float g = diff > -hp.margin ? hp.inv_bk : (diff == -hp.margin ? 0.5f * hp.inv_bk : 0.f);
-        if (!act) g = 0.f;
-        loss += fmaxf(diff, -hp.margin);
-        cp += g;
-        // a switched-off margin term has exactly zero gradients everywhere: skip (warp-uniform)
-        if (__any_sync(0xffffffffu, g != 0.f)) {
-            float Uc[L::NF];
-#pragma unroll
-            for (int i = 0; i < L::NF; ++i) {
-                const float v = -g * dn[i];  // dL/dn_j = -g ; d n_j / d(h + r - t) = dn
-                UR[i] += v;
-                if (head_replaced) { Uc[i] = v; UT[i] -= v; }
-                else               { Uc[i] = -v; UH[i] += v; }
-            }
-            ent_backward<MODEL, L>(cx, hp, lane, tc, act && g != 0.f, rel, pc, Uc);
-        }
-    }
-    const bool upd = act && cp != 0.f;
-    if (__any_sync(0xffffffffu, cp != 0.f)) {
-#pragma unroll
-        for (int i = 0; i < L::NF; ++i) {
-            const float v = cp * dirp[i];
-            UH[i] += v;
-            UR[i] += v;
-            UT[i] -= v;
-        }
-        ent_backward<MODEL, L>(cx, hp, lane, th, upd, rel, ph, UH);
-        ent_backward<MODEL, L>(cx, hp, lane, tt, upd, rel, pt, UT);
-        // raw relation gradients (w.r.t. r^ and w^ / r_p): summed per relation in fixed point; the
-        // normalisation backward and the update happen once per relation after the barrier
-        if (upd) {
-            int32_t* pr = rc.acc + (size_t)r * ntR * 3 * hp.d;
-            fix_add_row<L>(pr, hp.d, lane, UR);
-            if constexpr (MODEL != TRANSE) fix_add_row<L>(pr + 3 * hp.d, hp.d, lane, rel.gw);
-        }
-    }
-    return loss;
-}
-
 template <int MODEL, class L, int NT, int STAGE>
 __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__ K2Params P) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -390,9 +320,9 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
     float* g_ent[2];   // this universe's tables in global memory
     float* g_rel[2];
     float* g_rel_state[2];
-    K2Ctx<L, ntE> cx;
+    K2Ctx<L, ntE, ntR> cx;
     RelCache rc;
-    cx.d = d; cx.opt = P.opt; cx.lr = U.lr;
+    cx.d = d; cx.opt = P.opt; cx.lr = U.lr; cx.B = B;
     rc.mR = P.mR;
     for (int i = 0; i < 2; ++i) {
         g_ent[i] = (i < ntE) ? P.ent[i] + (size_t)U.ent_off * d : nullptr;
@@ -406,6 +336,9 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
     }
     rc.n = reinterpret_cast<float*>(smem + S.reln);
     rc.acc = reinterpret_cast<int32_t*>(smem + S.relacc);
+    cx.rel_acc = rc.acc;
+    cx.rel_c[0] = rc.c[0];
+    cx.rel_c[1] = MODEL == TRANSD ? rc.rel[1] : rc.c[1];
     cx.scratch = reinterpret_cast<float*>(smem + S.scratch);
     int32_t* map = reinterpret_cast<int32_t*>(smem + S.map);   // per table row: count (low 16) | slot << 16
     float* lossv = reinterpret_cast<float*>(smem + S.lossv);
@@ -552,11 +485,13 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
             if (step + 1 < steps) produce(buf ^ 1);
         } else {
             const BatchView bv(smem + S.batch[0] + (size_t)buf * batch_stride, B, k, S.slots, S.nrelcap);
+            cx.bh = bv.h; cx.bt = bv.t; cx.br = bv.r; cx.bc = bv.c;
+            cx.code_h = bv.code_h; cx.code_t = bv.code_t; cx.code_c = bv.code_c;
             // ---- phase A: forward + analytic backward; singly-occurring entity rows updated in place
             for (int base = 0; base < B; base += NG) {
                 const int b = base + grp;
                 const bool act = b < B;
-                const float l = k2_sample<MODEL, L>(cx, rc, hp, lane, B, b, act, bv);
+                const float l = train_sample<MODEL, L>(cx, hp, lane, b, act);
                 if (act && lane == 0) lossv[b] = l;
             }
             named_barrier(1, n_cons);
