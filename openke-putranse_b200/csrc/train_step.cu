@@ -20,7 +20,7 @@
 //   k1_apply     optimizer for the queued rows and the touched relations (copies summed,
 //                normalisation backward once per relation, cache of normalised relation operands
 //                refreshed), occurrence counters back to zero, loss reduced in a fixed order;
-//   k1_finish    queues emptied, sampler streams advanced by one batch.
+//                (the last block to finish also empties the queues and advances the sampler streams).
 //
 // The sparse update is exactly the reference's dense one: SGD and Adagrad (lr_decay = 0,
 // weight_decay = 0, reference Trainer.py:34-35,65-70,84-88) leave zero-gradient rows bit-unchanged.
@@ -81,6 +81,10 @@ struct K1Params {
     int32_t* ids;
     float* loss_part;
     float* loss;        // [steps] indexed by *step_ctr
+    uint64_t* lcg;      // sampler streams to advance after the step (NULL when the batch was supplied)
+    const uint64_t* jump;
+    int64_t per;
+    int W;
     int64_t B;
     int64_t n_ent, n_rel;
     int d, k, p_norm, norm_flag, opt;
@@ -209,7 +213,7 @@ struct K1Ctx {
 
 // ---- K1 main
 template <int MODEL, class L>
-__global__ void __launch_bounds__(K1_THREADS) k1_grad(const __grid_constant__ K1Params P) {
+__global__ void __launch_bounds__(K1_THREADS, 2) k1_grad(const __grid_constant__ K1Params P) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int GPW = 32 / L::G, NW = K1_THREADS / 32;
     constexpr int NTE = MODEL == TRANSD ? 2 : 1, NTR = MODEL == TRANSE ? 1 : 2;
@@ -331,14 +335,18 @@ __global__ void __launch_bounds__(K1_THREADS) k1_apply(const __grid_constant__ K
                 float sum[L::NF];
 #pragma unroll
                 for (int i = 0; i < L::NF; ++i) sum[i] = 0.f;
-                for (int c = 0; c < P.rel_copies; ++c) {
-                    float* arow = P.acc_rel + (((size_t)c * NTR + t) * P.n_rel + r) * d;
-                    float v[L::NF];
-                    ld_row<L>(arow, d, lane, v);
-                    bool nz = false;
+                for (int c0 = 0; c0 < P.rel_copies; c0 += 4) {   // four copies' loads in flight at a time
+                    float v[4][L::NF];
 #pragma unroll
-                    for (int i = 0; i < L::NF; ++i) { sum[i] += v[i]; nz |= v[i] != 0.f; v[i] = 0.f; }
-                    if (nz) st_row<L>(arow, d, lane, v);
+                    for (int u = 0; u < 4; ++u)
+                        ld_row<L>(P.acc_rel + (((size_t)(c0 + u) * NTR + t) * P.n_rel + r) * d, d, lane, v[u], c0 + u < P.rel_copies);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        bool nz = false;
+#pragma unroll
+                        for (int i = 0; i < L::NF; ++i) { sum[i] += v[u][i]; nz |= v[u][i] != 0.f; v[u][i] = 0.f; }
+                        if (nz) st_row<L>(P.acc_rel + (((size_t)(c0 + u) * NTR + t) * P.n_rel + r) * d, d, lane, v[u]);
+                    }
                 }
 #pragma unroll
                 for (int i = 0; i < L::NF; ++i) {
@@ -405,15 +413,28 @@ __global__ void __launch_bounds__(K1_THREADS) k1_apply(const __grid_constant__ K
         P.cnt_rel[P.ids[2 * P.B + i]] = 0;
         for (int j = 0; j < P.k; ++j) P.cnt_ent[P.ids[(3 + (int64_t)j) * P.B + i] & 0x7fffffff] = 0;
     }
-    if (blockIdx.x == 0 && tid < 32) {
-        float s = 0.f;
-        for (int i = tid; i < P.grad_blocks; i += 32) s += P.loss_part[i];
-        s = gsum<32>(s);
-        if (tid == 0) {
-            const int64_t step = *P.step_ctr;
-            if (P.loss) P.loss[step] = bad ? nanf("") : s / (float)(P.B * P.k) + P.margin;
-            *P.step_ctr = step + 1;
+    // the last block to get here closes the step: loss, queues emptied, sampler streams one batch on
+    __shared__ int last;
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        last = atomicAdd(&P.counters[3], 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && tid < 64) {
+        if (tid < 32) {
+            float s = 0.f;
+            for (int i = tid; i < P.grad_blocks; i += 32) s += P.loss_part[i];
+            s = gsum<32>(s);
+            if (tid == 0) {
+                const int64_t step = *P.step_ctr;
+                if (P.loss) P.loss[step] = bad ? nanf("") : s / (float)(P.B * P.k) + P.margin;
+                *P.step_ctr = step + 1;
+            }
         }
+        if (tid < 2) P.counters[tid] = 0;
+        if (tid == 3) P.counters[3] = 0;
+        if (P.lcg && tid < P.W) P.lcg[tid] = P.jump[2 * P.per + tid] * P.lcg[tid] + P.jump[2 * P.per + 64 + tid];
     }
 }
 
@@ -502,12 +523,17 @@ struct PrepParams {
 };
 
 constexpr int PREP_QCAP = K1_THREADS * 3;
+constexpr int PREP_RELBITS = 32768;   // relations de-duplicated per block in a shared-memory bitmap up to this many
 
 __global__ void __launch_bounds__(K1_THREADS) k1_prepare(const __grid_constant__ PrepParams S) {
     __shared__ int32_t q_ent[PREP_QCAP], q_rel[K1_THREADS];
+    __shared__ unsigned rel_seen[PREP_RELBITS / 32];
     __shared__ int n_qe, n_qr, base_e, base_r;
     const int64_t b = (int64_t)blockIdx.x * K1_THREADS + threadIdx.x;
+    const bool rel_bitmap = S.n_rel <= PREP_RELBITS;
     if (threadIdx.x == 0) { n_qe = 0; n_qr = 0; }
+    if (rel_bitmap)
+        for (int i = threadIdx.x; i < (int)((S.n_rel + 31) / 32); i += K1_THREADS) rel_seen[i] = 0u;
     __syncthreads();
     int32_t h = 0, t = 0, r = 0;
     bool ok = b < S.B;
@@ -572,7 +598,11 @@ __global__ void __launch_bounds__(K1_THREADS) k1_prepare(const __grid_constant__
         };
         if (atomicAdd(&S.cnt_ent[h], 1) == 1) push_ent(h);
         if (atomicAdd(&S.cnt_ent[t], 1) == 1) push_ent(t);
-        if (atomicAdd(&S.cnt_rel[r], 1) == 0) q_rel[atomicAdd(&n_qr, 1)] = r;
+        // a hot relation is in a tenth of the samples: one global atomic per sample would serialise in
+        // L2, so samples of a block are de-duplicated in a shared-memory bitmap first
+        bool first_in_block = true;
+        if (rel_bitmap) first_in_block = !((atomicOr(&rel_seen[r >> 5], 1u << (r & 31)) >> (r & 31)) & 1u);
+        if (first_in_block && atomicExch(&S.cnt_rel[r], 1) == 0) q_rel[atomicAdd(&n_qr, 1)] = r;
         for (int n = 0; n < S.k; ++n) {
             const int32_t c = S.ids[(3 + (int64_t)n) * S.B + b] & 0x7fffffff;
             if (atomicAdd(&S.cnt_ent[c], 1) == 1) push_ent(c);
@@ -587,13 +617,6 @@ __global__ void __launch_bounds__(K1_THREADS) k1_prepare(const __grid_constant__
     __syncthreads();
     for (int i = threadIdx.x; i < nqe; i += K1_THREADS) S.dup_ent[base_e + i] = q_ent[i];
     for (int i = threadIdx.x; i < n_qr; i += K1_THREADS) S.touched_rel[base_r + i] = q_rel[i];
-}
-
-// after a step: queues empty again, sampler streams one batch further
-__global__ void k1_finish(int32_t* counters, uint64_t* lcg, const uint64_t* jump, int64_t per, int W) {
-    const int id = threadIdx.x;
-    if (id < 2) counters[id] = 0;
-    if (lcg && id < W) lcg[id] = jump[2 * per + id] * lcg[id] + jump[2 * per + 64 + id];
 }
 
 // ---- K0 stand-alone: one reference sampling() call in the reference's output layout
@@ -733,6 +756,7 @@ void fill_params(K1Params& P, const pk_model_cfg* cfg, const pk_tables* tab, pk_
     P.ids = ws->ids;
     P.loss_part = ws->loss_part;
     P.loss = d_loss;
+    P.lcg = nullptr; P.jump = ws->jump; P.per = 0; P.W = 0;
     P.B = B; P.n_ent = ws->n_ent; P.n_rel = ws->n_rel;
     P.d = cfg->dim; P.k = cfg->neg_ent; P.p_norm = cfg->p_norm; P.norm_flag = cfg->norm_flag; P.opt = cfg->opt;
     P.margin = margin; P.lr = lr;
@@ -902,8 +926,6 @@ extern "C" int pk_train_step(const pk_model_cfg* cfg, const pk_tables* tab, pk_w
     PK_LAUNCHED("k1_prepare");
     rc = step_model(cfg->model, g.lay, P, 1, g.grad_blocks, g.apply_blocks, g.smem, st);
     if (rc != PK_OK) return rc;
-    k1_finish<<<1, 64, 0, st>>>(ws->counters, nullptr, nullptr, 0, 0);
-    PK_LAUNCHED("k1_finish");
     return PK_OK;
 }
 
@@ -936,6 +958,7 @@ extern "C" int pk_train_steps(const pk_model_cfg* cfg, const pk_tables* tab, con
     if (rc != PK_OK) return rc;
     P.grad_blocks = g.grad_blocks;
     const int64_t per = (B % W == 0) ? B / W : B / W + 1;
+    P.lcg = smp->lcg; P.per = per; P.W = W;
     PrepParams S;
     fill_prep(S, cfg, ws, B);
     S.sv.by_head = smp->by_head; S.sv.by_tail = smp->by_tail; S.sv.left_mean = smp->left_mean; S.sv.right_mean = smp->right_mean;
@@ -950,10 +973,7 @@ extern "C" int pk_train_steps(const pk_model_cfg* cfg, const pk_tables* tab, con
         k1_prepare<<<sb, K1_THREADS, 0, st>>>(S);
         PK_LAUNCHED("k1_prepare");
         int r2 = step_model(cfg->model, g.lay, P, 1, g.grad_blocks, g.apply_blocks, g.smem, st);
-        if (r2 != PK_OK) return r2;
-        k1_finish<<<1, 64, 0, st>>>(ws->counters, smp->lcg, ws->jump, per, W);
-        PK_LAUNCHED("k1_finish");
-        return PK_OK;
+        return r2;
     };
     // Every launch parameter is step-invariant (the step index and the sampler streams live on the
     // device), so a chunk of steps is captured once into a CUDA graph and replayed.
