@@ -152,19 +152,20 @@ struct K1Ctx {
     using Tgt = K1Tgt;
     const K1Params* P;
     float* sample;          // this group's sample in the current stage
-    const int32_t* cnts;    // this lane's private slot of the stage: occurrence counts of h, t, c
+    const int32_t* cnts;    // this lane's private slot of the stage: occurrence counts of h, t, c | one id
+    const int32_t* gids;    // slot of the group's lane 0: word 3 of lanes 0..3 holds h, t, r, c of the sample
     int rows_per_slot;      // NTE * (1 + adagrad)
     int copy;               // which privatised relation accumulator this block adds to
     __device__ __forceinline__ float* slot_row(int slot, int tbl, bool state) const {
         return sample + (size_t)(NTR + slot * rows_per_slot + (state ? NTE : 0) + tbl) * P->d;
     }
     __device__ __forceinline__ void load_pos(int64_t b, bool act, Tgt& th, Tgt& tt, int32_t& r) const {
-        th.id = act ? P->ids[b] : 0;           th.code = (act && cnts[0] > 1) ? 1 : -1; th.slot = 0;
-        tt.id = act ? P->ids[P->B + b] : 0;    tt.code = (act && cnts[1] > 1) ? 1 : -1; tt.slot = 1;
-        r = act ? P->ids[2 * P->B + b] : 0;
+        th.id = act ? gids[3] : 0;        th.code = (act && cnts[0] > 1) ? 1 : -1; th.slot = 0;
+        tt.id = act ? gids[4 + 3] : 0;    tt.code = (act && cnts[1] > 1) ? 1 : -1; tt.slot = 1;
+        r = act ? gids[8 + 3] : 0;
     }
     __device__ __forceinline__ bool load_neg(int j, int64_t b, bool act, Tgt& tc) const {
-        const int32_t cj = act ? P->ids[(3 + (int64_t)j) * P->B + b] : 0;
+        const int32_t cj = act ? (j == 0 ? gids[12 + 3] : P->ids[(3 + (int64_t)j) * P->B + b]) : 0;
         tc.id = cj & 0x7fffffff;
         if (j == 0) {
             tc.code = (act && cnts[2] > 1) ? 1 : -1; tc.slot = 2;
@@ -179,12 +180,23 @@ struct K1Ctx {
     __device__ __forceinline__ void prefetch(Tgt&, int, bool) const {}
     __device__ __forceinline__ const float* rel_y(int) const { return sample; }
     __device__ __forceinline__ const float* rel_w(int) const { return sample + P->d; }
+    // row += g with native reductions: one 128-bit RED per chunk when the layout is float4
     __device__ __forceinline__ void red_row(float* p, const float (&g)[L::NF], int lane) const {
         const int d = P->d;
+        if constexpr (L::V == 4) {
 #pragma unroll
-        for (int i = 0; i < L::NF; ++i) {
-            const int e = elem_of<L>(lane, i);
-            if (e < d && g[i] != 0.f) atomicAdd(p + e, g[i]);
+            for (int c = 0; c < L::CPL; ++c) {
+                const int e = (lane + c * L::G) * 4;
+                if (e < d && (g[c * 4] != 0.f || g[c * 4 + 1] != 0.f || g[c * 4 + 2] != 0.f || g[c * 4 + 3] != 0.f))
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p + e), "f"(g[c * 4]), "f"(g[c * 4 + 1]),
+                                 "f"(g[c * 4 + 2]), "f"(g[c * 4 + 3]) : "memory");
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < L::NF; ++i) {
+                const int e = elem_of<L>(lane, i);
+                if (e < d && g[i] != 0.f) atomicAdd(p + e, g[i]);
+            }
         }
     }
     __device__ __forceinline__ void rel_add(int tbl, int r, const float (&g)[L::NF], int lane) const {
@@ -251,7 +263,7 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_grad(const __grid_constant__
         Meta m;
         const int64_t b = tile * GPW + grp;
         m.act = tile < ntiles && b < P.B;
-        m.h = m.act ? idh[b] : 0; m.t = m.act ? idt[b] : 0; m.r = m.act ? idr[b] : 0; m.c = m.act ? (idc[b] & 0x7fffffff) : 0;
+        m.h = m.act ? idh[b] : 0; m.t = m.act ? idt[b] : 0; m.r = m.act ? idr[b] : 0; m.c = m.act ? idc[b] : 0;
         return m;
     };
     // request everything the sample needs: cached relation operands, the three entity operands'
@@ -261,13 +273,15 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_grad(const __grid_constant__
         float* sp = reinterpret_cast<float*>(sb) + (size_t)grp * sample_floats;
         int32_t* mt = reinterpret_cast<int32_t*>(sb + rows_bytes) + wl * 4;
         if (m.act) {
+            const int32_t mc = m.c & 0x7fffffff;
+            if (lane < 4) mt[3] = lane == 0 ? m.h : (lane == 1 ? m.t : (lane == 2 ? m.r : m.c));
             cp_async<4>(mt + 0, P.cnt_ent + m.h);
             cp_async<4>(mt + 1, P.cnt_ent + m.t);
-            cp_async<4>(mt + 2, P.cnt_ent + m.c);
+            cp_async<4>(mt + 2, P.cnt_ent + mc);
             stage_row<L>(sp, P.relc[0] + (size_t)m.r * d, d, lane);
             if constexpr (MODEL == TRANSH) stage_row<L>(sp + d, P.relc[1] + (size_t)m.r * d, d, lane);
             if constexpr (MODEL == TRANSD) stage_row<L>(sp + d, P.rel[1] + (size_t)m.r * d, d, lane);
-            const int32_t e3[3] = {m.h, m.t, m.c};
+            const int32_t e3[3] = {m.h, m.t, mc};
 #pragma unroll
             for (int s = 0; s < 3; ++s) {
 #pragma unroll
@@ -292,9 +306,11 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_grad(const __grid_constant__
         const Meta mb = load_meta(tile + 3 * wtotal);
         issue(ma, stage >= 1 ? stage - 1 : K1_STAGES - 1);   // (stage + 2) % 3: the stage computed last iteration
         cp_async_wait<K1_STAGES - 1>();           // this tile's rows have landed
+        __syncwarp();                             // ... and the ids its group's lanes stored two iterations ago are visible
         unsigned char* sb = wbase + (size_t)stage * stage_bytes;
         cx.sample = reinterpret_cast<float*>(sb) + (size_t)grp * sample_floats;
         cx.cnts = reinterpret_cast<const int32_t*>(sb + rows_bytes) + wl * 4;
+        cx.gids = reinterpret_cast<const int32_t*>(sb + rows_bytes) + (wl - lane) * 4;
         const int64_t b = tile * GPW + grp;
         const bool act = b < P.B;
         const float l = train_sample<MODEL, L>(cx, hp, lane, b, act);
