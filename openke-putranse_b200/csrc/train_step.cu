@@ -26,6 +26,7 @@
 // weight_decay = 0, reference Trainer.py:34-35,65-70,84-88) leave zero-gradient rows bit-unchanged.
 // Bound on big tables (E*d*4 >> L2): HBM, ~(3+k) rows read + written per positive.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "common.hpp"
@@ -36,23 +37,28 @@ using namespace pkd;
 struct pk_workspace {
     pk_model_cfg cfg;
     int64_t n_ent, n_rel, max_batch;
-    int32_t* cnt_ent = nullptr;   // [n_ent] occurrences in the current batch
-    int32_t* cnt_rel = nullptr;   // [n_rel]
+    // two "batch sets" (counts, compact ids, queues, counters): while step s trains on set s % 2,
+    // the batch of step s + 1 is prepared into the other one
+    int32_t* cnt_ent[2] = {nullptr, nullptr};   // [n_ent] occurrences in the batch
+    int32_t* cnt_rel[2] = {nullptr, nullptr};   // [n_rel]
     float* acc_ent[2] = {nullptr, nullptr};  // dense gradient accumulators for multiply-occurring rows
     float* acc_rel = nullptr;     // [C][ntR][n_rel][d] privatised relation gradient sums
     float* relc[2] = {nullptr, nullptr};     // cached r^ ; w^ (TransH)
     float* reln = nullptr;        // [2][n_rel] clamped norms
-    int32_t* dup_ent = nullptr;   // queue of multiply-occurring entity rows
-    int32_t* touched_rel = nullptr;
-    int32_t* counters = nullptr;  // [0] queued entities, [1] touched relations, [2] error flag
+    int32_t* dup_ent[2] = {nullptr, nullptr};   // queue of multiply-occurring entity rows
+    int32_t* touched_rel[2] = {nullptr, nullptr};
+    int32_t* counters[2] = {nullptr, nullptr};  // [0] queued entities, [1] touched relations, [2] error flag, [3] block ticket
     int64_t* step_ctr = nullptr;  // index of the next loss slot
-    int32_t* ids = nullptr;       // h[B] | t[B] | r[B] | c[k][B]
+    int32_t* ids[2] = {nullptr, nullptr};       // h[B] | t[B] | r[B] | c[k][B]
     float* loss_part = nullptr;   // per-block partial sums of k1_grad
     uint64_t* jump = nullptr;     // A[per] | C[per] | Aadv[64] | Cadv[64]  (LCG jump tables)
     int64_t jump_B = -1;
     int jump_W = -1, jump_k = -1;
     int64_t jump_cap = 0;
     cudaStream_t own_stream = nullptr;  // blocking stream used when the caller hands us the legacy default stream
+    cudaStream_t side_stream = nullptr; // the next batch is prepared here, beside the current step
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool memset_reset = true;           // counts cleared with memsets (small tables) or by scattering over the batch
     int64_t dup_cap_ent = 0;
     int rel_copies = 1;
     int max_blocks = 0;
@@ -422,14 +428,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_apply(const __grid_constant__ K
             }
         }
     }
-    // occurrence counters back to zero (every id the prepare kernel stored; equal values race benignly)
-    for (int64_t i = (int64_t)blockIdx.x * K1_THREADS + tid; i < P.B; i += (int64_t)gridDim.x * K1_THREADS) {
-        P.cnt_ent[P.ids[i]] = 0;
-        P.cnt_ent[P.ids[P.B + i]] = 0;
-        P.cnt_rel[P.ids[2 * P.B + i]] = 0;
-        for (int j = 0; j < P.k; ++j) P.cnt_ent[P.ids[(3 + (int64_t)j) * P.B + i] & 0x7fffffff] = 0;
-    }
-    // the last block to get here closes the step: loss, queues emptied, sampler streams one batch on
+    // the last block to get here closes the step: loss, queues emptied
     __shared__ int last;
     __syncthreads();
     if (tid == 0) {
@@ -450,6 +449,8 @@ __global__ void __launch_bounds__(K1_THREADS) k1_apply(const __grid_constant__ K
         }
         if (tid < 2) P.counters[tid] = 0;
         if (tid == 3) P.counters[3] = 0;
+        // sequential schedule: the sampler streams move one batch on here (P.lcg is NULL when a side
+        // stream does it right after the gradient kernel, or when the batch was supplied)
         if (P.lcg && tid < P.W) P.lcg[tid] = P.jump[2 * P.per + tid] * P.lcg[tid] + P.jump[2 * P.per + 64 + tid];
     }
 }
@@ -536,6 +537,7 @@ struct PrepParams {
     int32_t* counters;
     int64_t B, n_ent, n_rel;
     int k, bern, filter;
+    int ahead;                 // 1: draw the batch AFTER the one the stream states stand at (they advance when the current step closes)
 };
 
 constexpr int PREP_QCAP = K1_THREADS * 3;
@@ -559,7 +561,9 @@ __global__ void __launch_bounds__(K1_THREADS) k1_prepare(const __grid_constant__
                       fm_ent = make_fastmod((uint64_t)(S.sv.n_ent - 1));
         const int id = (int)(b / S.per);
         const int64_t j = b - (int64_t)id * S.per;
-        uint64_t s = S.jump[j] * S.lcg[id] + S.jump[S.per + j];
+        uint64_t s0 = S.lcg[id];
+        if (S.ahead) s0 = S.jump[2 * S.per + id] * s0 + S.jump[2 * S.per + 64 + id];
+        uint64_t s = S.jump[j] * s0 + S.jump[S.per + j];
         const int64_t i = (int64_t)fastmod(lcg_next(s), fm_tri);
         h = S.sv.by_head[i * 3 + 0]; r = S.sv.by_head[i * 3 + 1]; t = S.sv.by_head[i * 3 + 2];
         float prob = 500.f;
@@ -635,6 +639,16 @@ __global__ void __launch_bounds__(K1_THREADS) k1_prepare(const __grid_constant__
     for (int i = threadIdx.x; i < n_qr; i += K1_THREADS) S.touched_rel[base_r + i] = q_rel[i];
 }
 
+// occurrence counters back to zero by scattering over the ids the prepare kernel stored
+__global__ void __launch_bounds__(K1_THREADS) k1_scatter_reset(int32_t* cnt_ent, int32_t* cnt_rel, const int32_t* ids, int64_t B, int k) {
+    for (int64_t i = (int64_t)blockIdx.x * K1_THREADS + threadIdx.x; i < B; i += (int64_t)gridDim.x * K1_THREADS) {
+        cnt_ent[ids[i]] = 0;
+        cnt_ent[ids[B + i]] = 0;
+        cnt_rel[ids[2 * B + i]] = 0;
+        for (int j = 0; j < k; ++j) cnt_ent[ids[(3 + (int64_t)j) * B + i] & 0x7fffffff] = 0;
+    }
+}
+
 // ---- K0 stand-alone: one reference sampling() call in the reference's output layout
 struct SampleParams {
     SamplerView sv;
@@ -701,10 +715,14 @@ int launch_step(const K1Params& P, int what, int grad_blocks, int apply_blocks, 
         PK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k1_grad<MODEL, L>, K1_THREADS, smem));
         return nb;
     }
-    k1_grad<MODEL, L><<<grad_blocks, K1_THREADS, smem, st>>>(P);
-    PK_LAUNCHED("k1_grad");
-    k1_apply<MODEL, L><<<apply_blocks, K1_THREADS, 0, st>>>(P);
-    PK_LAUNCHED("k1_apply");
+    if (what == 1 || what == 3) {
+        k1_grad<MODEL, L><<<grad_blocks, K1_THREADS, smem, st>>>(P);
+        PK_LAUNCHED("k1_grad");
+    }
+    if (what == 1 || what == 4) {
+        k1_apply<MODEL, L><<<apply_blocks, K1_THREADS, 0, st>>>(P);
+        PK_LAUNCHED("k1_apply");
+    }
     return PK_OK;
 }
 
@@ -756,6 +774,13 @@ int num_sms() {
     return sms;
 }
 
+void use_set(K1Params& P, pk_workspace* ws, int set) {
+    P.cnt_ent = ws->cnt_ent[set]; P.cnt_rel = ws->cnt_rel[set];
+    P.dup_ent = ws->dup_ent[set]; P.touched_rel = ws->touched_rel[set];
+    P.counters = ws->counters[set];
+    P.ids = ws->ids[set];
+}
+
 void fill_params(K1Params& P, const pk_model_cfg* cfg, const pk_tables* tab, pk_workspace* ws, int64_t B, float margin, float lr,
                  float* d_loss) {
     for (int i = 0; i < 2; ++i) {
@@ -766,10 +791,8 @@ void fill_params(K1Params& P, const pk_model_cfg* cfg, const pk_tables* tab, pk_
         P.relc[i] = ws->relc[i];
     }
     P.acc_rel = ws->acc_rel; P.reln = ws->reln;
-    P.cnt_ent = ws->cnt_ent; P.cnt_rel = ws->cnt_rel;
-    P.dup_ent = ws->dup_ent; P.touched_rel = ws->touched_rel;
-    P.counters = ws->counters; P.step_ctr = ws->step_ctr;
-    P.ids = ws->ids;
+    use_set(P, ws, 0);
+    P.step_ctr = ws->step_ctr;
     P.loss_part = ws->loss_part;
     P.loss = d_loss;
     P.lcg = nullptr; P.jump = ws->jump; P.per = 0; P.W = 0;
@@ -810,7 +833,7 @@ int step_geometry(const pk_model_cfg* cfg, const K1Params& P, pk_workspace* ws, 
     const int64_t tiles = (P.B + gpw - 1) / gpw;
     g.grad_blocks = (int)std::max<int64_t>(1, std::min<int64_t>((tiles + nw - 1) / nw, (int64_t)num_sms() * std::max(per_sm, 1)));
     g.grad_blocks = std::min(g.grad_blocks, ws->max_blocks);
-    g.apply_blocks = std::max(1, std::min(ws->max_blocks, (int)((P.B * (2 + P.k) + K1_THREADS - 1) / K1_THREADS)));
+    g.apply_blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ws->max_blocks, (P.B * (2 + P.k) / 2 + ws->n_rel + 31) / 32));
     return PK_OK;
 }
 
@@ -837,10 +860,27 @@ void fill_prep(PrepParams& S, const pk_model_cfg* cfg, pk_workspace* ws, int64_t
     S.sv.n_tri = 0; S.sv.n_ent = (int32_t)ws->n_ent; S.sv.n_rel = (int32_t)ws->n_rel;
     S.lcg = nullptr; S.jump = ws->jump; S.per = 0;
     S.gh = S.gt = S.gr = nullptr;
-    S.ids = ws->ids; S.cnt_ent = ws->cnt_ent; S.cnt_rel = ws->cnt_rel;
-    S.dup_ent = ws->dup_ent; S.touched_rel = ws->touched_rel; S.counters = ws->counters;
     S.B = B; S.n_ent = ws->n_ent; S.n_rel = ws->n_rel;
     S.k = cfg->neg_ent; S.bern = cfg->bern; S.filter = cfg->filter;
+    S.ahead = 0;
+}
+
+void use_set(PrepParams& S, pk_workspace* ws, int set) {
+    S.ids = ws->ids[set]; S.cnt_ent = ws->cnt_ent[set]; S.cnt_rel = ws->cnt_rel[set];
+    S.dup_ent = ws->dup_ent[set]; S.touched_rel = ws->touched_rel[set]; S.counters = ws->counters[set];
+}
+
+// occurrence counts of one batch set back to zero
+int clear_set(pk_workspace* ws, int set, int64_t B, int k, cudaStream_t st) {
+    if (ws->memset_reset) {
+        PK_CUDA(cudaMemsetAsync(ws->cnt_ent[set], 0, (size_t)ws->n_ent * 4, st));
+        PK_CUDA(cudaMemsetAsync(ws->cnt_rel[set], 0, (size_t)ws->n_rel * 4, st));
+    } else {
+        const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ws->max_blocks, (B + K1_THREADS - 1) / K1_THREADS));
+        k1_scatter_reset<<<blocks, K1_THREADS, 0, st>>>(ws->cnt_ent[set], ws->cnt_rel[set], ws->ids[set], B, k);
+        PK_LAUNCHED("k1_scatter_reset");
+    }
+    return PK_OK;
 }
 
 }  // namespace pkk1
@@ -867,14 +907,20 @@ extern "C" pk_workspace* pk_workspace_create(const pk_model_cfg* cfg, int64_t n_
         if (cudaMalloc(p, bytes) != cudaSuccess) return false;
         return cudaMemset(*p, 0, bytes) == cudaSuccess;
     };
-    bool ok = alloc0((void**)&ws->cnt_ent, (size_t)n_ent * 4) && alloc0((void**)&ws->cnt_rel, (size_t)n_rel * 4) &&
-              alloc0((void**)&ws->dup_ent, (size_t)ws->dup_cap_ent * 4) && alloc0((void**)&ws->touched_rel, (size_t)n_rel * 4) &&
-              alloc0((void**)&ws->counters, 16) && alloc0((void**)&ws->step_ctr, 8) &&
-              alloc0((void**)&ws->ids, (size_t)(3 + k) * max_batch * 4) && alloc0((void**)&ws->loss_part, (size_t)ws->max_blocks * 4) &&
+    // clearing the counts with two memsets beats scattering over the batch unless the tables are huge
+    ws->memset_reset = n_ent <= 16 * (int64_t)(2 + k) * max_batch;
+    bool ok = alloc0((void**)&ws->step_ctr, 8) && alloc0((void**)&ws->loss_part, (size_t)ws->max_blocks * 4) &&
               alloc0((void**)&ws->acc_rel, one * ws->rel_copies) && alloc0((void**)&ws->reln, (size_t)2 * n_rel * 4);
+    for (int s = 0; ok && s < 2; ++s)
+        ok = alloc0((void**)&ws->cnt_ent[s], (size_t)n_ent * 4) && alloc0((void**)&ws->cnt_rel[s], (size_t)n_rel * 4) &&
+             alloc0((void**)&ws->dup_ent[s], (size_t)ws->dup_cap_ent * 4) && alloc0((void**)&ws->touched_rel[s], (size_t)n_rel * 4) &&
+             alloc0((void**)&ws->counters[s], 16) && alloc0((void**)&ws->ids[s], (size_t)(3 + k) * max_batch * 4);
     for (int i = 0; ok && i < ntE; ++i) ok = alloc0((void**)&ws->acc_ent[i], (size_t)n_ent * d * 4);
     for (int i = 0; ok && i < (cfg->model == PK_TRANSH ? 2 : 1); ++i) ok = alloc0((void**)&ws->relc[i], (size_t)n_rel * d * 4);
-    ok = ok && cudaStreamCreate(&ws->own_stream) == cudaSuccess;
+    ok = ok && cudaStreamCreate(&ws->own_stream) == cudaSuccess &&
+         cudaStreamCreateWithFlags(&ws->side_stream, cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&ws->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&ws->ev_join, cudaEventDisableTiming) == cudaSuccess;
     if (!ok) {
         pk::cuda_fail(cudaGetLastError(), "pk_workspace_create: cudaMalloc");
         pk_workspace_free(ws);
@@ -885,11 +931,17 @@ extern "C" pk_workspace* pk_workspace_create(const pk_model_cfg* cfg, int64_t n_
 
 extern "C" void pk_workspace_free(pk_workspace* ws) {
     if (!ws) return;
-    cudaFree(ws->cnt_ent); cudaFree(ws->cnt_rel); cudaFree(ws->dup_ent); cudaFree(ws->touched_rel);
-    cudaFree(ws->counters); cudaFree(ws->step_ctr); cudaFree(ws->ids); cudaFree(ws->loss_part);
+    cudaFree(ws->step_ctr); cudaFree(ws->loss_part);
     cudaFree(ws->acc_rel); cudaFree(ws->reln); cudaFree(ws->jump);
-    for (int i = 0; i < 2; ++i) { cudaFree(ws->acc_ent[i]); cudaFree(ws->relc[i]); }
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(ws->acc_ent[i]); cudaFree(ws->relc[i]);
+        cudaFree(ws->cnt_ent[i]); cudaFree(ws->cnt_rel[i]); cudaFree(ws->dup_ent[i]); cudaFree(ws->touched_rel[i]);
+        cudaFree(ws->counters[i]); cudaFree(ws->ids[i]);
+    }
     if (ws->own_stream) cudaStreamDestroy(ws->own_stream);
+    if (ws->side_stream) cudaStreamDestroy(ws->side_stream);
+    if (ws->ev_fork) cudaEventDestroy(ws->ev_fork);
+    if (ws->ev_join) cudaEventDestroy(ws->ev_join);
     delete ws;
 }
 
@@ -934,6 +986,7 @@ extern "C" int pk_train_step(const pk_model_cfg* cfg, const pk_tables* tab, pk_w
     P.grad_blocks = g.grad_blocks;
     PrepParams S;
     fill_prep(S, cfg, ws, B);
+    use_set(S, ws, 0);
     S.gh = d_h; S.gt = d_t; S.gr = d_r;
     PK_CUDA(cudaMemsetAsync(ws->step_ctr, 0, 8, st));   // single steps write loss[0]
     rc = step_model(cfg->model, g.lay, P, 0, 0, g.apply_blocks, 0, st);   // relation cache from the live tables
@@ -942,7 +995,7 @@ extern "C" int pk_train_step(const pk_model_cfg* cfg, const pk_tables* tab, pk_w
     PK_LAUNCHED("k1_prepare");
     rc = step_model(cfg->model, g.lay, P, 1, g.grad_blocks, g.apply_blocks, g.smem, st);
     if (rc != PK_OK) return rc;
-    return PK_OK;
+    return clear_set(ws, 0, B, cfg->neg_ent, st);
 }
 
 extern "C" int pk_train_steps(const pk_model_cfg* cfg, const pk_tables* tab, const pk_sampler* smp, pk_workspace* ws, int64_t B,
@@ -984,23 +1037,64 @@ extern "C" int pk_train_steps(const pk_model_cfg* cfg, const pk_tables* tab, con
     PK_CUDA(cudaMemsetAsync(ws->step_ctr, 0, 8, st));
     rc = step_model(cfg->model, g.lay, P, 0, 0, g.apply_blocks, 0, st);
     if (rc != PK_OK) return rc;
-
-    auto one_step = [&]() -> int {
-        k1_prepare<<<sb, K1_THREADS, 0, st>>>(S);
+    // Two schedules.  Sequential (default): prepare -> grad -> apply (its last block advances the
+    // sampler streams) -> counts cleared, all on one batch set.  Overlapped (PK_K1_OVERLAP=1): once the
+    // gradient kernel of step s has consumed its batch, a side stream advances the sampler streams,
+    // prepares the batch of step s + 1 into the other set and clears this set's counts beside the
+    // optimizer tail.  On B200 the cross-stream graph measured slower (155 vs 110 us/step on S1), so
+    // it is kept as an experiment only.
+    const bool overlap = getenv("PK_K1_OVERLAP") != nullptr;
+    cudaStream_t side = ws->side_stream;
+    auto prepare = [&](int set, int ahead, cudaStream_t on) -> int {
+        use_set(S, ws, set);
+        S.ahead = ahead;
+        k1_prepare<<<sb, K1_THREADS, 0, on>>>(S);
         PK_LAUNCHED("k1_prepare");
-        int r2 = step_model(cfg->model, g.lay, P, 1, g.grad_blocks, g.apply_blocks, g.smem, st);
-        return r2;
+        return PK_OK;
     };
+    auto one_step = [&](int64_t s) -> int {
+        if (!overlap) {
+            int r3 = prepare(0, 0, st);
+            if (r3 != PK_OK) return r3;
+            r3 = step_model(cfg->model, g.lay, P, 1, g.grad_blocks, g.apply_blocks, g.smem, st);
+            if (r3 != PK_OK) return r3;
+            return clear_set(ws, 0, B, k, st);
+        }
+        const int set = (int)(s & 1);
+        use_set(P, ws, set);
+        int r2 = step_model(cfg->model, g.lay, P, 3, g.grad_blocks, g.apply_blocks, g.smem, st);   // grad
+        if (r2 != PK_OK) return r2;
+        // beside the optimizer tail of this step: the next batch, and this batch's counts back to zero
+        PK_CUDA(cudaEventRecord(ws->ev_fork, st));
+        PK_CUDA(cudaStreamWaitEvent(side, ws->ev_fork, 0));
+        k0_commit_lcg<<<1, 64, 0, side>>>(smp->lcg, B, W, k);   // the batch has been consumed: streams one batch on
+        PK_LAUNCHED("k0_commit_lcg");
+        r2 = prepare(set ^ 1, 0, side);
+        if (r2 != PK_OK) return r2;
+        r2 = clear_set(ws, set, B, k, side);
+        if (r2 != PK_OK) return r2;
+        PK_CUDA(cudaEventRecord(ws->ev_join, side));
+        r2 = step_model(cfg->model, g.lay, P, 4, g.grad_blocks, g.apply_blocks, g.smem, st);   // apply
+        if (r2 != PK_OK) return r2;
+        PK_CUDA(cudaStreamWaitEvent(st, ws->ev_join, 0));
+        return PK_OK;
+    };
+    if (overlap) {
+        P.lcg = nullptr;
+        rc = prepare(0, 0, st);
+        if (rc != PK_OK) return rc;
+    }
     // Every launch parameter is step-invariant (the step index and the sampler streams live on the
-    // device), so a chunk of steps is captured once into a CUDA graph and replayed.
-    const int64_t chunk = std::min<int64_t>(steps, 64);
+    // device), so a chunk of steps is captured once into a CUDA graph and replayed.  The chunk is even,
+    // so that every replay starts on batch set 0.
+    const int64_t chunk = steps >= 64 ? 64 : (steps & ~(int64_t)1);
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     int64_t done = 0;
-    if (steps >= 4) {
+    if (chunk >= 4) {
         const int before = pk::launch_counter();
         PK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        for (int64_t i = 0; i < chunk && rc == PK_OK; ++i) rc = one_step();
+        for (int64_t i = 0; i < chunk && rc == PK_OK; ++i) rc = one_step(i);
         cudaError_t ce = cudaStreamEndCapture(st, &graph);
         if (rc != PK_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
         if (ce != cudaSuccess) return pk::cuda_fail(ce, "cudaStreamEndCapture");
@@ -1013,7 +1107,13 @@ extern "C" int pk_train_steps(const pk_model_cfg* cfg, const pk_tables* tab, con
         }
         pk::launch_counter() = launches;
     }
-    for (; done < steps && rc == PK_OK; ++done) rc = one_step();
+    for (; done < steps && rc == PK_OK; ++done) rc = one_step(done);
+    if (rc == PK_OK && overlap) {
+        // the batch prepared for the step that never runs: its counts and queues go back to zero
+        const int set = (int)(steps & 1);
+        rc = clear_set(ws, set, B, k, st);
+        if (rc == PK_OK && cudaMemsetAsync(ws->counters[set], 0, 16, st) != cudaSuccess) rc = pk::cuda_fail(cudaGetLastError(), "cudaMemsetAsync");
+    }
     if (exec) {
         // the graph must outlive its queued launches
         cudaStreamSynchronize(st);
@@ -1026,10 +1126,10 @@ extern "C" int pk_train_steps(const pk_model_cfg* cfg, const pk_tables* tab, con
 extern "C" int pk_workspace_check(pk_workspace* ws, void* stream) {
     if (!ws) return pk::fail(PK_ERR_ARG, "pk_workspace_check: null workspace");
     int32_t c[4] = {0, 0, 0, 0};
-    PK_CUDA(cudaMemcpyAsync(c, ws->counters, 16, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    PK_CUDA(cudaMemcpyAsync(c, ws->counters[0], 16, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     PK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     if (c[2]) {
-        cudaMemsetAsync(ws->counters + 2, 0, 4, (cudaStream_t)stream);
+        cudaMemsetAsync(ws->counters[0] + 2, 0, 4, (cudaStream_t)stream);
         return pk::fail(PK_ERR_ARG, "train step refused a batch: an id is out of range, a negative does not share its positive's relation, or it replaces both entities");
     }
     return PK_OK;
