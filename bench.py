@@ -111,6 +111,8 @@ def make_pu(path, seed_offset=0):
                                   checkpoint_dir=None, valid_steps=10 ** 9, save_steps=None, training_setting="static",
                                   incremental_strategy=None, **STATIC_RANGES)
     pu.initial_random_seed += seed_offset
+    if os.environ.get("PK_PIECE"):
+        pu.piece_size = int(os.environ["PK_PIECE"])
     return pu
 
 
@@ -218,6 +220,25 @@ def run_ours(args):
         e2e_pos = float(tot[0])
     e2e_value = e2e_pos / e2e_elapsed
 
+    # ---- evaluation leg: link prediction of the universes trained by the e2e leg over the WN18 test
+    # set (5000 triples, both sides, raw + filtered; min-energy aggregation, NCCL min all-reduce when
+    # the universes are sharded over ranks).  Reported beside the throughput, not part of `value`.
+    ev = None
+    if not args.no_eval:
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        t0 = time.perf_counter()
+        mrr, mr, hit10, hit3, hit1 = p2.run_link_prediction()
+        torch.cuda.synchronize()
+        ev_s = time.perf_counter() - t0
+        ev = {"universes": int(p2.next_universe_id), "test_triples": int(p2.last_ranks.shape[0]), "seconds": ev_s,
+              "test_triples_per_s": p2.last_ranks.shape[0] / ev_s, "filtered": {"mrr": float(mrr), "mr": float(mr), "hits10": float(hit10),
+                                                                                 "hits3": float(hit3), "hits1": float(hit1)}}
+
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     peak, peak_src = measured_peaks()
@@ -241,9 +262,31 @@ def run_ours(args):
                      "note": "K2 is latency-bound: universe tables are shared-memory/L2 resident, see DESIGN.md"},
         "clocks": clk,
     }
+    if ev is not None:
+        line["eval"] = ev
+    if world == 1 and not args.no_s1:
+        line["roofline_s1"] = s1_roofline(args)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference_leg(path, budget_s=args.cpu_budget)
-    print(json.dumps(line))
+    _OUT.emit(json.dumps(line))
+
+
+def s1_roofline(args):
+    """The HBM-bound configuration of the same train step (SURVEY.md 8(d) "S1"): one embedding space
+    with 1 M entities / 10 M triples, TransE d=64, k=1, B=100 000, Adagrad — tables far beyond L2, so
+    every gathered row comes from DRAM.  Run as a child process (tools/bench_k1.py) so that its 1.5 GB
+    of tables do not stay resident; its JSON line is embedded."""
+    try:
+        out = subprocess.run([sys.executable, os.path.join(REPO, "tools", "bench_k1.py"), "--opt", "adagrad", "--steps", "100",
+                              "--reps", "3"], capture_output=True, text=True, timeout=600)
+        last = [l for l in out.stdout.strip().splitlines() if l.startswith("{")][-1]
+        d = json.loads(last)
+        r = d["roofline"]
+        r.update(workload=d["workload"], kernel="k1_prepare + k1_grad + k1_apply (whole step)", us_per_step=d["us_per_step"],
+                 positive_triples_per_s=d["positive_triples_per_s"], algorithmic_bytes_per_positive=d["algorithmic_bytes_per_positive"])
+        return r
+    except Exception as e:   # the headline line must not depend on this extra
+        return {"error": "%s: %s" % (type(e).__name__, e)}
 
 
 def prepare_resident_launch(pu, ids, dev):
@@ -461,7 +504,30 @@ def run_reference(args):
             "config": {"workload": "m2: PuTransE static WN18 (bounded sample: universe 0, epochs capped at %d per step)" % args.ref_epochs},
             "cpu_baseline": base,
             "e2e": {"value": v, "unit": "positive triples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    _OUT.emit(json.dumps(line))
+
+
+class _StdoutToStderr(object):
+    """Everything the run prints (Python and the library's C printf) goes to stderr; stdout carries
+    exactly ONE line, the JSON result, written by emit()."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self.saved, (text + "\n").encode())
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+_OUT = None
 
 
 def main():
@@ -475,13 +541,17 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--ref-epochs", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eval", action="store_true")
+    ap.add_argument("--no-s1", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    global _OUT
+    with _StdoutToStderr() as _OUT:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
 
 
 if __name__ == "__main__":
