@@ -195,21 +195,17 @@ def run_ours(args):
         dist.barrier()
     p2.timings.clear()
     pos0 = p2.positive_triples
-    n_chunks = len(p2._chunks)
+    h2d0, d2h0 = p2.h2d_bytes, p2.d2h_bytes
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         p2.train_parallel_universes(nU)
-        for ck in p2._chunks[n_chunks:]:
-            h2d += sum(t.numel() * 4 for t in ck.tables.values()) + int(ck.toff[-1]) * 12
-            d2h += sum(p2.universe_losses[u].nbytes for u in ck.ids)
-        n_chunks = len(p2._chunks)
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
     e2e_elapsed = time.perf_counter() - t0
     e2e_pos = p2.positive_triples - pos0
-    h2d //= e2e_steps
-    d2h //= e2e_steps
+    h2d = (p2.h2d_bytes - h2d0) // e2e_steps
+    d2h = (p2.d2h_bytes - d2h0) // e2e_steps
     timings = {k_: v_ / e2e_steps for k_, v_ in p2.timings.items()}
     if dist:
         t = torch.tensor([e2e_elapsed], device=dev, dtype=torch.float64)

@@ -169,6 +169,12 @@ typedef struct {
     int64_t n_tri, n_ent, n_rel;
 } pk_sampler;
 
+/* pk_torch_init_tables on the DEVICE: same arguments (host arrays), but d_out[t] are device tables.
+ * One thread block per space replays torch's MT19937 stream; removes the host RNG time and the H2D
+ * copy of the tables from the end-to-end path.  Bit-identical to the host version (tests). */
+int pk_init_tables_device(int n, const int64_t* seeds, int n_tables, const int64_t* rows, const int32_t* dims,
+                          float* const* d_out, const int64_t* row_off, const double* bounds, int fused, void* stream);
+
 /* K0: one reference sampling() call on the device.  d_h/d_t/d_r are int32 [B*(1+k)] in the
  * reference's layout [B positives | B negatives#1 | ...] (Base.cpp:216-232). */
 int pk_sample_batch(const pk_model_cfg* cfg, const pk_sampler* smp, int64_t batch_size,

@@ -110,6 +110,7 @@ def _declare(L):
         "pk_universes_sizes": (ctypes.c_int, [vp, vp, vp, vp, vp]),
         "pk_universes_export": (ctypes.c_int, [vp] * 9),
         "pk_torch_init_tables": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_int, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int]),
+        "pk_init_tables_device": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_int, vp, vp, vp, vp, vp, ctypes.c_int, vp]),
         # pk_* device
         "pk_sample_batch": (ctypes.c_int, [ctypes.POINTER(ModelCfg), ctypes.POINTER(Sampler), I, vp, vp, vp, vp]),
         "pk_workspace_create": (vp, [ctypes.POINTER(ModelCfg), I, I, I]),

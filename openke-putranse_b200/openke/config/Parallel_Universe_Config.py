@@ -118,10 +118,14 @@ class Parallel_Universe_Config(Tester):
         self.max_chunk = 1024             # universes per train_parallel_universes chunk
         self.piece_size = 1 << 30         # universes per launch inside a chunk (set smaller to pipeline host prep and GPU)
         self._streams = None
+        self._pinned = {}
+        self._pinned_busy = None
         self.max_energy_bytes = 8 << 30   # size of one [keys, E] energy tile
         self.training_duration = 0.0
         self.positive_triples = 0         # sum over universes of epochs * nbatches * batch_size
         self.gpu_launches = 0
+        self.h2d_bytes = 0                # bytes copied host -> device by training (index, descriptors, tables if host-initialised)
+        self.d2h_bytes = 0                # bytes copied device -> host by training (per-step losses)
         self._rank_cache = {}
         self.timings = defaultdict(float)
 
@@ -216,6 +220,7 @@ class Parallel_Universe_Config(Tester):
     def _finish_piece(self, ck):
         if ck.d_loss is not None:
             host = ck.d_loss.cpu().numpy()
+            self.d2h_bytes += host.nbytes
             o = 0
             for u in ck.ids:
                 steps = self.universe_hyper[u]["epochs"] * self.universe_hyper[u]["nbatches"]
@@ -264,18 +269,27 @@ class Parallel_Universe_Config(Tester):
         model_cls, param = self.embedding_model, self.embedding_model_param
         specs0 = model_cls.table_specs(2, 1, **param)
         ent_names = set(model_cls._ent_tables)
-        packed_host = {attr: torch.empty((sE if attr in ent_names else sR, dim), dtype=torch.float32, pin_memory=True)
-                       for attr, _, dim in specs0}
-        offs = {attr: (eoff if attr in ent_names else roff) for attr in packed_host}
+        offs = {attr: (eoff if attr in ent_names else roff) for attr, _, _ in specs0}
         fused = self._native_init_mode()
-        if fused is not None and param.get("margin") is None and min(int(nR.min()), int(nE.min())) * min(s_[2] for s_ in specs0) >= 16:
-            # host threads, bit-identical to torch's generator (verified once per process in _native_init_mode)
-            self._native_init(model_cls, param, seeds, nE, nR, packed_host, offs, fused)
+        native_ok = (fused is not None and param.get("margin") is None
+                     and min(int(nR.min()), int(nE.min())) * min(s_[2] for s_ in specs0) >= 16)
+        tables = None
+        if native_ok and self._device_init_ok(fused):
+            # the torch generator is replayed on the GPU: no host RNG time, no H2D copy of the tables
+            tables = {attr: torch.empty((sE if attr in ent_names else sR, dim), dtype=torch.float32, device=dev)
+                      for attr, _, dim in specs0}
+            self._native_init(model_cls, param, seeds, nE, nR, tables, offs, fused, device_stream=(
+                stream if stream is not None else torch.cuda.current_stream(dev)).cuda_stream)
         else:
-            for i, u in enumerate(universe_ids):
-                torch.manual_seed(int(seeds[i]))
-                views = {attr: packed_host[attr][offs[attr][i]:offs[attr][i + 1]] for attr in packed_host}
-                model_cls.initial_tables_into(int(nE[i]), int(nR[i]), views, **param)
+            packed_host = {attr: self._pinned_rows(attr, sE if attr in ent_names else sR, dim) for attr, _, dim in specs0}
+            if native_ok:
+                # host threads, bit-identical to torch's generator (verified once per process in _native_init_mode)
+                self._native_init(model_cls, param, seeds, nE, nR, packed_host, offs, fused)
+            else:
+                for i, u in enumerate(universe_ids):
+                    torch.manual_seed(int(seeds[i]))
+                    views = {attr: packed_host[attr][offs[attr][i]:offs[attr][i + 1]] for attr in packed_host}
+                    model_cls.initial_tables_into(int(nE[i]), int(nR[i]), views, **param)
         proto = self._proto()
         t2 = time.perf_counter()
         self.timings["table_init"] += t2 - t1
@@ -285,7 +299,12 @@ class Parallel_Universe_Config(Tester):
         ck.nT, ck.nE, ck.nR, ck.eoff, ck.roff, ck.toff = nT, nE, nR, eoff, roff, toff
         ck.ent_remap, ck.rel_remap = ent_remap, rel_remap
         ck.proto = proto
-        ck.tables = {name: t.to(dev, non_blocking=True) for name, t in packed_host.items()}
+        if tables is None:
+            tables = {name: t.to(dev, non_blocking=True) for name, t in packed_host.items()}
+            self.h2d_bytes += sum(t.numel() * 4 for t in packed_host.values())
+            self._pinned_busy = torch.cuda.Event()
+            self._pinned_busy.record(stream if stream is not None else torch.cuda.current_stream(dev))
+        ck.tables = tables
         adagrad = True  # reference :241-242 hard-codes opt_method='Adagrad' for universes
         ck.state = {name: torch.zeros_like(t) for name, t in ck.tables.items()} if adagrad else None
         d_by_head = torch.from_numpy(by_head).to(dev, non_blocking=True)
@@ -326,7 +345,9 @@ class Parallel_Universe_Config(Tester):
                                        desc, n, d_loss.data_ptr() if d_loss is not None else None, st),
                 "pk_train_universes")
         self.gpu_launches += lib.pk_last_launch_count()
-        ck.train_inputs = (d_by_head, d_by_tail, d_lm, d_rm, packed_host)  # keep alive until the stream is done
+        ck.train_inputs = (d_by_head, d_by_tail, d_lm, d_rm)  # keep alive until the stream is done
+        self.h2d_bytes += sum(t.numel() * t.element_size() for t in ck.train_inputs if t is not None) + ctypes.sizeof(desc) \
+            + n * (8 + len(ck.tables) * 20)   # + seeds / rows / offsets / bounds of the device initialiser
         ck.d_loss = d_loss
         t3 = time.perf_counter()
         self.timings["launch"] += t3 - t2
@@ -339,7 +360,21 @@ class Parallel_Universe_Config(Tester):
         self._rank_cache.clear()
         return ck
 
-    def _native_init(self, model_cls, param, seeds, nE, nR, packed_host, offs, fused):
+    def _pinned_rows(self, name, rows, dim):
+        """[rows, dim] view of a grow-only pinned staging buffer per table (cudaHostAlloc costs
+        milliseconds, so it is not repeated per chunk).  The previous chunk's H2D copy must have
+        finished before the buffer is overwritten."""
+        if self._pinned_busy is not None:
+            self._pinned_busy.synchronize()
+            self._pinned_busy = None
+        buf = self._pinned.get(name)
+        need = rows * dim
+        if buf is None or buf.numel() < need:
+            buf = torch.empty(int(need * 1.25) + 1024, dtype=torch.float32, pin_memory=True)
+            self._pinned[name] = buf
+        return buf[:need].view(rows, dim)
+
+    def _native_init(self, model_cls, param, seeds, nE, nR, packed_host, offs, fused, device_stream=None):
         import math
         specs0 = model_cls.table_specs(2, 1, **param)
         ent_names = set(model_cls._ent_tables)
@@ -351,11 +386,43 @@ class Parallel_Universe_Config(Tester):
         bounds = np.array([[math.sqrt(3.0) * (1.0 * math.sqrt(2.0 / float(int(rows[i, t]) + int(dims[t])))) for t in range(T)]
                            for i in range(n)], dtype=np.float64)
         ptrs = (ctypes.c_void_p * T)(*[packed_host[attr].data_ptr() for attr, _, _ in specs0])
-        N.check(self.lib.pk_torch_init_tables(n, N.addr(np.ascontiguousarray(seeds, dtype=np.int64)), T, N.addr(np.ascontiguousarray(rows)),
-                                              N.addr(dims), ptrs, N.addr(np.ascontiguousarray(row_off)), N.addr(bounds), int(fused),
-                                              int(self.sampler_threads)), "pk_torch_init_tables")
+        seeds64, rows, row_off = np.ascontiguousarray(seeds, dtype=np.int64), np.ascontiguousarray(rows), np.ascontiguousarray(row_off)
+        if device_stream is not None:
+            N.check(self.lib.pk_init_tables_device(n, N.addr(seeds64), T, N.addr(rows), N.addr(dims), ptrs, N.addr(row_off),
+                                                   N.addr(bounds), int(fused), device_stream), "pk_init_tables_device")
+            self.gpu_launches += self.lib.pk_last_launch_count()
+        else:
+            N.check(self.lib.pk_torch_init_tables(n, N.addr(seeds64), T, N.addr(rows), N.addr(dims), ptrs, N.addr(row_off),
+                                                  N.addr(bounds), int(fused), int(self.sampler_threads)), "pk_torch_init_tables")
 
     _INIT_MODE = {}
+    _DEVICE_INIT = {}
+
+    def _device_init_ok(self, fused):
+        """Whether pk_init_tables_device reproduces pk_torch_init_tables bit-for-bit for this model on
+        this GPU (checked once per process on three small spaces that straddle the generator's
+        624-word refill and the 16-element tail rule)."""
+        key = (self.embedding_model, tuple(sorted((k, str(v)) for k, v in self.embedding_model_param.items())), int(fused))
+        if key not in Parallel_Universe_Config._DEVICE_INIT:
+            ok = False
+            try:
+                model_cls, param = self.embedding_model, self.embedding_model_param
+                specs0 = model_cls.table_specs(2, 1, **param)
+                ent_names = set(model_cls._ent_tables)
+                nE, nR, seeds = np.array([37, 64, 700]), np.array([5, 16, 9]), np.array([12345, (1 << 33) + 7, 99])
+                eo, ro = np.concatenate([[0], np.cumsum(nE)]), np.concatenate([[0], np.cumsum(nR)])
+                host = {a: torch.empty((int(eo[-1]) if a in ent_names else int(ro[-1]), dim)) for a, _, dim in specs0}
+                offs = {a: (eo if a in ent_names else ro) for a in host}
+                self._native_init(model_cls, param, seeds, nE, nR, host, offs, fused)
+                dev = self._device()
+                devt = {a: torch.full_like(t, float("nan"), device=dev) for a, t in host.items()}
+                self._native_init(model_cls, param, seeds, nE, nR, devt, offs, fused,
+                                  device_stream=torch.cuda.current_stream(dev).cuda_stream)
+                ok = all(torch.equal(devt[a].cpu(), host[a]) for a in host)
+            except Exception:
+                ok = False
+            Parallel_Universe_Config._DEVICE_INIT[key] = ok
+        return Parallel_Universe_Config._DEVICE_INIT[key]
 
     def _native_init_mode(self):
         """Which rounding variant of pk_torch_init_tables reproduces THIS torch build's CPU generator

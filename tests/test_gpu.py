@@ -408,3 +408,35 @@ def test_reference_style_manual_loop_testhead_testtail(tmp_path):
     manual = (lib.getTestLinkMRR(0), lib.getTestLinkMR(0), lib.getTestLinkHit10(0), lib.getTestLinkHit3(0), lib.getTestLinkHit1(0))
     fused = Tester(model=m, data_loader=tl, use_gpu=True).run_link_prediction()
     assert np.allclose(manual, fused, rtol=1e-6, atol=1e-7), (manual, fused)
+
+
+# ------------------------------------------------------------------------------------------ table init
+@pytest.mark.parametrize("cls_name,param", [("TransE", {"dim": 20}), ("TransH", {"dim": 20}), ("TransD", {"dim_e": 20, "dim_r": 20}),
+                                            ("TransE", {"dim": 50})])
+def test_device_table_init_replays_torch_generator(cls_name, param):
+    """pk_init_tables_device must leave exactly what ``torch.manual_seed(seed); Model(nE, nR, ...)`` leaves
+    on the CPU (reference model constructors + torch's nn.Embedding default init)."""
+    import torch
+    import openke.module.model as M
+    from openke.config.Parallel_Universe_Config import Parallel_Universe_Config as PU
+    cls = getattr(M, cls_name)
+    pu = PU.__new__(PU)
+    pu.embedding_model, pu.embedding_model_param, pu.sampler_threads, pu.gpu_launches, pu.use_gpu = cls, param, 2, 0, True
+    pu.lib = N.lib()
+    fused = pu._native_init_mode()
+    assert fused in (0, 1)
+    nE, nR = np.array([583, 2632, 1084, 801]), np.array([11, 17, 13, 4])
+    seeds = np.array([4, 5, (1 << 40) + 6, 7])
+    specs = cls.table_specs(2, 1, **param)
+    ent = set(cls._ent_tables)
+    eo, ro = np.concatenate([[0], np.cumsum(nE)]), np.concatenate([[0], np.cumsum(nR)])
+    dev = torch.device("cuda", 0)
+    devt = {a: torch.full((int(eo[-1]) if a in ent else int(ro[-1]), d), float("nan"), device=dev) for a, _, d in specs}
+    offs = {a: (eo if a in ent else ro) for a in devt}
+    pu._native_init(cls, param, seeds, nE, nR, devt, offs, fused, device_stream=torch.cuda.current_stream(dev).cuda_stream)
+    for i in range(4):
+        torch.manual_seed(int(seeds[i]))
+        m = cls(int(nE[i]), int(nR[i]), **param)
+        for a in devt:
+            assert torch.equal(devt[a][offs[a][i]:offs[a][i + 1]].cpu(), getattr(m, a).weight.data), (cls_name, i, a)
+    assert pu.gpu_launches >= 1
