@@ -19,8 +19,10 @@
 //                (a hot relation is in 10 % of the samples: one copy would serialise in L2);
 //   k1_apply     optimizer for the queued rows and the touched relations (copies summed,
 //                normalisation backward once per relation, cache of normalised relation operands
-//                refreshed), occurrence counters back to zero, loss reduced in a fixed order;
-//                (the last block to finish also empties the queues and advances the sampler streams).
+//                refreshed), occurrence counters back to zero, loss reduced in a fixed order.  Inside
+//                pk_train_steps it is launched FUSED with the next batch's k1_prepare
+//                (k1_apply_prepare: two block roles in one grid — both are latency-bound and share
+//                the SMs; batches alternate between two "batch sets").
 //
 // The sparse update is exactly the reference's dense one: SGD and Adagrad (lr_decay = 0,
 // weight_decay = 0, reference Trainer.py:34-35,65-70,84-88) leave zero-gradient rows bit-unchanged.
@@ -56,9 +58,7 @@ struct pk_workspace {
     int jump_W = -1, jump_k = -1;
     int64_t jump_cap = 0;
     cudaStream_t own_stream = nullptr;  // blocking stream used when the caller hands us the legacy default stream
-    cudaStream_t side_stream = nullptr; // the next batch is prepared here, beside the current step
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    bool memset_reset = true;           // counts cleared with memsets (small tables) or by scattering over the batch
+    bool memset_reset = true;           // counts cleared by zeroing the arrays (small tables) or by scattering over the batch
     int64_t dup_cap_ent = 0;
     int rel_copies = 1;
     int max_blocks = 0;
@@ -87,16 +87,179 @@ struct K1Params {
     int32_t* ids;
     float* loss_part;
     float* loss;        // [steps] indexed by *step_ctr
-    uint64_t* lcg;      // sampler streams to advance after the step (NULL when the batch was supplied)
-    const uint64_t* jump;
-    int64_t per;
-    int W;
     int64_t B;
     int64_t n_ent, n_rel;
     int d, k, p_norm, norm_flag, opt;
     float margin, lr;
     int grad_blocks, rel_copies;
+    int apply_blocks;   // blocks that take the optimizer-tail role (the fused kernel appends prepare blocks)
+    int clear_mode;     // occurrence counts of this batch set after the step: 0 keep, 1 zero the whole arrays, 2 scatter over the batch
 };
+
+// ---- shared by the plain and the fused tail kernels
+// ---- multiply-high modulo and LCG jump coefficients (same as the universe kernel's producer)
+struct FastMod { uint64_t n, m; };
+__device__ __forceinline__ FastMod make_fastmod(uint64_t n) {
+    FastMod f;
+    f.n = n;
+    f.m = ~0ULL / n;
+    return f;
+}
+__device__ __forceinline__ uint64_t fastmod(uint64_t x, const FastMod& f) {
+    const uint64_t q = __umul64hi(x, f.m);
+    uint64_t r = x - q * f.n;
+    if (r >= f.n) r -= f.n;
+    if (r >= f.n) r -= f.n;
+    return r;
+}
+__device__ __forceinline__ void lcg_affine(uint64_t n, uint64_t& A, uint64_t& C) {
+    uint64_t a = kLcgMul, c = kLcgInc, ra = 1, rc = 0;
+    while (n) {
+        if (n & 1) { ra = ra * a; rc = rc * a + c; }
+        c = (a + 1) * c;
+        a = a * a;
+        n >>= 1;
+    }
+    A = ra;
+    C = rc;
+}
+
+// ---- k1_prepare: the batch in compact form + occurrence counts + queues
+struct PrepParams {
+    SamplerView sv;
+    const uint64_t* lcg;       // W stream states at the start of this batch (sampling mode), else NULL
+    const uint64_t* jump;
+    int64_t per;
+    const int32_t* gh;         // supplied batch in the reference layout [B pos | B neg#1 | ...] (convert mode)
+    const int32_t* gt;
+    const int32_t* gr;
+    int32_t* ids;              // out: h[B] | t[B] | r[B] | c[k][B]
+    int32_t* cnt_ent;
+    int32_t* cnt_rel;
+    int32_t* dup_ent;
+    int32_t* touched_rel;
+    int32_t* counters;
+    int64_t B, n_ent, n_rel;
+    int k, bern, filter, W;
+    int ahead;                 // 1: draw the batch AFTER the one the stream states stand at
+    uint64_t* lcg_out;         // non-NULL: the last prepare block moves the streams one batch on (ticket in counters[3])
+    int nblocks;               // blocks of the prepare grid
+};
+
+constexpr int PREP_QCAP = K1_THREADS * 3;
+constexpr int PREP_RELBITS = 32768;   // relations de-duplicated per block in a shared-memory bitmap up to this many
+
+// the work of one block of the prepare grid (block index `bid`); K1_THREADS threads
+__device__ __forceinline__ void prepare_block(const PrepParams& S, int bid) {
+    __shared__ int32_t q_ent[PREP_QCAP], q_rel[K1_THREADS];
+    __shared__ unsigned rel_seen[PREP_RELBITS / 32];
+    __shared__ int n_qe, n_qr, base_e, base_r;
+    const int64_t b = (int64_t)bid * K1_THREADS + threadIdx.x;
+    const bool rel_bitmap = S.n_rel <= PREP_RELBITS;
+    if (threadIdx.x == 0) { n_qe = 0; n_qr = 0; }
+    if (rel_bitmap)
+        for (int i = threadIdx.x; i < (int)((S.n_rel + 31) / 32); i += K1_THREADS) rel_seen[i] = 0u;
+    __syncthreads();
+    int32_t h = 0, t = 0, r = 0;
+    bool ok = b < S.B;
+    if (ok && S.lcg) {
+        // the reference sampling() (Base.cpp:185-264), one thread per positive, bit-exact
+        const FastMod fm_tri = make_fastmod((uint64_t)S.sv.n_tri), fm_coin = make_fastmod(1000ULL),
+                      fm_ent = make_fastmod((uint64_t)(S.sv.n_ent - 1));
+        const int id = (int)(b / S.per);
+        const int64_t j = b - (int64_t)id * S.per;
+        uint64_t s0 = S.lcg[id];
+        if (S.ahead) s0 = S.jump[2 * S.per + id] * s0 + S.jump[2 * S.per + 64 + id];
+        uint64_t s = S.jump[j] * s0 + S.jump[S.per + j];
+        const int64_t i = (int64_t)fastmod(lcg_next(s), fm_tri);
+        h = S.sv.by_head[i * 3 + 0]; r = S.sv.by_head[i * 3 + 1]; t = S.sv.by_head[i * 3 + 2];
+        float prob = 500.f;
+        if (S.bern) {
+            const float rm = S.sv.right_mean[r], lm = S.sv.left_mean[r];
+            prob = __fdiv_rn(__fmul_rn(1000.f, rm), __fadd_rn(rm, lm));  // Base.cpp:220-221
+        }
+        for (int n = 0; n < S.k; ++n) {
+            const uint64_t coin = fastmod(lcg_next(s), fm_coin);
+            const uint64_t x = lcg_next(s);
+            int32_t c, side;
+            if ((float)coin < prob) {   // keep head, replace tail
+                if (!S.filter) { const int64_t tmp = (int64_t)fastmod(x, fm_ent); c = (int32_t)(tmp < h ? tmp : tmp + 1); }
+                else c = corrupt_entity(x, S.sv.by_head, S.sv.n_tri, S.sv.n_ent, h, r, 0, 2, true);
+                side = 0;
+            } else {                    // keep tail, replace head
+                if (!S.filter) { const int64_t tmp = (int64_t)fastmod(x, fm_ent); c = (int32_t)(tmp < t ? tmp : tmp + 1); }
+                else c = corrupt_entity(x, S.sv.by_tail, S.sv.n_tri, S.sv.n_ent, t, r, 2, 0, true);
+                side = 1;
+            }
+            S.ids[(3 + (int64_t)n) * S.B + b] = (int32_t)((uint32_t)c | ((uint32_t)side << 31));
+        }
+    } else if (ok) {
+        // a caller-supplied batch: every negative must keep its positive's relation and differ from
+        // it in at most one entity (what the reference sampler produces); anything else is refused
+        h = S.gh[b]; t = S.gt[b]; r = S.gr[b];
+        bool good = r >= 0 && r < S.n_rel && h >= 0 && h < S.n_ent && t >= 0 && t < S.n_ent;
+        for (int n = 0; n < S.k && good; ++n) {
+            const int64_t o = b + (int64_t)(1 + n) * S.B;
+            const int32_t nh = S.gh[o], nt = S.gt[o];
+            good = S.gr[o] == r && nh >= 0 && nh < S.n_ent && nt >= 0 && nt < S.n_ent && (nh == h || nt == t);
+        }
+        if (!good) {
+            atomicExch(&S.counters[2], 1);
+            ok = false;
+        } else {
+            for (int n = 0; n < S.k; ++n) {
+                const int64_t o = b + (int64_t)(1 + n) * S.B;
+                const int32_t nh = S.gh[o], nt = S.gt[o];
+                const int32_t side = nh == h ? 0 : 1, c = nh == h ? nt : nh;
+                S.ids[(3 + (int64_t)n) * S.B + b] = (int32_t)((uint32_t)c | ((uint32_t)side << 31));
+            }
+        }
+    }
+    if (ok) {
+        S.ids[b] = h; S.ids[S.B + b] = t; S.ids[2 * S.B + b] = r;
+        // occurrence counts; the SECOND occurrence of an entity row queues it, the FIRST of a relation queues it
+        auto push_ent = [&](int32_t e) {
+            const int slot = atomicAdd(&n_qe, 1);
+            if (slot < PREP_QCAP) q_ent[slot] = e;
+            else S.dup_ent[atomicAdd(&S.counters[0], 1)] = e;   // block queue full (k > 1): straight to the global one
+        };
+        if (atomicAdd(&S.cnt_ent[h], 1) == 1) push_ent(h);
+        if (atomicAdd(&S.cnt_ent[t], 1) == 1) push_ent(t);
+        // a hot relation is in a tenth of the samples: one global atomic per sample would serialise in
+        // L2, so samples of a block are de-duplicated in a shared-memory bitmap first
+        bool first_in_block = true;
+        if (rel_bitmap) first_in_block = !((atomicOr(&rel_seen[r >> 5], 1u << (r & 31)) >> (r & 31)) & 1u);
+        if (first_in_block && atomicExch(&S.cnt_rel[r], 1) == 0) q_rel[atomicAdd(&n_qr, 1)] = r;
+        for (int n = 0; n < S.k; ++n) {
+            const int32_t c = S.ids[(3 + (int64_t)n) * S.B + b] & 0x7fffffff;
+            if (atomicAdd(&S.cnt_ent[c], 1) == 1) push_ent(c);
+        }
+    }
+    __syncthreads();
+    const int nqe = min(n_qe, PREP_QCAP);
+    if (threadIdx.x == 0) {
+        base_e = nqe ? atomicAdd(&S.counters[0], nqe) : 0;
+        base_r = n_qr ? atomicAdd(&S.counters[1], n_qr) : 0;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nqe; i += K1_THREADS) S.dup_ent[base_e + i] = q_ent[i];
+    for (int i = threadIdx.x; i < n_qr; i += K1_THREADS) S.touched_rel[base_r + i] = q_rel[i];
+    if (S.lcg_out) {   // every block has read the stream states: the last one to finish advances them
+        __shared__ int last_prep;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            last_prep = atomicAdd(&S.counters[3], 1) == S.nblocks - 1;
+        }
+        __syncthreads();
+        if (last_prep) {
+            if ((int)threadIdx.x < S.W)
+                S.lcg_out[threadIdx.x] = S.jump[2 * S.per + threadIdx.x] * S.lcg_out[threadIdx.x] + S.jump[2 * S.per + 64 + threadIdx.x];
+            if (threadIdx.x == 0) S.counters[3] = 0;
+        }
+    }
+}
+
 
 #ifdef PK_MODEL_TU
 
@@ -340,15 +503,16 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_grad(const __grid_constant__
 
 // ---- K1 tail: optimizer for multiply-occurring entity rows and for the touched relations, cleanup, loss
 template <int MODEL, class L>
-__global__ void __launch_bounds__(K1_THREADS) k1_apply(const __grid_constant__ K1Params P) {
+__device__ __forceinline__ void apply_block(const K1Params& P, int bid) {
     constexpr int NG = K1_THREADS / L::G;
+    const int nblk = P.apply_blocks;
     constexpr int NTE = MODEL == TRANSD ? 2 : 1, NTR = MODEL == TRANSE ? 1 : 2;
     const int tid = threadIdx.x, lane = tid % L::G, grp = tid / L::G;
     const unsigned gmask = group_mask<L::G>(tid);
     const int d = P.d;
     const bool bad = P.counters[2] != 0;
     const int nqe = bad ? 0 : P.counters[0], nqr = bad ? 0 : P.counters[1];
-    for (int64_t it = (int64_t)blockIdx.x * NG + grp; it < (int64_t)nqe + nqr; it += (int64_t)gridDim.x * NG) {
+    for (int64_t it = (int64_t)bid * NG + grp; it < (int64_t)nqe + nqr; it += (int64_t)nblk * NG) {
         if (it < nqr) {   // a relation of the batch: sum the privatised copies, then treat as one row
             const int r = P.touched_rel[it];
             float g0[L::NF], g1[NTR == 2 ? L::NF : 1];
@@ -428,12 +592,24 @@ __global__ void __launch_bounds__(K1_THREADS) k1_apply(const __grid_constant__ K
             }
         }
     }
+    // occurrence counts of this batch set back to zero (the gradient kernel was their only reader)
+    if (P.clear_mode == 1) {
+        for (int64_t i = (int64_t)bid * K1_THREADS + tid; i < P.n_ent; i += (int64_t)nblk * K1_THREADS) P.cnt_ent[i] = 0;
+        for (int64_t i = (int64_t)bid * K1_THREADS + tid; i < P.n_rel; i += (int64_t)nblk * K1_THREADS) P.cnt_rel[i] = 0;
+    } else if (P.clear_mode == 2) {
+        for (int64_t i = (int64_t)bid * K1_THREADS + tid; i < P.B; i += (int64_t)nblk * K1_THREADS) {
+            P.cnt_ent[P.ids[i]] = 0;
+            P.cnt_ent[P.ids[P.B + i]] = 0;
+            P.cnt_rel[P.ids[2 * P.B + i]] = 0;
+            for (int j = 0; j < P.k; ++j) P.cnt_ent[P.ids[(3 + (int64_t)j) * P.B + i] & 0x7fffffff] = 0;
+        }
+    }
     // the last block to get here closes the step: loss, queues emptied
     __shared__ int last;
     __syncthreads();
     if (tid == 0) {
         __threadfence();
-        last = atomicAdd(&P.counters[3], 1) == (int)gridDim.x - 1;
+        last = atomicAdd(&P.counters[3], 1) == nblk - 1;
     }
     __syncthreads();
     if (last && tid < 64) {
@@ -449,10 +625,21 @@ __global__ void __launch_bounds__(K1_THREADS) k1_apply(const __grid_constant__ K
         }
         if (tid < 2) P.counters[tid] = 0;
         if (tid == 3) P.counters[3] = 0;
-        // sequential schedule: the sampler streams move one batch on here (P.lcg is NULL when a side
-        // stream does it right after the gradient kernel, or when the batch was supplied)
-        if (P.lcg && tid < P.W) P.lcg[tid] = P.jump[2 * P.per + tid] * P.lcg[tid] + P.jump[2 * P.per + 64 + tid];
     }
+}
+
+template <int MODEL, class L>
+__global__ void __launch_bounds__(K1_THREADS) k1_apply(const __grid_constant__ K1Params P) {
+    apply_block<MODEL, L>(P, (int)blockIdx.x);
+}
+
+// The optimizer tail of step s and the preparation of batch s + 1 in ONE launch: both are latency-bound
+// (IPC ~0.4), so blocks of the two roles share the SMs well; the first P.apply_blocks blocks take the
+// tail, the rest the batch (which lives in the other batch set and does not depend on the embeddings).
+template <int MODEL, class L>
+__global__ void __launch_bounds__(K1_THREADS) k1_apply_prepare(const __grid_constant__ K1Params P, const __grid_constant__ PrepParams S) {
+    if ((int)blockIdx.x < P.apply_blocks) apply_block<MODEL, L>(P, (int)blockIdx.x);
+    else prepare_block(S, (int)blockIdx.x - P.apply_blocks);
 }
 
 // cached relation operands from the tables (start of every pk_train_step / pk_train_steps call)
@@ -482,33 +669,6 @@ __global__ void __launch_bounds__(K1_THREADS) k1_relcache(const __grid_constant_
 #endif
 
 #ifndef PK_MODEL_TU
-// ---- multiply-high modulo and LCG jump coefficients (same as the universe kernel's producer)
-struct FastMod { uint64_t n, m; };
-__device__ __forceinline__ FastMod make_fastmod(uint64_t n) {
-    FastMod f;
-    f.n = n;
-    f.m = ~0ULL / n;
-    return f;
-}
-__device__ __forceinline__ uint64_t fastmod(uint64_t x, const FastMod& f) {
-    const uint64_t q = __umul64hi(x, f.m);
-    uint64_t r = x - q * f.n;
-    if (r >= f.n) r -= f.n;
-    if (r >= f.n) r -= f.n;
-    return r;
-}
-__device__ __forceinline__ void lcg_affine(uint64_t n, uint64_t& A, uint64_t& C) {
-    uint64_t a = kLcgMul, c = kLcgInc, ra = 1, rc = 0;
-    while (n) {
-        if (n & 1) { ra = ra * a; rc = rc * a + c; }
-        c = (a + 1) * c;
-        a = a * a;
-        n >>= 1;
-    }
-    A = ra;
-    C = rc;
-}
-
 // jump[0..per) = A_j, jump[per..2per) = C_j : j samples into a slice; then Aadv[64], Cadv[64]: one batch
 __global__ void k1_build_jump(uint64_t* jump, int64_t per, int64_t B, int W, int k) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -520,134 +680,7 @@ __global__ void k1_build_jump(uint64_t* jump, int64_t per, int64_t B, int W, int
     }
 }
 
-// ---- k1_prepare: the batch in compact form + occurrence counts + queues
-struct PrepParams {
-    SamplerView sv;
-    const uint64_t* lcg;       // W stream states at the start of this batch (sampling mode), else NULL
-    const uint64_t* jump;
-    int64_t per;
-    const int32_t* gh;         // supplied batch in the reference layout [B pos | B neg#1 | ...] (convert mode)
-    const int32_t* gt;
-    const int32_t* gr;
-    int32_t* ids;              // out: h[B] | t[B] | r[B] | c[k][B]
-    int32_t* cnt_ent;
-    int32_t* cnt_rel;
-    int32_t* dup_ent;
-    int32_t* touched_rel;
-    int32_t* counters;
-    int64_t B, n_ent, n_rel;
-    int k, bern, filter;
-    int ahead;                 // 1: draw the batch AFTER the one the stream states stand at (they advance when the current step closes)
-};
-
-constexpr int PREP_QCAP = K1_THREADS * 3;
-constexpr int PREP_RELBITS = 32768;   // relations de-duplicated per block in a shared-memory bitmap up to this many
-
-__global__ void __launch_bounds__(K1_THREADS) k1_prepare(const __grid_constant__ PrepParams S) {
-    __shared__ int32_t q_ent[PREP_QCAP], q_rel[K1_THREADS];
-    __shared__ unsigned rel_seen[PREP_RELBITS / 32];
-    __shared__ int n_qe, n_qr, base_e, base_r;
-    const int64_t b = (int64_t)blockIdx.x * K1_THREADS + threadIdx.x;
-    const bool rel_bitmap = S.n_rel <= PREP_RELBITS;
-    if (threadIdx.x == 0) { n_qe = 0; n_qr = 0; }
-    if (rel_bitmap)
-        for (int i = threadIdx.x; i < (int)((S.n_rel + 31) / 32); i += K1_THREADS) rel_seen[i] = 0u;
-    __syncthreads();
-    int32_t h = 0, t = 0, r = 0;
-    bool ok = b < S.B;
-    if (ok && S.lcg) {
-        // the reference sampling() (Base.cpp:185-264), one thread per positive, bit-exact
-        const FastMod fm_tri = make_fastmod((uint64_t)S.sv.n_tri), fm_coin = make_fastmod(1000ULL),
-                      fm_ent = make_fastmod((uint64_t)(S.sv.n_ent - 1));
-        const int id = (int)(b / S.per);
-        const int64_t j = b - (int64_t)id * S.per;
-        uint64_t s0 = S.lcg[id];
-        if (S.ahead) s0 = S.jump[2 * S.per + id] * s0 + S.jump[2 * S.per + 64 + id];
-        uint64_t s = S.jump[j] * s0 + S.jump[S.per + j];
-        const int64_t i = (int64_t)fastmod(lcg_next(s), fm_tri);
-        h = S.sv.by_head[i * 3 + 0]; r = S.sv.by_head[i * 3 + 1]; t = S.sv.by_head[i * 3 + 2];
-        float prob = 500.f;
-        if (S.bern) {
-            const float rm = S.sv.right_mean[r], lm = S.sv.left_mean[r];
-            prob = __fdiv_rn(__fmul_rn(1000.f, rm), __fadd_rn(rm, lm));  // Base.cpp:220-221
-        }
-        for (int n = 0; n < S.k; ++n) {
-            const uint64_t coin = fastmod(lcg_next(s), fm_coin);
-            const uint64_t x = lcg_next(s);
-            int32_t c, side;
-            if ((float)coin < prob) {   // keep head, replace tail
-                if (!S.filter) { const int64_t tmp = (int64_t)fastmod(x, fm_ent); c = (int32_t)(tmp < h ? tmp : tmp + 1); }
-                else c = corrupt_entity(x, S.sv.by_head, S.sv.n_tri, S.sv.n_ent, h, r, 0, 2, true);
-                side = 0;
-            } else {                    // keep tail, replace head
-                if (!S.filter) { const int64_t tmp = (int64_t)fastmod(x, fm_ent); c = (int32_t)(tmp < t ? tmp : tmp + 1); }
-                else c = corrupt_entity(x, S.sv.by_tail, S.sv.n_tri, S.sv.n_ent, t, r, 2, 0, true);
-                side = 1;
-            }
-            S.ids[(3 + (int64_t)n) * S.B + b] = (int32_t)((uint32_t)c | ((uint32_t)side << 31));
-        }
-    } else if (ok) {
-        // a caller-supplied batch: every negative must keep its positive's relation and differ from
-        // it in at most one entity (what the reference sampler produces); anything else is refused
-        h = S.gh[b]; t = S.gt[b]; r = S.gr[b];
-        bool good = r >= 0 && r < S.n_rel && h >= 0 && h < S.n_ent && t >= 0 && t < S.n_ent;
-        for (int n = 0; n < S.k && good; ++n) {
-            const int64_t o = b + (int64_t)(1 + n) * S.B;
-            const int32_t nh = S.gh[o], nt = S.gt[o];
-            good = S.gr[o] == r && nh >= 0 && nh < S.n_ent && nt >= 0 && nt < S.n_ent && (nh == h || nt == t);
-        }
-        if (!good) {
-            atomicExch(&S.counters[2], 1);
-            ok = false;
-        } else {
-            for (int n = 0; n < S.k; ++n) {
-                const int64_t o = b + (int64_t)(1 + n) * S.B;
-                const int32_t nh = S.gh[o], nt = S.gt[o];
-                const int32_t side = nh == h ? 0 : 1, c = nh == h ? nt : nh;
-                S.ids[(3 + (int64_t)n) * S.B + b] = (int32_t)((uint32_t)c | ((uint32_t)side << 31));
-            }
-        }
-    }
-    if (ok) {
-        S.ids[b] = h; S.ids[S.B + b] = t; S.ids[2 * S.B + b] = r;
-        // occurrence counts; the SECOND occurrence of an entity row queues it, the FIRST of a relation queues it
-        auto push_ent = [&](int32_t e) {
-            const int slot = atomicAdd(&n_qe, 1);
-            if (slot < PREP_QCAP) q_ent[slot] = e;
-            else S.dup_ent[atomicAdd(&S.counters[0], 1)] = e;   // block queue full (k > 1): straight to the global one
-        };
-        if (atomicAdd(&S.cnt_ent[h], 1) == 1) push_ent(h);
-        if (atomicAdd(&S.cnt_ent[t], 1) == 1) push_ent(t);
-        // a hot relation is in a tenth of the samples: one global atomic per sample would serialise in
-        // L2, so samples of a block are de-duplicated in a shared-memory bitmap first
-        bool first_in_block = true;
-        if (rel_bitmap) first_in_block = !((atomicOr(&rel_seen[r >> 5], 1u << (r & 31)) >> (r & 31)) & 1u);
-        if (first_in_block && atomicExch(&S.cnt_rel[r], 1) == 0) q_rel[atomicAdd(&n_qr, 1)] = r;
-        for (int n = 0; n < S.k; ++n) {
-            const int32_t c = S.ids[(3 + (int64_t)n) * S.B + b] & 0x7fffffff;
-            if (atomicAdd(&S.cnt_ent[c], 1) == 1) push_ent(c);
-        }
-    }
-    __syncthreads();
-    const int nqe = min(n_qe, PREP_QCAP);
-    if (threadIdx.x == 0) {
-        base_e = nqe ? atomicAdd(&S.counters[0], nqe) : 0;
-        base_r = n_qr ? atomicAdd(&S.counters[1], n_qr) : 0;
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < nqe; i += K1_THREADS) S.dup_ent[base_e + i] = q_ent[i];
-    for (int i = threadIdx.x; i < n_qr; i += K1_THREADS) S.touched_rel[base_r + i] = q_rel[i];
-}
-
-// occurrence counters back to zero by scattering over the ids the prepare kernel stored
-__global__ void __launch_bounds__(K1_THREADS) k1_scatter_reset(int32_t* cnt_ent, int32_t* cnt_rel, const int32_t* ids, int64_t B, int k) {
-    for (int64_t i = (int64_t)blockIdx.x * K1_THREADS + threadIdx.x; i < B; i += (int64_t)gridDim.x * K1_THREADS) {
-        cnt_ent[ids[i]] = 0;
-        cnt_ent[ids[B + i]] = 0;
-        cnt_rel[ids[2 * B + i]] = 0;
-        for (int j = 0; j < k; ++j) cnt_ent[ids[(3 + (int64_t)j) * B + i] & 0x7fffffff] = 0;
-    }
-}
+__global__ void __launch_bounds__(K1_THREADS) k1_prepare(const __grid_constant__ PrepParams S) { prepare_block(S, (int)blockIdx.x); }
 
 // ---- K0 stand-alone: one reference sampling() call in the reference's output layout
 struct SampleParams {
@@ -707,8 +740,13 @@ inline size_t grad_smem(int model, const LaySel& l, int d, int opt) {
 
 #ifdef PK_MODEL_TU
 template <int MODEL, int V, int G, int CPL>
-int launch_step(const K1Params& P, int what, int grad_blocks, int apply_blocks, size_t smem, cudaStream_t st) {
+int launch_step(const K1Params& P, const PrepParams* S, int what, int grad_blocks, int apply_blocks, size_t smem, cudaStream_t st) {
     using L = Lay<V, G, CPL>;
+    if (what == 5) {
+        k1_apply_prepare<MODEL, L><<<apply_blocks + S->nblocks, K1_THREADS, 0, st>>>(P, *S);
+        PK_LAUNCHED("k1_apply_prepare");
+        return PK_OK;
+    }
     if (what == 0) {
         k1_relcache<MODEL, L><<<apply_blocks, K1_THREADS, 0, st>>>(P);
         PK_LAUNCHED("k1_relcache");
@@ -732,8 +770,8 @@ int launch_step(const K1Params& P, int what, int grad_blocks, int apply_blocks, 
 }
 
 template <int MODEL>
-int dispatch_step(const LaySel& l, const K1Params& P, int what, int gb, int ab, size_t smem, cudaStream_t st) {
-#define PK_CASE(v, g, c) if (l.V == v && l.G == g && l.CPL == c) return launch_step<MODEL, v, g, c>(P, what, gb, ab, smem, st);
+int dispatch_step(const LaySel& l, const K1Params& P, const PrepParams* S, int what, int gb, int ab, size_t smem, cudaStream_t st) {
+#define PK_CASE(v, g, c) if (l.V == v && l.G == g && l.CPL == c) return launch_step<MODEL, v, g, c>(P, S, what, gb, ab, smem, st);
     PK_CASE(4, 16, 1)
     PK_CASE(4, 8, 1) PK_CASE(4, 8, 2) PK_CASE(4, 32, 1) PK_CASE(4, 32, 2)
     PK_CASE(2, 8, 1) PK_CASE(2, 8, 2) PK_CASE(2, 8, 4) PK_CASE(2, 32, 1) PK_CASE(2, 32, 2) PK_CASE(2, 32, 4)
@@ -744,19 +782,20 @@ int dispatch_step(const LaySel& l, const K1Params& P, int what, int gb, int ab, 
 
 #define PK_CAT2(a, b) a##b
 #define PK_CAT(a, b) PK_CAT2(a, b)
-int PK_CAT(step_model, PK_MODEL_TU)(const LaySel& l, const K1Params& P, int what, int gb, int ab, size_t smem, cudaStream_t st) {
-    return dispatch_step<PK_MODEL_TU>(l, P, what, gb, ab, smem, st);
+int PK_CAT(step_model, PK_MODEL_TU)(const LaySel& l, const K1Params& P, const PrepParams* S, int what, int gb, int ab, size_t smem, cudaStream_t st) {
+    return dispatch_step<PK_MODEL_TU>(l, P, S, what, gb, ab, smem, st);
 }
 }  // namespace pkk1
 #else
-int step_model0(const LaySel& l, const K1Params& P, int what, int gb, int ab, size_t smem, cudaStream_t st);
-int step_model1(const LaySel& l, const K1Params& P, int what, int gb, int ab, size_t smem, cudaStream_t st);
-int step_model2(const LaySel& l, const K1Params& P, int what, int gb, int ab, size_t smem, cudaStream_t st);
+int step_model0(const LaySel& l, const K1Params& P, const PrepParams* S, int what, int gb, int ab, size_t smem, cudaStream_t st);
+int step_model1(const LaySel& l, const K1Params& P, const PrepParams* S, int what, int gb, int ab, size_t smem, cudaStream_t st);
+int step_model2(const LaySel& l, const K1Params& P, const PrepParams* S, int what, int gb, int ab, size_t smem, cudaStream_t st);
 
-int step_model(int model, const LaySel& l, const K1Params& P, int what, int gb, int ab, size_t smem, cudaStream_t st) {
-    if (model == PK_TRANSE) return step_model0(l, P, what, gb, ab, smem, st);
-    if (model == PK_TRANSH) return step_model1(l, P, what, gb, ab, smem, st);
-    return step_model2(l, P, what, gb, ab, smem, st);
+int step_model(int model, const LaySel& l, const K1Params& P, int what, int gb, int ab, size_t smem, cudaStream_t st,
+               const PrepParams* S = nullptr) {
+    if (model == PK_TRANSE) return step_model0(l, P, S, what, gb, ab, smem, st);
+    if (model == PK_TRANSH) return step_model1(l, P, S, what, gb, ab, smem, st);
+    return step_model2(l, P, S, what, gb, ab, smem, st);
 }
 
 int check_cfg(const pk_model_cfg* cfg, const char* who) {
@@ -801,12 +840,13 @@ void fill_params(K1Params& P, const pk_model_cfg* cfg, const pk_tables* tab, pk_
     P.step_ctr = ws->step_ctr;
     P.loss_part = ws->loss_part;
     P.loss = d_loss;
-    P.lcg = nullptr; P.jump = ws->jump; P.per = 0; P.W = 0;
     P.B = B; P.n_ent = ws->n_ent; P.n_rel = ws->n_rel;
     P.d = cfg->dim; P.k = cfg->neg_ent; P.p_norm = cfg->p_norm; P.norm_flag = cfg->norm_flag; P.opt = cfg->opt;
     P.margin = margin; P.lr = lr;
     P.rel_copies = ws->rel_copies;
     P.grad_blocks = 1;
+    P.apply_blocks = 1;
+    P.clear_mode = ws->memset_reset ? 1 : 2;
 }
 
 int check_tables(const pk_model_cfg* cfg, const pk_tables* tab, const pk_workspace* ws, const char* who) {
@@ -869,24 +909,14 @@ void fill_prep(PrepParams& S, const pk_model_cfg* cfg, pk_workspace* ws, int64_t
     S.B = B; S.n_ent = ws->n_ent; S.n_rel = ws->n_rel;
     S.k = cfg->neg_ent; S.bern = cfg->bern; S.filter = cfg->filter;
     S.ahead = 0;
+    S.W = cfg->work_threads;
+    S.lcg_out = nullptr;
+    S.nblocks = (int)((B + K1_THREADS - 1) / K1_THREADS);
 }
 
 void use_set(PrepParams& S, pk_workspace* ws, int set) {
     S.ids = ws->ids[set]; S.cnt_ent = ws->cnt_ent[set]; S.cnt_rel = ws->cnt_rel[set];
     S.dup_ent = ws->dup_ent[set]; S.touched_rel = ws->touched_rel[set]; S.counters = ws->counters[set];
-}
-
-// occurrence counts of one batch set back to zero
-int clear_set(pk_workspace* ws, int set, int64_t B, int k, cudaStream_t st) {
-    if (ws->memset_reset) {
-        PK_CUDA(cudaMemsetAsync(ws->cnt_ent[set], 0, (size_t)ws->n_ent * 4, st));
-        PK_CUDA(cudaMemsetAsync(ws->cnt_rel[set], 0, (size_t)ws->n_rel * 4, st));
-    } else {
-        const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ws->max_blocks, (B + K1_THREADS - 1) / K1_THREADS));
-        k1_scatter_reset<<<blocks, K1_THREADS, 0, st>>>(ws->cnt_ent[set], ws->cnt_rel[set], ws->ids[set], B, k);
-        PK_LAUNCHED("k1_scatter_reset");
-    }
-    return PK_OK;
 }
 
 }  // namespace pkk1
@@ -923,10 +953,7 @@ extern "C" pk_workspace* pk_workspace_create(const pk_model_cfg* cfg, int64_t n_
              alloc0((void**)&ws->counters[s], 16) && alloc0((void**)&ws->ids[s], (size_t)(3 + k) * max_batch * 4);
     for (int i = 0; ok && i < ntE; ++i) ok = alloc0((void**)&ws->acc_ent[i], (size_t)n_ent * d * 4);
     for (int i = 0; ok && i < (cfg->model == PK_TRANSH ? 2 : 1); ++i) ok = alloc0((void**)&ws->relc[i], (size_t)n_rel * d * 4);
-    ok = ok && cudaStreamCreate(&ws->own_stream) == cudaSuccess &&
-         cudaStreamCreateWithFlags(&ws->side_stream, cudaStreamNonBlocking) == cudaSuccess &&
-         cudaEventCreateWithFlags(&ws->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
-         cudaEventCreateWithFlags(&ws->ev_join, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaStreamCreate(&ws->own_stream) == cudaSuccess;
     if (!ok) {
         pk::cuda_fail(cudaGetLastError(), "pk_workspace_create: cudaMalloc");
         pk_workspace_free(ws);
@@ -945,9 +972,6 @@ extern "C" void pk_workspace_free(pk_workspace* ws) {
         cudaFree(ws->counters[i]); cudaFree(ws->ids[i]);
     }
     if (ws->own_stream) cudaStreamDestroy(ws->own_stream);
-    if (ws->side_stream) cudaStreamDestroy(ws->side_stream);
-    if (ws->ev_fork) cudaEventDestroy(ws->ev_fork);
-    if (ws->ev_join) cudaEventDestroy(ws->ev_join);
     delete ws;
 }
 
@@ -990,6 +1014,7 @@ extern "C" int pk_train_step(const pk_model_cfg* cfg, const pk_tables* tab, pk_w
     rc = step_geometry(cfg, P, ws, g);
     if (rc != PK_OK) return rc;
     P.grad_blocks = g.grad_blocks;
+    P.apply_blocks = g.apply_blocks;
     PrepParams S;
     fill_prep(S, cfg, ws, B);
     use_set(S, ws, 0);
@@ -999,9 +1024,7 @@ extern "C" int pk_train_step(const pk_model_cfg* cfg, const pk_tables* tab, pk_w
     if (rc != PK_OK) return rc;
     k1_prepare<<<(unsigned)((B + K1_THREADS - 1) / K1_THREADS), K1_THREADS, 0, st>>>(S);
     PK_LAUNCHED("k1_prepare");
-    rc = step_model(cfg->model, g.lay, P, 1, g.grad_blocks, g.apply_blocks, g.smem, st);
-    if (rc != PK_OK) return rc;
-    return clear_set(ws, 0, B, cfg->neg_ent, st);
+    return step_model(cfg->model, g.lay, P, 1, g.grad_blocks, g.apply_blocks, g.smem, st);   // grad + apply (clears the counts)
 }
 
 extern "C" int pk_train_steps(const pk_model_cfg* cfg, const pk_tables* tab, const pk_sampler* smp, pk_workspace* ws, int64_t B,
@@ -1033,7 +1056,6 @@ extern "C" int pk_train_steps(const pk_model_cfg* cfg, const pk_tables* tab, con
     if (rc != PK_OK) return rc;
     P.grad_blocks = g.grad_blocks;
     const int64_t per = (B % W == 0) ? B / W : B / W + 1;
-    P.lcg = smp->lcg; P.per = per; P.W = W;
     PrepParams S;
     fill_prep(S, cfg, ws, B);
     S.sv.by_head = smp->by_head; S.sv.by_tail = smp->by_tail; S.sv.left_mean = smp->left_mean; S.sv.right_mean = smp->right_mean;
@@ -1043,83 +1065,55 @@ extern "C" int pk_train_steps(const pk_model_cfg* cfg, const pk_tables* tab, con
     PK_CUDA(cudaMemsetAsync(ws->step_ctr, 0, 8, st));
     rc = step_model(cfg->model, g.lay, P, 0, 0, g.apply_blocks, 0, st);
     if (rc != PK_OK) return rc;
-    // Two schedules.  Sequential (default): prepare -> grad -> apply (its last block advances the
-    // sampler streams) -> counts cleared, all on one batch set.  Overlapped (PK_K1_OVERLAP=1): once the
-    // gradient kernel of step s has consumed its batch, a side stream advances the sampler streams,
-    // prepares the batch of step s + 1 into the other set and clears this set's counts beside the
-    // optimizer tail.  On B200 the cross-stream graph measured slower (155 vs 110 us/step on S1), so
-    // it is kept as an experiment only.
-    const bool overlap = getenv("PK_K1_OVERLAP") != nullptr;
-    cudaStream_t side = ws->side_stream;
-    auto prepare = [&](int set, int ahead, cudaStream_t on) -> int {
+    // Schedule: batch s lives in batch set s % 2.  prepare(0) runs alone; then every step is
+    //   k1_grad(set s)  ->  k1_apply_prepare: tail of step s  ||  prepare(batch s + 1 into the other set)
+    // and the last step ends with the plain tail.  Each prepare advances the sampler streams once all
+    // its blocks have read them, so after N steps they stand exactly N batches further.
+    P.apply_blocks = g.apply_blocks;
+    auto prepare_alone = [&](int set) -> int {
         use_set(S, ws, set);
-        S.ahead = ahead;
-        k1_prepare<<<sb, K1_THREADS, 0, on>>>(S);
+        k1_prepare<<<sb, K1_THREADS, 0, st>>>(S);
         PK_LAUNCHED("k1_prepare");
         return PK_OK;
     };
-    auto one_step = [&](int64_t s) -> int {
-        if (!overlap) {
-            int r3 = prepare(0, 0, st);
-            if (r3 != PK_OK) return r3;
-            r3 = step_model(cfg->model, g.lay, P, 1, g.grad_blocks, g.apply_blocks, g.smem, st);
-            if (r3 != PK_OK) return r3;
-            return clear_set(ws, 0, B, k, st);
-        }
+    auto step = [&](int64_t s, bool fused) -> int {
         const int set = (int)(s & 1);
         use_set(P, ws, set);
         int r2 = step_model(cfg->model, g.lay, P, 3, g.grad_blocks, g.apply_blocks, g.smem, st);   // grad
         if (r2 != PK_OK) return r2;
-        // beside the optimizer tail of this step: the next batch, and this batch's counts back to zero
-        PK_CUDA(cudaEventRecord(ws->ev_fork, st));
-        PK_CUDA(cudaStreamWaitEvent(side, ws->ev_fork, 0));
-        k0_commit_lcg<<<1, 64, 0, side>>>(smp->lcg, B, W, k);   // the batch has been consumed: streams one batch on
-        PK_LAUNCHED("k0_commit_lcg");
-        r2 = prepare(set ^ 1, 0, side);
-        if (r2 != PK_OK) return r2;
-        r2 = clear_set(ws, set, B, k, side);
-        if (r2 != PK_OK) return r2;
-        PK_CUDA(cudaEventRecord(ws->ev_join, side));
-        r2 = step_model(cfg->model, g.lay, P, 4, g.grad_blocks, g.apply_blocks, g.smem, st);   // apply
-        if (r2 != PK_OK) return r2;
-        PK_CUDA(cudaStreamWaitEvent(st, ws->ev_join, 0));
-        return PK_OK;
+        if (!fused) return step_model(cfg->model, g.lay, P, 4, g.grad_blocks, g.apply_blocks, g.smem, st);   // plain tail
+        use_set(S, ws, set ^ 1);
+        return step_model(cfg->model, g.lay, P, 5, g.grad_blocks, g.apply_blocks, g.smem, st, &S);      // tail || next batch
     };
-    if (overlap) {
-        P.lcg = nullptr;
-        rc = prepare(0, 0, st);
-        if (rc != PK_OK) return rc;
-    }
+    S.lcg_out = smp->lcg;
+    rc = prepare_alone(0);
+    if (rc != PK_OK) return rc;
     // Every launch parameter is step-invariant (the step index and the sampler streams live on the
-    // device), so a chunk of steps is captured once into a CUDA graph and replayed.  The chunk is even,
-    // so that every replay starts on batch set 0.
-    const int64_t chunk = steps >= 64 ? 64 : (steps & ~(int64_t)1);
+    // device), so a chunk of fused steps is captured once into a CUDA graph and replayed; the chunk is
+    // even, so every replay starts on batch set 0.  The final step is never part of a replay.
+    const int64_t fused_steps = steps - 1;
+    const int64_t chunk = fused_steps >= 64 ? 64 : (fused_steps & ~(int64_t)1);
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     int64_t done = 0;
     if (chunk >= 4) {
         const int before = pk::launch_counter();
         PK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        for (int64_t i = 0; i < chunk && rc == PK_OK; ++i) rc = one_step(i);
+        for (int64_t i = 0; i < chunk && rc == PK_OK; ++i) rc = step(i, true);
         cudaError_t ce = cudaStreamEndCapture(st, &graph);
         if (rc != PK_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
         if (ce != cudaSuccess) return pk::cuda_fail(ce, "cudaStreamEndCapture");
         const int per_chunk = pk::launch_counter() - before;
         PK_CUDA(cudaGraphInstantiate(&exec, graph, 0));
         int launches = before;
-        for (; done + chunk <= steps; done += chunk) {
+        for (; done + chunk <= fused_steps; done += chunk) {
             PK_CUDA(cudaGraphLaunch(exec, st));
             launches += per_chunk;
         }
         pk::launch_counter() = launches;
     }
-    for (; done < steps && rc == PK_OK; ++done) rc = one_step(done);
-    if (rc == PK_OK && overlap) {
-        // the batch prepared for the step that never runs: its counts and queues go back to zero
-        const int set = (int)(steps & 1);
-        rc = clear_set(ws, set, B, k, st);
-        if (rc == PK_OK && cudaMemsetAsync(ws->counters[set], 0, 16, st) != cudaSuccess) rc = pk::cuda_fail(cudaGetLastError(), "cudaMemsetAsync");
-    }
+    for (; done < fused_steps && rc == PK_OK; ++done) rc = step(done, true);
+    if (rc == PK_OK) rc = step(steps - 1, false);
     if (exec) {
         // the graph must outlive its queued launches
         cudaStreamSynchronize(st);

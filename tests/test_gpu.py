@@ -443,8 +443,9 @@ def test_device_table_init_replays_torch_generator(cls_name, param):
 
 
 # ------------------------------------------------------------------------------------------ K1 at scale
-@pytest.mark.parametrize("model,opt,d", [("transe", "adagrad", 64), ("transe", "sgd", 64), ("transh", "adagrad", 20), ("transd", "sgd", 20)])
-def test_pipelined_train_steps_match_single_steps_and_oracle(model, opt, d):
+@pytest.mark.parametrize("model,opt,d,k", [("transe", "adagrad", 64, 1), ("transe", "sgd", 64, 1), ("transh", "adagrad", 20, 1),
+                                           ("transd", "sgd", 20, 1), ("transe", "adagrad", 50, 3), ("transh", "sgd", 20, 2)])
+def test_pipelined_train_steps_match_single_steps_and_oracle(model, opt, d, k):
     """pk_train_steps (device sampler + cp.async-pipelined gradient kernel + CUDA graph) against
     (a) the same steps taken one by one through pk_sample_batch + pk_train_step, and (b) the torch
     oracle, on a synthetic graph large enough for hot rows, multiply-occurring rows and both lane
@@ -458,7 +459,7 @@ def test_pipelined_train_steps_match_single_steps_and_oracle(model, opt, d):
     from oracle.model_math import TorchOracle
     L = N.lib()
     dev = torch.device("cuda", 0)
-    E, R, T, B, k, steps = 20000, 40, 200000, 5000, 1, 6
+    E, R, T, B, steps = 20000, 40, 200000, 5000, 6
     tri = bench_k1.synthetic_graph(E, R, T, seed=7)
     by_head = tri.astype(np.int32)
     by_tail = by_head[np.argsort((tri[:, 2] * R + tri[:, 1]) * E + tri[:, 0], kind="stable")]
@@ -523,9 +524,13 @@ def test_pipelined_train_steps_match_single_steps_and_oracle(model, opt, d):
     L.pk_workspace_free(ws)
     l1 = loss1.cpu().numpy()
     assert np.array_equal(lcg1.cpu().numpy(), lcg2.cpu().numpy()), "sampler streams must end in the same state"
-    assert np.allclose(l1, loss2, rtol=2e-5), (l1, loss2)
+    # hub rows collect hundreds of fp32 atomic contributions whose order differs between runs; with
+    # plain SGD on rows of norm ~0.05 that 1e-7 noise grows ~15x per step (L1 sign flips), so only
+    # the first steps are compared tightly
+    assert np.allclose(l1[:3], loss2[:3], rtol=LOSS_RTOL_EARLY), (l1, loss2)
+    assert np.allclose(l1, loss2, rtol=LOSS_RTOL_LATE), (l1, loss2)
     assert np.allclose(l1[:3], loss3, rtol=LOSS_RTOL_EARLY), (l1[:3], loss3)
     for n in tabs1:
-        _close_tables(tabs1[n].cpu().numpy(), tabs2[n].cpu().numpy(), atol=1e-5, frac=1e-4)
+        _close_tables(tabs1[n].cpu().numpy(), tabs2[n].cpu().numpy())
     for n, v in orc.t.items():   # after 3 oracle steps the oracle is behind; compare the first-step effect only through losses
         assert np.isfinite(tabs1[n].cpu().numpy()).all()
