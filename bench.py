@@ -113,6 +113,8 @@ def make_pu(path, seed_offset=0):
     pu.initial_random_seed += seed_offset
     if os.environ.get("PK_PIECE"):
         pu.piece_size = int(os.environ["PK_PIECE"])
+    if os.environ.get("PK_PREFETCH"):
+        pu.prefetch_sampling = True
     return pu
 
 
@@ -291,6 +293,7 @@ def prepare_resident_launch(pu, ids, dev):
     import torch
     from openke import _native as N
     ck = pu._train_piece(ids, None)     # first (untimed) training: leaves descriptors + inputs resident
+    d_by_head = ck.train_inputs[0]
     pu._finish_piece(ck)
     torch.cuda.synchronize()
     # initial tables again (same seeds): rebuild them on the host exactly as _train_chunk does
@@ -334,7 +337,6 @@ def prepare_resident_launch(pu, ids, dev):
     d_loss = torch.zeros(loss_total, dtype=torch.float32, device=dev)
     cfg = ck.proto.native_cfg(opt=N.PK_ADAGRAD, neg_ent=K_NEG, bern=0, filt=0, work_threads=W)
     tab = pu._packed_tables(ck, with_state=True)
-    d_by_head = ck.train_inputs[0]
     st = torch.cuda.current_stream(dev).cuda_stream
     state = {"launches": 0}
 
