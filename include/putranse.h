@@ -242,6 +242,15 @@ int pk_universe_energies(const pk_model_cfg* cfg, const pk_tables* packed, const
                          const int64_t* d_rel_off, const int32_t* d_n_ent, const int32_t* d_ent_remap,
                          const pk_energy_item* d_items, int64_t n_items, float* d_energy,
                          int64_t n_ent_global, void* stream);
+/* PuTransE missing_embedding_handling='null_vector' (reference Parallel_Universe_Config.py:378-388,
+ * 494-514,634-640).  pk_universe_tuple_scores folds, for every work item, the score of (zero vector,
+ * relation, fixed entity) of that universe into d_tuple[key_row] with a minimum (d_tuple must start
+ * at +inf; min-all-reduce it across ranks like the energies); pk_fill_missing_energies then gives
+ * every still-+inf candidate of a key row that row's tuple score, if it is finite. */
+int pk_universe_tuple_scores(const pk_model_cfg* cfg, const pk_tables* packed, const int64_t* d_ent_off,
+                             const int64_t* d_rel_off, const pk_energy_item* d_items, int64_t n_items, float* d_tuple,
+                             void* stream);
+int pk_fill_missing_energies(float* d_energy, int64_t n_rows, int64_t n_ent_global, const float* d_tuple, void* stream);
 /* rank n queries from energy rows: query i reads row d_key_row[i], truth entity d_truth[i];
  * known-true candidates from the CSR.  Implements Test.h:118-238 including the +inf branch
  * (:181-206).  d_ranks int32 [n*2] = raw, filtered. */

@@ -272,6 +272,45 @@ __global__ void __launch_bounds__(R_THREADS) k3u_energies(const __grid_constant_
     }
 }
 
+// PuTransE 'null_vector' handling (reference Parallel_Universe_Config.py:378-388,494-514): the tuple
+// score of a key in one universe is the model's _calc() with the missing side replaced by a zero
+// vector and WITHOUT the TransH / TransD projection (the reference calls _calc on the raw embedding
+// rows):  head batch ||0 + (r^ - e^)||_p ,  tail batch ||(e^ + r^) - 0||_p ,  e^ = normalize(e_fixed).
+// One thread per work item; min over universes with atomicMin on the bit pattern (scores >= 0).
+__global__ void __launch_bounds__(128) k3u_tuple_scores(const __grid_constant__ EnergyParams P, float* tuple) {
+    const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (i >= P.n_items) return;
+    const pk_energy_item it = P.items[i];
+    const int d = P.sp.d;
+    const float* e = P.sp.ent[0] + ((size_t)P.ent_off[it.universe] + it.fixed_local) * d;
+    const float* r = P.sp.rel[0] + ((size_t)P.rel_off[it.universe] + it.rel_local) * d;
+    float ne = 1.f, nr = 1.f;
+    if (P.sp.norm_flag) {
+        float se = 0.f, sr = 0.f;
+        for (int j = 0; j < d; ++j) { se = __fmaf_rn(e[j], e[j], se); sr = __fmaf_rn(r[j], r[j], sr); }
+        ne = fmaxf(__fsqrt_rn(se), kNormEps);
+        nr = fmaxf(__fsqrt_rn(sr), kNormEps);
+    }
+    float acc = 0.f;
+    for (int j = 0; j < d; ++j) {
+        const float eh = __fdiv_rn(e[j], ne), rh = __fdiv_rn(r[j], nr);
+        const float s = it.side == 0 ? __fadd_rn(0.f, __fsub_rn(rh, eh)) : __fsub_rn(__fadd_rn(eh, rh), 0.f);
+        acc = P.sp.p_norm == 1 ? __fadd_rn(acc, fabsf(s)) : __fmaf_rn(s, s, acc);
+    }
+    if (P.sp.p_norm != 1) acc = __fsqrt_rn(acc);
+    atomicMin(reinterpret_cast<unsigned int*>(tuple) + it.key_row, __float_as_uint(acc));
+}
+
+// every still-unscored candidate of a key row gets the key's tuple score (if some universe has one)
+__global__ void k3u_fill_missing(float* energy, int64_t n_rows, int64_t E, const float* tuple) {
+    const int64_t row = blockIdx.y;
+    const float t = tuple[row];
+    if (isinf(t)) return;
+    float* p = energy + (size_t)row * E;
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < E; c += (int64_t)gridDim.x * blockDim.x)
+        if (isinf(p[c])) p[c] = t;
+}
+
 struct FromEnergyParams {
     const float* energy;
     int64_t E, n;
@@ -433,6 +472,33 @@ extern "C" int pk_universe_energies(const pk_model_cfg* cfg, const pk_tables* pa
     const size_t smem = 2 * (size_t)cfg->dim * sizeof(float);
     k3u_energies<<<(unsigned)n_items, R_THREADS, smem, (cudaStream_t)stream>>>(P);
     PK_LAUNCHED("k3u_energies");
+    return PK_OK;
+}
+
+extern "C" int pk_universe_tuple_scores(const pk_model_cfg* cfg, const pk_tables* packed, const int64_t* d_ent_off,
+                                        const int64_t* d_rel_off, const pk_energy_item* d_items, int64_t n_items, float* d_tuple,
+                                        void* stream) {
+    pk::launch_counter() = 0;
+    EnergyParams P;
+    int rc = fill_space(P.sp, cfg, packed, "pk_universe_tuple_scores");
+    if (rc != PK_OK) return rc;
+    if (!d_ent_off || !d_rel_off || !d_tuple || (n_items > 0 && !d_items)) return pk::fail(PK_ERR_ARG, "pk_universe_tuple_scores: null argument");
+    if (n_items == 0) return PK_OK;
+    P.ent_off = d_ent_off; P.rel_off = d_rel_off; P.n_ent = nullptr; P.ent_remap = nullptr;
+    P.items = d_items; P.n_items = n_items; P.energy = nullptr; P.E = 0;
+    k3u_tuple_scores<<<(unsigned)((n_items + 127) / 128), 128, 0, (cudaStream_t)stream>>>(P, d_tuple);
+    PK_LAUNCHED("k3u_tuple_scores");
+    return PK_OK;
+}
+
+extern "C" int pk_fill_missing_energies(float* d_energy, int64_t n_rows, int64_t n_ent_global, const float* d_tuple, void* stream) {
+    pk::launch_counter() = 0;
+    if (!d_energy || !d_tuple || n_rows < 0) return pk::fail(PK_ERR_ARG, "pk_fill_missing_energies: null argument");
+    if (n_rows == 0) return PK_OK;
+    if (n_rows > 65535) return pk::fail(PK_ERR_UNSUPPORTED, "pk_fill_missing_energies: at most 65535 rows per call");
+    dim3 grid((unsigned)std::min<int64_t>((n_ent_global + 255) / 256, 64), (unsigned)n_rows);
+    k3u_fill_missing<<<grid, 256, 0, (cudaStream_t)stream>>>(d_energy, n_rows, n_ent_global, d_tuple);
+    PK_LAUNCHED("k3u_fill_missing");
     return PK_OK;
 }
 

@@ -120,6 +120,8 @@ def _declare(L):
         "pk_train_universes": (ctypes.c_int, [ctypes.POINTER(ModelCfg), ctypes.POINTER(Tables), vp, vp, vp, vp, vp, ctypes.c_int, vp, vp]),
         "pk_rank_space": (ctypes.c_int, [ctypes.POINTER(ModelCfg), ctypes.POINTER(Tables), I, vp, vp, vp, vp, vp, vp, vp]),
         "pk_universe_energies": (ctypes.c_int, [ctypes.POINTER(ModelCfg), ctypes.POINTER(Tables), vp, vp, vp, vp, vp, I, vp, I, vp]),
+        "pk_universe_tuple_scores": (ctypes.c_int, [ctypes.POINTER(ModelCfg), ctypes.POINTER(Tables), vp, vp, vp, I, vp, vp]),
+        "pk_fill_missing_energies": (ctypes.c_int, [vp, I, I, vp, vp]),
         "pk_rank_from_energy": (ctypes.c_int, [vp, I, I, vp, vp, vp, vp, vp, vp]),
         "pk_rank_candidate_row": (ctypes.c_int, [vp, I, vp, vp, vp, vp, vp]),
         "pk_score_batch": (ctypes.c_int, [ctypes.POINTER(ModelCfg), ctypes.POINTER(Tables), vp, I, vp, I, vp, I, ctypes.c_int, vp, vp, vp]),

@@ -67,8 +67,8 @@ class Parallel_Universe_Config(Tester):
         super().__init__(data_loader=test_dataloader, use_gpu=torch.cuda.is_available())
         if training_setting != "static":
             raise NotImplementedError("incremental PuTransE is outside the B200 hot path (SURVEY.md 8(f))")
-        if missing_embedding_handling != "last_rank":
-            raise NotImplementedError("missing_embedding_handling='null_vector' is not implemented (SURVEY.md 8(f))")
+        if missing_embedding_handling not in ("last_rank", "null_vector"):
+            raise ValueError("missing_embedding_handling must be 'last_rank' or 'null_vector'")
         self.train_dataloader = train_dataloader
         self.ent_tot = train_dataloader.entTotal
         self.rel_tot = train_dataloader.relTotal
@@ -640,6 +640,11 @@ class Parallel_Universe_Config(Tester):
             k1 = min(K, k0 + rows_per_tile)
             energy = torch.empty((k1 - k0, E), dtype=torch.float32, device=dev)
             N.check(lib.pk_fill_inf(energy.data_ptr(), energy.numel(), st), "pk_fill_inf")
+            null_vector = self.missing_embedding_handling == "null_vector"
+            tuple_score = None
+            if null_vector:   # reference :494-514: per key, min over universes of the (zero vector, r, fixed) score
+                tuple_score = torch.empty(k1 - k0, dtype=torch.float32, device=dev)
+                N.check(lib.pk_fill_inf(tuple_score.data_ptr(), tuple_score.numel(), st), "pk_fill_inf")
             for ck, ix in zip(self._chunks, per_chunk):
                 items = self._energy_items(ix, k_fixed[k0:k1], k_rel[k0:k1], k_side[k0:k1])
                 if items.shape[0] == 0:
@@ -651,8 +656,21 @@ class Parallel_Universe_Config(Tester):
                                                  d_items.data_ptr(), items.shape[0], energy.data_ptr(), E, st),
                         "pk_universe_energies")
                 self.gpu_launches += lib.pk_last_launch_count()
+                if null_vector:
+                    N.check(lib.pk_universe_tuple_scores(ctypes.byref(cfg), ctypes.byref(tab), ix["d_eoff"].data_ptr(),
+                                                         ix["d_roff"].data_ptr(), d_items.data_ptr(), items.shape[0],
+                                                         tuple_score.data_ptr(), st), "pk_universe_tuple_scores")
+                    self.gpu_launches += lib.pk_last_launch_count()
             if dist is not None and world > 1:
                 dist.all_reduce(energy, op=dist.ReduceOp.MIN)   # NCCL min over NVLink: the one exchange step
+                if null_vector:
+                    dist.all_reduce(tuple_score, op=dist.ReduceOp.MIN)
+            if null_vector:   # reference :634-640: candidates no universe scored get the key's tuple score
+                for r0 in range(0, k1 - k0, 65535):
+                    r1 = min(k1 - k0, r0 + 65535)
+                    N.check(lib.pk_fill_missing_energies(energy[r0:r1].data_ptr(), r1 - r0, E, tuple_score[r0:r1].data_ptr(), st),
+                            "pk_fill_missing_energies")
+                    self.gpu_launches += lib.pk_last_launch_count()
             lo, hi = np.searchsorted(sorted_keys, k0), np.searchsorted(sorted_keys, k1)
             if hi > lo:
                 q = order[lo:hi]
@@ -761,6 +779,8 @@ class Parallel_Universe_Config(Tester):
         st = torch.cuda.current_stream(dev).cuda_stream
         energy = torch.empty((1, self.ent_tot), dtype=torch.float32, device=dev)
         N.check(self.lib.pk_fill_inf(energy.data_ptr(), energy.numel(), st), "pk_fill_inf")
+        null_vector = self.missing_embedding_handling == "null_vector"
+        tuple_score = torch.full((1,), float("inf"), dtype=torch.float32, device=dev) if null_vector else None
         for ck in self._chunks:
             ix = self._chunk_index(ck)
             items = self._energy_items(ix, np.array([fixed]), np.array([int(r[0])]), np.array([side]))
@@ -771,6 +791,13 @@ class Parallel_Universe_Config(Tester):
                                                       ix["d_roff"].data_ptr(), ix["d_nE"].data_ptr(), ix["d_remap"].data_ptr(),
                                                       d_items.data_ptr(), items.shape[0], energy.data_ptr(), self.ent_tot, st),
                         "pk_universe_energies")
+                if null_vector:
+                    N.check(self.lib.pk_universe_tuple_scores(ctypes.byref(cfg), ctypes.byref(tab), ix["d_eoff"].data_ptr(),
+                                                              ix["d_roff"].data_ptr(), d_items.data_ptr(), items.shape[0],
+                                                              tuple_score.data_ptr(), st), "pk_universe_tuple_scores")
+        if null_vector:
+            N.check(self.lib.pk_fill_missing_energies(energy.data_ptr(), 1, self.ent_tot, tuple_score.data_ptr(), st),
+                    "pk_fill_missing_energies")
         return energy[0].cpu().numpy()[cands.astype(np.int64)]
 
     def test_one_step(self, data):

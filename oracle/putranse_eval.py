@@ -32,6 +32,34 @@ def universe_energies(spaces, n_ent_global, fixed, rel, side, model="transe", p_
     return out
 
 
+def tuple_score(spaces, fixed, rel, side, p_norm=1):
+    """missing_embedding_handling='null_vector' (reference Parallel_Universe_Config.py:378-388,494-514):
+    min over universes holding (fixed, rel) of _calc() with the missing side replaced by a zero vector,
+    on the RAW embedding rows (the reference does not apply the TransH/TransD projection here)."""
+    import torch
+    import torch.nn.functional as F
+    best = np.float32(np.inf)
+    for sp in spaces:
+        er, rr = sp["ent_remap"], sp["rel_remap"]
+        fl, rl = np.nonzero(er == fixed)[0], np.nonzero(rr == rel)[0]
+        if fl.size == 0 or rl.size == 0:
+            continue
+        e = F.normalize(torch.from_numpy(np.asarray(sp["tables"]["ent_embeddings"][fl[0]], dtype=np.float32)), 2, -1)
+        r = F.normalize(torch.from_numpy(np.asarray(sp["tables"]["rel_embeddings"][rl[0]], dtype=np.float32)), 2, -1)
+        zero = torch.zeros(1)
+        s = zero + (r - e) if side == 0 else (e + r) - zero
+        best = min(best, np.float32(torch.norm(s, p_norm, -1).item()))
+    return best
+
+
+def fill_missing(energy, tuple_sc):
+    """reference global_energy_estimation :634-640"""
+    out = energy.copy()
+    if np.isfinite(tuple_sc):
+        out[np.isinf(out)] = tuple_sc
+    return out
+
+
 def rank_from_energy(energy, truth, known):
     """(raw, filtered) 0-based ranks; `known` = known-true candidates other than the truth."""
     E = energy.shape[0]

@@ -260,7 +260,14 @@ def topic_rank():
 
 
 # --------------------------------------------------------------------------- putranse
-def topic_putranse():
+def topic_putranse_nullvec():
+    """Same run as topic_putranse but evaluated with missing_embedding_handling='null_vector'
+    (reference Parallel_Universe_Config.py:378-388,494-514,634-640): candidates no universe can score
+    get the key's tuple score ||0 + r^ - t^|| resp. ||h^ + r^ - 0|| instead of +inf."""
+    topic_putranse(null_vector=True)
+
+
+def topic_putranse(null_vector=False):
     """Static PuTransE script behaviour (seeds 4..), few epochs, then the reference evaluation."""
     _setup_ref_import()
     import torch
@@ -279,7 +286,8 @@ def topic_putranse():
                                   max_balance=0.5, embedding_model=TransE,
                                   embedding_model_param={"dim": 20, "p_norm": 1, "norm_flag": 1},
                                   checkpoint_dir="/tmp/", valid_steps=10 ** 9, save_steps=10 ** 9,
-                                  training_setting="static", incremental_strategy=None)
+                                  training_setting="static", incremental_strategy=None,
+                                  missing_embedding_handling="null_vector" if null_vector else "last_rank")
     pu.use_gpu = False
     assert pu.initial_random_seed == 4
     pu.train_parallel_universes(n_univ)
@@ -306,11 +314,15 @@ def topic_putranse():
     res["metrics"] = np.array(out, dtype=np.float32)
     res["test_sorted"] = _triples(pu.lib, "testList", test.testTotal).astype(np.int32)
     print("putranse metrics", out)
+    if null_vector:   # the universes are those of putranse_wn18.npz (same seeds): keep only the evaluation
+        res = {k: v for k, v in res.items() if not k.startswith("u")}
+        np.savez_compressed(os.path.join(OUT, "putranse_nullvec_wn18.npz"), **res)
+        return
     np.savez_compressed(os.path.join(OUT, "putranse_wn18.npz"), **res)
 
 
 TOPICS = {"dataset": topic_dataset, "sampler": topic_sampler, "universe": topic_universe, "train": topic_train,
-          "rank": topic_rank, "putranse": topic_putranse}
+          "rank": topic_rank, "putranse": topic_putranse, "putranse_nullvec": topic_putranse_nullvec}
 
 if __name__ == "__main__":
     args = sys.argv[1:] or list(TOPICS)

@@ -284,6 +284,37 @@ def test_energy_aggregation_on_reference_tables(wn18_dir, golden):
     assert np.array_equal(np.isfinite(row), fin) and np.allclose(row[fin], want[fin], rtol=2e-6, atol=1e-6)
 
 
+def test_null_vector_handling_on_reference_tables(wn18_dir, golden):
+    """missing_embedding_handling='null_vector' (reference Parallel_Universe_Config.py:378-388,494-514,634-640)
+    on the REFERENCE-trained universe tables against the reference's own per-triple ranks."""
+    import torch
+    g, gn = golden["putranse_wn18"], golden["putranse_nullvec_wn18"]
+    pu = _putranse(wn18_dir, int(g["n_univ"]), 0)
+    pu.missing_embedding_handling = "null_vector"
+    ck = pu._chunks[0]
+    for i, u in enumerate(ck.ids):
+        ck.tables["ent_embeddings"][ck.eoff[i]:ck.eoff[i + 1]].copy_(torch.from_numpy(g["u%d_ent" % u]))
+        ck.tables["rel_embeddings"][ck.roff[i]:ck.roff[i + 1]].copy_(torch.from_numpy(g["u%d_rel" % u]))
+    pu._rank_cache.clear()
+    mrr, mr, hit10, hit3, hit1 = pu.run_link_prediction()
+    same = (pu.last_ranks == gn["ranks"]).all(1).mean()
+    assert same > 0.999, same
+    assert (pu.last_ranks != g["ranks"]).any(), "null-vector ranks must differ from last-rank ranks"
+    want = gn["metrics"]
+    assert abs(mrr - want[0]) <= 1e-4 * want[0] and abs(mr - want[1]) <= 1e-4 * want[1] and abs(hit10 - want[2]) <= 1.0 / 5000 + 1e-7
+    # the reference-API row path gives the same filled row
+    idx = int(np.nonzero((g["ranks"] != gn["ranks"]).any(1))[0][0])
+    h, r, t = g["test_sorted"][idx].tolist()
+    row = pu.global_energy_estimation({"batch_h": np.arange(40943), "batch_t": np.array([t]), "batch_r": np.array([r]),
+                                       "mode": "head_batch"})
+    from oracle import putranse_eval
+    spaces = [dict(tables={"ent_embeddings": g["u%d_ent" % u], "rel_embeddings": g["u%d_rel" % u]},
+                   ent_remap=g["u%d_ent_remap" % u], rel_remap=g["u%d_rel_remap" % u]) for u in range(int(g["n_univ"]))]
+    want_row = putranse_eval.fill_missing(putranse_eval.universe_energies(spaces, 40943, t, r, 0), putranse_eval.tuple_score(spaces, t, r, 0))
+    fin = np.isfinite(want_row)
+    assert np.array_equal(np.isfinite(row), fin) and np.allclose(row[fin], want_row[fin], rtol=2e-6, atol=1e-6)
+
+
 @pytest.mark.parametrize("cls,param", [("TransH", {"dim": 20, "p_norm": 1, "norm_flag": 1}),
                                        ("TransD", {"dim_e": 20, "dim_r": 20, "p_norm": 1, "norm_flag": 1}),
                                        ("TransE", {"dim": 50, "p_norm": 2, "norm_flag": 1})])

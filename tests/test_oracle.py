@@ -161,6 +161,30 @@ def test_putranse_aggregation_restatement_matches_reference(golden):
         assert [raw, filt, raw2, filt2] == g["ranks"][idx].tolist(), idx
 
 
+def test_null_vector_restatement_matches_reference(golden):
+    """missing_embedding_handling='null_vector': per-triple ranks of the unmodified reference on the same
+    eight universes (tests/golden/putranse_nullvec_wn18.npz, minted by make_golden.py putranse_nullvec)."""
+    g, gn, w = golden["putranse_wn18"], golden["putranse_nullvec_wn18"], golden["wn18"]
+    assert np.array_equal(g["test_sorted"], gn["test_sorted"])
+    n_univ = int(g["n_univ"])
+    spaces = [dict(tables={"ent_embeddings": g["u%d_ent" % u], "rel_embeddings": g["u%d_rel" % u]},
+                   ent_remap=g["u%d_ent_remap" % u], rel_remap=g["u%d_rel_remap" % u]) for u in range(n_univ)]
+    tri = g["test_sorted"]
+    allt = np.concatenate([w["train"], w["valid"], w["test"]])[:, [0, 2, 1]]
+    changed = np.nonzero((g["ranks"] != gn["ranks"]).any(1))[0]
+    assert changed.size > 0, "the null-vector run must differ from the last-rank run somewhere"
+    same = np.nonzero((g["ranks"] == gn["ranks"]).all(1))[0]
+    for idx in list(changed[:20]) + list(same[:5]):
+        h, r, t = tri[idx].tolist()
+        en = putranse_eval.fill_missing(putranse_eval.universe_energies(spaces, 40943, t, r, 0), putranse_eval.tuple_score(spaces, t, r, 0))
+        known = sorted(set(allt[(allt[:, 1] == r) & (allt[:, 2] == t)][:, 0].tolist()) - {h})
+        raw, filt = putranse_eval.rank_from_energy(en, h, known)
+        en2 = putranse_eval.fill_missing(putranse_eval.universe_energies(spaces, 40943, h, r, 1), putranse_eval.tuple_score(spaces, h, r, 1))
+        known2 = sorted(set(allt[(allt[:, 0] == h) & (allt[:, 1] == r)][:, 2].tolist()) - {t})
+        raw2, filt2 = putranse_eval.rank_from_energy(en2, t, known2)
+        assert [raw, filt, raw2, filt2] == gn["ranks"][idx].tolist(), idx
+
+
 @pytest.mark.skipif(not os.path.exists(on.REF_SO), reason="oracle/_ref/Base.so not built")
 def test_restatement_against_live_reference_library(tmp_path):
     """Fresh synthetic graph, seeds never seen by the golden files: oracle == reference library."""
