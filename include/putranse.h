@@ -167,6 +167,11 @@ typedef struct {
     const float*   right_mean;
     uint64_t*      lcg;        /* [work_threads] stream states, advanced in place */
     int64_t n_tri, n_ent, n_rel;
+    /* optional: [n_ent + 1] first record of every head in by_head / of every tail in by_tail.  They only
+     * shorten the binary searches of filtered corruption (Corrupt.h:27-56) from the whole index to one
+     * entity's records; NULL = search the whole index.  Results are identical either way. */
+    const int64_t* head_off;
+    const int64_t* tail_off;
 } pk_sampler;
 
 /* pk_torch_init_tables on the DEVICE: same arguments (host arrays), but d_out[t] are device tables.

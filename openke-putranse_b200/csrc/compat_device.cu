@@ -87,6 +87,7 @@ int do_sampling(PK_INT* bh, PK_INT* bt, PK_INT* br, PK_REAL* by, PK_INT B, PK_IN
     pk_sampler smp;
     smp.by_head = g_dev.by_head; smp.by_tail = g_dev.by_tail; smp.left_mean = g_dev.left_mean; smp.right_mean = g_dev.right_mean;
     smp.lcg = g_dev.lcg; smp.n_tri = ix.n_tri(); smp.n_ent = ix.n_ent; smp.n_rel = ix.n_rel;
+    smp.head_off = nullptr; smp.tail_off = nullptr;
     rc = pk_sample_batch(&cfg, &smp, B, g_dev.ids, g_dev.ids + n, g_dev.ids + 2 * n, nullptr);
     if (rc != PK_OK) return rc;
     PK_CUDA(cudaMemcpy(g_dev.host_ids.data(), g_dev.ids, 3 * n * 4, cudaMemcpyDeviceToHost));

@@ -29,6 +29,7 @@
 // Bound on big tables (E*d*4 >> L2): HBM, ~(3+k) rows read + written per positive.
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "common.hpp"
@@ -62,6 +63,12 @@ struct pk_workspace {
     int64_t dup_cap_ent = 0;
     int rel_copies = 1;
     int max_blocks = 0;
+    // the captured chunk of steps, kept across pk_train_steps calls with identical launch parameters
+    // (an epoch loop calls with the same tables, sampler, batch size and loss buffer every time)
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    std::vector<unsigned char> graph_key;
+    int graph_launches = 0;
 };
 
 namespace pkk1 {
@@ -184,11 +191,11 @@ __device__ __forceinline__ void prepare_block(const PrepParams& S, int bid) {
             int32_t c, side;
             if ((float)coin < prob) {   // keep head, replace tail
                 if (!S.filter) { const int64_t tmp = (int64_t)fastmod(x, fm_ent); c = (int32_t)(tmp < h ? tmp : tmp + 1); }
-                else c = corrupt_entity(x, S.sv.by_head, S.sv.n_tri, S.sv.n_ent, h, r, 0, 2, true);
+                else c = corrupt_entity(x, S.sv.by_head, S.sv.n_tri, S.sv.n_ent, h, r, 0, 2, true, S.sv.head_off);
                 side = 0;
             } else {                    // keep tail, replace head
                 if (!S.filter) { const int64_t tmp = (int64_t)fastmod(x, fm_ent); c = (int32_t)(tmp < t ? tmp : tmp + 1); }
-                else c = corrupt_entity(x, S.sv.by_tail, S.sv.n_tri, S.sv.n_ent, t, r, 2, 0, true);
+                else c = corrupt_entity(x, S.sv.by_tail, S.sv.n_tri, S.sv.n_ent, t, r, 2, 0, true, S.sv.tail_off);
                 side = 1;
             }
             S.ids[(3 + (int64_t)n) * S.B + b] = (int32_t)((uint32_t)c | ((uint32_t)side << 31));
@@ -904,6 +911,7 @@ int ensure_jump(pk_workspace* ws, int64_t B, int W, int k, cudaStream_t st) {
 void fill_prep(PrepParams& S, const pk_model_cfg* cfg, pk_workspace* ws, int64_t B) {
     S.sv.by_head = nullptr; S.sv.by_tail = nullptr; S.sv.left_mean = nullptr; S.sv.right_mean = nullptr;
     S.sv.n_tri = 0; S.sv.n_ent = (int32_t)ws->n_ent; S.sv.n_rel = (int32_t)ws->n_rel;
+    S.sv.head_off = nullptr; S.sv.tail_off = nullptr;
     S.lcg = nullptr; S.jump = ws->jump; S.per = 0;
     S.gh = S.gt = S.gr = nullptr;
     S.B = B; S.n_ent = ws->n_ent; S.n_rel = ws->n_rel;
@@ -971,6 +979,11 @@ extern "C" void pk_workspace_free(pk_workspace* ws) {
         cudaFree(ws->cnt_ent[i]); cudaFree(ws->cnt_rel[i]); cudaFree(ws->dup_ent[i]); cudaFree(ws->touched_rel[i]);
         cudaFree(ws->counters[i]); cudaFree(ws->ids[i]);
     }
+    if (ws->graph_exec) {
+        cudaDeviceSynchronize();
+        cudaGraphExecDestroy(ws->graph_exec);
+        cudaGraphDestroy(ws->graph);
+    }
     if (ws->own_stream) cudaStreamDestroy(ws->own_stream);
     delete ws;
 }
@@ -988,6 +1001,7 @@ extern "C" int pk_sample_batch(const pk_model_cfg* cfg, const pk_sampler* smp, i
     SampleParams S;
     S.sv.by_head = smp->by_head; S.sv.by_tail = smp->by_tail; S.sv.left_mean = smp->left_mean; S.sv.right_mean = smp->right_mean;
     S.sv.n_tri = smp->n_tri; S.sv.n_ent = (int32_t)smp->n_ent; S.sv.n_rel = (int32_t)smp->n_rel;
+    S.sv.head_off = smp->head_off; S.sv.tail_off = smp->tail_off;
     S.lcg = smp->lcg;
     S.bh = d_h; S.bt = d_t; S.br = d_r;
     S.B = B; S.W = cfg->work_threads; S.k = cfg->neg_ent; S.bern = cfg->bern; S.filter = cfg->filter;
@@ -1050,16 +1064,20 @@ extern "C" int pk_train_steps(const pk_model_cfg* cfg, const pk_tables* tab, con
     rc = ensure_jump(ws, B, W, k, st);
     if (rc != PK_OK) return rc;
     K1Params P;
+    memset(&P, 0, sizeof(P));
     fill_params(P, cfg, tab, ws, B, margin, lr, d_loss);
     StepGeom g;
+    memset(&g, 0, sizeof(g));
     rc = step_geometry(cfg, P, ws, g);
     if (rc != PK_OK) return rc;
     P.grad_blocks = g.grad_blocks;
     const int64_t per = (B % W == 0) ? B / W : B / W + 1;
     PrepParams S;
+    memset(&S, 0, sizeof(S));
     fill_prep(S, cfg, ws, B);
     S.sv.by_head = smp->by_head; S.sv.by_tail = smp->by_tail; S.sv.left_mean = smp->left_mean; S.sv.right_mean = smp->right_mean;
     S.sv.n_tri = smp->n_tri;
+    S.sv.head_off = smp->head_off; S.sv.tail_off = smp->tail_off;
     S.lcg = smp->lcg; S.per = per;
     const unsigned sb = (unsigned)((B + K1_THREADS - 1) / K1_THREADS);
     PK_CUDA(cudaMemsetAsync(ws->step_ctr, 0, 8, st));
@@ -1093,33 +1111,50 @@ extern "C" int pk_train_steps(const pk_model_cfg* cfg, const pk_tables* tab, con
     // even, so every replay starts on batch set 0.  The final step is never part of a replay.
     const int64_t fused_steps = steps - 1;
     const int64_t chunk = fused_steps >= 64 ? 64 : (fused_steps & ~(int64_t)1);
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t exec = nullptr;
     int64_t done = 0;
     if (chunk >= 4) {
-        const int before = pk::launch_counter();
-        PK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        for (int64_t i = 0; i < chunk && rc == PK_OK; ++i) rc = step(i, true);
-        cudaError_t ce = cudaStreamEndCapture(st, &graph);
-        if (rc != PK_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
-        if (ce != cudaSuccess) return pk::cuda_fail(ce, "cudaStreamEndCapture");
-        const int per_chunk = pk::launch_counter() - before;
-        PK_CUDA(cudaGraphInstantiate(&exec, graph, 0));
-        int launches = before;
-        for (; done + chunk <= fused_steps; done += chunk) {
-            PK_CUDA(cudaGraphLaunch(exec, st));
-            launches += per_chunk;
+        // key = every byte that ends up in a launch: kernel parameters (set 0), geometry, chunk, stream
+        use_set(P, ws, 0);
+        use_set(S, ws, 1);
+        std::vector<unsigned char> key(sizeof(P) + sizeof(S) + sizeof(g) + sizeof(chunk) + sizeof(st) + sizeof(int));
+        unsigned char* kp = key.data();
+        memcpy(kp, &P, sizeof(P)); kp += sizeof(P);
+        memcpy(kp, &S, sizeof(S)); kp += sizeof(S);
+        memcpy(kp, &g, sizeof(g)); kp += sizeof(g);
+        memcpy(kp, &chunk, sizeof(chunk)); kp += sizeof(chunk);
+        memcpy(kp, &st, sizeof(st)); kp += sizeof(st);
+        memcpy(kp, &cfg->model, sizeof(int));
+        if (!ws->graph_exec || ws->graph_key != key) {
+            if (ws->graph_exec) {   // parameters changed: the old graph may still be queued on its stream
+                cudaDeviceSynchronize();
+                cudaGraphExecDestroy(ws->graph_exec);
+                cudaGraphDestroy(ws->graph);
+                ws->graph_exec = nullptr;
+                ws->graph = nullptr;
+            }
+            const int before = pk::launch_counter();
+            PK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            for (int64_t i = 0; i < chunk && rc == PK_OK; ++i) rc = step(i, true);
+            cudaGraph_t graph = nullptr;
+            cudaError_t ce = cudaStreamEndCapture(st, &graph);
+            if (rc != PK_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (ce != cudaSuccess) return pk::cuda_fail(ce, "cudaStreamEndCapture");
+            ws->graph_launches = pk::launch_counter() - before;
+            pk::launch_counter() = before;
+            cudaGraphExec_t exec = nullptr;
+            ce = cudaGraphInstantiate(&exec, graph, 0);
+            if (ce != cudaSuccess) { cudaGraphDestroy(graph); return pk::cuda_fail(ce, "cudaGraphInstantiate"); }
+            ws->graph = graph;
+            ws->graph_exec = exec;
+            ws->graph_key = key;
         }
-        pk::launch_counter() = launches;
+        for (; done + chunk <= fused_steps; done += chunk) {
+            PK_CUDA(cudaGraphLaunch(ws->graph_exec, st));
+            pk::launch_counter() += ws->graph_launches;
+        }
     }
     for (; done < fused_steps && rc == PK_OK; ++done) rc = step(done, true);
     if (rc == PK_OK) rc = step(steps - 1, false);
-    if (exec) {
-        // the graph must outlive its queued launches
-        cudaStreamSynchronize(st);
-        cudaGraphExecDestroy(exec);
-        cudaGraphDestroy(graph);
-    }
     return rc;
 }
 

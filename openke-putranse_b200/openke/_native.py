@@ -35,7 +35,8 @@ class Tables(ctypes.Structure):
 
 class Sampler(ctypes.Structure):
     _fields_ = [("by_head", vp), ("by_tail", vp), ("left_mean", vp), ("right_mean", vp), ("lcg", vp),
-                ("n_tri", ctypes.c_int64), ("n_ent", ctypes.c_int64), ("n_rel", ctypes.c_int64)]
+                ("n_tri", ctypes.c_int64), ("n_ent", ctypes.c_int64), ("n_rel", ctypes.c_int64),
+                ("head_off", vp), ("tail_off", vp)]
 
 
 class UniverseDesc(ctypes.Structure):

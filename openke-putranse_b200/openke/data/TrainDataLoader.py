@@ -128,7 +128,11 @@ class TrainDataLoader(object):
         N.check(self.lib.pk_train_index(N.addr(by_head), N.addr(by_tail), N.addr(lm), N.addr(rm)), "pk_train_index")
         lcg = np.zeros(max(self.work_threads, 1), dtype=np.uint64)
         N.check(self.lib.pk_get_lcg(N.addr(lcg)), "pk_get_lcg")
+        # first record of every head / tail: filtered corruption then searches one entity's records only
+        head_off = np.searchsorted(by_head[:, 0], np.arange(nE + 1)).astype(np.int64)
+        tail_off = np.searchsorted(by_tail[:, 2], np.arange(nE + 1)).astype(np.int64)
         dev = {"device": device, "n_tri": nT, "n_ent": nE, "n_rel": nR,
+               "head_off": torch.from_numpy(head_off).to(device), "tail_off": torch.from_numpy(tail_off).to(device),
                "by_head": torch.from_numpy(by_head).to(device), "by_tail": torch.from_numpy(by_tail).to(device),
                "left_mean": torch.from_numpy(lm).to(device), "right_mean": torch.from_numpy(rm).to(device),
                "lcg": torch.from_numpy(lcg.view(np.int64)).to(device)}
@@ -137,6 +141,7 @@ class TrainDataLoader(object):
         s.left_mean, s.right_mean = dev["left_mean"].data_ptr(), dev["right_mean"].data_ptr()
         s.lcg = dev["lcg"].data_ptr()
         s.n_tri, s.n_ent, s.n_rel = nT, nE, nR
+        s.head_off, s.tail_off = dev["head_off"].data_ptr(), dev["tail_off"].data_ptr()
         dev["struct"] = s
         self._dev = dev
         return dev

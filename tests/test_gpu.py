@@ -69,6 +69,28 @@ def test_device_sampler_bit_exact_with_reference(wn18_dir, golden):
     assert np.array_equal(np.stack([d["batch_h"], d["batch_t"], d["batch_r"]]), g["odd_B1001_t3_seed11_f1k2"])
 
 
+def test_filtered_corruption_with_entity_offsets_is_identical(wn18_dir):
+    """pk_sampler.head_off / tail_off only shorten the binary searches of filtered corruption: the batch
+    must equal the one the offset-free path (the Base.so-compatible sampling() export) draws from the same
+    stream states, which in turn is pinned to the reference by the test above."""
+    import torch
+    from openke.data import TrainDataLoader
+    fresh_library_state()
+    dl = TrainDataLoader(in_path=wn18_dir, nbatches=100, threads=8, bern_flag=1, filter_flag=1, neg_ent=2, random_seed=4)
+    dev = torch.device("cuda", 0)
+    smp = dl.device_sampler(dev)           # copies the current stream states to the device
+    assert smp["struct"].head_off and smp["struct"].tail_off
+    B, k = dl.batch_size, 2
+    cfg = N.ModelCfg(model=N.PK_TRANSE, dim=8, p_norm=1, norm_flag=1, opt=N.PK_SGD, neg_ent=k, bern=1, filter=1, work_threads=8, reserved=0)
+    ids = [torch.zeros(B * (1 + k), dtype=torch.int32, device=dev) for _ in range(3)]
+    for _ in range(2):                     # two consecutive batches: the stream hand-over is covered too
+        N.check(N.lib().pk_sample_batch(ctypes.byref(cfg), ctypes.byref(smp["struct"]), B, ids[0].data_ptr(), ids[1].data_ptr(),
+                                        ids[2].data_ptr(), torch.cuda.current_stream(dev).cuda_stream), "pk_sample_batch")
+        host = dl.sampling()
+        for got, key in zip(ids, ("batch_h", "batch_t", "batch_r")):
+            assert np.array_equal(got.cpu().numpy().astype(np.int64), host[key]), key
+
+
 def test_device_sampler_inside_universes(wn18_dir, golden):
     from openke.data import TrainDataLoader
     U = golden["universe"]
