@@ -223,6 +223,11 @@ int pk_train_universes(const pk_model_cfg* cfg, const pk_tables* packed, const i
                        const int32_t* d_by_tail, const float* d_left_mean, const float* d_right_mean,
                        const pk_universe_desc* h_desc /*HOST array*/, int n_universes, float* d_loss,
                        void* stream);
+/* How pk_train_universes would run a universe of this shape: 0 = tables staged in shared memory,
+ * 1 = entity tables in global memory (relation tables and batch scratch in shared memory),
+ * 2 = does not fit the universe kernel (relation-rich graph or very large batch): train it with
+ * pk_train_steps on its slice of the packed tables.  Negative on error. */
+int pk_universe_kernel_class(const pk_model_cfg* cfg, int64_t n_ent, int64_t n_rel, int64_t batch_size);
 /* number of kernel launches the last pk_* call on this thread issued (for bench accounting) */
 int pk_last_launch_count(void);
 

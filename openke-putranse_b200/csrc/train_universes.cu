@@ -679,6 +679,21 @@ DescSlot* acquire_desc(size_t bytes) {
 
 using namespace pkk2;
 
+extern "C" int pk_universe_kernel_class(const pk_model_cfg* cfg, int64_t n_ent, int64_t n_rel, int64_t batch_size) {
+    if (!cfg || cfg->model < 0 || cfg->model > 2 || cfg->dim <= 0 || cfg->neg_ent < 1 || cfg->work_threads < 1 || n_ent < 2 || n_rel < 1 ||
+        batch_size < 1)
+        return pk::fail(PK_ERR_ARG, "pk_universe_kernel_class: bad argument");
+    int dev = 0, max_smem = 0;
+    PK_CUDA(cudaGetDevice(&dev));
+    PK_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const int k = cfg->neg_ent;
+    if ((long long)(3 + k) * batch_size >= 32768 || (long long)batch_size * k > 2047 || cfg->dim > 256 || cfg->work_threads > 8) return 2;
+    K2Smem a(cfg->model, cfg->dim, k, cfg->work_threads, (int)n_ent, (int)n_rel, (int)batch_size, 1);
+    if (a.total <= (size_t)max_smem) return 0;
+    K2Smem b(cfg->model, cfg->dim, k, cfg->work_threads, (int)n_ent, (int)n_rel, (int)batch_size, 0);
+    return b.total <= (size_t)max_smem ? 1 : 2;
+}
+
 extern "C" int pk_train_universes(const pk_model_cfg* cfg, const pk_tables* packed, const int32_t* d_by_head,
                                   const int32_t* d_by_tail, const float* d_left_mean, const float* d_right_mean,
                                   const pk_universe_desc* h_desc, int n, float* d_loss, void* stream) {
@@ -756,8 +771,40 @@ extern "C" int pk_train_universes(const pk_model_cfg* cfg, const pk_tables* pack
         if (cls[c].empty()) continue;
         st = (both && c == 1) ? g_side.st : caller;
         K2Smem s(cfg->model, d, k, W, mE[c], mR[c], mB[c], c == 0);
-        if (s.total > (size_t)max_smem)
-            return pk::fail(PK_ERR_UNSUPPORTED, "pk_train_universes: a universe's batch scratch exceeds shared memory; use pk_train_steps");
+        if (s.total > (size_t)max_smem) {
+            // the class maxima do not fit together (c == 1 only): one launch per universe, each with its
+            // own carve-up; a universe that does not fit alone belongs to pk_train_steps
+            // (pk_universe_kernel_class tells the caller beforehand)
+            for (const auto& u : cls[c]) {
+                K2Smem own(cfg->model, d, k, W, u.n_ent, u.n_rel, u.batch_size, 0);
+                if (own.total > (size_t)max_smem)
+                    return pk::fail(PK_ERR_UNSUPPORTED, "pk_train_universes: a universe's relation tables and batch scratch exceed shared memory; train it with pk_train_steps (see pk_universe_kernel_class)");
+            }
+            for (const auto& u : cls[c]) {
+                K2Smem own(cfg->model, d, k, W, u.n_ent, u.n_rel, u.batch_size, 0);
+                DescSlot* slot1 = acquire_desc(sizeof(pk_universe_desc));
+                if (!slot1) return pk::cuda_fail(cudaGetLastError(), "pk_train_universes: descriptor buffer");
+                PK_CUDA(cudaMemcpyAsync(slot1->d, &u, sizeof(pk_universe_desc), cudaMemcpyHostToDevice, st));
+                K2Params P1;
+                P1.desc = slot1->d;
+                for (int i = 0; i < 2; ++i) {
+                    P1.ent[i] = packed->ent[i]; P1.rel[i] = packed->rel[i];
+                    P1.ent_state[i] = packed->ent_state[i]; P1.rel_state[i] = packed->rel_state[i];
+                }
+                P1.by_head = d_by_head; P1.by_tail = d_by_tail; P1.left_mean = d_left_mean; P1.right_mean = d_right_mean;
+                P1.loss = d_loss;
+                P1.d = d; P1.k = k; P1.p_norm = cfg->p_norm; P1.norm_flag = cfg->norm_flag; P1.opt = cfg->opt;
+                P1.bern = cfg->bern; P1.filter = cfg->filter; P1.W = W;
+                P1.mE = u.n_ent; P1.mR = u.n_rel; P1.mB = u.batch_size;
+                P1.np = np;
+                int rc1 = cfg->model == PK_TRANSE ? launch_model0(lay, P1, 0, 1, own.total, st)
+                          : (cfg->model == PK_TRANSH ? launch_model1(lay, P1, 0, 1, own.total, st) : launch_model2(lay, P1, 0, 1, own.total, st));
+                if (rc1 != PK_OK) return rc1;
+                slot1->busy = true;
+                PK_CUDA(cudaEventRecord(slot1->done, st));
+            }
+            continue;
+        }
         // the longest universes first: blocks are scheduled in index order
         std::stable_sort(cls[c].begin(), cls[c].end(), [](const pk_universe_desc& a, const pk_universe_desc& b) {
             return (long long)a.epochs * a.nbatches * a.batch_size > (long long)b.epochs * b.nbatches * b.batch_size;

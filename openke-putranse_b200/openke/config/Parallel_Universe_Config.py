@@ -131,6 +131,7 @@ class Parallel_Universe_Config(Tester):
         self.training_duration = 0.0
         self.positive_triples = 0         # sum over universes of epochs * nbatches * batch_size
         self.gpu_launches = 0
+        self.universes_on_single_space_path = 0   # universes that did not fit the batched kernel (relation-rich graphs)
         self.h2d_bytes = 0                # bytes copied host -> device by training (index, descriptors, tables if host-initialised)
         self.d2h_bytes = 0                # bytes copied device -> host by training (per-step losses)
         self._rank_cache = {}
@@ -383,13 +384,30 @@ class Parallel_Universe_Config(Tester):
                                filt=1 if dl.filter else 0, work_threads=W)
         tab = self._packed_tables(ck, with_state=True)
         st = (stream if stream is not None else torch.cuda.current_stream(dev)).cuda_stream
-        N.check(lib.pk_train_universes(ctypes.byref(cfg), ctypes.byref(tab), d_by_head.data_ptr(),
-                                       d_by_tail.data_ptr() if d_by_tail is not None else None,
-                                       d_lm.data_ptr() if d_lm is not None else None,
-                                       d_rm.data_ptr() if d_rm is not None else None,
-                                       desc, n, d_loss.data_ptr() if d_loss is not None else None, st),
-                "pk_train_universes")
-        self.gpu_launches += lib.pk_last_launch_count()
+        # universes whose relation tables / batch scratch do not fit the universe kernel (relation-rich
+        # graphs such as FB15K) are trained one by one with the single-space kernels on their slice
+        klass = [lib.pk_universe_kernel_class(ctypes.byref(cfg), int(nE[i]), int(nR[i]), int(desc[i].batch_size)) for i in range(n)]
+        if min(klass) < 0:
+            raise N.NativeError("pk_universe_kernel_class: %s" % N.last_error())
+        big = [i for i in range(n) if klass[i] == 2]
+        if big:
+            small = [i for i in range(n) if klass[i] != 2]
+            desc_k2 = (N.UniverseDesc * max(len(small), 1))()
+            for j, i in enumerate(small):
+                ctypes.memmove(ctypes.byref(desc_k2[j]), ctypes.byref(desc[i]), ctypes.sizeof(N.UniverseDesc))
+        else:
+            small, desc_k2 = list(range(n)), desc
+        if small:
+            N.check(lib.pk_train_universes(ctypes.byref(cfg), ctypes.byref(tab), d_by_head.data_ptr(),
+                                           d_by_tail.data_ptr() if d_by_tail is not None else None,
+                                           d_lm.data_ptr() if d_lm is not None else None,
+                                           d_rm.data_ptr() if d_rm is not None else None,
+                                           desc_k2, len(small), d_loss.data_ptr() if d_loss is not None else None, st),
+                    "pk_train_universes")
+            self.gpu_launches += lib.pk_last_launch_count()
+        for i in big:
+            self._train_single_space(ck, cfg, i, desc[i], d_by_head, d_by_tail, d_lm, d_rm, lcg[i], d_loss, st, dev)
+        self.universes_on_single_space_path += len(big)
         if prefetch_ids and self.prefetch_sampling:
             # the GPU is busy with this launch: sample the subgraphs the next call will most likely ask for
             if self._pool is None:
@@ -532,6 +550,42 @@ class Parallel_Universe_Config(Tester):
                 mode = None
             Parallel_Universe_Config._INIT_MODE[key] = mode
         return Parallel_Universe_Config._INIT_MODE[key]
+
+    def _train_single_space(self, ck, cfg, i, dd, d_by_head, d_by_tail, d_lm, d_rm, lcg_i, d_loss, st, dev):
+        """One universe through K1 (pk_train_steps) on its row range of the packed tables: the path for
+        universes that do not fit the batched-universe kernel.  Same sampler streams, same arithmetic."""
+        lib = self.lib
+        e0, r0, t0 = int(dd.ent_off), int(dd.rel_off), int(dd.tri_off)
+        nE, nR, nT, B = int(dd.n_ent), int(dd.n_rel), int(dd.n_tri), int(dd.batch_size)
+        d = ck.proto.dim_native
+        t = N.Tables()
+        for j in range(2):
+            t.ent[j] = t.rel[j] = t.ent_state[j] = t.rel_state[j] = None
+        for j, name in enumerate(ck.proto._ent_tables):
+            t.ent[j] = ck.tables[name].data_ptr() + e0 * d * 4
+            t.ent_state[j] = ck.state[name].data_ptr() + e0 * d * 4
+        for j, name in enumerate(ck.proto._rel_tables):
+            t.rel[j] = ck.tables[name].data_ptr() + r0 * d * 4
+            t.rel_state[j] = ck.state[name].data_ptr() + r0 * d * 4
+        t.n_ent, t.n_rel = nE, nR
+        d_lcg = torch.from_numpy(np.ascontiguousarray(lcg_i).view(np.int64).copy()).to(dev)
+        smp = N.Sampler(by_head=d_by_head.data_ptr() + t0 * 12, by_tail=(d_by_tail.data_ptr() + t0 * 12) if d_by_tail is not None else None,
+                        left_mean=(d_lm.data_ptr() + r0 * 4) if d_lm is not None else None,
+                        right_mean=(d_rm.data_ptr() + r0 * 4) if d_rm is not None else None,
+                        lcg=d_lcg.data_ptr(), n_tri=nT, n_ent=nE, n_rel=nR, head_off=None, tail_off=None)
+        ws = lib.pk_workspace_create(ctypes.byref(cfg), nE, nR, B)
+        if not ws:
+            raise N.NativeError("pk_workspace_create: %s" % N.last_error())
+        try:
+            steps = int(dd.epochs) * int(dd.nbatches)
+            loss = d_loss if d_loss is not None else torch.zeros(max(steps, 1), dtype=torch.float32, device=dev)
+            off = int(dd.loss_off) if d_loss is not None else 0
+            N.check(lib.pk_train_steps(ctypes.byref(cfg), ctypes.byref(t), ctypes.byref(smp), ws, B, steps, float(dd.margin), float(dd.lr),
+                                       loss.data_ptr() + off * 4, st), "pk_train_steps")
+            self.gpu_launches += lib.pk_last_launch_count()
+            torch.cuda.current_stream(dev).synchronize() if st == torch.cuda.current_stream(dev).cuda_stream else torch.cuda.synchronize()
+        finally:
+            lib.pk_workspace_free(ws)
 
     def _proto(self):
         """A 2-entity instance of the embedding model: carries dim / p_norm / norm_flag / table names."""

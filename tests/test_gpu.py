@@ -371,6 +371,58 @@ def test_batched_universes_match_oracle_steps(wn18_dir, cls, param):
             _close_tables(getattr(sp, n).weight.detach().cpu().numpy(), v)
 
 
+@pytest.mark.parametrize("cls,param,want_single", [("TransE", {"dim": 20, "p_norm": 1, "norm_flag": 1}, False),
+                                                   ("TransH", {"dim": 48, "p_norm": 1, "norm_flag": 1}, True)])
+def test_relation_rich_graph_universes(tmp_path, cls, param, want_single):
+    """FB15K-shaped input (BASELINE.json configs[3]: 1 345 relations): universes hold hundreds of relations,
+    so their relation tables stop fitting the batched kernel's shared memory at some point.  TransE d=20 still
+    runs in K2 (entity tables in L2); TransH d=48 universes are routed through the single-space kernels.  Either
+    way per-step losses must follow the oracle."""
+    import sys
+    import torch
+    import openke.module.model as M
+    from oracle import native as on
+    from oracle.model_math import TorchOracle
+    tools = os.path.join(util.REPO, "tools")
+    if tools not in sys.path:
+        sys.path.insert(0, tools)
+    import bench_k1
+    E, R, T = 4000, 600, 40000
+    tri = bench_k1.synthetic_graph(E, R, T, seed=11)          # (h, r, t)
+    htr = tri[:, [0, 2, 1]]
+    rng = np.random.default_rng(5)
+    hold = rng.choice(T, size=400, replace=False)
+    mask = np.ones(T, bool)
+    mask[hold] = False
+    path = util.write_dataset(str(tmp_path / "rich"), htr[mask], htr[hold[:200]], htr[hold[200:]], E, R)
+    torch.set_num_threads(2)
+    pu = _putranse(path, 3, 2, model_cls=getattr(M, cls), param=param, record=True)
+    assert (pu.universes_on_single_space_path > 0) == want_single, pu.universes_on_single_space_path
+    assert max(h["nR"] for h in pu.universe_hyper.values()) > 60
+    o = on.Oracle(threads=8, bern=0)
+    o.import_train(htr[mask], E, R)
+    for u in range(3):
+        hy = pu.universe_hyper[u]
+        o.seed(4 + u)
+        _, er, rr = o.universe(hy["tc"], hy["balance"])
+        assert len(er) == hy["nE"] and len(rr) == hy["nR"]
+        torch.manual_seed(4 + u)
+        ref_model = getattr(M, cls)(len(er), len(rr), **param)
+        tabs = {n: getattr(ref_model, n).weight.detach().numpy() for n in ref_model.table_names()}
+        orc = TorchOracle(cls.lower(), tabs, p_norm=1, opt="adagrad", lr=hy["lr"], margin=hy["margin"], k=1)
+        o.swap()
+        want = [orc.step(*o.sampling(hy["batch_size"], 1, 0)) for _ in range(hy["epochs"] * hy["nbatches"])]
+        o.swap()
+        got = pu.universe_losses[u]
+        assert np.allclose(got[:5], want[:5], rtol=LOSS_RTOL_EARLY), (cls, u, got[:5], want[:5])
+        assert np.allclose(got, want, rtol=LOSS_RTOL_LATE)
+        sp = pu.trained_embedding_spaces[u]
+        for n, v in orc.tables().items():
+            _close_tables(getattr(sp, n).weight.detach().cpu().numpy(), v)
+    out = pu.run_link_prediction()
+    assert pu.last_ranks.shape == (200, 4) and np.isfinite(out[0])
+
+
 # ------------------------------------------------------------------------------------------ K3
 @pytest.mark.parametrize("p", [1, 2])
 def test_rank_space_known_answer_transh_checkpoint(wn18_dir, golden, p):
