@@ -41,6 +41,22 @@ STATIC_RANGES = dict(min_margin=1, max_margin=4, min_lr=0.001, max_lr=0.1, min_n
                      min_triple_constraint=500, max_triple_constraint=2000, min_balance=0.25, max_balance=0.5)
 MODEL_PARAM = {"dim": 20, "p_norm": 1, "norm_flag": 1}
 NBATCHES, K_NEG = 20, 1
+MODEL = "transe"     # --model transh / transd = BASELINE.json configs[2] (PuTransH / PuTransD on WN18)
+
+
+def set_model(name):
+    """configs[2]: experiments/static_experiment_PuTransH_on_WN18.py (nbatches 20) and ...PuTransD... (nbatches 10,
+    dim_e = dim_r = 20)."""
+    global MODEL, MODEL_PARAM, NBATCHES
+    MODEL = name
+    if name == "transd":
+        MODEL_PARAM = {"dim_e": 20, "dim_r": 20, "p_norm": 1, "norm_flag": 1}
+        NBATCHES = 10
+
+
+def model_class():
+    import openke.module.model as M
+    return {"transe": M.TransE, "transh": M.TransH, "transd": M.TransD}[MODEL]
 
 
 def algorithmic_bytes_per_positive(model="transe", d=20, k=1, opt="adagrad"):
@@ -102,12 +118,11 @@ def dist_env():
 def make_pu(path, seed_offset=0):
     from openke.config import Parallel_Universe_Config
     from openke.data import TrainDataLoader, TestDataLoader
-    from openke.module.model import TransE
     train = TrainDataLoader(in_path=path, nbatches=NBATCHES, threads=8, sampling_mode="normal", bern_flag=0, filter_flag=0,
                             neg_ent=K_NEG, neg_rel=0, random_seed=123)
     test = TestDataLoader(path, "link")          # re-seeds the shared state with 4, like the static script
     pu = Parallel_Universe_Config(training_identifier="bench", train_dataloader=train, test_dataloader=test,
-                                  initial_num_universes=None, embedding_model=TransE, embedding_model_param=MODEL_PARAM,
+                                  initial_num_universes=None, embedding_model=model_class(), embedding_model_param=MODEL_PARAM,
                                   checkpoint_dir=None, valid_steps=10 ** 9, save_steps=None, training_setting="static",
                                   incremental_strategy=None, **STATIC_RANGES)
     pu.initial_random_seed += seed_offset
@@ -243,15 +258,15 @@ def run_ours(args):
     if rank != 0:
         return
     peak, peak_src = measured_peaks()
-    bpp = algorithmic_bytes_per_positive("transe", MODEL_PARAM["dim"], K_NEG, "adagrad")
+    bpp = algorithmic_bytes_per_positive(MODEL, 20, K_NEG, "adagrad")
     achieved = positives * bpp / (np.mean(kernel_ms) * 1e-3) / 1e9
     line = {
         "metric": "PuTransE positive triples/sec (all universes)", "value": value, "unit": "positive triples/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "WN18 graph (repacked reference benchmark files, tests/golden/wn18.npz); universes sampled from it",
-        "config": {"workload": "m2: PuTransE static WN18, %d universes/GPU (seeds 4..), TransE d=20 L1 Adagrad, nbatches=20, k=1"
-                               % nU, "universes_per_gpu": nU, "l2": "flushed between steps (256 MiB write)",
+        "config": {"workload": "m2: PuTransE static WN18, %d universes/GPU (seeds 4..), %s d=20 L1 Adagrad, nbatches=%d, k=1"
+                               % (nU, {"transe": "TransE", "transh": "TransH", "transd": "TransD"}[MODEL], NBATCHES), "universes_per_gpu": nU, "l2": "flushed between steps (256 MiB write)",
                    "positive_triples_per_step_per_gpu": positives, "final_loss_last_universe": final_loss},
         "e2e": {"value": e2e_value, "unit": "positive triples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "ms_per_step": e2e_elapsed / e2e_steps * 1e3,
@@ -377,7 +392,7 @@ def cpu_reference_leg(path, budget_s=20.0, universes=None, max_epochs=None):
     from oracle import native as on
     from oracle.model_math import TorchOracle
     from openke.config import Parallel_Universe_Config
-    from openke.module.model import TransE
+    TransE = model_class()
     cores = os.cpu_count() or 1
     w = np.load(os.path.join(REPO, "tests", "golden", "wn18.npz"))
     R = on.load_reference()
@@ -418,7 +433,7 @@ def cpu_reference_leg(path, budget_s=20.0, universes=None, max_epochs=None):
             o.swap()
         B = nT // NBATCHES
         ref = TransE(nE, nR, **MODEL_PARAM)
-        orc = TorchOracle("transe", {n: getattr(ref, n).weight.detach().numpy() for n in ref.table_names()}, p_norm=1,
+        orc = TorchOracle(MODEL, {n: getattr(ref, n).weight.detach().numpy() for n in ref.table_names()}, p_norm=1,
                           opt="adagrad", lr=hy["lr"], margin=hy["margin"], k=K_NEG)
         n = B * (1 + K_NEG)
         bh, bt, br, by = np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n, np.float32)
@@ -543,10 +558,12 @@ def main():
     ap.add_argument("--ref-epochs", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eval", action="store_true")
+    ap.add_argument("--model", default="transe", choices=["transe", "transh", "transd"])
     ap.add_argument("--no-s1", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
+    set_model(args.model)
     global _OUT
     with _StdoutToStderr() as _OUT:
         if args.impl == "reference":

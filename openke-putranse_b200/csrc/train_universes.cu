@@ -593,7 +593,7 @@ inline LaySel pick_layout(int model, int d) {
 }
 
 // threads per block: as many consumer warps as the register budget allows
-constexpr int k2_threads(int model, int nf) { return (model != 2 && nf <= 4) ? 512 : 256; }
+constexpr int k2_threads(int model, int nf) { return nf > 4 ? 256 : (model == 2 ? 384 : 512); }
 
 #ifdef PK_MODEL_TU
 template <int MODEL, int V, int G, int CPL>
@@ -754,7 +754,7 @@ extern "C" int pk_train_universes(const pk_model_cfg* cfg, const pk_tables* pack
 
     const LaySel lay = pick_layout(cfg->model, d);
     const int threads = k2_threads(cfg->model, lay.V * lay.CPL);
-    int np = threads == 512 ? 3 : 2;
+    int np = threads >= 512 ? 3 : 2;
     if (const char* e = getenv("PK_K2_PRODUCERS")) np = std::max(1, std::min(threads / 32 - 1, atoi(e)));
     const bool both = !cls[0].empty() && !cls[1].empty();
     cudaStream_t caller = st;
