@@ -202,14 +202,15 @@ def run_ours(args):
     # ---- end-to-end leg through the public API: one Parallel_Universe_Config (loaders built once,
     # as a user would), every step = train_parallel_universes(nU) on the NEXT nU universes of the
     # seed sequence: host subgraph sampling + table init + H2D + K2 + D2H of the per-step losses.
-    # (rank r works on universes [r * nU * (steps + 1), ...) of the sequence: disjoint across ranks)
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     h2d, d2h = 0, 0
     # one long-lived orchestrator, as a user has; its first call (untimed warm-up) also allocates the
     # table slab and the per-chunk scratch buffers that every later chunk reuses
-    p2 = make_pu(path, seed_offset=rank * nU * (e2e_steps + 1))
+    # with torch.distributed initialised the orchestrator shards universe ids over the ranks itself
+    # (u % world == rank), so every call asks for nU * world universes: nU per GPU (weak scaling)
+    p2 = make_pu(path)
     p2.record_losses = True
-    p2.train_parallel_universes(nU)
+    p2.train_parallel_universes(nU * world)
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
@@ -218,7 +219,7 @@ def run_ours(args):
     h2d0, d2h0 = p2.h2d_bytes, p2.d2h_bytes
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        p2.train_parallel_universes(nU)
+        p2.train_parallel_universes(nU * world)
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
