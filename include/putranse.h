@@ -189,8 +189,10 @@ int pk_sample_batch(const pk_model_cfg* cfg, const pk_sampler* smp, int64_t batc
 typedef struct pk_workspace pk_workspace;
 pk_workspace* pk_workspace_create(const pk_model_cfg* cfg, int64_t n_ent, int64_t n_rel, int64_t max_batch);
 void pk_workspace_free(pk_workspace* ws);
-/* synchronises `stream` and reports whether a train step refused its batch (ids out of range, or a
- * negative whose relation differs from its positive's: relation corruption is not on this path) */
+/* synchronises `stream` and reports whether a train step refused its batch: an id out of range, a
+ * negative whose relation differs from its positive's (relation corruption is not on this path), or
+ * a negative that replaces BOTH entities of its positive (the reference sampler replaces one,
+ * Base.cpp:216-232).  A refused batch leaves the tables untouched and its loss is NaN. */
 int pk_workspace_check(pk_workspace* ws, void* stream);
 
 /* K1: one fused train step on given ids: gather, project, normalise, energy, margin loss, analytic
@@ -200,8 +202,10 @@ int pk_train_step(const pk_model_cfg* cfg, const pk_tables* tab, pk_workspace* w
                   const int32_t* d_h, const int32_t* d_t, const int32_t* d_r, float margin, float lr,
                   float* d_loss, void* stream);
 
-/* K0+K1 looped: `steps` consecutive sampling()+train_one_step pairs without leaving the device
- * (captured once into a CUDA graph per (ws, batch_size)).  d_loss is [steps].
+/* K0+K1 looped: `steps` consecutive sampling()+train_one_step pairs without leaving the device.
+ * 64 steps are captured into a CUDA graph that the workspace keeps and re-launches for later calls
+ * with identical arguments (an epoch loop); the call returns without synchronising.  d_loss is
+ * [steps]; smp->lcg ends `steps` batches further, exactly like `steps` reference sampling() calls.
  * Equivalent of the body of Trainer.run (reference Trainer.py:91-99). */
 int pk_train_steps(const pk_model_cfg* cfg, const pk_tables* tab, const pk_sampler* smp, pk_workspace* ws,
                    int64_t batch_size, int64_t steps, float margin, float lr, float* d_loss, void* stream);
