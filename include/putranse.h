@@ -232,6 +232,9 @@ int pk_train_universes(const pk_model_cfg* cfg, const pk_tables* packed, const i
  * 2 = does not fit the universe kernel (relation-rich graph or very large batch): train it with
  * pk_train_steps on its slice of the packed tables.  Negative on error. */
 int pk_universe_kernel_class(const pk_model_cfg* cfg, int64_t n_ent, int64_t n_rel, int64_t batch_size);
+/* Profiling aid: when d_buf is non-NULL every universe block of later pk_train_universes calls
+ * writes (loss_off, nanoseconds it ran) into d_buf[2i], d_buf[2i+1] (device, 2*n_universes int64). */
+int pk_debug_universe_timer(long long* d_buf);
 /* number of kernel launches the last pk_* call on this thread issued (for bench accounting) */
 int pk_last_launch_count(void);
 

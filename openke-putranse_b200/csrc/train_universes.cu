@@ -30,6 +30,7 @@
 // staged table IS the universe's whole embedding space).  The Adagrad accumulators stay in global
 // memory (L2-resident).
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <vector>
 
@@ -54,6 +55,8 @@ struct K2Params {
     int d, k, p_norm, norm_flag, opt, bern, filter, W;
     int mE, mR, mB;         // launch-wide maxima: the shared-memory carve-up is uniform
     int np;                 // producer warps
+    long long* timer;       // optional (pk_debug_universe_timer): per block (loss_off, ns spent)
+    int timer_base;
 };
 
 __host__ __device__ inline size_t up16(size_t x) { return (x + 15) & ~(size_t)15; }
@@ -309,6 +312,8 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
     const pk_universe_desc& U = P.desc[blockIdx.x];
     const K2Smem S(MODEL, P.d, P.k, P.W, P.mE, P.mR, P.mB, STAGE);
     const int tid = threadIdx.x;
+    long long t_begin = 0;
+    if (P.timer && tid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_begin));
     const int d = P.d, k = P.k, B = U.batch_size, nE = U.n_ent, nR = U.n_rel, W = P.W;
     const int NC = NT / 32 - P.np;          // consumer warps
     const int n_cons = NC * 32, n_prod = P.np * 32;
@@ -572,6 +577,12 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
                 if (g_rel_state[t]) g_rel_state[t][i] = rc.state[t][i];
             }
     }
+    if (P.timer && tid == 0) {
+        long long t_end;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_end));
+        P.timer[2 * (size_t)(P.timer_base + blockIdx.x)] = U.loss_off;
+        P.timer[2 * (size_t)(P.timer_base + blockIdx.x) + 1] = t_end - t_begin;
+    }
 }
 
 #endif  // PK_MODEL_TU
@@ -580,6 +591,15 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
 struct LaySel { int V, G, CPL; };
 
 inline LaySel pick_layout(int model, int d) {
+    // PK_K2_LAYOUT=V,G,CPL forces one of the instantiated layouts (experiments)
+    if (const char* e = getenv("PK_K2_LAYOUT")) {
+        LaySel f{0, 0, 0};
+        if (sscanf(e, "%d,%d,%d", &f.V, &f.G, &f.CPL) == 3 && f.V * f.G * f.CPL >= d) return f;
+    }
+    // Short rows (the PuTrans* scripts all use d = 20): four lanes per row with scalar chunks keep every
+    // lane busy (d = 20: 4 lanes x 5 floats, against 5 of 8 lanes with 128-bit chunks) and put EIGHT
+    // samples in a warp, so a batch of up to 104 positives is one pass of the 13 consumer warps.
+    if (d <= 20 && d % 4 == 0 && d / 4 <= 5) return LaySel{1, 4, d / 4};
     const int V = d % 4 == 0 ? 4 : (d % 2 == 0 ? 2 : 1);
     const int chunks = d / V;
     const int nf_cap = model == TRANSD ? 4 : 8;  // registers per row per lane
@@ -593,7 +613,7 @@ inline LaySel pick_layout(int model, int d) {
 }
 
 // threads per block: as many consumer warps as the register budget allows
-constexpr int k2_threads(int model, int nf) { return nf > 4 ? 256 : (model == 2 ? 384 : 512); }
+constexpr int k2_threads(int model, int nf) { return nf > 5 ? 256 : (model == 2 ? 384 : 512); }
 
 #ifdef PK_MODEL_TU
 template <int MODEL, int V, int G, int CPL>
@@ -615,6 +635,7 @@ int launch_k2(const K2Params& P, int stage, int n, size_t smem, cudaStream_t st)
 template <int MODEL>
 int dispatch_layout(const LaySel& l, const K2Params& P, int stage, int n, size_t smem, cudaStream_t st) {
 #define PK_CASE(v, g, c) if (l.V == v && l.G == g && l.CPL == c) return launch_k2<MODEL, v, g, c>(P, stage, n, smem, st);
+    PK_CASE(1, 4, 1) PK_CASE(1, 4, 2) PK_CASE(1, 4, 3) PK_CASE(1, 4, 4) PK_CASE(1, 4, 5)
     PK_CASE(4, 8, 1) PK_CASE(4, 8, 2) PK_CASE(4, 32, 1) PK_CASE(4, 32, 2)
     PK_CASE(2, 8, 1) PK_CASE(2, 8, 2) PK_CASE(2, 8, 4) PK_CASE(2, 32, 1) PK_CASE(2, 32, 2) PK_CASE(2, 32, 4)
     PK_CASE(1, 8, 1) PK_CASE(1, 8, 2) PK_CASE(1, 8, 4) PK_CASE(1, 8, 8) PK_CASE(1, 32, 1) PK_CASE(1, 32, 2) PK_CASE(1, 32, 4) PK_CASE(1, 32, 8)
@@ -653,6 +674,7 @@ struct SideStream {
     cudaEvent_t fork = nullptr, join = nullptr;
 };
 thread_local SideStream g_side;
+long long* g_timer = nullptr;   // pk_debug_universe_timer
 
 DescSlot* acquire_desc(size_t bytes) {
     for (auto& s : g_desc_pool)
@@ -678,6 +700,13 @@ DescSlot* acquire_desc(size_t bytes) {
 }  // namespace pkk2
 
 using namespace pkk2;
+
+// Debug/profiling aid: when set, every universe block of later pk_train_universes calls writes
+// (loss_off, nanoseconds it ran) to d_buf[2*i], d_buf[2*i+1] (i = launch order; n_universes pairs).
+extern "C" int pk_debug_universe_timer(long long* d_buf) {
+    g_timer = d_buf;
+    return PK_OK;
+}
 
 extern "C" int pk_universe_kernel_class(const pk_model_cfg* cfg, int64_t n_ent, int64_t n_rel, int64_t batch_size) {
     if (!cfg || cfg->model < 0 || cfg->model > 2 || cfg->dim <= 0 || cfg->neg_ent < 1 || cfg->work_threads < 1 || n_ent < 2 || n_rel < 1 ||
@@ -797,6 +826,7 @@ extern "C" int pk_train_universes(const pk_model_cfg* cfg, const pk_tables* pack
                 P1.bern = cfg->bern; P1.filter = cfg->filter; P1.W = W;
                 P1.mE = u.n_ent; P1.mR = u.n_rel; P1.mB = u.batch_size;
                 P1.np = np;
+                P1.timer = nullptr; P1.timer_base = 0;
                 int rc1 = cfg->model == PK_TRANSE ? launch_model0(lay, P1, 0, 1, own.total, st)
                           : (cfg->model == PK_TRANSH ? launch_model1(lay, P1, 0, 1, own.total, st) : launch_model2(lay, P1, 0, 1, own.total, st));
                 if (rc1 != PK_OK) return rc1;
@@ -826,6 +856,7 @@ extern "C" int pk_train_universes(const pk_model_cfg* cfg, const pk_tables* pack
         P.bern = cfg->bern; P.filter = cfg->filter; P.W = W;
         P.mE = mE[c]; P.mR = mR[c]; P.mB = mB[c];
         P.np = np;
+        P.timer = g_timer; P.timer_base = c == 1 ? (int)cls[0].size() : 0;
         // descriptors were copied from pageable host memory owned by this call: the copy has
         // completed (or been staged) when cudaMemcpyAsync returns, so cls[c] may go out of scope
         int rc = PK_OK;

@@ -120,6 +120,7 @@ def _declare(L):
         "pk_train_steps": (ctypes.c_int, [ctypes.POINTER(ModelCfg), ctypes.POINTER(Tables), ctypes.POINTER(Sampler), vp, I, I, F, F, vp, vp]),
         "pk_train_universes": (ctypes.c_int, [ctypes.POINTER(ModelCfg), ctypes.POINTER(Tables), vp, vp, vp, vp, vp, ctypes.c_int, vp, vp]),
         "pk_universe_kernel_class": (ctypes.c_int, [ctypes.POINTER(ModelCfg), I, I, I]),
+        "pk_debug_universe_timer": (ctypes.c_int, [ctypes.c_void_p]),
         "pk_rank_space": (ctypes.c_int, [ctypes.POINTER(ModelCfg), ctypes.POINTER(Tables), I, vp, vp, vp, vp, vp, vp, vp]),
         "pk_universe_energies": (ctypes.c_int, [ctypes.POINTER(ModelCfg), ctypes.POINTER(Tables), vp, vp, vp, vp, vp, I, vp, I, vp]),
         "pk_universe_tuple_scores": (ctypes.c_int, [ctypes.POINTER(ModelCfg), ctypes.POINTER(Tables), vp, vp, vp, I, vp, vp]),

@@ -21,7 +21,9 @@ def main():
     pu = bench.make_pu(path)
     pu.const_num_epochs = epochs
     dev = torch.device("cuda", 0)
-    launch = bench.prepare_resident_launch(pu, list(range(n)), dev)
+    ids = [int(x) for x in os.environ["K2_PROBE_IDS"].split(",")] if os.environ.get("K2_PROBE_IDS") else list(range(n))
+    n = len(ids)
+    launch = bench.prepare_resident_launch(pu, ids, dev)
     ts = []
     for _ in range(reps):
         launch["reset"]()
@@ -33,7 +35,7 @@ def main():
         torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
     steps = epochs * bench.NBATCHES
-    sizes = [(pu.universe_hyper[u]["nE"], pu.universe_hyper[u]["batch_size"]) for u in range(n)]
+    sizes = [(pu.universe_hyper[u]["nE"], pu.universe_hyper[u]["batch_size"]) for u in ids]
     print("universes=%d epochs=%d steps/universe=%d  kernel ms=%s  => %.2f us/step (slowest universe)  sizes(nE,B)=%s"
           % (n, epochs, steps, ["%.3f" % t for t in ts], min(ts) * 1e3 / steps, sizes))
 
