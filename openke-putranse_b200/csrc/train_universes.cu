@@ -87,7 +87,7 @@ struct K2Smem {
         // one batch buffer: h | t | r | c[k] | code_h | code_t | code_c[k] | dup[slots] | rel_ids | ndup | nrel
         batch_ints = (int)((3 + k) * (long long)mB + occ) + slots + nrelcap + 4;
         for (int i = 0; i < 2; ++i) { batch[i] = o; o = up16(o + (size_t)batch_ints * 4); }
-        lossv = o;   o = up16(o + (size_t)mB * 4);
+        lossv = o;   o = up16(o + (size_t)2 * mB * 4);   // per-sample loss terms, double-buffered
         // s0[8] | Aadv[8] | Cadv[8] | A[per] | C[per]
         lcg = o;     o = up16(o + (size_t)(24 + 2 * per) * 8);
         total = o;
@@ -179,7 +179,13 @@ __device__ __forceinline__ void apply_update(float* x_row, float* s_row, float (
 #pragma unroll
         for (int i = 0; i < L::NF; ++i) {
             s[i] = fmaf(g[i], g[i], s[i]);
-            x[i] = fmaf(-lr * g[i], rcp_nr(sqrt0(s[i]) + 1e-10f), x[i]);
+            // 1 / (sqrt(s) + 1e-10) from the two approximate units (rsqrt: 2^-22.4, rcp: 1 ulp): the step
+            // lr*g/(...) is then within ~4 ulp OF THE STEP, i.e. below half an ulp of x for lr <= 0.1
+            float r;
+            asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaxf(s[i], 1.17549435e-38f)));
+            float inv;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(fmaf(s[i], r, 1e-10f)));
+            x[i] = fmaf(-lr * g[i], inv, x[i]);
         }
         st_row<L>(s_row, d, lane, s);
     } else {
@@ -218,35 +224,35 @@ struct K2Ctx {
         r = act ? br[b] : 0;
     }
     __device__ __forceinline__ bool load_neg(int j, int64_t b, bool act, Tgt& tc) const {
-        const int32_t cj = act ? bc[(size_t)j * B + b] : 0;
+        const int32_t cj = act ? bc[(uint32_t)(j * B) + (uint32_t)b] : 0;
         tc.id = cj & 0x7fffffff;
-        tc.code = act ? code_c[(size_t)j * B + b] : 0;
+        tc.code = act ? code_c[(uint32_t)(j * B) + (uint32_t)b] : 0;
         return cj < 0;
     }
-    __device__ __forceinline__ const float* rel_y(int r) const { return rel_c[0] + (size_t)r * d; }
-    __device__ __forceinline__ const float* rel_w(int r) const { return rel_c[1] + (size_t)r * d; }
+    __device__ __forceinline__ const float* rel_y(int r) const { return rel_c[0] + (uint32_t)r * (uint32_t)d; }
+    __device__ __forceinline__ const float* rel_w(int r) const { return rel_c[1] + (uint32_t)r * (uint32_t)d; }
     __device__ __forceinline__ void rel_add(int tbl, int r, const float (&g)[L::NF], int lane) const {
-        fix_add_row<L>(rel_acc + ((size_t)r * NTR + tbl) * 3 * d, d, lane, g);
+        fix_add_row<L>(rel_acc + (uint32_t)((r * NTR + tbl) * 3 * d), d, lane, g);
     }
-    __device__ __forceinline__ const float* ent_row(int tbl, const Tgt& tg) const { return ent[tbl] + (size_t)tg.id * d; }
+    __device__ __forceinline__ const float* ent_row(int tbl, const Tgt& tg) const { return ent[tbl] + (uint32_t)tg.id * (uint32_t)d; }
     // issue the loads of a singly-occurring row's optimizer state early; they complete behind the math
     __device__ __forceinline__ void prefetch(K2Tgt<L, NTE>& tg, int lane, bool pred) const {
         if (opt != PK_ADAGRAD) return;
 #pragma unroll
-        for (int t = 0; t < NTE; ++t) ld_row<L>(ent_state[t] + (size_t)tg.id * d, d, lane, tg.st[t], pred && tg.code < 0);
+        for (int t = 0; t < NTE; ++t) ld_row<L>(ent_state[t] + (uint32_t)tg.id * (uint32_t)d, d, lane, tg.st[t], pred && tg.code < 0);
     }
     __device__ __forceinline__ void add_ent(int tbl, const K2Tgt<L, NTE>& tgc, const float (&g)[L::NF], int lane, bool pred) const {
         if (!pred) return;
         K2Tgt<L, NTE>& tg = const_cast<K2Tgt<L, NTE>&>(tgc);
         if (tg.code < 0) {
-            apply_update<L>(ent[tbl] + (size_t)tg.id * d, ent_state[tbl] ? ent_state[tbl] + (size_t)tg.id * d : nullptr, tg.st[tbl], g, d,
+            apply_update<L>(ent[tbl] + (uint32_t)tg.id * (uint32_t)d, ent_state[tbl] ? ent_state[tbl] + (uint32_t)tg.id * (uint32_t)d : nullptr, tg.st[tbl], g, d,
                             lane, opt, lr);
         } else {
-            float* p = scratch + ((size_t)tg.code * NTE + tbl) * d;
+            float* p = scratch + (uint32_t)((tg.code * NTE + tbl) * d);
 #pragma unroll
             for (int i = 0; i < L::NF; ++i) {
                 const int e = elem_of<L>(lane, i);
-                if (e < d && g[i] != 0.f) atomicAdd(p + e, g[i]);
+                if (in_row<L>(e, d) && g[i] != 0.f) atomicAdd(p + e, g[i]);
             }
         }
     }
@@ -278,7 +284,7 @@ __device__ __forceinline__ void fix_add_row(int32_t* row, int d, int lane, const
 #pragma unroll
     for (int i = 0; i < L::NF; ++i) {
         const int e = elem_of<L>(lane, i);
-        if (e < d && g[i] != 0.f) {
+        if (in_row<L>(e, d) && g[i] != 0.f) {
             const long long v = __float2ll_rn(fminf(fmaxf(g[i], -kFixClamp), kFixClamp) * kFixScale);
             atomicAdd(row + e, (int32_t)(v & 0xfffff));
             atomicAdd(row + d + e, (int32_t)((v >> 20) & 0xfffff));
@@ -294,7 +300,7 @@ __device__ __forceinline__ bool fix_take_row(int32_t* row, int d, int lane, floa
     for (int i = 0; i < L::NF; ++i) {
         const int e = elem_of<L>(lane, i);
         long long v = 0;
-        if (e < d) {
+        if (in_row<L>(e, d)) {
             const int32_t a0 = row[e], a1 = row[d + e], a2 = row[2 * d + e];
             if ((a0 | a1 | a2) != 0) { row[e] = 0; row[d + e] = 0; row[2 * d + e] = 0; }
             v = ((long long)a2 << 40) + ((long long)a1 << 20) + (long long)a0;
@@ -305,16 +311,20 @@ __device__ __forceinline__ bool fix_take_row(int32_t* row, int d, int lane, floa
     return nz;
 }
 
-template <int MODEL, class L, int NT, int STAGE>
+// FAST = the configuration every PuTrans* experiment script uses (k = 1, L1 energy, normalised operands,
+// Adagrad): those launch parameters become compile-time constants.  With an exact layout (L::EX) the
+// row length is a constant too.
+template <int MODEL, class L, int NT, int STAGE, int FAST>
 __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__ K2Params P) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int ntE = MODEL == TRANSD ? 2 : 1, ntR = MODEL == TRANSE ? 1 : 2;
     const pk_universe_desc& U = P.desc[blockIdx.x];
-    const K2Smem S(MODEL, P.d, P.k, P.W, P.mE, P.mR, P.mB, STAGE);
+    const K2Smem S(MODEL, L::EX ? L::D : P.d, FAST ? 1 : P.k, P.W, P.mE, P.mR, P.mB, STAGE);
     const int tid = threadIdx.x;
     long long t_begin = 0;
     if (P.timer && tid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_begin));
-    const int d = P.d, k = P.k, B = U.batch_size, nE = U.n_ent, nR = U.n_rel, W = P.W;
+    const int d = L::EX ? L::D : P.d, k = FAST ? 1 : P.k, B = U.batch_size, nE = U.n_ent, nR = U.n_rel, W = P.W;
+    const int opt = FAST ? (int)PK_ADAGRAD : P.opt, p_norm = FAST ? 1 : P.p_norm, norm_flag = FAST ? 1 : P.norm_flag;
     const int NC = NT / 32 - P.np;          // consumer warps
     const int n_cons = NC * 32, n_prod = P.np * 32;
     const bool producer = tid >= n_cons;
@@ -327,13 +337,13 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
     float* g_rel_state[2];
     K2Ctx<L, ntE, ntR> cx;
     RelCache rc;
-    cx.d = d; cx.opt = P.opt; cx.lr = U.lr; cx.B = B;
+    cx.d = d; cx.opt = opt; cx.lr = U.lr; cx.B = B;
     rc.mR = P.mR;
     for (int i = 0; i < 2; ++i) {
         g_ent[i] = (i < ntE) ? P.ent[i] + (size_t)U.ent_off * d : nullptr;
         g_rel[i] = (i < ntR) ? P.rel[i] + (size_t)U.rel_off * d : nullptr;
-        g_rel_state[i] = (i < ntR && P.opt == PK_ADAGRAD) ? P.rel_state[i] + (size_t)U.rel_off * d : nullptr;
-        cx.ent_state[i] = (i < ntE && P.opt == PK_ADAGRAD) ? P.ent_state[i] + (size_t)U.ent_off * d : nullptr;
+        g_rel_state[i] = (i < ntR && opt == PK_ADAGRAD) ? P.rel_state[i] + (size_t)U.rel_off * d : nullptr;
+        cx.ent_state[i] = (i < ntE && opt == PK_ADAGRAD) ? P.ent_state[i] + (size_t)U.ent_off * d : nullptr;
         cx.ent[i] = STAGE ? reinterpret_cast<float*>(smem + S.ent[i]) : g_ent[i];
         rc.rel[i] = reinterpret_cast<float*>(smem + S.rel[i]);
         rc.state[i] = reinterpret_cast<float*>(smem + S.rel_state[i]);
@@ -359,16 +369,16 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
     // groups of one warp work on different relations)
     auto recache = [&](int r) {
         float x[L::NF];
-        ld_row<L>(rc.rel[0] + (size_t)r * d, d, lane, x);
+        ld_row<L>(rc.rel[0] + (uint32_t)r * (uint32_t)d, d, lane, x);
         float n = 1.f;
         bool fr = false;
-        if (P.norm_flag) n = normalize_row<L>(x, fr, gmask);
-        st_row<L>(rc.c[0] + (size_t)r * d, d, lane, x);
+        if (norm_flag) n = normalize_row<L>(x, fr, gmask);
+        st_row<L>(rc.c[0] + (uint32_t)r * (uint32_t)d, d, lane, x);
         if (lane == 0) rc.n[r] = n;
         if constexpr (MODEL == TRANSH) {
-            ld_row<L>(rc.rel[1] + (size_t)r * d, d, lane, x);
+            ld_row<L>(rc.rel[1] + (uint32_t)r * (uint32_t)d, d, lane, x);
             n = normalize_row<L>(x, fr, gmask);
-            st_row<L>(rc.c[1] + (size_t)r * d, d, lane, x);
+            st_row<L>(rc.c[1] + (uint32_t)r * (uint32_t)d, d, lane, x);
             if (lane == 0) rc.n[rc.mR + r] = n;
         }
     };
@@ -474,19 +484,32 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
         if (ptid < W) s0[ptid] = Aadv[ptid] * s0[ptid] + Cadv[ptid];
     };
 
+    // deterministic loss reduction by the first producer warp: mean + margin (MarginLoss.py:28)
+    auto reduce_loss = [&](long long st) {
+        const int ptid = tid - n_cons;
+        if (ptid < 32 && U.loss_off >= 0) {
+            const float* lv = lossv + (int)(st & 1) * P.mB;
+            float acc = 0.f;
+            for (int b = ptid; b < B; b += 32) acc += lv[b];
+            acc = gsum<32>(acc);
+            if (ptid == 0) P.loss[U.loss_off + st] = acc / (float)((long long)B * k) + U.margin;
+        }
+    };
     if (producer && steps > 0) produce(0);
     __syncthreads();   // also orders the initial recache() before the first step
 
     // ------------------------------------------------------------------------------------ consumers
     const int NG = NC * GPW;
     Hyper hp;
-    hp.d = d; hp.k = k; hp.p_norm = P.p_norm; hp.norm_flag = P.norm_flag;
+    hp.d = d; hp.k = k; hp.p_norm = p_norm; hp.norm_flag = norm_flag;
     hp.margin = U.margin;
     hp.inv_bk = 1.f / (float)((long long)B * k);
 
     for (long long step = 0; step < steps; ++step) {
         const int buf = (int)(step & 1);
         if (producer) {
+            // the loss of the step that just finished is reduced here, off the consumers' critical path
+            if (step > 0) reduce_loss(step - 1);
             if (step + 1 < steps) produce(buf ^ 1);
         } else {
             const BatchView bv(smem + S.batch[0] + (size_t)buf * batch_stride, B, k, S.slots, S.nrelcap);
@@ -497,7 +520,7 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
                 const int b = base + grp;
                 const bool act = b < B;
                 const float l = train_sample<MODEL, L>(cx, hp, lane, b, act);
-                if (act && lane == 0) lossv[b] = l;
+                if (act && lane == 0) lossv[buf * P.mB + b] = l;
             }
             named_barrier(1, n_cons);
             // ---- phase B: one item per distinct relation (take the fixed-point gradient sums, normalisation
@@ -506,28 +529,28 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
             for (int it = grp; it < nrel + nd; it += NG) {
                 if (it < nrel) {
                     const int r = bv.rel_ids[it];
-                    int32_t* pr = rc.acc + (size_t)r * ntR * 3 * d;
+                    int32_t* pr = rc.acc + (uint32_t)(r * ntR * 3 * d);
                     float g0[L::NF], g1[ntR == 2 ? L::NF : 1];
                     bool nz = fix_take_row<L>(pr, d, lane, g0);
                     if constexpr (ntR == 2) nz |= fix_take_row<L>(pr + 3 * d, d, lane, g1);
                     // an all-zero sum updates nothing (SGD and Adagrad leave zero-gradient rows unchanged)
                     if (__ballot_sync(gmask, nz) != 0u) {
                         float y[L::NF], st[L::NF];
-                        if (P.norm_flag) {
-                            ld_row<L>(rc.c[0] + (size_t)r * d, d, lane, y);
+                        if (norm_flag) {
+                            ld_row<L>(rc.c[0] + (uint32_t)r * (uint32_t)d, d, lane, y);
                             const float n = rc.n[r];
                             normalize_bwd<L>(y, n, n > kNormEps, g0, gmask);
                         }
-                        ld_row<L>(rc.state[0] + (size_t)r * d, d, lane, st);
-                        apply_update<L>(rc.rel[0] + (size_t)r * d, rc.state[0] + (size_t)r * d, st, g0, d, lane, P.opt, U.lr);
+                        ld_row<L>(rc.state[0] + (uint32_t)r * (uint32_t)d, d, lane, st);
+                        apply_update<L>(rc.rel[0] + (uint32_t)r * (uint32_t)d, rc.state[0] + (uint32_t)r * (uint32_t)d, st, g0, d, lane, opt, U.lr);
                         if constexpr (MODEL == TRANSH) {
-                            ld_row<L>(rc.c[1] + (size_t)r * d, d, lane, y);
+                            ld_row<L>(rc.c[1] + (uint32_t)r * (uint32_t)d, d, lane, y);
                             const float n = rc.n[rc.mR + r];
                             normalize_bwd<L>(y, n, n > kNormEps, g1, gmask);
                         }
                         if constexpr (ntR == 2) {
-                            ld_row<L>(rc.state[1] + (size_t)r * d, d, lane, st);
-                            apply_update<L>(rc.rel[1] + (size_t)r * d, rc.state[1] + (size_t)r * d, st, g1, d, lane, P.opt, U.lr);
+                            ld_row<L>(rc.state[1] + (uint32_t)r * (uint32_t)d, d, lane, st);
+                            apply_update<L>(rc.rel[1] + (uint32_t)r * (uint32_t)d, rc.state[1] + (uint32_t)r * (uint32_t)d, st, g1, d, lane, opt, U.lr);
                         }
                         recache(r);
                     }
@@ -536,28 +559,24 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
                     const int id = bv.dup[s];
 #pragma unroll
                     for (int t = 0; t < ntE; ++t) {
-                        float* grow = cx.scratch + ((size_t)s * ntE + t) * d;
+                        float* grow = cx.scratch + (uint32_t)((s * ntE + t) * d);
                         float g[L::NF], st[L::NF];
                         ld_row<L>(grow, d, lane, g);
-                        float* xrow = cx.ent[t] + (size_t)id * d;
-                        float* srow = P.opt == PK_ADAGRAD ? cx.ent_state[t] + (size_t)id * d : nullptr;
-                        ld_row<L>(srow, d, lane, st, P.opt == PK_ADAGRAD);
-                        apply_update<L>(xrow, srow, st, g, d, lane, P.opt, U.lr);
+                        float* xrow = cx.ent[t] + (uint32_t)id * (uint32_t)d;
+                        float* srow = opt == PK_ADAGRAD ? cx.ent_state[t] + (uint32_t)id * (uint32_t)d : nullptr;
+                        ld_row<L>(srow, d, lane, st, opt == PK_ADAGRAD);
+                        apply_update<L>(xrow, srow, st, g, d, lane, opt, U.lr);
 #pragma unroll
                         for (int i = 0; i < L::NF; ++i) g[i] = 0.f;
                         st_row<L>(grow, d, lane, g);
                     }
                 }
             }
-            if (tid < 32 && U.loss_off >= 0) {  // deterministic loss reduction: mean + margin (MarginLoss.py:28)
-                float acc = 0.f;
-                for (int b = tid; b < B; b += 32) acc += lossv[b];
-                acc = gsum<32>(acc);
-                if (tid == 0) P.loss[U.loss_off + step] = acc / (float)((long long)B * k) + U.margin;
-            }
         }
         __syncthreads();
     }
+
+    if (producer && steps > 0) reduce_loss(steps - 1);
 
     // ---- write staged tables back
     {
@@ -588,18 +607,20 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
 #endif  // PK_MODEL_TU
 
 // ---- dispatch over (model, layout)
-struct LaySel { int V, G, CPL; };
+struct LaySel { int V, G, CPL, NQ; };
 
 inline LaySel pick_layout(int model, int d) {
     // PK_K2_LAYOUT=V,G,CPL forces one of the instantiated layouts (experiments)
     if (const char* e = getenv("PK_K2_LAYOUT")) {
-        LaySel f{0, 0, 0};
-        if (sscanf(e, "%d,%d,%d", &f.V, &f.G, &f.CPL) == 3 && f.V * f.G * f.CPL >= d) return f;
+        LaySel f{0, 0, 0, 0};
+        if (sscanf(e, "%d,%d,%d,%d", &f.V, &f.G, &f.CPL, &f.NQ) >= 3 && f.G * (4 * f.NQ + f.V * f.CPL) >= d &&
+            (f.G != 4 || f.G * (4 * f.NQ + f.V * f.CPL) == d))
+            return f;
     }
     // Short rows (the PuTrans* scripts all use d = 20): four lanes per row with scalar chunks keep every
     // lane busy (d = 20: 4 lanes x 5 floats, against 5 of 8 lanes with 128-bit chunks) and put EIGHT
     // samples in a warp, so a batch of up to 104 positives is one pass of the 13 consumer warps.
-    if (d <= 20 && d % 4 == 0 && d / 4 <= 5) return LaySel{1, 4, d / 4};
+    if (d <= 20 && d % 4 == 0) return LaySel{1, 4, d / 4, 0};
     const int V = d % 4 == 0 ? 4 : (d % 2 == 0 ? 2 : 1);
     const int chunks = d / V;
     const int nf_cap = model == TRANSD ? 4 : 8;  // registers per row per lane
@@ -607,24 +628,24 @@ inline LaySel pick_layout(int model, int d) {
         int cpl = (chunks + G - 1) / G;
         int c2 = 1;
         while (c2 < cpl) c2 *= 2;
-        if (c2 * V <= nf_cap || G == 32) return LaySel{V, G, std::max(c2, 1)};
+        if (c2 * V <= nf_cap || G == 32) return LaySel{V, G, std::max(c2, 1), 0};
     }
-    return LaySel{V, 32, 1};
+    return LaySel{V, 32, 1, 0};
 }
 
 // threads per block: as many consumer warps as the register budget allows
 constexpr int k2_threads(int model, int nf) { return nf > 5 ? 256 : (model == 2 ? 384 : 512); }
 
 #ifdef PK_MODEL_TU
-template <int MODEL, int V, int G, int CPL>
+template <int MODEL, class L, int FAST>
 int launch_k2(const K2Params& P, int stage, int n, size_t smem, cudaStream_t st) {
-    constexpr int NT = k2_threads(MODEL, V * CPL);
+    constexpr int NT = k2_threads(MODEL, L::NF);
     if (stage) {
-        auto kern = k2_train_universes<MODEL, Lay<V, G, CPL>, NT, 1>;
+        auto kern = k2_train_universes<MODEL, L, NT, 1, FAST>;
         PK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<n, NT, smem, st>>>(P);
     } else {
-        auto kern = k2_train_universes<MODEL, Lay<V, G, CPL>, NT, 0>;
+        auto kern = k2_train_universes<MODEL, L, NT, 0, FAST>;
         PK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<n, NT, smem, st>>>(P);
     }
@@ -634,8 +655,15 @@ int launch_k2(const K2Params& P, int stage, int n, size_t smem, cudaStream_t st)
 
 template <int MODEL>
 int dispatch_layout(const LaySel& l, const K2Params& P, int stage, int n, size_t smem, cudaStream_t st) {
-#define PK_CASE(v, g, c) if (l.V == v && l.G == g && l.CPL == c) return launch_k2<MODEL, v, g, c>(P, stage, n, smem, st);
-    PK_CASE(1, 4, 1) PK_CASE(1, 4, 2) PK_CASE(1, 4, 3) PK_CASE(1, 4, 4) PK_CASE(1, 4, 5)
+    // four-lane layouts are only ever picked when they fit the row exactly (pick_layout)
+    const bool fast = P.k == 1 && P.p_norm == 1 && P.norm_flag == 1 && P.opt == PK_ADAGRAD;
+#define PK_CASE4(c, q)                                                                          \
+    if (l.V == 1 && l.G == 4 && l.CPL == c && l.NQ == q && P.d == 4 * (4 * q + c))              \
+        return fast ? launch_k2<MODEL, Lay<1, 4, c, 1, q>, 1>(P, stage, n, smem, st)            \
+                    : launch_k2<MODEL, Lay<1, 4, c, 1, q>, 0>(P, stage, n, smem, st);
+    PK_CASE4(1, 0) PK_CASE4(2, 0) PK_CASE4(3, 0) PK_CASE4(4, 0) PK_CASE4(5, 0) PK_CASE4(1, 1)
+#undef PK_CASE4
+#define PK_CASE(v, g, c) if (l.V == v && l.G == g && l.CPL == c && l.NQ == 0) return launch_k2<MODEL, Lay<v, g, c>, 0>(P, stage, n, smem, st);
     PK_CASE(4, 8, 1) PK_CASE(4, 8, 2) PK_CASE(4, 32, 1) PK_CASE(4, 32, 2)
     PK_CASE(2, 8, 1) PK_CASE(2, 8, 2) PK_CASE(2, 8, 4) PK_CASE(2, 32, 1) PK_CASE(2, 32, 2) PK_CASE(2, 32, 4)
     PK_CASE(1, 8, 1) PK_CASE(1, 8, 2) PK_CASE(1, 8, 4) PK_CASE(1, 8, 8) PK_CASE(1, 32, 1) PK_CASE(1, 32, 2) PK_CASE(1, 32, 4) PK_CASE(1, 32, 8)
@@ -782,7 +810,7 @@ extern "C" int pk_train_universes(const pk_model_cfg* cfg, const pk_tables* pack
     }
 
     const LaySel lay = pick_layout(cfg->model, d);
-    const int threads = k2_threads(cfg->model, lay.V * lay.CPL);
+    const int threads = k2_threads(cfg->model, lay.V * lay.CPL + 4 * lay.NQ);
     int np = threads >= 512 ? 3 : 2;
     if (const char* e = getenv("PK_K2_PRODUCERS")) np = std::max(1, std::min(threads / 32 - 1, atoi(e)));
     const bool both = !cls[0].empty() && !cls[1].empty();
