@@ -57,6 +57,9 @@ struct K2Params {
     int np;                 // producer warps
     long long* timer;       // optional (pk_debug_universe_timer): per block (loss_off, ns spent)
     int timer_base;
+    int dbg;                // PK_K2_DBG: timing experiments only (results are wrong when set)
+    float* scratch;         // global (L2-resident) gradient sums of multiply-occurring entity rows: [blocks][slots][ntE][d]
+    size_t scratch_stride;  // floats per block
 };
 
 __host__ __device__ inline size_t up16(size_t x) { return (x + 15) & ~(size_t)15; }
@@ -82,10 +85,10 @@ struct K2Smem {
         for (int i = 0; i < 2; ++i) { relc[i] = o; if (i < nrc) o = up16(o + (size_t)mR * d * 4); }
         reln = o;    o = up16(o + (size_t)2 * mR * 4);
         relacc = o;  o = up16(o + (size_t)mR * ntR * d * 12);  // fixed-point relation gradient sums, three int32 limbs
-        scratch = o; o = up16(o + (size_t)slots * ntE * d * 4);
+        scratch = o;   // (the entity scratch rows live in global memory, see K2Params::scratch)
         map = o;     o = up16(o + ((size_t)mE + mR) * 4);
-        // one batch buffer: h | t | r | c[k] | code_h | code_t | code_c[k] | dup[slots] | rel_ids | ndup | nrel
-        batch_ints = (int)((3 + k) * (long long)mB + occ) + slots + nrelcap + 4;
+        // one batch buffer: h | t | r | c[k] | code_h | code_t | code_c[k] | dup[slots] | dupslot[slots] | rel_ids | ndup | nrel
+        batch_ints = (int)((3 + k) * (long long)mB + occ) + 2 * slots + nrelcap + 4;
         for (int i = 0; i < 2; ++i) { batch[i] = o; o = up16(o + (size_t)batch_ints * 4); }
         lossv = o;   o = up16(o + (size_t)2 * mB * 4);   // per-sample loss terms, double-buffered
         // s0[8] | Aadv[8] | Cadv[8] | A[per] | C[per]
@@ -138,10 +141,11 @@ struct BatchView {
     int32_t* t;
     int32_t* r;
     int32_t* c;            // [k][B]  corrupted entity | (side << 31); side 0: tail replaced, 1: head replaced
-    int32_t* code_h;       // -1: the entity row occurs once in this batch (update in place); else scratch slot
+    int32_t* code_h;       // -1: the entity row occurs once in this batch (update in place); else its scratch row
     int32_t* code_t;
     int32_t* code_c;
-    int32_t* dup;          // entity id of every scratch slot
+    int32_t* dup;          // multiply-occurring entity rows of the batch ...
+    int32_t* dupslot;      // ... and the scratch row each accumulates in (the owner's occurrence index)
     int32_t* rel_ids;      // distinct relations of the batch
     int32_t* ndup;
     int32_t* nrel;
@@ -155,6 +159,7 @@ struct BatchView {
         code_t = p; p += B;
         code_c = p; p += (size_t)B * k;
         dup = p; p += slots;
+        dupslot = p; p += slots;
         rel_ids = p; p += nrelcap;
         ndup = p;
         nrel = p + 1;
@@ -168,11 +173,21 @@ struct K2Tgt {
     float st[NTE][L::NF];
 };
 
+// a row read straight from L2 (scalar accesses: only the short scratch rows are read this way)
+template <class L>
+__device__ __forceinline__ void ld_row_cg(const float* p, int d, int lane, float (&x)[L::NF]) {
+#pragma unroll
+    for (int i = 0; i < L::NF; ++i) {
+        const int e = elem_of<L>(lane, i);
+        x[i] = in_row<L>(e, d) ? __ldcg(p + e) : 0.f;
+    }
+}
+
 // x <- optimizer(x, g): SGD  x -= lr g ;  Adagrad  s += g^2, x -= lr g / (sqrt(s) + 1e-10)
 // (torch.optim.SGD / Adagrad as configured by reference Trainer.py:65-70,84-88; lr_decay = weight_decay = 0)
 template <class L>
 __device__ __forceinline__ void apply_update(float* x_row, float* s_row, float (&s)[L::NF], const float (&g)[L::NF], int d, int lane,
-                                             int opt, float lr) {
+                                             int opt, float lr, bool store_state = true) {
     float x[L::NF];
     ld_row<L>(x_row, d, lane, x);
     if (opt == PK_ADAGRAD) {
@@ -187,7 +202,7 @@ __device__ __forceinline__ void apply_update(float* x_row, float* s_row, float (
             asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(fmaf(s[i], r, 1e-10f)));
             x[i] = fmaf(-lr * g[i], inv, x[i]);
         }
-        st_row<L>(s_row, d, lane, s);
+        if (store_state) st_row<L>(s_row, d, lane, s);
     } else {
 #pragma unroll
         for (int i = 0; i < L::NF; ++i) x[i] = fmaf(-lr, g[i], x[i]);
@@ -218,20 +233,24 @@ struct K2Ctx {
     int B;
     int d, opt;
     float lr;
+    int dbg;
     __device__ __forceinline__ void load_pos(int64_t b, bool act, Tgt& th, Tgt& tt, int32_t& r) const {
         th.id = act ? bh[b] : 0; th.code = act ? code_h[b] : 0;
         tt.id = act ? bt[b] : 0; tt.code = act ? code_t[b] : 0;
+        if (dbg & 2) { th.code = -1; tt.code = -1; }
         r = act ? br[b] : 0;
     }
     __device__ __forceinline__ bool load_neg(int j, int64_t b, bool act, Tgt& tc) const {
         const int32_t cj = act ? bc[(uint32_t)(j * B) + (uint32_t)b] : 0;
         tc.id = cj & 0x7fffffff;
         tc.code = act ? code_c[(uint32_t)(j * B) + (uint32_t)b] : 0;
+        if (dbg & 2) tc.code = -1;
         return cj < 0;
     }
     __device__ __forceinline__ const float* rel_y(int r) const { return rel_c[0] + (uint32_t)r * (uint32_t)d; }
     __device__ __forceinline__ const float* rel_w(int r) const { return rel_c[1] + (uint32_t)r * (uint32_t)d; }
     __device__ __forceinline__ void rel_add(int tbl, int r, const float (&g)[L::NF], int lane) const {
+        if (dbg & 4) return;
         fix_add_row<L>(rel_acc + (uint32_t)((r * NTR + tbl) * 3 * d), d, lane, g);
     }
     __device__ __forceinline__ const float* ent_row(int tbl, const Tgt& tg) const { return ent[tbl] + (uint32_t)tg.id * (uint32_t)d; }
@@ -239,15 +258,17 @@ struct K2Ctx {
     __device__ __forceinline__ void prefetch(K2Tgt<L, NTE>& tg, int lane, bool pred) const {
         if (opt != PK_ADAGRAD) return;
 #pragma unroll
-        for (int t = 0; t < NTE; ++t) ld_row<L>(ent_state[t] + (uint32_t)tg.id * (uint32_t)d, d, lane, tg.st[t], pred && tg.code < 0);
+        for (int t = 0; t < NTE; ++t) ld_row<L>(ent_state[t] + (uint32_t)tg.id * (uint32_t)d, d, lane, tg.st[t], pred && tg.code < 0 && !(dbg & 8));
     }
     __device__ __forceinline__ void add_ent(int tbl, const K2Tgt<L, NTE>& tgc, const float (&g)[L::NF], int lane, bool pred) const {
         if (!pred) return;
         K2Tgt<L, NTE>& tg = const_cast<K2Tgt<L, NTE>&>(tgc);
         if (tg.code < 0) {
             apply_update<L>(ent[tbl] + (uint32_t)tg.id * (uint32_t)d, ent_state[tbl] ? ent_state[tbl] + (uint32_t)tg.id * (uint32_t)d : nullptr, tg.st[tbl], g, d,
-                            lane, opt, lr);
+                            lane, opt, lr, !(dbg & 8));
         } else {
+            // fire-and-forget RED.ADD.F32 at L2 (a shared-memory float add is a compare-and-swap loop whose
+            // round trips, five per row, sat on the critical path of every sample)
             float* p = scratch + (uint32_t)((tg.code * NTE + tbl) * d);
 #pragma unroll
             for (int i = 0; i < L::NF; ++i) {
@@ -337,7 +358,7 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
     float* g_rel_state[2];
     K2Ctx<L, ntE, ntR> cx;
     RelCache rc;
-    cx.d = d; cx.opt = opt; cx.lr = U.lr; cx.B = B;
+    cx.d = d; cx.opt = opt; cx.lr = U.lr; cx.B = B; cx.dbg = P.dbg;
     rc.mR = P.mR;
     for (int i = 0; i < 2; ++i) {
         g_ent[i] = (i < ntE) ? P.ent[i] + (size_t)U.ent_off * d : nullptr;
@@ -354,8 +375,8 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
     cx.rel_acc = rc.acc;
     cx.rel_c[0] = rc.c[0];
     cx.rel_c[1] = MODEL == TRANSD ? rc.rel[1] : rc.c[1];
-    cx.scratch = reinterpret_cast<float*>(smem + S.scratch);
-    int32_t* map = reinterpret_cast<int32_t*>(smem + S.map);   // per table row: count (low 16) | slot << 16
+    cx.scratch = P.scratch + (size_t)blockIdx.x * P.scratch_stride;
+    int32_t* map = reinterpret_cast<int32_t*>(smem + S.map);   // per table row: owner occurrence | (occurs again) << 31
     float* lossv = reinterpret_cast<float*>(smem + S.lossv);
     uint64_t* s0 = reinterpret_cast<uint64_t*>(smem + S.lcg);  // stream states at the start of the next batch
     uint64_t* Aadv = s0 + 8;
@@ -400,9 +421,8 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
                 rc.rel[t][i] = g_rel[t][i];
                 rc.state[t][i] = g_rel_state[t] ? g_rel_state[t][i] : 0.f;
             }
-        for (int i = tid; i < S.slots * ntE * d; i += NT) cx.scratch[i] = 0.f;
+        for (int i = tid; i < (2 + k) * P.mB * ntE * d; i += NT) __stcg(cx.scratch + i, 0.f);
         for (int i = tid; i < nR * ntR * 3 * d; i += NT) rc.acc[i] = 0;
-        for (int i = tid; i < nE + nR; i += NT) map[i] = 0;
         if (tid < 8) s0[tid] = U.lcg[tid];
         if (tid < W) {
             int64_t lef, rig;
@@ -423,63 +443,112 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
     const int32_t* by_tail = P.by_tail ? P.by_tail + (size_t)U.tri_off * 3 : nullptr;
     const FastMod fm_tri = make_fastmod((uint64_t)U.n_tri), fm_coin = make_fastmod(1000ULL),
                   fm_ent = make_fastmod((uint64_t)(nE - 1));
-    auto count_ent = [&](int32_t e, const BatchView& bv) {
-        const int32_t old = atomicAdd(&map[e], 1);
-        if ((old & 0xffff) == 1) {   // second occurrence: the row needs a scratch slot
-            const int32_t s = atomicAdd(bv.ndup, 1);
-            bv.dup[s] = e;
-            atomicAdd(&map[e], s << 16);
-        }
-    };
-    auto code_of = [&](int32_t e) -> int32_t {
-        const int32_t m = map[e];
-        return (m & 0xffff) > 1 ? (m >> 16) : -1;
+    // Occurrence analysis without read-modify-write chains (the producers' dependent shared-memory
+    // round trips are what bounds a step once the consumers are busy).  Every table-row occurrence of a
+    // batch has an index occ = role * B + b (role 0: head, 1: tail, 2 + j: negative j).
+    //   pass 1  each occurrence stores occ into its row's word of `map` (plain stores: whichever lands
+    //           last is the row's OWNER); relations likewise (owner = a sample index);
+    //   pass 2  an occurrence that is not the owner sets the word's top bit (all of them write the same value);
+    //   pass 3  top bit set: the row occurs several times and accumulates in scratch row `owner`; else -1.
+    //           Owners of such rows and owners of relations append themselves to the step's work lists.
+    // Pass 1 of the next batch overwrites every word before it is read again: nothing to clear.
+    // The positives of the batch AFTER the one being produced are requested one call early, so the
+    // triple-index loads (L2) are off the chain as well.
+    struct PDraw { uint64_t s; int32_t h, r, t; };
+    PDraw nxt[2];
+    bool have_nxt = false;
+    auto draw_pos = [&](int b, bool following, PDraw& o) {
+        const int id = b / per, j = b - id * per;
+        uint64_t st = s0[id];
+        if (following) st = Aadv[id] * st + Cadv[id];
+        uint64_t sx = Aj[j] * st + Cj[j];
+        const int64_t i = (int64_t)fastmod(lcg_next(sx), fm_tri);
+        o.s = sx;
+        o.h = by_head[i * 3 + 0]; o.r = by_head[i * 3 + 1]; o.t = by_head[i * 3 + 2];
     };
     auto produce = [&](int buf) {
         const int ptid = tid - n_cons;
         BatchView bv(smem + S.batch[0] + (size_t)buf * batch_stride, B, k, S.slots, S.nrelcap);
         if (ptid == 0) { *bv.ndup = 0; *bv.nrel = 0; }
-        named_barrier(2, n_prod);
-        for (int b = ptid; b < B; b += n_prod) {
-            const int id = b / per, j = b - id * per;
-            uint64_t s = Aj[j] * s0[id] + Cj[j];
-            const int64_t i = (int64_t)fastmod(lcg_next(s), fm_tri);
-            const int32_t h = by_head[i * 3 + 0], r = by_head[i * 3 + 1], t = by_head[i * 3 + 2];
-            bv.h[b] = h; bv.t[b] = t; bv.r[b] = r;
-            count_ent(h, bv); count_ent(t, bv);
-            if (atomicAdd(&map[nE + r], 1) == 0) bv.rel_ids[atomicAdd(bv.nrel, 1)] = r;   // distinct relations of the batch
-            float prob = 500.f;
-            if (P.bern) {
-                const float rm = P.right_mean[U.rel_off + r], lm = P.left_mean[U.rel_off + r];
-                prob = __fdiv_rn(__fmul_rn(1000.f, rm), __fadd_rn(rm, lm));  // Base.cpp:220-221
+        // ---- pass 1: the reference sampling() call (Base.cpp:185-310, Corrupt.h:9-105), bit-exact
+        for (int base = 0; base < B; base += 2 * n_prod) {
+            PDraw cur[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int b = base + q * n_prod + ptid;
+                if (base == 0 && have_nxt) cur[q] = nxt[q];
+                else if (b < B) draw_pos(b, false, cur[q]);
             }
-            for (int n = 0; n < k; ++n) {
-                const uint64_t coin = fastmod(lcg_next(s), fm_coin);
-                const uint64_t x = lcg_next(s);
-                int32_t c, side;
-                if ((float)coin < prob) {   // keep head, replace tail (corrupt_head, Corrupt.h:9-57)
-                    if (!P.filter) { const int64_t tmp = (int64_t)fastmod(x, fm_ent); c = (int32_t)(tmp < h ? tmp : tmp + 1); }
-                    else c = corrupt_entity(x, by_head, U.n_tri, nE, h, r, 0, 2, true);
-                    side = 0;
-                } else {                    // keep tail, replace head (corrupt_tail, Corrupt.h:59-105)
-                    if (!P.filter) { const int64_t tmp = (int64_t)fastmod(x, fm_ent); c = (int32_t)(tmp < t ? tmp : tmp + 1); }
-                    else c = corrupt_entity(x, by_tail, U.n_tri, nE, t, r, 2, 0, true);
-                    side = 1;
+            if (base == 0) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int b = q * n_prod + ptid;
+                    if (b < B) draw_pos(b, true, nxt[q]);
                 }
-                bv.c[(size_t)n * B + b] = (int32_t)((uint32_t)c | ((uint32_t)side << 31));
-                count_ent(c, bv);
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int b = base + q * n_prod + ptid;
+                if (b >= B) continue;
+                uint64_t sx = cur[q].s;
+                const int32_t h = cur[q].h, r = cur[q].r, t = cur[q].t;
+                bv.h[b] = h; bv.t[b] = t; bv.r[b] = r;
+                map[h] = b; map[t] = B + b; map[nE + r] = b;
+                float prob = 500.f;
+                if (P.bern) {
+                    const float rm = P.right_mean[U.rel_off + r], lm = P.left_mean[U.rel_off + r];
+                    prob = __fdiv_rn(__fmul_rn(1000.f, rm), __fadd_rn(rm, lm));  // Base.cpp:220-221
+                }
+                for (int n = 0; n < k; ++n) {
+                    const uint64_t coin = fastmod(lcg_next(sx), fm_coin);
+                    const uint64_t x = lcg_next(sx);
+                    int32_t c, side;
+                    if ((float)coin < prob) {   // keep head, replace tail (corrupt_head, Corrupt.h:9-57)
+                        if (!P.filter) { const int64_t tmp = (int64_t)fastmod(x, fm_ent); c = (int32_t)(tmp < h ? tmp : tmp + 1); }
+                        else c = corrupt_entity(x, by_head, U.n_tri, nE, h, r, 0, 2, true);
+                        side = 0;
+                    } else {                    // keep tail, replace head (corrupt_tail, Corrupt.h:59-105)
+                        if (!P.filter) { const int64_t tmp = (int64_t)fastmod(x, fm_ent); c = (int32_t)(tmp < t ? tmp : tmp + 1); }
+                        else c = corrupt_entity(x, by_tail, U.n_tri, nE, t, r, 2, 0, true);
+                        side = 1;
+                    }
+                    bv.c[(uint32_t)(n * B) + (uint32_t)b] = (int32_t)((uint32_t)c | ((uint32_t)side << 31));
+                    map[c] = (2 + n) * B + b;
+                }
             }
         }
+        have_nxt = true;
         named_barrier(2, n_prod);
+        // ---- pass 2: losers flag their row
+        auto flag = [&](int32_t e, int32_t occ) {
+            const int32_t m = map[e];
+            if ((m & 0x7fffffff) != occ) map[e] = m | (int32_t)0x80000000;
+        };
         for (int b = ptid; b < B; b += n_prod) {
-            bv.code_h[b] = code_of(bv.h[b]);
-            bv.code_t[b] = code_of(bv.t[b]);
-            for (int n = 0; n < k; ++n) bv.code_c[(size_t)n * B + b] = code_of(bv.c[(size_t)n * B + b] & 0x7fffffff);
+            flag(bv.h[b], b);
+            flag(bv.t[b], B + b);
+            for (int n = 0; n < k; ++n) flag(bv.c[(uint32_t)(n * B) + (uint32_t)b] & 0x7fffffff, (2 + n) * B + b);
         }
         named_barrier(2, n_prod);
+        // ---- pass 3: codes and work lists
+        auto code_of = [&](int32_t e, int32_t occ) -> int32_t {
+            const int32_t m = map[e];
+            if (m >= 0) return -1;
+            const int32_t own = m & 0x7fffffff;
+            if (own == occ) {
+                const int32_t i = atomicAdd(bv.ndup, 1);
+                bv.dup[i] = e;
+                bv.dupslot[i] = own;
+            }
+            return own;
+        };
         for (int b = ptid; b < B; b += n_prod) {
-            map[bv.h[b]] = 0; map[bv.t[b]] = 0; map[nE + bv.r[b]] = 0;
-            for (int n = 0; n < k; ++n) map[bv.c[(size_t)n * B + b] & 0x7fffffff] = 0;
+            bv.code_h[b] = code_of(bv.h[b], b);
+            bv.code_t[b] = code_of(bv.t[b], B + b);
+            for (int n = 0; n < k; ++n)
+                bv.code_c[(uint32_t)(n * B) + (uint32_t)b] = code_of(bv.c[(uint32_t)(n * B) + (uint32_t)b] & 0x7fffffff, (2 + n) * B + b);
+            const int32_t r = bv.r[b];
+            if (map[nE + r] == b) bv.rel_ids[atomicAdd(bv.nrel, 1)] = r;   // distinct relations of the batch
         }
         if (ptid < W) s0[ptid] = Aadv[ptid] * s0[ptid] + Cadv[ptid];
     };
@@ -505,18 +574,25 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
     hp.margin = U.margin;
     hp.inv_bk = 1.f / (float)((long long)B * k);
 
-    for (long long step = 0; step < steps; ++step) {
-        const int buf = (int)(step & 1);
-        if (producer) {
+    // The two roles run SEPARATE step loops (their register allocations stay independent) and meet once
+    // per step at barrier 0 (bar.sync counts arriving threads, whichever instruction they arrive from).
+    if (producer) {
+        for (long long step = 0; step < steps; ++step) {
+            const int buf = (int)(step & 1);
+            if (step + 1 < steps && !((P.dbg & 16) && step > 1)) produce(buf ^ 1);
             // the loss of the step that just finished is reduced here, off the consumers' critical path
             if (step > 0) reduce_loss(step - 1);
-            if (step + 1 < steps) produce(buf ^ 1);
-        } else {
+            named_barrier(0, NT);
+        }
+    } else {
+      for (long long step = 0; step < steps; ++step) {
+        const int buf = (int)(step & 1);
+        {
             const BatchView bv(smem + S.batch[0] + (size_t)buf * batch_stride, B, k, S.slots, S.nrelcap);
             cx.bh = bv.h; cx.bt = bv.t; cx.br = bv.r; cx.bc = bv.c;
             cx.code_h = bv.code_h; cx.code_t = bv.code_t; cx.code_c = bv.code_c;
             // ---- phase A: forward + analytic backward; singly-occurring entity rows updated in place
-            for (int base = 0; base < B; base += NG) {
+            for (int base = 0; base < B && !(P.dbg & 32); base += NG) {
                 const int b = base + grp;
                 const bool act = b < B;
                 const float l = train_sample<MODEL, L>(cx, hp, lane, b, act);
@@ -525,7 +601,7 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
             named_barrier(1, n_cons);
             // ---- phase B: one item per distinct relation (take the fixed-point gradient sums, normalisation
             //      backward, update, refresh the cache) and per multiply-occurring entity row
-            const int nrel = *bv.nrel, nd = *bv.ndup;
+            const int nrel = (P.dbg & 1) ? 0 : *bv.nrel, nd = (P.dbg & 3) ? 0 : *bv.ndup;
             for (int it = grp; it < nrel + nd; it += NG) {
                 if (it < nrel) {
                     const int r = bv.rel_ids[it];
@@ -555,25 +631,28 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
                         recache(r);
                     }
                 } else {
-                    const int s = it - nrel;
-                    const int id = bv.dup[s];
+                    const int id = bv.dup[it - nrel];
+                    const int s = bv.dupslot[it - nrel];
 #pragma unroll
                     for (int t = 0; t < ntE; ++t) {
                         float* grow = cx.scratch + (uint32_t)((s * ntE + t) * d);
                         float g[L::NF], st[L::NF];
-                        ld_row<L>(grow, d, lane, g);
+                        ld_row_cg<L>(grow, d, lane, g);   // summed by L2 reductions: must not come from L1
                         float* xrow = cx.ent[t] + (uint32_t)id * (uint32_t)d;
                         float* srow = opt == PK_ADAGRAD ? cx.ent_state[t] + (uint32_t)id * (uint32_t)d : nullptr;
                         ld_row<L>(srow, d, lane, st, opt == PK_ADAGRAD);
                         apply_update<L>(xrow, srow, st, g, d, lane, opt, U.lr);
 #pragma unroll
-                        for (int i = 0; i < L::NF; ++i) g[i] = 0.f;
-                        st_row<L>(grow, d, lane, g);
+                        for (int i = 0; i < L::NF; ++i) {
+                            const int e = elem_of<L>(lane, i);
+                            if (in_row<L>(e, d) && g[i] != 0.f) __stcg(grow + e, 0.f);
+                        }
                     }
                 }
             }
         }
-        __syncthreads();
+        named_barrier(0, NT);
+      }
     }
 
     if (producer && steps > 0) reduce_loss(steps - 1);
@@ -661,6 +740,11 @@ int dispatch_layout(const LaySel& l, const K2Params& P, int stage, int n, size_t
     if (l.V == 1 && l.G == 4 && l.CPL == c && l.NQ == q && P.d == 4 * (4 * q + c))              \
         return fast ? launch_k2<MODEL, Lay<1, 4, c, 1, q>, 1>(P, stage, n, smem, st)            \
                     : launch_k2<MODEL, Lay<1, 4, c, 1, q>, 0>(P, stage, n, smem, st);
+#ifdef PK_K2_DEV
+    PK_CASE4(5, 0)
+#undef PK_CASE4
+    return pk::fail(PK_ERR_UNSUPPORTED, "PK_K2_DEV build: only d = 20");
+#else
     PK_CASE4(1, 0) PK_CASE4(2, 0) PK_CASE4(3, 0) PK_CASE4(4, 0) PK_CASE4(5, 0) PK_CASE4(1, 1)
 #undef PK_CASE4
 #define PK_CASE(v, g, c) if (l.V == v && l.G == g && l.CPL == c && l.NQ == 0) return launch_k2<MODEL, Lay<v, g, c>, 0>(P, stage, n, smem, st);
@@ -669,6 +753,7 @@ int dispatch_layout(const LaySel& l, const K2Params& P, int stage, int n, size_t
     PK_CASE(1, 8, 1) PK_CASE(1, 8, 2) PK_CASE(1, 8, 4) PK_CASE(1, 8, 8) PK_CASE(1, 32, 1) PK_CASE(1, 32, 2) PK_CASE(1, 32, 4) PK_CASE(1, 32, 8)
 #undef PK_CASE
     return pk::fail(PK_ERR_UNSUPPORTED, "embedding dimension not supported by the universe kernel (d <= 256)");
+#endif
 }
 
 // one translation unit per model keeps the build parallel: -DPK_MODEL_TU=0|1|2
@@ -694,6 +779,7 @@ struct DescSlot {
     bool busy = false;
 };
 thread_local std::vector<DescSlot> g_desc_pool;
+constexpr size_t kDescArea = 256;   // one descriptor (128 B), padded
 
 // The unstaged class (universes whose tables do not fit in shared memory) runs beside the staged one
 // on a side stream: fork from / join into the caller's stream with events.
@@ -839,7 +925,8 @@ extern "C" int pk_train_universes(const pk_model_cfg* cfg, const pk_tables* pack
             }
             for (const auto& u : cls[c]) {
                 K2Smem own(cfg->model, d, k, W, u.n_ent, u.n_rel, u.batch_size, 0);
-                DescSlot* slot1 = acquire_desc(sizeof(pk_universe_desc));
+                const size_t stride1 = (size_t)(2 + k) * u.batch_size * (cfg->model == PK_TRANSD ? 2 : 1) * d;
+                DescSlot* slot1 = acquire_desc(kDescArea + stride1 * sizeof(float));
                 if (!slot1) return pk::cuda_fail(cudaGetLastError(), "pk_train_universes: descriptor buffer");
                 PK_CUDA(cudaMemcpyAsync(slot1->d, &u, sizeof(pk_universe_desc), cudaMemcpyHostToDevice, st));
                 K2Params P1;
@@ -854,7 +941,9 @@ extern "C" int pk_train_universes(const pk_model_cfg* cfg, const pk_tables* pack
                 P1.bern = cfg->bern; P1.filter = cfg->filter; P1.W = W;
                 P1.mE = u.n_ent; P1.mR = u.n_rel; P1.mB = u.batch_size;
                 P1.np = np;
-                P1.timer = nullptr; P1.timer_base = 0;
+                P1.timer = nullptr; P1.timer_base = 0; P1.dbg = 0;
+                P1.scratch = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(slot1->d) + kDescArea);
+                P1.scratch_stride = stride1;
                 int rc1 = cfg->model == PK_TRANSE ? launch_model0(lay, P1, 0, 1, own.total, st)
                           : (cfg->model == PK_TRANSH ? launch_model1(lay, P1, 0, 1, own.total, st) : launch_model2(lay, P1, 0, 1, own.total, st));
                 if (rc1 != PK_OK) return rc1;
@@ -868,7 +957,10 @@ extern "C" int pk_train_universes(const pk_model_cfg* cfg, const pk_tables* pack
             return (long long)a.epochs * a.nbatches * a.batch_size > (long long)b.epochs * b.nbatches * b.batch_size;
         });
         const size_t bytes = cls[c].size() * sizeof(pk_universe_desc);
-        DescSlot* slot = acquire_desc(bytes);
+        // behind the descriptors: every block's scratch rows (zeroed by the block itself)
+        const size_t desc_area = (bytes + 255) & ~(size_t)255;
+        const size_t stride = (size_t)(2 + k) * mB[c] * (cfg->model == PK_TRANSD ? 2 : 1) * d;
+        DescSlot* slot = acquire_desc(desc_area + cls[c].size() * stride * sizeof(float));
         if (!slot) return pk::cuda_fail(cudaGetLastError(), "pk_train_universes: descriptor buffer");
         pk_universe_desc* d_desc = slot->d;
         PK_CUDA(cudaMemcpyAsync(d_desc, cls[c].data(), bytes, cudaMemcpyHostToDevice, st));
@@ -885,6 +977,9 @@ extern "C" int pk_train_universes(const pk_model_cfg* cfg, const pk_tables* pack
         P.mE = mE[c]; P.mR = mR[c]; P.mB = mB[c];
         P.np = np;
         P.timer = g_timer; P.timer_base = c == 1 ? (int)cls[0].size() : 0;
+        P.dbg = getenv("PK_K2_DBG") ? atoi(getenv("PK_K2_DBG")) : 0;
+        P.scratch = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(slot->d) + desc_area);
+        P.scratch_stride = stride;
         // descriptors were copied from pageable host memory owned by this call: the copy has
         // completed (or been staged) when cudaMemcpyAsync returns, so cls[c] may go out of scope
         int rc = PK_OK;
