@@ -66,6 +66,17 @@ def algorithmic_bytes_per_positive(model="transe", d=20, k=1, opt="adagrad"):
     return rows * d * 4 * rw + 12 + 4 * k
 
 
+def k2_traffic(model):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant (staged) K2 launch of THIS workload, from
+    the committed `ncu --set full` capture (profiles/r1_k2_traffic.json, written by tools/ncu_traffic.py);
+    None when no capture of this model's launch is committed."""
+    try:
+        d = json.load(open(os.path.join(REPO, "profiles", "r1_k2_traffic.json")))
+        return float(d["traffic_bytes"]) if model == "transe" else None
+    except Exception:
+        return None
+
+
 def measured_peaks():
     try:
         with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
@@ -83,7 +94,26 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.rows, self._stop_ev = index, [], threading.Event()
 
+    def _nvml_loop(self):
+        """NVML in-process: a sample every 5 ms (an nvidia-smi process takes longer than a whole step)."""
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        bits = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+        while not self._stop_ev.is_set():
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+            self.rows.append([str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx), "0"] +
+                             ["Active" if r & b else "Not Active" for _, b in bits])
+            self._stop_ev.wait(0.005)
+
     def run(self):
+        try:
+            self._nvml_loop()
+            return
+        except Exception:
+            pass
         while not self._stop_ev.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
@@ -275,7 +305,7 @@ def run_ours(args):
         "gpu_launches": launches,
         "kernel_ms_per_step": float(np.mean(kernel_ms)),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_positive": bpp,
+                     "traffic": k2_traffic(MODEL), "peak_source": peak_src, "algorithmic_bytes_per_positive": bpp,
                      "note": "K2 is latency-bound: universe tables are shared-memory/L2 resident, see DESIGN.md"},
         "clocks": clk,
     }

@@ -12,23 +12,29 @@
 // LATENCY of one step on one SM, not bandwidth.  The block is therefore split into two roles that
 // run concurrently (warp specialisation, named barriers):
 //
-//   producer warps   draw batch s+1 with the reference's LCG streams (bit-exact; affine jump tables
-//                    and multiply-high modulo instead of 64-bit division), count how often every
-//                    table row occurs in that batch and give each multiply-occurring row a scratch
-//                    slot.  None of this depends on the embeddings, so it is off the critical path.
+//   producer warps   draw batch s+1 with the reference's LCG streams (bit-exact).  A producer thread owns
+//                    the same samples of every batch, so its stream position lives in registers and
+//                    advances by one affine map per batch (no jump tables, no division, multiply-high
+//                    modulo); the triple-index loads of the batch after next are issued a call early.
+//                    Which table rows occur more than once is found WITHOUT read-modify-write chains:
+//                    every occurrence stores its index into the row's word (last store = the row's
+//                    owner), losers flag the word, a third pass reads the verdict.  None of this
+//                    depends on the embeddings, so it is off the critical path.
 //   consumer warps   step s: one lane group per positive sample gathers h, t, r and the corrupted
 //                    entity (shared memory), forward, margin loss, analytic backward.  A row that
 //                    occurs ONCE in the batch is updated in place by the group that read it, with
 //                    its Adagrad state prefetched from L2 at the start of the sample; a row that
-//                    occurs several times accumulates into its scratch slot and is updated after a
-//                    consumer-only barrier.  Samples whose margin term is switched off skip the
-//                    backward pass (all their gradients are exactly zero).
+//                    occurs several times accumulates into the scratch row of its owner occurrence with
+//                    fire-and-forget L2 reductions (RED.ADD.F32; a shared-memory float add is a
+//                    compare-and-swap loop) and is updated after a consumer-only barrier.  Samples
+//                    whose margin term is switched off skip the backward pass (all their gradients
+//                    are exactly zero).
 //
 // Data layout.  All universes of a launch are packed: entity tables [sum nE, d], relation tables
 // [sum nR, d], sorted triple lists [sum nT, 3]; a descriptor per universe holds the offsets.  A
 // block stages its universe's tables in shared memory when they fit (local ids are dense, so the
-// staged table IS the universe's whole embedding space).  The Adagrad accumulators stay in global
-// memory (L2-resident).
+// staged table IS the universe's whole embedding space).  The Adagrad accumulators of the entity
+// tables and the scratch rows stay in global memory (L2-resident).
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -57,7 +63,6 @@ struct K2Params {
     int np;                 // producer warps
     long long* timer;       // optional (pk_debug_universe_timer): per block (loss_off, ns spent)
     int timer_base;
-    int dbg;                // PK_K2_DBG: timing experiments only (results are wrong when set)
     float* scratch;         // global (L2-resident) gradient sums of multiply-occurring entity rows: [blocks][slots][ntE][d]
     size_t scratch_stride;  // floats per block
 };
@@ -187,7 +192,7 @@ __device__ __forceinline__ void ld_row_cg(const float* p, int d, int lane, float
 // (torch.optim.SGD / Adagrad as configured by reference Trainer.py:65-70,84-88; lr_decay = weight_decay = 0)
 template <class L>
 __device__ __forceinline__ void apply_update(float* x_row, float* s_row, float (&s)[L::NF], const float (&g)[L::NF], int d, int lane,
-                                             int opt, float lr, bool store_state = true) {
+                                             int opt, float lr) {
     float x[L::NF];
     ld_row<L>(x_row, d, lane, x);
     if (opt == PK_ADAGRAD) {
@@ -202,7 +207,7 @@ __device__ __forceinline__ void apply_update(float* x_row, float* s_row, float (
             asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(fmaf(s[i], r, 1e-10f)));
             x[i] = fmaf(-lr * g[i], inv, x[i]);
         }
-        if (store_state) st_row<L>(s_row, d, lane, s);
+        st_row<L>(s_row, d, lane, s);
     } else {
 #pragma unroll
         for (int i = 0; i < L::NF; ++i) x[i] = fmaf(-lr, g[i], x[i]);
@@ -213,8 +218,10 @@ __device__ __forceinline__ void apply_update(float* x_row, float* s_row, float (
 struct RelCache;
 template <class L>
 __device__ __forceinline__ void fix_add_row(int32_t* row, int d, int lane, const float (&g)[L::NF]);
+template <class L>
+__device__ __forceinline__ void fix1_add_row(int32_t* row, int d, int lane, const float (&g)[L::NF]);
 
-template <class L, int NTE_, int NTR_>
+template <class L, int NTE_, int NTR_, int FAST_>
 struct K2Ctx {
     static constexpr int NTE = NTE_, NTR = NTR_;
     using Tgt = K2Tgt<L, NTE_>;
@@ -233,39 +240,36 @@ struct K2Ctx {
     int B;
     int d, opt;
     float lr;
-    int dbg;
     __device__ __forceinline__ void load_pos(int64_t b, bool act, Tgt& th, Tgt& tt, int32_t& r) const {
         th.id = act ? bh[b] : 0; th.code = act ? code_h[b] : 0;
         tt.id = act ? bt[b] : 0; tt.code = act ? code_t[b] : 0;
-        if (dbg & 2) { th.code = -1; tt.code = -1; }
         r = act ? br[b] : 0;
     }
     __device__ __forceinline__ bool load_neg(int j, int64_t b, bool act, Tgt& tc) const {
         const int32_t cj = act ? bc[(uint32_t)(j * B) + (uint32_t)b] : 0;
         tc.id = cj & 0x7fffffff;
         tc.code = act ? code_c[(uint32_t)(j * B) + (uint32_t)b] : 0;
-        if (dbg & 2) tc.code = -1;
         return cj < 0;
     }
     __device__ __forceinline__ const float* rel_y(int r) const { return rel_c[0] + (uint32_t)r * (uint32_t)d; }
     __device__ __forceinline__ const float* rel_w(int r) const { return rel_c[1] + (uint32_t)r * (uint32_t)d; }
     __device__ __forceinline__ void rel_add(int tbl, int r, const float (&g)[L::NF], int lane) const {
-        if (dbg & 4) return;
-        fix_add_row<L>(rel_acc + (uint32_t)((r * NTR + tbl) * 3 * d), d, lane, g);
+        if (FAST_ && tbl == 0) fix1_add_row<L>(rel_acc + (uint32_t)(r * NTR * 3 * d), d, lane, g);
+        else fix_add_row<L>(rel_acc + (uint32_t)((r * NTR + tbl) * 3 * d), d, lane, g);
     }
     __device__ __forceinline__ const float* ent_row(int tbl, const Tgt& tg) const { return ent[tbl] + (uint32_t)tg.id * (uint32_t)d; }
     // issue the loads of a singly-occurring row's optimizer state early; they complete behind the math
     __device__ __forceinline__ void prefetch(K2Tgt<L, NTE>& tg, int lane, bool pred) const {
         if (opt != PK_ADAGRAD) return;
 #pragma unroll
-        for (int t = 0; t < NTE; ++t) ld_row<L>(ent_state[t] + (uint32_t)tg.id * (uint32_t)d, d, lane, tg.st[t], pred && tg.code < 0 && !(dbg & 8));
+        for (int t = 0; t < NTE; ++t) ld_row<L>(ent_state[t] + (uint32_t)tg.id * (uint32_t)d, d, lane, tg.st[t], pred && tg.code < 0);
     }
     __device__ __forceinline__ void add_ent(int tbl, const K2Tgt<L, NTE>& tgc, const float (&g)[L::NF], int lane, bool pred) const {
         if (!pred) return;
         K2Tgt<L, NTE>& tg = const_cast<K2Tgt<L, NTE>&>(tgc);
         if (tg.code < 0) {
             apply_update<L>(ent[tbl] + (uint32_t)tg.id * (uint32_t)d, ent_state[tbl] ? ent_state[tbl] + (uint32_t)tg.id * (uint32_t)d : nullptr, tg.st[tbl], g, d,
-                            lane, opt, lr, !(dbg & 8));
+                            lane, opt, lr);
         } else {
             // fire-and-forget RED.ADD.F32 at L2 (a shared-memory float add is a compare-and-swap loop whose
             // round trips, five per row, sat on the critical path of every sample)
@@ -313,6 +317,36 @@ __device__ __forceinline__ void fix_add_row(int32_t* row, int d, int lane, const
         }
     }
 }
+// One-limb variant for the gradient w.r.t. the relation operand r^ under the L1 energy (FAST): every
+// element of a sample's term is a sum of (1 + k) directions in [-1, 1] weighted by g_j <= 1/(B k), so
+// |term| <= 2/B and |sum over the batch| <= 2: 2^-29 fixed point fits one int32 with a bit to spare,
+// each add is ONE fire-and-forget ATOMS.ADD and the conversion is one F2I (exact to 2^-30 per term).
+constexpr float kFix1Scale = 536870912.f;   // 2^29
+constexpr float kFix1Inv = 1.f / 536870912.f;
+template <class L>
+__device__ __forceinline__ void fix1_add_row(int32_t* row, int d, int lane, const float (&g)[L::NF]) {
+#pragma unroll
+    for (int i = 0; i < L::NF; ++i) {
+        const int e = elem_of<L>(lane, i);
+        if (in_row<L>(e, d) && g[i] != 0.f) atomicAdd(row + e, __float2int_rn(fminf(fmaxf(g[i], -2.f), 2.f) * kFix1Scale));
+    }
+}
+template <class L>
+__device__ __forceinline__ bool fix1_take_row(int32_t* row, int d, int lane, float (&g)[L::NF]) {
+    bool nz = false;
+#pragma unroll
+    for (int i = 0; i < L::NF; ++i) {
+        const int e = elem_of<L>(lane, i);
+        int32_t v = 0;
+        if (in_row<L>(e, d)) {
+            v = row[e];
+            if (v != 0) row[e] = 0;
+        }
+        nz |= v != 0;
+        g[i] = (float)v * kFix1Inv;
+    }
+    return nz;
+}
 // read a fixed-point row as fp32 and reset it; returns whether this lane saw a non-zero sum
 template <class L>
 __device__ __forceinline__ bool fix_take_row(int32_t* row, int d, int lane, float (&g)[L::NF]) {
@@ -356,9 +390,9 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
     float* g_ent[2];   // this universe's tables in global memory
     float* g_rel[2];
     float* g_rel_state[2];
-    K2Ctx<L, ntE, ntR> cx;
+    K2Ctx<L, ntE, ntR, FAST> cx;
     RelCache rc;
-    cx.d = d; cx.opt = opt; cx.lr = U.lr; cx.B = B; cx.dbg = P.dbg;
+    cx.d = d; cx.opt = opt; cx.lr = U.lr; cx.B = B;
     rc.mR = P.mR;
     for (int i = 0; i < 2; ++i) {
         g_ent[i] = (i < ntE) ? P.ent[i] + (size_t)U.ent_off * d : nullptr;
@@ -454,77 +488,110 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
     // Pass 1 of the next batch overwrites every word before it is read again: nothing to clear.
     // The positives of the batch AFTER the one being produced are requested one call early, so the
     // triple-index loads (L2) are off the chain as well.
-    struct PDraw { uint64_t s; int32_t h, r, t; };
-    PDraw nxt[2];
-    bool have_nxt = false;
-    auto draw_pos = [&](int b, bool following, PDraw& o) {
-        const int id = b / per, j = b - id * per;
-        uint64_t st = s0[id];
-        if (following) st = Aadv[id] * st + Cadv[id];
-        uint64_t sx = Aj[j] * st + Cj[j];
+    // Fast path (k = 1, unfiltered; at most two samples per producer thread): a producer thread owns
+    // the same samples b = ptid, ptid + n_prod of every batch, so everything that does not change between
+    // batches stays in registers.  Its position in its LCG stream advances by the same affine map
+    // every batch:  x' = Aadv x + K  with  K = Aj Cadv + Cj (1 - Aadv)  (x = Aj s0 + Cj), so no shared
+    // jump tables are read per step; all three draws of the batch AFTER the one being handed over are
+    // evaluated, and its triple-index loads issued, one call early.
+    struct PState {
+        uint64_t x, Aad, K;                 // stream position before the sample's first draw; its per-batch advance
+        int32_t h, r, t, coin, tmp;         // the next batch's positive and raw draws
+        bool on;
+    };
+    PState ps[2];
+    const bool pfast = producer && k == 1 && !P.filter;
+    auto draw_next = [&](PState& q) {
+        uint64_t sx = q.x;
         const int64_t i = (int64_t)fastmod(lcg_next(sx), fm_tri);
-        o.s = sx;
-        o.h = by_head[i * 3 + 0]; o.r = by_head[i * 3 + 1]; o.t = by_head[i * 3 + 2];
+        q.h = by_head[i * 3 + 0]; q.r = by_head[i * 3 + 1]; q.t = by_head[i * 3 + 2];
+        q.coin = (int32_t)fastmod(lcg_next(sx), fm_coin);
+        q.tmp = (int32_t)fastmod(lcg_next(sx), fm_ent);
+        q.x = q.Aad * q.x + q.K;
+    };
+    if (producer) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int b = q * n_prod + (tid - n_cons);
+            ps[q].on = pfast && b < B;
+            if (ps[q].on) {
+                const int id = b / per, j = b - id * per;
+                ps[q].Aad = Aadv[id];
+                ps[q].x = Aj[j] * s0[id] + Cj[j];
+                ps[q].K = Aj[j] * Cadv[id] + Cj[j] * (1ULL - ps[q].Aad);
+                draw_next(ps[q]);
+            }
+        }
+    }
+    // one sample drawn from the shared jump tables (any k, filtered corruption, samples beyond the fast path)
+    auto sample_generic = [&](int b, const BatchView& bv) {
+        const int id = b / per, j = b - id * per;
+        uint64_t sx = Aj[j] * s0[id] + Cj[j];
+        const int64_t i = (int64_t)fastmod(lcg_next(sx), fm_tri);
+        const int32_t h = by_head[i * 3 + 0], r = by_head[i * 3 + 1], t = by_head[i * 3 + 2];
+        bv.h[b] = h; bv.t[b] = t; bv.r[b] = r;
+        map[h] = b; map[t] = B + b; map[nE + r] = b;
+        float prob = 500.f;
+        if (P.bern) {
+            const float rm = P.right_mean[U.rel_off + r], lm = P.left_mean[U.rel_off + r];
+            prob = __fdiv_rn(__fmul_rn(1000.f, rm), __fadd_rn(rm, lm));  // Base.cpp:220-221
+        }
+        for (int n = 0; n < k; ++n) {
+            const uint64_t coin = fastmod(lcg_next(sx), fm_coin);
+            const uint64_t x = lcg_next(sx);
+            int32_t c, side;
+            if ((float)coin < prob) {   // keep head, replace tail (corrupt_head, Corrupt.h:9-57)
+                if (!P.filter) { const int64_t tmp = (int64_t)fastmod(x, fm_ent); c = (int32_t)(tmp < h ? tmp : tmp + 1); }
+                else c = corrupt_entity(x, by_head, U.n_tri, nE, h, r, 0, 2, true);
+                side = 0;
+            } else {                    // keep tail, replace head (corrupt_tail, Corrupt.h:59-105)
+                if (!P.filter) { const int64_t tmp = (int64_t)fastmod(x, fm_ent); c = (int32_t)(tmp < t ? tmp : tmp + 1); }
+                else c = corrupt_entity(x, by_tail, U.n_tri, nE, t, r, 2, 0, true);
+                side = 1;
+            }
+            bv.c[(uint32_t)(n * B) + (uint32_t)b] = (int32_t)((uint32_t)c | ((uint32_t)side << 31));
+            map[c] = (2 + n) * B + b;
+        }
     };
     auto produce = [&](int buf) {
         const int ptid = tid - n_cons;
         BatchView bv(smem + S.batch[0] + (size_t)buf * batch_stride, B, k, S.slots, S.nrelcap);
         if (ptid == 0) { *bv.ndup = 0; *bv.nrel = 0; }
         // ---- pass 1: the reference sampling() call (Base.cpp:185-310, Corrupt.h:9-105), bit-exact
-        for (int base = 0; base < B; base += 2 * n_prod) {
-            PDraw cur[2];
+        int32_t eh[2], et[2], ec[2];   // this thread's fast-path samples, kept for passes 2 and 3
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int b = base + q * n_prod + ptid;
-                if (base == 0 && have_nxt) cur[q] = nxt[q];
-                else if (b < B) draw_pos(b, false, cur[q]);
+        for (int q = 0; q < 2; ++q) {
+            if (!ps[q].on) continue;
+            const int b = q * n_prod + ptid;
+            const int32_t h = ps[q].h, r = ps[q].r, t = ps[q].t, coin = ps[q].coin, tmp = ps[q].tmp;
+            draw_next(ps[q]);   // the batch after this one: its loads have a whole step to arrive
+            float prob = 500.f;
+            if (P.bern) {
+                const float rm = P.right_mean[U.rel_off + r], lm = P.left_mean[U.rel_off + r];
+                prob = __fdiv_rn(__fmul_rn(1000.f, rm), __fadd_rn(rm, lm));  // Base.cpp:220-221
             }
-            if (base == 0) {
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int b = q * n_prod + ptid;
-                    if (b < B) draw_pos(b, true, nxt[q]);
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int b = base + q * n_prod + ptid;
-                if (b >= B) continue;
-                uint64_t sx = cur[q].s;
-                const int32_t h = cur[q].h, r = cur[q].r, t = cur[q].t;
-                bv.h[b] = h; bv.t[b] = t; bv.r[b] = r;
-                map[h] = b; map[t] = B + b; map[nE + r] = b;
-                float prob = 500.f;
-                if (P.bern) {
-                    const float rm = P.right_mean[U.rel_off + r], lm = P.left_mean[U.rel_off + r];
-                    prob = __fdiv_rn(__fmul_rn(1000.f, rm), __fadd_rn(rm, lm));  // Base.cpp:220-221
-                }
-                for (int n = 0; n < k; ++n) {
-                    const uint64_t coin = fastmod(lcg_next(sx), fm_coin);
-                    const uint64_t x = lcg_next(sx);
-                    int32_t c, side;
-                    if ((float)coin < prob) {   // keep head, replace tail (corrupt_head, Corrupt.h:9-57)
-                        if (!P.filter) { const int64_t tmp = (int64_t)fastmod(x, fm_ent); c = (int32_t)(tmp < h ? tmp : tmp + 1); }
-                        else c = corrupt_entity(x, by_head, U.n_tri, nE, h, r, 0, 2, true);
-                        side = 0;
-                    } else {                    // keep tail, replace head (corrupt_tail, Corrupt.h:59-105)
-                        if (!P.filter) { const int64_t tmp = (int64_t)fastmod(x, fm_ent); c = (int32_t)(tmp < t ? tmp : tmp + 1); }
-                        else c = corrupt_entity(x, by_tail, U.n_tri, nE, t, r, 2, 0, true);
-                        side = 1;
-                    }
-                    bv.c[(uint32_t)(n * B) + (uint32_t)b] = (int32_t)((uint32_t)c | ((uint32_t)side << 31));
-                    map[c] = (2 + n) * B + b;
-                }
-            }
+            const bool keep_head = (float)coin < prob;
+            const int32_t fix = keep_head ? h : t;
+            const int32_t c = tmp < fix ? tmp : tmp + 1;
+            bv.h[b] = h; bv.t[b] = t; bv.r[b] = r;
+            bv.c[b] = (int32_t)((uint32_t)c | (keep_head ? 0u : 0x80000000u));
+            map[h] = b; map[t] = B + b; map[nE + r] = b; map[c] = 2 * B + b;
+            eh[q] = h; et[q] = t; ec[q] = c;
         }
-        have_nxt = true;
+        for (int b = (pfast ? 2 * n_prod : 0) + ptid; b < B; b += n_prod) sample_generic(b, bv);
         named_barrier(2, n_prod);
         // ---- pass 2: losers flag their row
         auto flag = [&](int32_t e, int32_t occ) {
             const int32_t m = map[e];
             if ((m & 0x7fffffff) != occ) map[e] = m | (int32_t)0x80000000;
         };
-        for (int b = ptid; b < B; b += n_prod) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            if (!ps[q].on) continue;
+            const int b = q * n_prod + ptid;
+            flag(eh[q], b); flag(et[q], B + b); flag(ec[q], 2 * B + b);
+        }
+        for (int b = (pfast ? 2 * n_prod : 0) + ptid; b < B; b += n_prod) {
             flag(bv.h[b], b);
             flag(bv.t[b], B + b);
             for (int n = 0; n < k; ++n) flag(bv.c[(uint32_t)(n * B) + (uint32_t)b] & 0x7fffffff, (2 + n) * B + b);
@@ -542,13 +609,23 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
             }
             return own;
         };
-        for (int b = ptid; b < B; b += n_prod) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            if (!ps[q].on) continue;
+            const int b = q * n_prod + ptid;
+            bv.code_h[b] = code_of(eh[q], b);
+            bv.code_t[b] = code_of(et[q], B + b);
+            bv.code_c[b] = code_of(ec[q], 2 * B + b);
+            const int32_t r = bv.r[b];
+            if (map[nE + r] == b) bv.rel_ids[atomicAdd(bv.nrel, 1)] = r;   // distinct relations of the batch
+        }
+        for (int b = (pfast ? 2 * n_prod : 0) + ptid; b < B; b += n_prod) {
             bv.code_h[b] = code_of(bv.h[b], b);
             bv.code_t[b] = code_of(bv.t[b], B + b);
             for (int n = 0; n < k; ++n)
                 bv.code_c[(uint32_t)(n * B) + (uint32_t)b] = code_of(bv.c[(uint32_t)(n * B) + (uint32_t)b] & 0x7fffffff, (2 + n) * B + b);
             const int32_t r = bv.r[b];
-            if (map[nE + r] == b) bv.rel_ids[atomicAdd(bv.nrel, 1)] = r;   // distinct relations of the batch
+            if (map[nE + r] == b) bv.rel_ids[atomicAdd(bv.nrel, 1)] = r;
         }
         if (ptid < W) s0[ptid] = Aadv[ptid] * s0[ptid] + Cadv[ptid];
     };
@@ -579,7 +656,7 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
     if (producer) {
         for (long long step = 0; step < steps; ++step) {
             const int buf = (int)(step & 1);
-            if (step + 1 < steps && !((P.dbg & 16) && step > 1)) produce(buf ^ 1);
+            if (step + 1 < steps) produce(buf ^ 1);
             // the loss of the step that just finished is reduced here, off the consumers' critical path
             if (step > 0) reduce_loss(step - 1);
             named_barrier(0, NT);
@@ -592,7 +669,7 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
             cx.bh = bv.h; cx.bt = bv.t; cx.br = bv.r; cx.bc = bv.c;
             cx.code_h = bv.code_h; cx.code_t = bv.code_t; cx.code_c = bv.code_c;
             // ---- phase A: forward + analytic backward; singly-occurring entity rows updated in place
-            for (int base = 0; base < B && !(P.dbg & 32); base += NG) {
+            for (int base = 0; base < B; base += NG) {
                 const int b = base + grp;
                 const bool act = b < B;
                 const float l = train_sample<MODEL, L>(cx, hp, lane, b, act);
@@ -601,13 +678,13 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
             named_barrier(1, n_cons);
             // ---- phase B: one item per distinct relation (take the fixed-point gradient sums, normalisation
             //      backward, update, refresh the cache) and per multiply-occurring entity row
-            const int nrel = (P.dbg & 1) ? 0 : *bv.nrel, nd = (P.dbg & 3) ? 0 : *bv.ndup;
+            const int nrel = *bv.nrel, nd = *bv.ndup;
             for (int it = grp; it < nrel + nd; it += NG) {
                 if (it < nrel) {
                     const int r = bv.rel_ids[it];
                     int32_t* pr = rc.acc + (uint32_t)(r * ntR * 3 * d);
                     float g0[L::NF], g1[ntR == 2 ? L::NF : 1];
-                    bool nz = fix_take_row<L>(pr, d, lane, g0);
+                    bool nz = FAST ? fix1_take_row<L>(pr, d, lane, g0) : fix_take_row<L>(pr, d, lane, g0);
                     if constexpr (ntR == 2) nz |= fix_take_row<L>(pr + 3 * d, d, lane, g1);
                     // an all-zero sum updates nothing (SGD and Adagrad leave zero-gradient rows unchanged)
                     if (__ballot_sync(gmask, nz) != 0u) {
@@ -699,6 +776,9 @@ inline LaySel pick_layout(int model, int d) {
     // Short rows (the PuTrans* scripts all use d = 20): four lanes per row with scalar chunks keep every
     // lane busy (d = 20: 4 lanes x 5 floats, against 5 of 8 lanes with 128-bit chunks) and put EIGHT
     // samples in a warp, so a batch of up to 104 positives is one pass of the 13 consumer warps.
+    // d = 20 exactly: one 128-bit access plus one 32-bit access per lane instead of five 32-bit ones (fewer
+    // memory instructions in flight, whole sectors of the L2-resident Adagrad state per request).
+    if (d == 20) return LaySel{1, 4, 1, 1};
     if (d <= 20 && d % 4 == 0) return LaySel{1, 4, d / 4, 0};
     const int V = d % 4 == 0 ? 4 : (d % 2 == 0 ? 2 : 1);
     const int chunks = d / V;
@@ -741,7 +821,7 @@ int dispatch_layout(const LaySel& l, const K2Params& P, int stage, int n, size_t
         return fast ? launch_k2<MODEL, Lay<1, 4, c, 1, q>, 1>(P, stage, n, smem, st)            \
                     : launch_k2<MODEL, Lay<1, 4, c, 1, q>, 0>(P, stage, n, smem, st);
 #ifdef PK_K2_DEV
-    PK_CASE4(5, 0)
+    PK_CASE4(5, 0) PK_CASE4(1, 1)
 #undef PK_CASE4
     return pk::fail(PK_ERR_UNSUPPORTED, "PK_K2_DEV build: only d = 20");
 #else
@@ -941,7 +1021,7 @@ extern "C" int pk_train_universes(const pk_model_cfg* cfg, const pk_tables* pack
                 P1.bern = cfg->bern; P1.filter = cfg->filter; P1.W = W;
                 P1.mE = u.n_ent; P1.mR = u.n_rel; P1.mB = u.batch_size;
                 P1.np = np;
-                P1.timer = nullptr; P1.timer_base = 0; P1.dbg = 0;
+                P1.timer = nullptr; P1.timer_base = 0;
                 P1.scratch = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(slot1->d) + kDescArea);
                 P1.scratch_stride = stride1;
                 int rc1 = cfg->model == PK_TRANSE ? launch_model0(lay, P1, 0, 1, own.total, st)
@@ -977,7 +1057,6 @@ extern "C" int pk_train_universes(const pk_model_cfg* cfg, const pk_tables* pack
         P.mE = mE[c]; P.mR = mR[c]; P.mB = mB[c];
         P.np = np;
         P.timer = g_timer; P.timer_base = c == 1 ? (int)cls[0].size() : 0;
-        P.dbg = getenv("PK_K2_DBG") ? atoi(getenv("PK_K2_DBG")) : 0;
         P.scratch = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(slot->d) + desc_area);
         P.scratch_stride = stride;
         // descriptors were copied from pageable host memory owned by this call: the copy has
