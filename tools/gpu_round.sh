@@ -10,6 +10,6 @@ python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${tag}_bench_
 python tools/k2_universe_times.py 100 > gpurun_out/${tag}_k2_universe_times.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-s1 --no-cpu-baseline --e2e-steps 1 > gpurun_out/${tag}_ncu_launches.log 2>&1
-ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:k2_train_universes.*512, 1, 1>' -s 2 -c 1 -o gpurun_out/${tag}_k2 -f \
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:k2_train_universes.*512, .int.1, .int.1>' -s 2 -c 1 -o gpurun_out/${tag}_k2 -f \
     python bench.py --steps 1 --warmup 3 --no-s1 --no-cpu-baseline --no-eval --e2e-steps 1 > gpurun_out/${tag}_ncu_k2.log 2>&1
 ls -la gpurun_out | tail -12
