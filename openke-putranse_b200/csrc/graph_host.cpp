@@ -176,6 +176,32 @@ bool Graph::import_train(std::string* err) {
         if (i == 0 || by_rel[(size_t)i - 1].r != r) lef_rel[(size_t)r] = i;
         rig_rel[(size_t)r] = i;
     }
+    // entity sets per relation and the triple ids of the (t,r,h) order: built once, read by every universe
+    rel_ent_off.assign((size_t)nr + 1, 0);
+    rel_ent.clear();
+    {
+        std::vector<int32_t> tmp;
+        for (int64_t r = 0; r < nr; ++r) {
+            tmp.clear();
+            if (rig_rel[(size_t)r] >= 0)
+                for (int64_t k = lef_rel[(size_t)r]; k <= rig_rel[(size_t)r]; ++k) {
+                    tmp.push_back(by_rel[(size_t)k].h);
+                    tmp.push_back(by_rel[(size_t)k].t);
+                }
+            std::sort(tmp.begin(), tmp.end());
+            tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+            rel_ent.insert(rel_ent.end(), tmp.begin(), tmp.end());
+            rel_ent_off[(size_t)r + 1] = (int64_t)rel_ent.size();
+        }
+    }
+    ent_range.resize((size_t)n_ent);
+    for (int64_t e = 0; e < n_ent; ++e)
+        ent_range[(size_t)e] = EntRange{(int32_t)train.lef_head[(size_t)e], (int32_t)train.rig_head[(size_t)e],
+                                         (int32_t)train.lef_tail[(size_t)e], (int32_t)train.rig_tail[(size_t)e]};
+    tail_to_head.resize(train.by_tail.size());
+    for (size_t k = 0; k < train.by_tail.size(); ++k)
+        tail_to_head[k] = (int32_t)(std::lower_bound(train.by_head.begin(), train.by_head.end(), train.by_tail[k], less_hrt) - train.by_head.begin());
+
     // Bernoulli statistics with the reference's import-count drift.
     import_count = same_shape ? import_count + 1 : 1;
     if (!same_shape) {
@@ -275,13 +301,6 @@ struct Fenwick {
     }
 };
 
-struct TriHash {
-    size_t operator()(const Tri& x) const {
-        uint64_t k = ((uint64_t)(uint32_t)x.h * 0x9E3779B97F4A7C15ULL) ^ ((uint64_t)(uint32_t)x.t * 0xC2B2AE3D27D4EB4FULL) ^
-                     ((uint64_t)(uint32_t)x.r * 0x165667B19E3779F9ULL);
-        return (size_t)(k ^ (k >> 29));
-    }
-};
 
 }  // namespace
 
@@ -314,16 +333,8 @@ bool Graph::walk_universe(GlibcRand& rng, int64_t tc, float balance, Universe* u
     u->focus = focus;
     const int64_t threshold = (int64_t)(balance * (float)tc);  // :345-346 (float product, truncated)
 
-    // entities that occur with the focus relation, ascending (:69-80)
-    std::vector<int32_t> frontier;
-    if (rig_rel[(size_t)focus] >= 0) {
-        for (int64_t i = lef_rel[(size_t)focus]; i <= rig_rel[(size_t)focus]; ++i) {
-            frontier.push_back(by_rel[(size_t)i].h);
-            frontier.push_back(by_rel[(size_t)i].t);
-        }
-        std::sort(frontier.begin(), frontier.end());
-        frontier.erase(std::unique(frontier.begin(), frontier.end()), frontier.end());
-    }
+    // entities that occur with the focus relation, ascending (:69-80): precomputed at import
+    std::vector<int32_t> frontier(rel_ent.begin() + rel_ent_off[(size_t)focus], rel_ent.begin() + rel_ent_off[(size_t)focus + 1]);
     if (threshold >= 0 && (int64_t)frontier.size() > threshold) {  // :352-354, :55-67
         Fenwick fw((int)frontier.size());
         std::vector<int32_t> subset;
@@ -345,9 +356,20 @@ bool Graph::walk_universe(GlibcRand& rng, int64_t tc, float balance, Universe* u
     std::vector<Tri>& got = u->collected;
     got.clear();
     got.reserve((size_t)tc);
-    std::unordered_set<Tri, TriHash> seen;
-    seen.reserve((size_t)tc * 2);
-    std::set<int32_t> next_points;  // survives rounds: skipped entities resurface one round later
+    // collected-before test: one stamp per training triple (by_head position), per thread, instead of hashing
+    static thread_local std::vector<uint32_t> seen, queued;
+    static thread_local uint32_t stamp = 0;
+    if (seen.size() != g.by_head.size() || queued.size() != (size_t)n_ent || stamp > 0xfffffff0u) {
+        seen.assign(g.by_head.size(), 0);
+        queued.assign((size_t)n_ent, 0);
+        stamp = 0;
+    }
+    const uint32_t seen_stamp = ++stamp;
+    // the reference's std::set of next starting points: a vector de-duplicated by stamps on insertion and
+    // sorted when the round ends; it survives rounds (skipped entities resurface one round later)
+    std::vector<int32_t> next_points;
+    uint32_t round_stamp = ++stamp;
+    bool zero_seen = false, neg_queued = false;
     int64_t target = tc;
     int32_t last_dup_entity = -1;
     int dup_tol = 5, stall_tol = 20;
@@ -360,24 +382,32 @@ bool Graph::walk_universe(GlibcRand& rng, int64_t tc, float balance, Universe* u
             const int32_t e = frontier[i];
             const bool head_first = (rng.next() % 1000) < 500;  // :122 (prob is the float 500)
             ++draws;
-            const bool has_h = g.rig_head[(size_t)e] != -1, has_t = g.rig_tail[(size_t)e] != -1;
+            const EntRange er = ent_range[(size_t)e];
+            const bool has_h = er.rig_head != -1, has_t = er.rig_tail != -1;
             int side;  // 0 head, 1 tail
             if (head_first) side = has_h ? 0 : (has_t ? 1 : -1);
             else            side = has_t ? 1 : (has_h ? 0 : -1);
             Tri x{0, 0, 0};
             int32_t nxt = -1;
+            int64_t tid = -1;   // the triple's position in by_head
             if (side == 0) {
-                const int64_t idx = rng.range(g.lef_head[(size_t)e], g.rig_head[(size_t)e] + 1);  // :40
+                const int64_t idx = rng.range(er.lef_head, (int64_t)er.rig_head + 1);  // :40
                 ++draws;
                 x = g.by_head[(size_t)idx];
                 nxt = x.t;
+                tid = idx;
             } else if (side == 1) {
-                const int64_t idx = rng.range(g.lef_tail[(size_t)e], g.rig_tail[(size_t)e] + 1);  // :48
+                const int64_t idx = rng.range(er.lef_tail, (int64_t)er.rig_tail + 1);  // :48
                 ++draws;
                 x = g.by_tail[(size_t)idx];
                 nxt = x.h;
+                tid = tail_to_head[(size_t)idx];
             }
-            if (seen.count(x)) {  // :141-154
+            if (tid < 0) {   // isolated entity: the reference compares the zero triple (0,0,0) (:141)
+                const auto it0 = std::lower_bound(g.by_head.begin(), g.by_head.end(), x, less_hrt);
+                if (it0 != g.by_head.end() && *it0 == x) tid = it0 - g.by_head.begin();
+            }
+            if (tid >= 0 ? seen[(size_t)tid] == seen_stamp : zero_seen) {  // :141-154
                 if (last_dup_entity == e) --dup_tol;
                 else last_dup_entity = e;
                 if (dup_tol == 0) {
@@ -388,15 +418,21 @@ bool Graph::walk_universe(GlibcRand& rng, int64_t tc, float balance, Universe* u
                 continue;
             }
             got.push_back(x);
-            seen.insert(x);
-            next_points.insert(nxt);
+            if (tid >= 0) seen[(size_t)tid] = seen_stamp; else zero_seen = true;
+            if (nxt >= 0 && queued[(size_t)nxt] != round_stamp) { queued[(size_t)nxt] = round_stamp; next_points.push_back(nxt); }
+            else if (nxt < 0 && !neg_queued) { neg_queued = true; next_points.push_back(nxt); }
             ++i;  // erase(it++)
         }
         for (; i < frontier.size(); ++i) leftover.push_back(frontier[i]);
         // entity_set.swap(new_starting_points) (:170)
-        frontier.assign(next_points.begin(), next_points.end());
+        std::sort(next_points.begin(), next_points.end());
+        frontier.swap(next_points);
         next_points.clear();
-        next_points.insert(leftover.begin(), leftover.end());
+        round_stamp = ++stamp;
+        neg_queued = false;
+        for (int32_t e2 : leftover)   // ascending and distinct already
+            if (e2 >= 0) { queued[(size_t)e2] = round_stamp; next_points.push_back(e2); }
+            else if (!neg_queued) { neg_queued = true; next_points.push_back(e2); }
         if ((int64_t)got.size() == last_size) --stall_tol;
         else { last_size = (int64_t)got.size(); stall_tol = 20; }
         if (stall_tol == 0) {  // :181-186
@@ -411,7 +447,9 @@ bool Graph::walk_universe(GlibcRand& rng, int64_t tc, float balance, Universe* u
     }
 
     // local ids by first appearance: h, then t, then r (:193-233)
-    std::vector<int32_t> emap((size_t)n_ent, -1), rmap((size_t)n_rel, -1);
+    static thread_local std::vector<int32_t> emap, rmap;   // all -1 between calls (touched entries are reset below)
+    if (emap.size() != (size_t)n_ent) emap.assign((size_t)n_ent, -1);
+    if (rmap.size() != (size_t)n_rel) rmap.assign((size_t)n_rel, -1);
     u->ent_remap.clear();
     u->rel_remap.clear();
     TripleIndex& L = u->local;
@@ -423,11 +461,35 @@ bool Graph::walk_universe(GlibcRand& rng, int64_t tc, float balance, Universe* u
         if (rmap[(size_t)x.r] < 0) { rmap[(size_t)x.r] = (int32_t)u->rel_remap.size(); u->rel_remap.push_back(x.r); }
         L.by_head[k] = Tri{emap[(size_t)x.h], rmap[(size_t)x.r], emap[(size_t)x.t]};
     }
+    for (int32_t e : u->ent_remap) emap[(size_t)e] = -1;
+    for (int32_t r : u->rel_remap) rmap[(size_t)r] = -1;
     L.n_ent = (int64_t)u->ent_remap.size();
     L.n_rel = (int64_t)u->rel_remap.size();
-    std::sort(L.by_head.begin(), L.by_head.end(), less_hrt);  // :236
-    L.by_tail = L.by_head;
-    std::sort(L.by_tail.begin(), L.by_tail.end(), less_trh);
+    L.by_tail.resize(got.size());
+    if (L.n_ent < (1 << 21) && L.n_rel < (1 << 21)) {
+        // the two orders (:236) as sorts of packed 63-bit keys
+        static thread_local std::vector<uint64_t> keys;
+        keys.resize(got.size());
+        for (size_t k = 0; k < got.size(); ++k) {
+            const Tri& x = L.by_head[k];
+            keys[k] = ((uint64_t)x.h << 42) | ((uint64_t)x.r << 21) | (uint64_t)x.t;
+        }
+        std::sort(keys.begin(), keys.end());
+        for (size_t k = 0; k < got.size(); ++k) {
+            const uint64_t v = keys[k];
+            L.by_head[k] = Tri{(int32_t)(v >> 42), (int32_t)((v >> 21) & 0x1fffff), (int32_t)(v & 0x1fffff)};
+            keys[k] = ((v & 0x1fffff) << 42) | (v & (0x1fffffULL << 21)) | (v >> 42);
+        }
+        std::sort(keys.begin(), keys.end());
+        for (size_t k = 0; k < got.size(); ++k) {
+            const uint64_t v = keys[k];
+            L.by_tail[k] = Tri{(int32_t)(v & 0x1fffff), (int32_t)((v >> 21) & 0x1fffff), (int32_t)(v >> 42)};
+        }
+    } else {
+        std::sort(L.by_head.begin(), L.by_head.end(), less_hrt);  // :236
+        L.by_tail = L.by_head;
+        std::sort(L.by_tail.begin(), L.by_tail.end(), less_trh);
+    }
     L.build_ranges();
     // universe-local Bernoulli statistics (:294-324); freshly allocated per universe, no drift
     std::vector<int64_t> freq((size_t)L.n_rel, 0), dh, dt;

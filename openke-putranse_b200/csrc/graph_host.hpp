@@ -91,6 +91,13 @@ struct Graph {
     TripleIndex train;
     std::vector<Tri> by_rel;   // train sorted (r,h,t) + ranges, for the universe focus set
     std::vector<int64_t> lef_rel, rig_rel;
+    // per relation: the entities it occurs with, ascending and distinct (offsets [n_rel+1] into rel_ent);
+    // this is what every universe of that focus relation starts from (UniverseConstructor.h:69-80)
+    std::vector<int64_t> rel_ent_off;
+    std::vector<int32_t> rel_ent;
+    std::vector<int32_t> tail_to_head;  // position in by_head of train.by_tail[i] (one id per triple)
+    struct EntRange { int32_t lef_head, rig_head, lef_tail, rig_tail; };   // rig = -1 if absent
+    std::vector<EntRange> ent_range;    // the four per-entity ranges of `train` in one cache line (the walk reads all four)
     std::vector<Tri> test, valid;  // sorted (r,h,t)   (reference Reader.h:311-312)
     std::vector<Tri> all_hrt;      // test ∪ train ∪ valid, distinct, sorted (h,r,t) (the filter set)
     std::vector<Tri> all_trh;      // same set sorted (t,r,h)

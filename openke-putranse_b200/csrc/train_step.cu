@@ -324,6 +324,7 @@ struct K1Tgt {
 //   then per operand slot s in {0,1,2}: NTE table rows, and NTE optimizer-state rows when Adagrad
 template <int MODEL, class L>
 struct K1Ctx {
+    static constexpr bool kMerge3 = false;
     static constexpr int NTE = MODEL == TRANSD ? 2 : 1, NTR = MODEL == TRANSE ? 1 : 2;
     using Tgt = K1Tgt;
     const K1Params* P;

@@ -224,6 +224,7 @@ __device__ __forceinline__ void fix1_add_row(int32_t* row, int d, int lane, cons
 template <class L, int NTE_, int NTR_, int FAST_>
 struct K2Ctx {
     static constexpr int NTE = NTE_, NTR = NTR_;
+    static constexpr bool kMerge3 = FAST_ != 0 && NTE_ == 1 && NTR_ == 1;   // FAST TransE: see train_sample
     using Tgt = K2Tgt<L, NTE_>;
     float* ent[2];        // working entity tables: shared memory when staged, else global
     float* ent_state[2];  // global; nullptr for SGD
@@ -263,6 +264,47 @@ struct K2Ctx {
         if (opt != PK_ADAGRAD) return;
 #pragma unroll
         for (int t = 0; t < NTE; ++t) ld_row<L>(ent_state[t] + (uint32_t)tg.id * (uint32_t)d, d, lane, tg.st[t], pred && tg.code < 0);
+    }
+    // Three rows at once (FAST: Adagrad): the in-place arithmetic runs for all of them unconditionally
+    // and only the stores are predicated, so nothing diverges and the 3 x NF rsqrt/rcp chains overlap.
+    __device__ __forceinline__ void add_ent3(const K2Tgt<L, NTE>& a, const float (&ga)[L::NF], const K2Tgt<L, NTE>& b,
+                                             const float (&gb)[L::NF], const K2Tgt<L, NTE>& c, const float (&gc)[L::NF], int lane,
+                                             bool pred) const {
+        const K2Tgt<L, NTE>* tg[3] = {&a, &b, &c};
+        const float* gg[3] = {ga, gb, gc};
+        float x[3][L::NF], s[3][L::NF];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) ld_row<L>(ent[0] + (uint32_t)tg[q]->id * (uint32_t)d, d, lane, x[q]);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+#pragma unroll
+            for (int i = 0; i < L::NF; ++i) {
+                const float g = gg[q][i];
+                s[q][i] = fmaf(g, g, tg[q]->st[0][i]);
+                float r, inv;
+                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaxf(s[q][i], 1.17549435e-38f)));
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(fmaf(s[q][i], r, 1e-10f)));
+                x[q][i] = fmaf(-lr * g, inv, x[q][i]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            if (pred && tg[q]->code < 0) {
+                st_row<L>(ent_state[0] + (uint32_t)tg[q]->id * (uint32_t)d, d, lane, s[q]);
+                st_row<L>(ent[0] + (uint32_t)tg[q]->id * (uint32_t)d, d, lane, x[q]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            if (pred && tg[q]->code >= 0) {
+                float* p = scratch + (uint32_t)(tg[q]->code * d);
+#pragma unroll
+                for (int i = 0; i < L::NF; ++i) {
+                    const int e = elem_of<L>(lane, i);
+                    if (in_row<L>(e, d) && gg[q][i] != 0.f) atomicAdd(p + e, gg[q][i]);
+                }
+            }
+        }
     }
     __device__ __forceinline__ void add_ent(int tbl, const K2Tgt<L, NTE>& tgc, const float (&g)[L::NF], int lane, bool pred) const {
         if (!pred) return;

@@ -45,6 +45,14 @@ def defaultdict_int(innerfactory=int):
     return defaultdict(innerfactory)
 
 
+def _host_cores():
+    """Cores this process may run on (a container's CPU set can be smaller than os.cpu_count())."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        return os.cpu_count() or 2
+
+
 def _dist():
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized():
@@ -231,6 +239,11 @@ class Parallel_Universe_Config(Tester):
 
     def _finish_piece(self, ck):
         if ck.d_loss is not None:
+            # sleep until the launch has finished instead of spinning in the copy: the core goes to the host
+            # threads that are sampling the next chunk's subgraphs (with several ranks per host they are scarce)
+            done = torch.cuda.Event(blocking=True)
+            done.record(torch.cuda.current_stream(ck.d_loss.device))
+            done.synchronize()
             host = ck.d_loss.cpu().numpy()
             self.d2h_bytes += host.nbytes
             o = 0
@@ -420,7 +433,7 @@ class Parallel_Universe_Config(Tester):
             ids_next = list(prefetch_ids)
             # leave cores to the launching thread, the CUDA driver's threads and the other ranks of this host
             _, _, world_ = _dist()
-            bg_threads = int(self.sampler_threads) or max(1, (os.cpu_count() or 2) // max(world_, 1) - 2)
+            bg_threads = int(self.sampler_threads) or max(2, _host_cores() // max(world_, 1) - 2)
             self._prefetched = (self._sampling_key(ids_next), self._pool.submit(self._sample_universes, ids_next, bg_threads))
         ck.train_inputs = (d_by_head, d_by_tail, d_lm, d_rm)  # keep alive until the stream is done
         self.h2d_bytes += sum(t.numel() * t.element_size() for t in ck.train_inputs if t is not None) + ctypes.sizeof(desc) \

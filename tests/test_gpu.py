@@ -348,6 +348,54 @@ def test_batched_universes_with_bernoulli_filtered_negatives(wn18_dir):
         assert np.allclose(got, want, rtol=LOSS_RTOL_LATE)
 
 
+@pytest.mark.parametrize("bern,nbatches,threads", [(1, 20, 8), (0, 4, 8), (0, 7, 3)])
+def test_batched_universes_register_resident_sampler(wn18_dir, bern, nbatches, threads):
+    """K2 producer fast path (k = 1, unfiltered: stream positions kept in registers, draws one batch ahead,
+    owner-based occurrence analysis) against the oracle sampler + torch oracle: with universe-local Bernoulli
+    means; with batches of several hundred positives (two samples per producer thread PLUS the table-driven
+    remainder, several consumer passes, many repeated rows); and with three sampler streams of unequal slices."""
+    import torch
+    from openke.config import Parallel_Universe_Config
+    from openke.data import TrainDataLoader, TestDataLoader
+    from openke.module.model import TransE
+    from oracle import native as on
+    from oracle.model_math import TorchOracle
+    fresh_library_state()
+    torch.set_num_threads(2)
+    train = TrainDataLoader(in_path=wn18_dir, nbatches=nbatches, threads=threads, sampling_mode="normal", bern_flag=bern, filter_flag=0,
+                            neg_ent=1, neg_rel=0, random_seed=123)
+    test = TestDataLoader(train.in_path, "link")
+    param = {"dim": 20, "p_norm": 1, "norm_flag": 1}
+    pu = Parallel_Universe_Config(training_identifier="t", train_dataloader=train, test_dataloader=test, initial_num_universes=None,
+                                  min_margin=1, max_margin=4, min_lr=0.001, max_lr=0.1, const_num_epochs=3,
+                                  min_triple_constraint=500, max_triple_constraint=2000, min_balance=0.25, max_balance=0.5,
+                                  embedding_model=TransE, embedding_model_param=param, checkpoint_dir=None, valid_steps=10 ** 9,
+                                  save_steps=None, training_setting="static", incremental_strategy=None)
+    pu.record_losses = True
+    pu.train_parallel_universes(3)
+    w = np.load(os.path.join(util.GOLDEN, "wn18.npz"))
+    o = on.Oracle(threads=threads, bern=bern)
+    o.import_train(w["train"], 40943, 18)
+    for u in range(3):
+        hy = pu.universe_hyper[u]
+        o.seed(4 + u)
+        o.universe(hy["tc"], hy["balance"])
+        torch.manual_seed(4 + u)
+        ref_model = TransE(hy["nE"], hy["nR"], **param)
+        orc = TorchOracle("transe", {n: getattr(ref_model, n).weight.detach().numpy() for n in ref_model.table_names()}, p_norm=1,
+                          opt="adagrad", lr=hy["lr"], margin=hy["margin"], k=1)
+        o.swap()
+        want = [orc.step(*o.sampling(hy["batch_size"], 1, 0)) for _ in range(hy["epochs"] * hy["nbatches"])]
+        o.swap()
+        got = pu.universe_losses[u]
+        assert len(got) == len(want) == 3 * nbatches
+        assert np.allclose(got[:5], want[:5], rtol=LOSS_RTOL_EARLY), (u, got[:5], want[:5])
+        assert np.allclose(got, want, rtol=LOSS_RTOL_LATE)
+        sp = pu.trained_embedding_spaces[u]
+        for n, v in orc.tables().items():
+            _close_tables(getattr(sp, n).weight.detach().cpu().numpy(), v)
+
+
 def test_null_vector_handling_on_reference_tables(wn18_dir, golden):
     """missing_embedding_handling='null_vector' (reference Parallel_Universe_Config.py:378-388,494-514,634-640)
     on the REFERENCE-trained universe tables against the reference's own per-triple ranks."""

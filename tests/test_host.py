@@ -145,6 +145,45 @@ def test_batched_threaded_builder_equals_sequential(wn18_dir, golden):
         assert np.all(np.lexsort((t[:, 0], t[:, 1], t[:, 2])) == np.arange(t.shape[0]))
 
 
+def test_builder_matches_oracle_on_many_seeds(wn18_dir):
+    """The product's universe builder (per-relation entity lists precomputed at import, triple-id stamps,
+    packed-key sorts) against the oracle's plain restatement of UniverseConstructor.h on 80 universes of the
+    static script's ranges plus edge cases (tiny and huge focus subsets, walks that stall)."""
+    import random
+    from oracle import native as on
+    L = N.lib()
+    _load(L, wn18_dir)
+    w = np.load(os.path.join(util.GOLDEN, "wn18.npz"))
+    o = on.Oracle(threads=8, bern=0)
+    o.import_train(w["train"], 40943, 18)
+    rng = random.Random(7)
+    cases = [(1000 + i, rng.randrange(500, 2000), rng.uniform(0.25, 0.5)) for i in range(72)]
+    cases += [(5, 50, 0.02), (6, 3000, 0.9), (8, 700, 1.0), (9, 12000, 0.5), (10, 3, 0.5), (11, 2, 1.0), (12, 6000, 0.05)]
+    n = len(cases)
+    seeds = np.array([c[0] for c in cases], np.int64)
+    tcs = np.array([c[1] for c in cases], np.int64)
+    bals = np.array([c[2] for c in cases], np.float32)
+    h = L.pk_universes_build(n, N.addr(seeds), N.addr(tcs), N.addr(bals), 3)
+    assert h, N.last_error()
+    nT, nE, nR, foc = (np.zeros(n, np.int64) for _ in range(4))
+    N.check(L.pk_universes_sizes(h, N.addr(nT), N.addr(nE), N.addr(nR), N.addr(foc)))
+    er, rr = np.zeros(nE.sum(), np.int32), np.zeros(nR.sum(), np.int32)
+    bh, bt, bg = (np.zeros((nT.sum(), 3), np.int32) for _ in range(3))
+    N.check(L.pk_universes_export(h, N.addr(bh), N.addr(bt), N.addr(bg), N.addr(er), N.addr(rr), None, None, None))
+    L.pk_universes_free(h)
+    eo, ro, to = (np.concatenate([[0], np.cumsum(x)]) for x in (nE, nR, nT))
+    for i, (seed, tc, bal) in enumerate(cases):
+        o.seed(seed)
+        tri, oer, orr = o.universe(tc, float(np.float32(bal)))
+        assert np.array_equal(bg[to[i]:to[i + 1]], tri), (i, seed, tc, bal)
+        assert np.array_equal(er[eo[i]:eo[i + 1]], oer) and np.array_equal(rr[ro[i]:ro[i + 1]], orr)
+        t = bt[to[i]:to[i + 1]]
+        assert np.all(np.lexsort((t[:, 0], t[:, 1], t[:, 2])) == np.arange(t.shape[0]))
+        hh = bh[to[i]:to[i + 1]]
+        assert np.all(np.lexsort((hh[:, 2], hh[:, 1], hh[:, 0])) == np.arange(hh.shape[0]))
+        assert sorted(map(tuple, hh.tolist())) == sorted(map(tuple, t.tolist()))
+
+
 def test_universe_invariants_on_synthetic_graph(tmp_path):
     """The reference's opt-in Checks.h invariants (openke/base/UniverseSetting.h:203-269) as properties."""
     tr, va, te = util.synthetic_graph(3000, 12, 20000, 200, seed=7)
