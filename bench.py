@@ -301,7 +301,9 @@ def run_ours(args):
                    "positive_triples_per_step_per_gpu": positives, "final_loss_last_universe": final_loss},
         "e2e": {"value": e2e_value, "unit": "positive triples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "ms_per_step": e2e_elapsed / e2e_steps * 1e3,
-                "host_breakdown_s_per_step": {k: v for k, v in timings.items()}},
+                "host_breakdown_s_per_step": {k: v for k, v in timings.items()},
+                "host": {"cores": len(os.sched_getaffinity(0)), "ranks_on_host": world,
+                         "note": "the next chunk's subgraphs are sampled on host threads beside the launch (bit-exact glibc rand() walk)"}},
         "gpu_launches": launches,
         "kernel_ms_per_step": float(np.mean(kernel_ms)),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

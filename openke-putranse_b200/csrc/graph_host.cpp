@@ -279,11 +279,7 @@ struct Fenwick {
     std::vector<int32_t> t;
     int n, top;
     explicit Fenwick(int n_) : t((size_t)n_ + 1, 0), n(n_) {
-        for (int i = 1; i <= n; ++i) {
-            t[(size_t)i] += 1;
-            int j = i + (i & -i);
-            if (j <= n) t[(size_t)j] += t[(size_t)i];
-        }
+        for (int i = 1; i <= n; ++i) t[(size_t)i] = i & -i;   // all ones: node i covers lowbit(i) elements
         top = 1;
         while (top * 2 <= n) top *= 2;
     }
@@ -334,21 +330,24 @@ bool Graph::walk_universe(GlibcRand& rng, int64_t tc, float balance, Universe* u
     const int64_t threshold = (int64_t)(balance * (float)tc);  // :345-346 (float product, truncated)
 
     // entities that occur with the focus relation, ascending (:69-80): precomputed at import
-    std::vector<int32_t> frontier(rel_ent.begin() + rel_ent_off[(size_t)focus], rel_ent.begin() + rel_ent_off[(size_t)focus + 1]);
-    if (threshold >= 0 && (int64_t)frontier.size() > threshold) {  // :352-354, :55-67
-        Fenwick fw((int)frontier.size());
-        std::vector<int32_t> subset;
-        int64_t remaining = (int64_t)frontier.size();
-        while ((int64_t)subset.size() < threshold) {
+    const int32_t* focus_ent = rel_ent.data() + rel_ent_off[(size_t)focus];
+    const int64_t n_focus = rel_ent_off[(size_t)focus + 1] - rel_ent_off[(size_t)focus];
+    std::vector<int32_t> frontier;
+    if (threshold >= 0 && n_focus > threshold) {  // :352-354, :55-67
+        Fenwick fw((int)n_focus);
+        int64_t remaining = n_focus;
+        frontier.reserve((size_t)threshold);
+        while ((int64_t)frontier.size() < threshold) {
             const int k = (int)((int64_t)rng.next() % remaining);
             ++draws;
             const int pos = fw.kth(k);
-            subset.push_back(frontier[(size_t)pos]);
+            frontier.push_back(focus_ent[pos]);
             fw.remove(pos);
             --remaining;
         }
-        std::sort(subset.begin(), subset.end());
-        frontier.swap(subset);
+        std::sort(frontier.begin(), frontier.end());
+    } else {
+        frontier.assign(focus_ent, focus_ent + n_focus);
     }
 
     // bidirectional random walk (:92-191)
@@ -356,19 +355,21 @@ bool Graph::walk_universe(GlibcRand& rng, int64_t tc, float balance, Universe* u
     std::vector<Tri>& got = u->collected;
     got.clear();
     got.reserve((size_t)tc);
-    // collected-before test: one stamp per training triple (by_head position), per thread, instead of hashing
-    static thread_local std::vector<uint32_t> seen, queued;
-    static thread_local uint32_t stamp = 0;
-    if (seen.size() != g.by_head.size() || queued.size() != (size_t)n_ent || stamp > 0xfffffff0u) {
-        seen.assign(g.by_head.size(), 0);
-        queued.assign((size_t)n_ent, 0);
-        stamp = 0;
+    // collected-before test: one BIT per training triple (by_head position), per thread, instead of hashing
+    // (17 KB for WN18: stays in L1/L2 beside the graph arrays); the bits set by a walk are cleared when it ends
+    static thread_local std::vector<uint64_t> seen, queued;
+    static thread_local std::vector<int32_t> got_tid;
+    if (seen.size() != (g.by_head.size() + 63) / 64 || queued.size() != ((size_t)n_ent + 63) / 64) {
+        seen.assign((g.by_head.size() + 63) / 64, 0);
+        queued.assign(((size_t)n_ent + 63) / 64, 0);
     }
-    const uint32_t seen_stamp = ++stamp;
-    // the reference's std::set of next starting points: a vector de-duplicated by stamps on insertion and
+    got_tid.clear();
+    auto test_bit = [](const std::vector<uint64_t>& v, int64_t i) { return (v[(size_t)i >> 6] >> (i & 63)) & 1ULL; };
+    auto set_bit = [](std::vector<uint64_t>& v, int64_t i) { v[(size_t)i >> 6] |= 1ULL << (i & 63); };
+    auto clr_bit = [](std::vector<uint64_t>& v, int64_t i) { v[(size_t)i >> 6] &= ~(1ULL << (i & 63)); };
+    // the reference's std::set of next starting points: a vector de-duplicated by a bitmap on insertion and
     // sorted when the round ends; it survives rounds (skipped entities resurface one round later)
     std::vector<int32_t> next_points;
-    uint32_t round_stamp = ++stamp;
     bool zero_seen = false, neg_queued = false;
     int64_t target = tc;
     int32_t last_dup_entity = -1;
@@ -382,6 +383,7 @@ bool Graph::walk_universe(GlibcRand& rng, int64_t tc, float balance, Universe* u
             const int32_t e = frontier[i];
             const bool head_first = (rng.next() % 1000) < 500;  // :122 (prob is the float 500)
             ++draws;
+            if (i + 1 < frontier.size()) __builtin_prefetch(&ent_range[(size_t)frontier[i + 1]]);
             const EntRange er = ent_range[(size_t)e];
             const bool has_h = er.rig_head != -1, has_t = er.rig_tail != -1;
             int side;  // 0 head, 1 tail
@@ -407,7 +409,7 @@ bool Graph::walk_universe(GlibcRand& rng, int64_t tc, float balance, Universe* u
                 const auto it0 = std::lower_bound(g.by_head.begin(), g.by_head.end(), x, less_hrt);
                 if (it0 != g.by_head.end() && *it0 == x) tid = it0 - g.by_head.begin();
             }
-            if (tid >= 0 ? seen[(size_t)tid] == seen_stamp : zero_seen) {  // :141-154
+            if (tid >= 0 ? test_bit(seen, tid) != 0 : zero_seen) {  // :141-154
                 if (last_dup_entity == e) --dup_tol;
                 else last_dup_entity = e;
                 if (dup_tol == 0) {
@@ -418,8 +420,8 @@ bool Graph::walk_universe(GlibcRand& rng, int64_t tc, float balance, Universe* u
                 continue;
             }
             got.push_back(x);
-            if (tid >= 0) seen[(size_t)tid] = seen_stamp; else zero_seen = true;
-            if (nxt >= 0 && queued[(size_t)nxt] != round_stamp) { queued[(size_t)nxt] = round_stamp; next_points.push_back(nxt); }
+            if (tid >= 0) { set_bit(seen, tid); got_tid.push_back((int32_t)tid); } else zero_seen = true;
+            if (nxt >= 0 && !test_bit(queued, nxt)) { set_bit(queued, nxt); next_points.push_back(nxt); }
             else if (nxt < 0 && !neg_queued) { neg_queued = true; next_points.push_back(nxt); }
             ++i;  // erase(it++)
         }
@@ -428,10 +430,11 @@ bool Graph::walk_universe(GlibcRand& rng, int64_t tc, float balance, Universe* u
         std::sort(next_points.begin(), next_points.end());
         frontier.swap(next_points);
         next_points.clear();
-        round_stamp = ++stamp;
+        for (int32_t e2 : frontier)   // (the old next_points) a new round: nothing is queued yet
+            if (e2 >= 0) clr_bit(queued, e2);
         neg_queued = false;
         for (int32_t e2 : leftover)   // ascending and distinct already
-            if (e2 >= 0) { queued[(size_t)e2] = round_stamp; next_points.push_back(e2); }
+            if (e2 >= 0) { set_bit(queued, e2); next_points.push_back(e2); }
             else if (!neg_queued) { neg_queued = true; next_points.push_back(e2); }
         if ((int64_t)got.size() == last_size) --stall_tol;
         else { last_size = (int64_t)got.size(); stall_tol = 20; }
@@ -440,6 +443,9 @@ bool Graph::walk_universe(GlibcRand& rng, int64_t tc, float balance, Universe* u
             break;
         }
     }
+    for (int32_t e2 : next_points)
+        if (e2 >= 0) clr_bit(queued, e2);
+    for (int32_t t2 : got_tid) clr_bit(seen, t2);
     u->draws = draws;
     if (got.empty()) {
         *err = "build_universe: random walk collected no triples";
