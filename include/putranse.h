@@ -211,7 +211,12 @@ int pk_train_steps(const pk_model_cfg* cfg, const pk_tables* tab, const pk_sampl
                    int64_t batch_size, int64_t steps, float margin, float lr, float* d_loss, void* stream);
 
 /* K2: many universes, one launch.  One thread block per universe runs all epochs x nbatches steps
- * of that universe with its tables staged in shared memory when they fit. */
+ * of that universe with its tables staged in shared memory when they fit.  The library keeps a small
+ * device buffer per calling thread for the descriptors and for the gradient sums of entity rows that
+ * occur more than once in a batch ((2 + neg_ent) * max batch_size rows per universe, L2-resident);
+ * everything else is caller-owned.  Entity rows that occur several times in one batch are summed with
+ * floating-point reductions whose order is not fixed: results are reproducible to rounding, not bit
+ * for bit (the reference's autograd scatter-add on a GPU has the same property). */
 typedef struct {
     int64_t tri_off;   /* first record of this universe in the packed by_head / by_tail arrays   */
     int64_t ent_off;   /* first row in the packed entity tables / entity state                  */
