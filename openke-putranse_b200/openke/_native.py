@@ -47,6 +47,14 @@ class UniverseDesc(ctypes.Structure):
                 ("lcg", ctypes.c_uint64 * 8)]
 
 
+# the same 128-byte record as a numpy dtype: descriptor arrays are filled column-wise, not per universe
+UNIVERSE_DESC_DTYPE = np.dtype([("tri_off", np.int64), ("ent_off", np.int64), ("rel_off", np.int64), ("loss_off", np.int64),
+                                ("n_tri", np.int32), ("n_ent", np.int32), ("n_rel", np.int32), ("batch_size", np.int32),
+                                ("nbatches", np.int32), ("epochs", np.int32), ("margin", np.float32), ("lr", np.float32),
+                                ("lcg", np.uint64, (8,))])
+assert UNIVERSE_DESC_DTYPE.itemsize == ctypes.sizeof(UniverseDesc) == 128
+
+
 class EnergyItem(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("key_row", "universe", "fixed_local", "rel_local", "side", "reserved")]
 

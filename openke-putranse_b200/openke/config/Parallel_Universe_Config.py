@@ -376,25 +376,29 @@ class Parallel_Universe_Config(Tester):
         d_rm = self._dev_scratch("rm", dev, rm) if dl.bern else None
 
         nb = dl.nbatches
-        desc = (N.UniverseDesc * n)()
-        loss_total = 0
+        Bs = np.asarray(nT, dtype=np.int64) // nb
+        if Bs.min() < 1:
+            i = int(np.argmin(Bs))
+            raise N.NativeError("universe %d has %d triples: fewer than nbatches=%d" % (universe_ids[i], nT[i], nb))
+        epochs = np.array([h["epochs"] for h in hyper], dtype=np.int64)
+        steps = epochs * nb
+        # the descriptor array column by column (a Python loop over ctypes fields costs ~1 ms per 100 universes,
+        # all of it with the GPU idle)
+        darr = np.zeros(n, dtype=N.UNIVERSE_DESC_DTYPE)
+        darr["tri_off"], darr["ent_off"], darr["rel_off"] = toff[:n], eoff[:n], roff[:n]
+        darr["n_tri"], darr["n_ent"], darr["n_rel"] = nT, nE, nR
+        darr["batch_size"], darr["nbatches"], darr["epochs"] = Bs, nb, epochs
+        darr["margin"] = np.array([h["margin"] for h in hyper], dtype=np.float32)
+        darr["lr"] = np.array([h["lr"] for h in hyper], dtype=np.float32)
+        darr["loss_off"] = (np.cumsum(steps) - steps) if self.record_losses else -1
+        darr["lcg"][:, :min(W, 8)] = lcg[:, :min(W, 8)]
+        desc = (N.UniverseDesc * n).from_buffer(darr)
+        loss_total = int(steps.sum())
+        self.positive_triples += int((steps * Bs).sum())
         for i in range(n):
-            B = int(nT[i]) // nb
-            if B < 1:
-                raise N.NativeError("universe %d has %d triples: fewer than nbatches=%d" % (universe_ids[i], nT[i], nb))
             h = hyper[i]
-            dd = desc[i]
-            dd.tri_off, dd.ent_off, dd.rel_off = int(toff[i]), int(eoff[i]), int(roff[i])
-            dd.n_tri, dd.n_ent, dd.n_rel = int(nT[i]), int(nE[i]), int(nR[i])
-            dd.batch_size, dd.nbatches, dd.epochs = B, nb, int(h["epochs"])
-            dd.margin, dd.lr = float(h["margin"]), float(h["lr"])
-            dd.loss_off = loss_total if self.record_losses else -1
-            for w in range(min(W, 8)):
-                dd.lcg[w] = int(lcg[i, w])
-            loss_total += h["epochs"] * nb
-            h.update(nT=int(nT[i]), nE=int(nE[i]), nR=int(nR[i]), focus=int(focus[i]), batch_size=B, nbatches=nb)
+            h.update(nT=int(nT[i]), nE=int(nE[i]), nR=int(nR[i]), focus=int(focus[i]), batch_size=int(Bs[i]), nbatches=nb)
             self.universe_hyper[universe_ids[i]] = h
-            self.positive_triples += h["epochs"] * nb * B
         d_loss = self._dev_scratch("loss", dev, None, numel=max(loss_total, 1), dtype=torch.float32) if self.record_losses else None
 
         cfg = proto.native_cfg(opt=N.PK_ADAGRAD, neg_ent=dl.negative_ent, bern=1 if dl.bern else 0,
@@ -403,7 +407,12 @@ class Parallel_Universe_Config(Tester):
         st = (stream if stream is not None else torch.cuda.current_stream(dev)).cuda_stream
         # universes whose relation tables / batch scratch do not fit the universe kernel (relation-rich
         # graphs such as FB15K) are trained one by one with the single-space kernels on their slice
-        klass = [lib.pk_universe_kernel_class(ctypes.byref(cfg), int(nE[i]), int(nR[i]), int(desc[i].batch_size)) for i in range(n)]
+        # (the class is monotone in every size: if the element-wise largest shape fits, all of them do)
+        worst = lib.pk_universe_kernel_class(ctypes.byref(cfg), int(np.max(nE)), int(np.max(nR)), int(Bs.max()))
+        if worst in (0, 1):
+            klass = [worst] * n
+        else:
+            klass = [lib.pk_universe_kernel_class(ctypes.byref(cfg), int(nE[i]), int(nR[i]), int(Bs[i])) for i in range(n)]
         if min(klass) < 0:
             raise N.NativeError("pk_universe_kernel_class: %s" % N.last_error())
         big = [i for i in range(n) if klass[i] == 2]
