@@ -913,21 +913,29 @@ thread_local SideStream g_side;
 long long* g_timer = nullptr;   // pk_debug_universe_timer
 
 DescSlot* acquire_desc(size_t bytes) {
-    for (auto& s : g_desc_pool)
-        if (!s.busy || cudaEventQuery(s.done) == cudaSuccess) {
-            s.busy = false;
-            if (s.cap < bytes) {
-                if (s.d) cudaFree(s.d);
-                s.d = nullptr;
-                s.cap = 0;
-                if (cudaMalloc(&s.d, bytes) != cudaSuccess) return nullptr;
-                s.cap = bytes;
-            }
-            return &s;
-        }
+    // a free buffer that is large enough (the smallest such), else the largest free one regrown with
+    // headroom (chunks differ in size from call to call; a cudaMalloc per call costs milliseconds), else a new one
+    DescSlot* fit = nullptr;
+    DescSlot* grow = nullptr;
+    for (auto& s : g_desc_pool) {
+        if (s.busy && cudaEventQuery(s.done) != cudaSuccess) continue;
+        s.busy = false;
+        if (s.cap >= bytes) { if (!fit || s.cap < fit->cap) fit = &s; }
+        else if (!grow || s.cap > grow->cap) grow = &s;
+    }
+    if (fit) return fit;
+    const size_t want = bytes + bytes / 2 + (1u << 20);
+    if (grow) {
+        if (grow->d) cudaFree(grow->d);
+        grow->d = nullptr;
+        grow->cap = 0;
+        if (cudaMalloc(&grow->d, want) != cudaSuccess) return nullptr;
+        grow->cap = want;
+        return grow;
+    }
     DescSlot s;
-    if (cudaMalloc(&s.d, bytes) != cudaSuccess) return nullptr;
-    s.cap = bytes;
+    if (cudaMalloc(&s.d, want) != cudaSuccess) return nullptr;
+    s.cap = want;
     if (cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) != cudaSuccess) { cudaFree(s.d); return nullptr; }
     g_desc_pool.push_back(s);
     return &g_desc_pool.back();
