@@ -440,9 +440,10 @@ class Parallel_Universe_Config(Tester):
                 from concurrent.futures import ThreadPoolExecutor
                 self._pool = ThreadPoolExecutor(max_workers=1)
             ids_next = list(prefetch_ids)
-            # leave cores to the launching thread, the CUDA driver's threads and the other ranks of this host
+            # this rank's share of the host's cores, minus one for the launching thread (which sleeps while the
+            # launch runs) and the CUDA driver's threads
             _, _, world_ = _dist()
-            bg_threads = int(self.sampler_threads) or max(2, _host_cores() // max(world_, 1) - 2)
+            bg_threads = int(self.sampler_threads) or max(2, _host_cores() // max(world_, 1) - 1)
             self._prefetched = (self._sampling_key(ids_next), self._pool.submit(self._sample_universes, ids_next, bg_threads))
         ck.train_inputs = (d_by_head, d_by_tail, d_lm, d_rm)  # keep alive until the stream is done
         self.h2d_bytes += sum(t.numel() * t.element_size() for t in ck.train_inputs if t is not None) + ctypes.sizeof(desc) \
