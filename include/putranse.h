@@ -88,6 +88,23 @@ PK_REAL getTestLinkHit10(bool type_constrain);
 PK_REAL getTestLinkHit3(bool type_constrain);
 PK_REAL getTestLinkHit1(bool type_constrain);
 PK_REAL getValidHit10(void);                             /* Valid.h:242-257 */
+/* Adjacency queries over the id space the sampler currently reads (openke/base/Base.cpp:312-468; bound
+ * unconditionally by the reference's TrainDataLoader, openke/data/TrainDataLoader.py:60-103).  Host work
+ * over the sorted indexes.  getEntityRelations writes ALL distinct relations in order (the reference
+ * never advances its output cursor, Base.cpp:441-468, and so leaves only the last one in slot 0). */
+PK_INT getNumOfNegatives(PK_INT entity, PK_INT relation, bool entity_is_tail);
+PK_INT getNumOfPositives(PK_INT entity, PK_INT relation, bool entity_is_tail);
+void   getNegativeEntities(PK_INT* out, PK_INT entity, PK_INT relation, bool entity_is_tail);
+void   getPositiveEntities(PK_INT* out, PK_INT entity, PK_INT relation, bool entity_is_tail);
+PK_INT getNumOfEntityRelations(PK_INT entity, bool entity_is_tail);
+void   getEntityRelations(PK_INT* out, PK_INT entity, bool entity_is_tail);
+void   activateLoadOfAllTriples(bool unused);            /* openke/base/Reader.h:240-244 */
+/* Triple classification inputs (openke/base/Test.h:573-599; bound by TestDataLoader.py:49-56): every
+ * test triple plus one corrupted twin.  Twin i consumes two draws of LCG stream 0 (coin, entity) and is
+ * corrupted with the FILTERED corruptors against the training index, so the device kernel jumps the
+ * stream ahead by 2i and is bit-identical to the reference's sequential loop.  HOST buffers [testTotal]. */
+void   getNegTest(void);
+void   getTestBatch(PK_INT* ph, PK_INT* pt, PK_INT* pr, PK_INT* nh, PK_INT* nt, PK_INT* nr);
 
 /* ===================================================================================== (B)
  * host-side exports of the graph state (for uploading to the device); ids are int32, triples are

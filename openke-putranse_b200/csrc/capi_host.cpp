@@ -204,6 +204,72 @@ void getTailBatch(PK_INT* ph, PK_INT* pt, PK_INT* pr) { fill_batch(G().graph.tes
 void getValidHeadBatch(PK_INT* ph, PK_INT* pt, PK_INT* pr) { fill_batch(G().graph.valid[(size_t)G().last_valid_head++], true, ph, pt, pr); }
 void getValidTailBatch(PK_INT* ph, PK_INT* pt, PK_INT* pr) { fill_batch(G().graph.valid[(size_t)G().last_valid_tail++], false, ph, pt, pr); }
 
+// ---------------------------------------------------------------- adjacency queries over the current id space
+// Reference openke/base/Base.cpp:312-468: scans of one entity's run in the (h,r,t) resp. (t,r,h) order
+// of whichever index the sampler currently reads (global graph, or the universe after swapHelpers).
+// The reference's Python loaders bind all six unconditionally (openke/data/TrainDataLoader.py:60-103).
+namespace {
+struct EntRun {
+    const pk::Tri* rec = nullptr;
+    int64_t n = 0;
+    bool tail = false;
+    int32_t other(int64_t i) const { return tail ? rec[i].h : rec[i].t; }
+};
+EntRun ent_run(PK_INT entity, bool entity_is_tail) {
+    EntRun run;
+    const pk::TripleIndex& ix = pk::current_index();
+    if (entity < 0 || entity >= ix.n_ent || ix.rig_head.empty()) return run;
+    const int64_t lef = entity_is_tail ? ix.lef_tail[(size_t)entity] : ix.lef_head[(size_t)entity];
+    const int64_t rig = entity_is_tail ? ix.rig_tail[(size_t)entity] : ix.rig_head[(size_t)entity];
+    if (rig < lef) return run;
+    run.rec = (entity_is_tail ? ix.by_tail.data() : ix.by_head.data()) + lef;
+    run.n = rig - lef + 1;
+    run.tail = entity_is_tail;
+    return run;
+}
+}  // namespace
+
+PK_INT getNumOfNegatives(PK_INT entity, PK_INT relation, bool entity_is_tail) {   // Base.cpp:313-335
+    const EntRun run = ent_run(entity, entity_is_tail);
+    PK_INT n = 0;
+    for (int64_t i = 0; i < run.n; ++i) n += run.rec[i].r != relation;
+    return n;
+}
+PK_INT getNumOfPositives(PK_INT entity, PK_INT relation, bool entity_is_tail) {   // Base.cpp:337-359
+    const EntRun run = ent_run(entity, entity_is_tail);
+    PK_INT n = 0;
+    for (int64_t i = 0; i < run.n; ++i) n += run.rec[i].r == relation;
+    return n;
+}
+void getNegativeEntities(PK_INT* out, PK_INT entity, PK_INT relation, bool entity_is_tail) {   // Base.cpp:361-385
+    const EntRun run = ent_run(entity, entity_is_tail);
+    for (int64_t i = 0, o = 0; i < run.n; ++i)
+        if (run.rec[i].r != relation) out[o++] = run.other(i);
+}
+void getPositiveEntities(PK_INT* out, PK_INT entity, PK_INT relation, bool entity_is_tail) {   // Base.cpp:387-411
+    const EntRun run = ent_run(entity, entity_is_tail);
+    for (int64_t i = 0, o = 0; i < run.n; ++i)
+        if (run.rec[i].r == relation) out[o++] = run.other(i);
+}
+PK_INT getNumOfEntityRelations(PK_INT entity, bool entity_is_tail) {   // Base.cpp:413-439
+    const EntRun run = ent_run(entity, entity_is_tail);
+    PK_INT n = 0;
+    for (int64_t i = 0; i < run.n; ++i) n += (i == 0 || run.rec[i].r != run.rec[i - 1].r);
+    return n;
+}
+// Base.cpp:441-468 never advances its output cursor, so it leaves only the LAST distinct relation in
+// slot 0.  The distinct relations are written in order here (slot 0 of the reference is then slot n-1);
+// nothing in the reference's Python calls it.
+void getEntityRelations(PK_INT* out, PK_INT entity, bool entity_is_tail) {
+    const EntRun run = ent_run(entity, entity_is_tail);
+    for (int64_t i = 0, o = 0; i < run.n; ++i)
+        if (i == 0 || run.rec[i].r != run.rec[i - 1].r) out[o++] = run.rec[i].r;
+}
+
+// Reference openke/base/Reader.h:240-244 (the argument is ignored there as well): the next
+// importTestFiles() reads the filter set from triple2id.txt instead of test ∪ train ∪ valid.
+void activateLoadOfAllTriples(bool) { G().graph.load_all_triples = true; }
+
 // ---------------------------------------------------------------- many universes, many threads
 struct pk_universe_set {
     std::vector<pk::Universe> u;

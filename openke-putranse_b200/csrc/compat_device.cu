@@ -155,6 +155,118 @@ void accumulate(Acc& a, int raw, int filt) {  // Test.h:213-223, float accumulat
 
 }  // namespace
 
+
+// ---------------------------------------------------------------------------------------------
+// Triple-classification negatives (openke/base/Test.h:573-599).  The reference walks the test list
+// once on LCG stream 0: per triple one draw for the coin (randd(0) % 1000 < 500 keeps the head) and
+// one inside the FILTERED corruptor (Corrupt.h:9-105, filter_flag defaults to true).  Two draws per
+// triple, always, so thread i starts 2i draws into the stream.
+//
+// The corruptor here restates the reference's searches with their exact sentinels instead of reusing
+// the sampler's corrupt_entity(): a test pair (entity, relation) need not occur in the training
+// index, and then the reference's two boundary searches do NOT produce an empty run — they settle on
+// a neighbouring record of the entity — so what is excluded depends on those sentinels.
+// An entity with no record on that side makes the reference read trainHead[-1] (undefined); it is
+// given an empty exclusion set here.
+__device__ int64_t neg_test_corrupt(uint64_t x, const int32_t* __restrict__ idx, const int64_t* __restrict__ lefs,
+                                    const int64_t* __restrict__ rigs, int64_t n_ent, int32_t fix, int32_t r, int col) {
+    const int64_t L = lefs[fix], R = rigs[fix];
+    if (R < 0) return (int64_t)(x % (uint64_t)n_ent);
+    int64_t lo = L - 1, hi = R;
+    while (lo + 1 < hi) {                       // Corrupt.h:27-33 / :77-83
+        const int64_t mid = (lo + hi) >> 1;
+        if (idx[mid * 3 + 1] >= r) hi = mid; else lo = mid;
+    }
+    const int64_t ll = hi;
+    lo = L; hi = R + 1;
+    while (lo + 1 < hi) {                       // Corrupt.h:35-42 / :85-92
+        const int64_t mid = (lo + hi) >> 1;
+        if (idx[mid * 3 + 1] <= r) lo = mid; else hi = mid;
+    }
+    const int64_t rr = lo;
+    const int64_t tmp = (int64_t)(x % (uint64_t)(n_ent - (rr - ll + 1)));
+    if (tmp < idx[ll * 3 + col]) return tmp;
+    if (tmp > idx[rr * 3 + col] - rr + ll - 1) return tmp + rr - ll + 1;
+    lo = ll; hi = rr + 1;
+    while (lo + 1 < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (idx[mid * 3 + col] - mid + ll - 1 < tmp) lo = mid; else hi = mid;
+    }
+    return tmp + lo - ll + 1;
+}
+
+__global__ void k_neg_test(const int32_t* __restrict__ test, int64_t n, const int32_t* __restrict__ by_head,
+                           const int32_t* __restrict__ by_tail, const int64_t* __restrict__ ranges /*[4][E]*/, int64_t n_ent,
+                           const uint64_t* __restrict__ lcg, int32_t* __restrict__ neg) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t s = lcg[0];
+    {   // 2i draws ahead: x -> A x + C by squaring
+        uint64_t a = 25214903917ULL, c = 11ULL, ra = 1, rc = 0, m = 2ULL * (uint64_t)i;
+        while (m) {
+            if (m & 1) { ra = ra * a; rc = rc * a + c; }
+            c = (a + 1) * c;
+            a = a * a;
+            m >>= 1;
+        }
+        s = ra * s + rc;
+    }
+    const int32_t h = test[i * 3 + 0], r = test[i * 3 + 1], t = test[i * 3 + 2];
+    s = s * 25214903917ULL + 11ULL;
+    const bool keep_head = (s % 1000ULL) < 500ULL;
+    s = s * 25214903917ULL + 11ULL;
+    int32_t nh = h, nt = t;
+    if (keep_head) nt = (int32_t)neg_test_corrupt(s, by_head, ranges, ranges + n_ent, n_ent, h, r, 2);
+    else nh = (int32_t)neg_test_corrupt(s, by_tail, ranges + 2 * n_ent, ranges + 3 * n_ent, n_ent, t, r, 0);
+    neg[i * 3 + 0] = nh; neg[i * 3 + 1] = r; neg[i * 3 + 2] = nt;
+}
+
+namespace {
+std::vector<int32_t> g_neg_test;   // (h, r, t) per test triple
+
+int do_neg_test() {
+    pk::Global& g = pk::G();
+    const size_t n = g.graph.test.size();
+    if (n == 0) return pk::fail(PK_ERR_STATE, "getNegTest: importTestFiles has not run");
+    int rc = upload_index();
+    if (rc != PK_OK) return rc;
+    const pk::TripleIndex& ix = pk::current_index();
+    const int64_t E = ix.n_ent;
+    std::vector<int64_t> ranges((size_t)(4 * E));
+    std::memcpy(ranges.data(), ix.lef_head.data(), (size_t)E * 8);
+    std::memcpy(ranges.data() + E, ix.rig_head.data(), (size_t)E * 8);
+    std::memcpy(ranges.data() + 2 * E, ix.lef_tail.data(), (size_t)E * 8);
+    std::memcpy(ranges.data() + 3 * E, ix.rig_tail.data(), (size_t)E * 8);
+    int64_t* d_ranges = nullptr;
+    int32_t* d_test = nullptr;
+    int32_t* d_neg = nullptr;
+    auto release = [&]() { cudaFree(d_ranges); cudaFree(d_test); cudaFree(d_neg); };
+    cudaError_t e = cudaMalloc(&d_ranges, ranges.size() * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&d_test, n * 12);
+    if (e == cudaSuccess) e = cudaMalloc(&d_neg, n * 12);
+    if (e == cudaSuccess) e = cudaMemcpy(d_ranges, ranges.data(), ranges.size() * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_test, g.graph.test.data(), n * 12, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(g_dev.lcg, g.lcg, 8, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { release(); return pk::cuda_fail(e, "getNegTest: staging"); }
+    k_neg_test<<<(unsigned)((n + 255) / 256), 256>>>(d_test, (int64_t)n, g_dev.by_head, g_dev.by_tail, d_ranges, E, g_dev.lcg, d_neg);
+    pk::launch_counter() = 1;
+    g_neg_test.resize(n * 3);
+    e = cudaMemcpy(g_neg_test.data(), d_neg, n * 12, cudaMemcpyDeviceToHost);
+    release();
+    if (e != cudaSuccess) return pk::cuda_fail(e, "getNegTest: kernel");
+    // stream 0 has consumed two draws per test triple
+    uint64_t a = 25214903917ULL, c = 11ULL, ra = 1, rc2 = 0, m = 2ULL * n;
+    while (m) {
+        if (m & 1) { ra = ra * a; rc2 = rc2 * a + c; }
+        c = (a + 1) * c;
+        a = a * a;
+        m >>= 1;
+    }
+    g.lcg[0] = ra * g.lcg[0] + rc2;
+    return PK_OK;
+}
+}  // namespace
+
 namespace pk {
 void test_metrics_reset() { g_l = Acc(); g_r = Acc(); }
 void valid_metrics_reset() { g_valid_l10 = g_valid_r10 = 0; }
@@ -200,6 +312,21 @@ void validTail(PK_REAL* con, PK_INT index) {
     int raw, filt;
     if (rank_row(con, 1, 1, index, &raw, &filt) == PK_OK) { if (filt < 10) g_valid_r10 += 1; }
     else fprintf(stderr, "putranse: validTail failed: %s\n", pk::last_error().c_str());
+}
+
+void getNegTest(void) {   // Test.h:573-586
+    if (do_neg_test() != PK_OK) fprintf(stderr, "putranse: getNegTest failed: %s\n", pk::last_error().c_str());
+}
+void getTestBatch(PK_INT* ph, PK_INT* pt, PK_INT* pr, PK_INT* nh, PK_INT* nt, PK_INT* nr) {   // Test.h:588-599
+    if (do_neg_test() != PK_OK) {
+        fprintf(stderr, "putranse: getTestBatch failed: %s\n", pk::last_error().c_str());
+        return;
+    }
+    const std::vector<pk::Tri>& q = pk::G().graph.test;
+    for (size_t i = 0; i < q.size(); ++i) {
+        ph[i] = q[i].h; pt[i] = q[i].t; pr[i] = q[i].r;
+        nh[i] = g_neg_test[i * 3]; nr[i] = g_neg_test[i * 3 + 1]; nt[i] = g_neg_test[i * 3 + 2];
+    }
 }
 
 void test_link_prediction(bool) {  // Test.h:398-454 (no table printing)

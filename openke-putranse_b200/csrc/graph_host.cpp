@@ -234,6 +234,9 @@ bool Graph::import_test(std::string* err) {
     all_hrt.insert(all_hrt.end(), test.begin(), test.end());
     all_hrt.insert(all_hrt.end(), tr.begin(), tr.end());
     all_hrt.insert(all_hrt.end(), valid.begin(), valid.end());
+    if (load_all_triples) {   // Reader.h:295-308: the filter set is replaced by the file's triples
+        if (!read_triples(in_path + "triple2id.txt", &all_hrt, &lines, err)) return false;
+    }
     for (const Tri& x : all_hrt)
         if (x.h < 0 || x.t < 0 || x.r < 0 || x.h >= ne || x.t >= ne || x.r >= nr) {
             *err = "triple id out of range under " + in_path;

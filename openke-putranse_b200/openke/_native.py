@@ -105,6 +105,10 @@ def _declare(L):
         "test_link_prediction": (None, [B]),
         "getTestLinkMRR": (F, [B]), "getTestLinkMR": (F, [B]), "getTestLinkHit10": (F, [B]),
         "getTestLinkHit3": (F, [B]), "getTestLinkHit1": (F, [B]), "getValidHit10": (F, []),
+        "getNumOfNegatives": (I, [I, I, B]), "getNumOfPositives": (I, [I, I, B]),
+        "getNegativeEntities": (None, [vp, I, I, B]), "getPositiveEntities": (None, [vp, I, I, B]),
+        "getNumOfEntityRelations": (I, [I, B]), "getEntityRelations": (None, [vp, I, B]),
+        "activateLoadOfAllTriples": (None, [B]), "getNegTest": (None, []), "getTestBatch": (None, [vp] * 6),
         # pk_* host
         "pk_last_error": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
         "pk_cuda_device_count": (ctypes.c_int, []), "pk_version": (ctypes.c_char_p, []),

@@ -120,15 +120,27 @@ class Parallel_Universe_Config(Tester):
 
         # B200 build state
         self.universe_hyper = {}          # universe id -> dict(tc, balance, margin, epochs, lr, nT, nE, nR, focus)
-        self.universe_losses = {}         # universe id -> np.float32 [epochs*nbatches] (if record_losses)
+        self._universe_losses = {}        # universe id -> np.float32 [epochs*nbatches] (if record_losses)
         self.record_losses = False
         self.sampler_threads = 0          # host threads for universe construction (0 = all cores)
         self.max_chunk = 1024             # universes per train_parallel_universes chunk
-        self.piece_size = 1 << 30         # universes per launch inside a chunk (set smaller to pipeline host prep and GPU)
-        self._streams = None
+        # Launch slots.  Every chunk is trained on the stream of the next slot (round robin); a slot owns its
+        # per-launch device buffers (triple index, means, Adagrad state, losses), so the launches of consecutive
+        # chunks may be in flight together: chunk i+1's thread blocks fill the SMs that chunk i's short universes
+        # have already left (a launch is as long as its slowest universe, and 100 universes cover 100 of 148 SMs).
+        # Nothing waits for a launch until its results are needed (evaluation, checkpoints, the reference's
+        # containers, per-step losses) or its slot comes round again.
+        self.launch_slots = 3
+        # False: train_parallel_universes returns when its universes are trained (the reference's behaviour, and
+        # what its "Time took for creation of embedding spaces" line measures).  True: it returns when they
+        # are LAUNCHED, so a caller that trains chunk after chunk keeps several launches in flight; anything
+        # that reads results synchronises by itself (synchronize()).
+        self.async_training = False
+        self._slots = None
+        self._launch_index = 0
         self._pinned = {}
         self._pinned_busy = None
-        self._arena, self._arena_used, self._state_scratch, self._scratch = None, 0, {}, {}
+        self._arena, self._arena_used = None, 0
         # sample the next chunk's subgraphs on a host thread while the GPU trains this one (the universe
         # ids of the next call are predictable: they continue the sequence).  Measured on the B200 box:
         # 38.5 -> 27.5 ms per 100 universes end to end, i.e. host sampling disappears behind the kernel.
@@ -206,53 +218,70 @@ class Parallel_Universe_Config(Tester):
         N.require_cuda()
         return torch.device("cuda", torch.cuda.current_device())
 
-    def _train_chunk(self, universe_ids, prefetch_ids=None):
-        """Train `universe_ids` as a pipeline of pieces: while the GPU trains piece i (its own
-        stream), the host samples and initialises piece i+1.  Pieces of one call run concurrently
-        on the device (one thread block per universe, 148 SMs)."""
-        dev = self._device()
-        piece = max(1, int(self.piece_size))
-        pieces = [universe_ids[i:i + piece] for i in range(0, len(universe_ids), piece)]
-        if len(pieces) == 1:
-            cks = [self._train_piece(pieces[0], None, prefetch_ids=prefetch_ids)]
-        else:
-            if self._streams is None:
-                self._streams = [torch.cuda.Stream(device=dev) for _ in range(4)]
-            cur = torch.cuda.current_stream(dev)
-            cks = []
-            for i, ids in enumerate(pieces):
-                st = self._streams[i % len(self._streams)]
-                st.wait_stream(cur)
-                with torch.cuda.stream(st):
-                    cks.append(self._train_piece(ids, st))
-            for st in self._streams:
-                cur.wait_stream(st)
-        t0 = time.perf_counter()
-        for ck in cks:
-            self._finish_piece(ck)
-        if self._prefetched is not None:
-            # the background sampler must not run beside the next call's CUDA work (its allocations
-            # stall the driver's memory operations): it has had the whole launch to finish, wait for it
-            self._prefetched[1].exception()
-        self.timings["bookkeeping"] += time.perf_counter() - t0
-        return cks[0] if len(cks) == 1 else cks
+    class _Slot(object):
+        """One in-flight launch: its stream, its per-launch device buffers and the event that ends it."""
 
-    def _finish_piece(self, ck):
+        def __init__(self, dev):
+            self.stream = torch.cuda.Stream(device=dev)
+            self.done = torch.cuda.Event(blocking=True)   # waiting on it sleeps (the cores go to the sampler threads)
+            self.busy = False
+            self.scratch, self.state = {}, {}
+            self.chunk = None
+            self.host_loss = None
+
+    def _train_chunk(self, universe_ids, prefetch_ids=None):
+        """Train `universe_ids` with ONE launch on the next launch slot's stream and return without waiting
+        for it (see launch_slots)."""
+        dev = self._device()
+        if self._slots is None:
+            self._slots = [Parallel_Universe_Config._Slot(dev) for _ in range(max(1, int(self.launch_slots)))]
+        slot = self._slots[self._launch_index % len(self._slots)]
+        self._launch_index += 1
+        self._retire(slot)                              # its previous launch must have left its buffers
+        slot.stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(slot.stream):
+            ck = self._train_piece(universe_ids, slot, prefetch_ids=prefetch_ids)
+            if ck.d_loss is not None:                   # per-step losses follow the launch into pinned memory
+                if slot.host_loss is None or slot.host_loss.numel() < ck.d_loss.numel():
+                    slot.host_loss = torch.empty(int(ck.d_loss.numel() * 1.5) + 1024, dtype=torch.float32, pin_memory=True)
+                slot.host_loss[:ck.d_loss.numel()].copy_(ck.d_loss, non_blocking=True)
+            slot.done.record(slot.stream)
+        slot.busy, slot.chunk = True, ck
+        return ck
+
+    def _retire(self, slot):
+        """Wait for the slot's launch (if any) and take its host-side results."""
+        if not slot.busy:
+            return
+        t0 = time.perf_counter()
+        slot.done.synchronize()
+        self.timings["wait_for_launch"] += time.perf_counter() - t0
+        ck, slot.busy, slot.chunk = slot.chunk, False, None
         if ck.d_loss is not None:
-            # sleep until the launch has finished instead of spinning in the copy: the core goes to the host
-            # threads that are sampling the next chunk's subgraphs (with several ranks per host they are scarce)
-            done = torch.cuda.Event(blocking=True)
-            done.record(torch.cuda.current_stream(ck.d_loss.device))
-            done.synchronize()
-            host = ck.d_loss.cpu().numpy()
+            host = slot.host_loss[:ck.d_loss.numel()].numpy()
             self.d2h_bytes += host.nbytes
             o = 0
             for u in ck.ids:
                 steps = self.universe_hyper[u]["epochs"] * self.universe_hyper[u]["nbatches"]
-                self.universe_losses[u] = host[o:o + steps].copy()
+                self._universe_losses[u] = host[o:o + steps].copy()
                 o += steps
             ck.d_loss = None
-        ck.train_inputs = None   # index / means go back to the caching allocator (stream-ordered reuse)
+        ck.train_inputs = None
+
+    @property
+    def universe_losses(self):
+        self.synchronize()
+        return self._universe_losses
+
+    def synchronize(self):
+        """Wait for every launch in flight (training is asynchronous between calls; everything that reads
+        trained tables goes through here first)."""
+        if self._slots:
+            for slot in self._slots:
+                self._retire(slot)
+            dev = self._device()
+            for slot in self._slots:   # later work on the caller's stream is ordered after the launches
+                torch.cuda.current_stream(dev).wait_stream(slot.stream)
 
     def _sampling_key(self, universe_ids):
         dl = self.train_dataloader
@@ -297,7 +326,7 @@ class Parallel_Universe_Config(Tester):
         return dict(hyper=hyper, seeds=seeds, nT=nT, nE=nE, nR=nR, focus=focus, by_head=by_head, by_tail=by_tail,
                     ent_remap=ent_remap, rel_remap=rel_remap, lm=lm, rm=rm, lcg=lcg)
 
-    def _train_piece(self, universe_ids, stream, prefetch_ids=None):
+    def _train_piece(self, universe_ids, slot, prefetch_ids=None):
         lib, dl = self.lib, self.train_dataloader
         dev = self._device()
         n = len(universe_ids)
@@ -341,8 +370,7 @@ class Parallel_Universe_Config(Tester):
             # the torch generator is replayed on the GPU: no host RNG time, no H2D copy of the tables
             tables = {attr: self._arena_rows(dev, sE if attr in ent_names else sR, dim) for attr, _, dim in specs0}
             self.timings["init_alloc"] += time.perf_counter() - ta
-            self._native_init(model_cls, param, seeds, nE, nR, tables, offs, fused, device_stream=(
-                stream if stream is not None else torch.cuda.current_stream(dev)).cuda_stream)
+            self._native_init(model_cls, param, seeds, nE, nR, tables, offs, fused, device_stream=slot.stream.cuda_stream)
         else:
             packed_host = {attr: self._pinned_rows(attr, sE if attr in ent_names else sR, dim) for attr, _, dim in specs0}
             if native_ok:
@@ -366,14 +394,14 @@ class Parallel_Universe_Config(Tester):
             tables = {name: self._arena_rows(dev, t.shape[0], t.shape[1]).copy_(t, non_blocking=True) for name, t in packed_host.items()}
             self.h2d_bytes += sum(t.numel() * 4 for t in packed_host.values())
             self._pinned_busy = torch.cuda.Event()
-            self._pinned_busy.record(stream if stream is not None else torch.cuda.current_stream(dev))
+            self._pinned_busy.record(slot.stream)
         ck.tables = tables
         adagrad = True  # reference :241-242 hard-codes opt_method='Adagrad' for universes
-        ck.state = {name: self._state_rows(name, t) for name, t in ck.tables.items()} if adagrad else None
-        d_by_head = self._dev_scratch("by_head", dev, by_head)
-        d_by_tail = self._dev_scratch("by_tail", dev, by_tail) if by_tail is not None else None
-        d_lm = self._dev_scratch("lm", dev, lm) if dl.bern else None
-        d_rm = self._dev_scratch("rm", dev, rm) if dl.bern else None
+        ck.state = {name: self._state_rows(slot, name, t) for name, t in ck.tables.items()} if adagrad else None
+        d_by_head = self._dev_scratch(slot, "by_head", dev, by_head)
+        d_by_tail = self._dev_scratch(slot, "by_tail", dev, by_tail) if by_tail is not None else None
+        d_lm = self._dev_scratch(slot, "lm", dev, lm) if dl.bern else None
+        d_rm = self._dev_scratch(slot, "rm", dev, rm) if dl.bern else None
 
         nb = dl.nbatches
         Bs = np.asarray(nT, dtype=np.int64) // nb
@@ -399,12 +427,12 @@ class Parallel_Universe_Config(Tester):
             h = hyper[i]
             h.update(nT=int(nT[i]), nE=int(nE[i]), nR=int(nR[i]), focus=int(focus[i]), batch_size=int(Bs[i]), nbatches=nb)
             self.universe_hyper[universe_ids[i]] = h
-        d_loss = self._dev_scratch("loss", dev, None, numel=max(loss_total, 1), dtype=torch.float32) if self.record_losses else None
+        d_loss = self._dev_scratch(slot, "loss", dev, None, numel=max(loss_total, 1), dtype=torch.float32) if self.record_losses else None
 
         cfg = proto.native_cfg(opt=N.PK_ADAGRAD, neg_ent=dl.negative_ent, bern=1 if dl.bern else 0,
                                filt=1 if dl.filter else 0, work_threads=W)
         tab = self._packed_tables(ck, with_state=True)
-        st = (stream if stream is not None else torch.cuda.current_stream(dev)).cuda_stream
+        st = slot.stream.cuda_stream
         # universes whose relation tables / batch scratch do not fit the universe kernel (relation-rich
         # graphs such as FB15K) are trained one by one with the single-space kernels on their slice
         # (the class is monotone in every size: if the element-wise largest shape fits, all of them do)
@@ -473,17 +501,19 @@ class Parallel_Universe_Config(Tester):
         self._arena_used += need_al
         return view
 
-    def _dev_scratch(self, name, dev, host=None, numel=None, dtype=None):
-        """Per-chunk device inputs/outputs (triple index, means, per-step losses) live in grow-only
-        buffers that every chunk reuses on the same stream: asking the allocator for slightly different
-        sizes every chunk costs a cudaMalloc now and then, which stalls the launch by tens of ms."""
+    def _dev_scratch(self, slot, name, dev, host=None, numel=None, dtype=None):
+        """Per-launch device inputs/outputs (triple index, means, per-step losses) live in grow-only
+        buffers owned by the launch slot (launches of different slots are in flight together and must not
+        share them; a slot is reused only after its previous launch has finished): asking the allocator for
+        slightly different sizes every chunk costs a cudaMalloc now and then, which stalls the launch by
+        tens of ms."""
         if host is not None:
             t = torch.from_numpy(np.ascontiguousarray(host))
             numel, dtype = t.numel(), t.dtype
-        buf = self._scratch.get(name)
+        buf = slot.scratch.get(name)
         if buf is None or buf.numel() < numel or buf.dtype != dtype or buf.device != dev:
             buf = torch.empty(int(numel * 1.5) + 1024, dtype=dtype, device=dev)
-            self._scratch[name] = buf
+            slot.scratch[name] = buf
         view = buf[:numel]
         if host is not None:
             view = view.view(t.shape)
@@ -492,13 +522,13 @@ class Parallel_Universe_Config(Tester):
             view.zero_()
         return view
 
-    def _state_rows(self, name, like):
-        """Zeroed optimizer state for one chunk: a grow-only scratch per table, reused by every chunk
+    def _state_rows(self, slot, name, like):
+        """Zeroed optimizer state for one launch: a grow-only scratch per table and launch slot
         (universes are trained once; their Adagrad sums are not needed afterwards)."""
-        buf = self._state_scratch.get(name)
+        buf = slot.state.get(name)
         if buf is None or buf.numel() < like.numel() or buf.device != like.device:
             buf = torch.empty(int(like.numel() * 1.25) + 1024, dtype=torch.float32, device=like.device)
-            self._state_scratch[name] = buf
+            slot.state[name] = buf
         view = buf[:like.numel()].view_as(like)
         view.zero_()
         return view
@@ -671,8 +701,8 @@ class Parallel_Universe_Config(Tester):
                 self._train_chunk(mine, prefetch_ids=[u + c for u in mine])
             self.next_universe_id += c
             done += c
-            if self.use_gpu:
-                torch.cuda.synchronize()
+            if not self.async_training:
+                self.synchronize()
             training_duration += time.time() - start
             if done % self.valid_steps == 0:
                 print("Universe %d has finished, validating..." % (self.next_universe_id - 1))
@@ -709,6 +739,7 @@ class Parallel_Universe_Config(Tester):
         (reference eval_universes :556-603 + global_energy_estimation :605-642 + Test.h ranking)."""
         lib = self.lib
         dev = self._device()
+        self.synchronize()
         dist, rank, world = _dist()
         tri, filt = loader.eval_arrays()
         n = tri.shape[0]
@@ -877,6 +908,7 @@ class Parallel_Universe_Config(Tester):
         cands = h if mode == "head_batch" else t
         side = 0 if mode == "head_batch" else 1
         dev = self._device()
+        self.synchronize()
         st = torch.cuda.current_stream(dev).cuda_stream
         energy = torch.empty((1, self.ent_tot), dtype=torch.float32, device=dev)
         N.check(self.lib.pk_fill_inf(energy.data_ptr(), energy.numel(), st), "pk_fill_inf")
@@ -912,6 +944,7 @@ class Parallel_Universe_Config(Tester):
         self.save_parameters(os.path.join("{}{}".format(self.checkpoint_dir, filename)))
 
     def extend_state_dict(self):
+        self.synchronize()
         chunks = []
         for ck in self._chunks:
             chunks.append({"ids": ck.ids, "nT": ck.nT, "nE": ck.nE, "nR": ck.nR, "ent_remap": ck.ent_remap,
@@ -959,6 +992,8 @@ class Parallel_Universe_Config(Tester):
 
     def extend_parallel_universe(self, other):
         """Append another instance's universes after this one's (reference :797-823)."""
+        self.synchronize()
+        other.synchronize()
         shift = self.next_universe_id
         for ck in other._chunks:
             ck.ids = [u + shift for u in ck.ids]

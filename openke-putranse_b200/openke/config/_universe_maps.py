@@ -53,6 +53,7 @@ class SpaceMap(_ChunkBacked):
             return self._cache[u]
         ck, i = self._o._where[u]
         o = self._o
+        o.synchronize()   # training is asynchronous: the tables are final only after their launch
         with torch.random.fork_rng(devices=[]):   # building the module must not disturb the caller's RNG
             space = o.embedding_model(int(ck.nE[i]), int(ck.nR[i]), **o.embedding_model_param)
         for name in space.table_names():

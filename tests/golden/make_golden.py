@@ -321,7 +321,90 @@ def topic_putranse(null_vector=False):
     np.savez_compressed(os.path.join(OUT, "putranse_wn18.npz"), **res)
 
 
-TOPICS = {"dataset": topic_dataset, "sampler": topic_sampler, "universe": topic_universe, "train": topic_train,
+# --------------------------------------------------------------------------- putranse at production length
+STATIC_RANGES = dict(min_margin=1, max_margin=4, min_lr=0.001, max_lr=0.1, min_num_epochs=50, max_num_epochs=200,
+                     min_triple_constraint=500, max_triple_constraint=2000, min_balance=0.25, max_balance=0.5)
+
+
+def _record_step_losses():
+    """Instrument (not modify) the reference Trainer: keep every value train_one_step returns."""
+    from openke.config import Trainer
+    log = []
+    orig = Trainer.train_one_step
+
+    def train_one_step(self, data):
+        loss = orig(self, data)
+        log.append(loss)
+        return loss
+    Trainer.train_one_step = train_one_step
+    return log
+
+
+def _run_full(in_path, out_name, n_univ, model_name, param, nbatches, ranges, torch_threads=8, store_tables=True):
+    """The static PuTrans* experiment exactly as experiments/static_experiment_PuTransE_on_WN18.py:43-88
+    drives it (seeds 4.., drawn epochs 50-199, Adagrad), on the first n_univ universes: per-step losses,
+    final tables, remaps, and the reference's own link-prediction ranks + metrics of the ensemble."""
+    _setup_ref_import()
+    import time
+    import torch
+    import openke.module.model as M
+    from openke.config import Parallel_Universe_Config
+    from openke.data import TrainDataLoader, TestDataLoader
+    torch.set_num_threads(torch_threads)
+    log = _record_step_losses()
+    train = TrainDataLoader(in_path=in_path, nbatches=nbatches, threads=8, sampling_mode="normal", bern_flag=0,
+                            filter_flag=0, neg_ent=1, neg_rel=0, random_seed=123)
+    test = TestDataLoader(train.in_path, "link")
+    pu = Parallel_Universe_Config(training_identifier="golden_full", train_dataloader=train, test_dataloader=test,
+                                  initial_num_universes=None, embedding_model=getattr(M, model_name),
+                                  embedding_model_param=param, checkpoint_dir="/tmp/", valid_steps=10 ** 9,
+                                  save_steps=10 ** 9, training_setting="static", incremental_strategy=None, **ranges)
+    pu.use_gpu = False
+    assert pu.initial_random_seed == 4
+    res = {"n_univ": np.int64(n_univ), "initial_seed": np.int64(pu.initial_random_seed), "nbatches": np.int64(nbatches),
+           "model": np.array(model_name)}
+    t0 = time.time()
+    positives = 0
+    for u in range(n_univ):
+        del log[:]
+        pu.train_parallel_universes(1)
+        res[f"u{u}_losses"] = np.array(log, dtype=np.float32)
+        sp = pu.trained_embedding_spaces[u]
+        if store_tables:
+            for k_, v in sp.state_dict().items():
+                if k_.endswith(".weight"):
+                    res[f"u{u}_{k_[:-7]}"] = v.detach().numpy().copy()
+        emap, rmap = pu.entity_id_mappings[u], pu.relation_id_mappings[u]
+        er = np.zeros(len(emap), dtype=np.int32)
+        for g, l in emap.items():
+            er[l] = g
+        rr = np.zeros(len(rmap), dtype=np.int32)
+        for g, l in rmap.items():
+            rr[l] = g
+        res[f"u{u}_ent_remap"], res[f"u{u}_rel_remap"] = er, rr
+        positives += len(log) * train.batch_size if False else 0
+        print("universe", u, "steps", len(log), "nE", len(er), "nR", len(rr), "last loss", log[-1], flush=True)
+    res["train_seconds"] = np.float64(time.time() - t0)
+    res["torch_threads"] = np.int64(torch_threads)
+    t0 = time.time()
+    with torch.no_grad():
+        pu.data_loader.set_sampling_mode("link")
+        pu.eval_universes(eval_mode="test")
+        res["ranks"] = _rank_all(pu.lib, pu.data_loader, pu.test_one_step, test.testTotal, test.entTotal)
+        out = super(Parallel_Universe_Config, pu).run_link_prediction(False)
+    res["eval_seconds"] = np.float64(time.time() - t0)
+    res["metrics"] = np.array(out, dtype=np.float32)   # mrr, mr, hit10, hit3, hit1 (filtered, head/tail averaged)
+    res["test_sorted"] = _triples(pu.lib, "testList", test.testTotal).astype(np.int32)
+    print(out_name, "metrics", out, "train s", float(res["train_seconds"]), "eval s", float(res["eval_seconds"]))
+    np.savez_compressed(os.path.join(OUT, out_name), **res)
+
+
+def topic_putranse_full():
+    """configs[1] at production length: 24 WN18 universes with their drawn epochs (1000-3980 steps each)."""
+    _run_full(WN18, "putranse_full_wn18.npz", 24, "TransE", {"dim": 20, "p_norm": 1, "norm_flag": 1}, 20, STATIC_RANGES)
+
+
+TOPICS = {"putranse_full": topic_putranse_full, "dataset": topic_dataset,"sampler": topic_sampler, "universe": topic_universe, "train": topic_train,
           "rank": topic_rank, "putranse": topic_putranse, "putranse_nullvec": topic_putranse_nullvec}
 
 if __name__ == "__main__":
