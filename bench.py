@@ -145,6 +145,28 @@ def dist_env():
     return rank, world, local
 
 
+WORKLOADS = {
+    "m2": "PuTransE static WN18 (BASELINE.json configs[1]): %(n)d universes per GPU per step (seeds 4..), %(model)s d=20 L1 Adagrad, "
+          "nbatches=%(nb)d, k=1, tc in [500,2000), epochs in [50,200)",
+    "m4": "PuTransE on an FB15K-shaped graph (BASELINE.json configs[3]; E=14951, R=1345, 483142 synthetic train triples, tools/synth.py "
+          "seed 1234): %(n)d universes per step IN TOTAL, sharded u %% n_gpus, %(model)s d=20 L1 Adagrad, nbatches=%(nb)d, k=1",
+}
+
+
+def workload_dataset(name):
+    """Materialise the workload's graph as the header-less files the loaders read; returns (path, data text)."""
+    import tempfile
+    import util
+    if name == "m4":
+        sys.path.insert(0, os.path.join(REPO, "tools"))
+        import synth
+        tr, va, te, ne, nr = synth.fb15k_shape()
+        path = synth.write_dataset(tempfile.mkdtemp(), tr, va, te, ne, nr)
+        return path, "synthetic FB15K-shaped graph (tools/synth.py, seed 1234, checksum %d); universes sampled from it" % synth.checksum(tr)
+    return (util.materialize_wn18(tempfile.mkdtemp()),
+            "WN18 graph (repacked reference benchmark files, tests/golden/wn18.npz); universes sampled from it")
+
+
 def make_pu(path, seed_offset=0):
     from openke.config import Parallel_Universe_Config
     from openke.data import TrainDataLoader, TestDataLoader
@@ -156,17 +178,19 @@ def make_pu(path, seed_offset=0):
                                   checkpoint_dir=None, valid_steps=10 ** 9, save_steps=None, training_setting="static",
                                   incremental_strategy=None, **STATIC_RANGES)
     pu.initial_random_seed += seed_offset
-    if os.environ.get("PK_PIECE"):
-        pu.piece_size = int(os.environ["PK_PIECE"])
     if os.environ.get("PK_NO_PREFETCH"):
         pu.prefetch_sampling = False
+    if os.environ.get("PK_SLOTS"):
+        pu.launch_slots = int(os.environ["PK_SLOTS"])
     return pu
+
+
+N_SETS = 4   # resident input sets of the device-resident leg (together larger than the 126 MB L2)
 
 
 # ------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
-    import util
     from openke import _native as N
     rank, world, local = dist_env()
     N.require_cuda()
@@ -176,71 +200,88 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    import tempfile
-    path = util.materialize_wn18(tempfile.mkdtemp())
+    path, data_text = workload_dataset(args.workload)
+    strong = args.workload == "m4"
     nU = args.universes
+    # m2: every rank trains its own nU universes per step (weak scaling); m4: the step's nU universes are
+    # sharded over the ranks (strong scaling)
+    my_ids = [u for u in range(nU) if u % world == rank] if strong else list(range(nU))
 
-    # ---- device-resident leg: build the launch once, replay it
-    pu = make_pu(path, seed_offset=rank * nU)
+    # ---- device-resident leg: N_SETS resident copies of the step's inputs, launched round robin on N_SETS
+    # streams with no host synchronisation between steps (a job of many chunks keeps the SMs full this way:
+    # a launch is as long as its slowest universe and 100 universes occupy 100 of 148 SMs)
+    pu = make_pu(path, seed_offset=0 if strong else rank * nU)
     pu.record_losses = True
-    ids = list(range(nU))
-    launch = prepare_resident_launch(pu, ids, dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    st = torch.cuda.current_stream(dev)
+    launch = prepare_resident_launch(pu, my_ids, dev, N_SETS)
+    evs = []
 
-    def one_step(timed):
-        launch["reset"]()
-        flush.fill_(1)
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record(st)
-        launch["run"]()
-        ev1.record(st)
-        if timed is not None:
-            timed.append((ev0, ev1))
+    def one_step(i, timed):
+        s = launch["sets"][i % N_SETS]
+        with torch.cuda.stream(s["stream"]):
+            s["reset"]()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(s["stream"])
+            s["run"]()
+            ev1.record(s["stream"])
+        if timed:
+            evs.append((ev0, ev1))
 
-    for _ in range(args.warmup):
-        one_step(None)
+    # one launch alone on an idle GPU: the latency of a single chunk (what round 1 reported as the step)
+    torch.cuda.synchronize()
+    single_ms = []
+    for i in range(max(3, args.warmup)):
+        one_step(i, True)
+        torch.cuda.synchronize()
+        single_ms.append(evs[-1][0].elapsed_time(evs[-1][1]))
+    del evs[:]
+    for i in range(args.warmup):
+        one_step(i, False)
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
     clocks = ClockSampler(local)
     clocks.start()
-    evs = []
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        one_step(evs)
+    for i in range(args.steps):
+        one_step(i, True)
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
     elapsed = time.perf_counter() - t0
     clk = clocks.stop()
-    kernel_ms = [a.elapsed_time(b) for a, b in evs]
+    launch_ms = [a.elapsed_time(b) for a, b in evs]
+    region_ms = evs[0][0].elapsed_time(evs[-1][1]) if len(evs) > 1 else launch_ms[0]
+    for a, b in evs:   # with several streams the last launch issued need not be the last to finish
+        region_ms = max(region_ms, evs[0][0].elapsed_time(b))
     launches = launch["launches"] * args.steps
     positives = launch["positives"]
-    final_loss = float(launch["loss"][-1].item())
+    final_loss = float(launch["sets"][0]["loss"][-1].item())
+    util_ = sm_time_util(pu, launch, dev, args.steps)
     if dist:
-        t = torch.tensor([elapsed, float(np.mean(kernel_ms))], device=dev, dtype=torch.float64)
+        t = torch.tensor([elapsed, region_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed, kms = float(t[0]), float(t[1])
+        elapsed, region_ms = float(t[0]), float(t[1])
         tot = torch.tensor([float(positives)], device=dev, dtype=torch.float64)
         dist.all_reduce(tot)
         positives_all = float(tot[0])
     else:
-        kms, positives_all = float(np.mean(kernel_ms)), float(positives)
+        positives_all = float(positives)
     value = positives_all * args.steps / elapsed
 
     # ---- end-to-end leg through the public API: one Parallel_Universe_Config (loaders built once,
-    # as a user would), every step = train_parallel_universes(nU) on the NEXT nU universes of the
-    # seed sequence: host subgraph sampling + table init + H2D + K2 + D2H of the per-step losses.
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    h2d, d2h = 0, 0
-    # one long-lived orchestrator, as a user has; its first call (untimed warm-up) also allocates the
-    # table slab and the per-chunk scratch buffers that every later chunk reuses
-    # with torch.distributed initialised the orchestrator shards universe ids over the ranks itself
-    # (u % world == rank), so every call asks for nU * world universes: nU per GPU (weak scaling)
+    # as a user would), every step = train_parallel_universes(...) on the NEXT universes of the seed
+    # sequence: host subgraph sampling + table init + H2D of the triple index and descriptors + K2 + D2H of the
+    # per-step losses into pinned memory.  async_training: a call returns when its launch is queued, so
+    # consecutive chunks overlap on the device exactly like the resident leg; the final synchronize() is
+    # inside the timed region.
+    e2e_steps = args.e2e_steps if args.e2e_steps > 0 else max(20, args.steps)
+    per_call = nU if strong else nU * world    # the orchestrator shards universe ids over the ranks itself
     p2 = make_pu(path)
     p2.record_losses = True
-    p2.train_parallel_universes(nU * world)
+    p2.async_training = True
+    for _ in range(3):                            # warm-up: slabs, per-slot scratch buffers, pinned loss buffers
+        p2.train_parallel_universes(per_call)
+    p2.synchronize()
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
@@ -249,7 +290,8 @@ def run_ours(args):
     h2d0, d2h0 = p2.h2d_bytes, p2.d2h_bytes
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        p2.train_parallel_universes(nU * world)
+        p2.train_parallel_universes(per_call)
+    p2.synchronize()
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
@@ -258,6 +300,7 @@ def run_ours(args):
     h2d = (p2.h2d_bytes - h2d0) // e2e_steps
     d2h = (p2.d2h_bytes - d2h0) // e2e_steps
     timings = {k_: v_ / e2e_steps for k_, v_ in p2.timings.items()}
+    loss_check = float(np.mean([p2.universe_losses[u][-1] for u in list(p2.universe_losses)[-5:]]))
     if dist:
         t = torch.tensor([e2e_elapsed], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -267,9 +310,9 @@ def run_ours(args):
         e2e_pos = float(tot[0])
     e2e_value = e2e_pos / e2e_elapsed
 
-    # ---- evaluation leg: link prediction of the universes trained by the e2e leg over the WN18 test
-    # set (5000 triples, both sides, raw + filtered; min-energy aggregation, NCCL min all-reduce when
-    # the universes are sharded over ranks).  Reported beside the throughput, not part of `value`.
+    # ---- evaluation leg: link prediction of the universes trained by the e2e leg over the test set (both sides,
+    # raw + filtered; min-energy aggregation, NCCL min all-reduce when the universes are sharded over ranks).
+    # Reported beside the throughput, not part of `value`.
     ev = None
     if not args.no_eval:
         torch.cuda.synchronize()
@@ -290,34 +333,142 @@ def run_ours(args):
         return
     peak, peak_src = measured_peaks()
     bpp = algorithmic_bytes_per_positive(MODEL, 20, K_NEG, "adagrad")
-    achieved = positives * bpp / (np.mean(kernel_ms) * 1e-3) / 1e9
+    eff_launch_ms = region_ms / args.steps          # launches overlap: device time of the region per launch
+    achieved = positives * bpp / (eff_launch_ms * 1e-3) / 1e9
+    names = {"transe": "TransE", "transh": "TransH", "transd": "TransD"}
     line = {
         "metric": "PuTransE positive triples/sec (all universes)", "value": value, "unit": "positive triples/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "WN18 graph (repacked reference benchmark files, tests/golden/wn18.npz); universes sampled from it",
-        "config": {"workload": "m2: PuTransE static WN18, %d universes/GPU (seeds 4..), %s d=20 L1 Adagrad, nbatches=%d, k=1"
-                               % (nU, {"transe": "TransE", "transh": "TransH", "transd": "TransD"}[MODEL], NBATCHES), "universes_per_gpu": nU, "l2": "flushed between steps (256 MiB write)",
-                   "positive_triples_per_step_per_gpu": positives, "final_loss_last_universe": final_loss},
+        "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32",
+        "data": data_text,
+        "config": bench_config(args, world),
         "e2e": {"value": e2e_value, "unit": "positive triples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "ms_per_step": e2e_elapsed / e2e_steps * 1e3,
                 "host_breakdown_s_per_step": {k: v for k, v in timings.items()},
+                "mean_final_loss_last_universes": loss_check,
                 "host": {"cores": len(os.sched_getaffinity(0)), "ranks_on_host": world,
                          "note": "the next chunk's subgraphs are sampled on host threads beside the launch (bit-exact glibc rand() walk)"}},
         "gpu_launches": launches,
-        "kernel_ms_per_step": float(np.mean(kernel_ms)),
+        "positive_triples_per_step_per_gpu": positives, "final_loss_last_universe": final_loss,
+        "launch_ms": {"alone_on_the_gpu": float(np.median(single_ms)), "inside_the_pipelined_region": float(np.mean(launch_ms)),
+                      "region_ms_per_launch": eff_launch_ms},
+        "single_chunk_value": positives / (float(np.median(single_ms)) * 1e-3),
+        "sm_time_util": util_,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": k2_traffic(MODEL), "peak_source": peak_src, "algorithmic_bytes_per_positive": bpp,
-                     "note": "K2 is latency-bound: universe tables are shared-memory/L2 resident, see DESIGN.md"},
+                     "units_per_launch": positives, "launch_duration_ms": eff_launch_ms,
+                     "note": "k2_train_universes; launches of consecutive steps overlap, so the duration is the timed region's device "
+                             "time per launch (CUDA events on the launch streams).  The kernel is latency-bound, not HBM-bound: "
+                             "universe tables are shared-memory/L2 resident (traffic << algorithmic bytes), see DESIGN.md and "
+                             "sm_time_util"},
         "clocks": clk,
     }
     if ev is not None:
         line["eval"] = ev
+    if world == 1 and not args.no_extras and args.workload == "m2" and MODEL == "transe":
+        line["extras"] = run_extras(args, path, dev)
     if world == 1 and not args.no_s1:
         line["roofline_s1"] = s1_roofline(args)
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_reference_leg(path, budget_s=args.cpu_budget)
+        line["cpu_baseline"] = reference_arm(path, budget_s=args.cpu_budget) or cpu_reference_leg(path, budget_s=args.cpu_budget)
     _OUT.emit(json.dumps(line))
+
+
+def bench_config(args, world):
+    names = {"transe": "TransE", "transh": "TransH", "transd": "TransD"}
+    return {"workload": args.workload + ": " + WORKLOADS[args.workload] % dict(n=args.universes, model=names[MODEL], nb=NBATCHES),
+            "universes_per_step": args.universes, "l2": "inputs larger than L2: %d resident input sets (tables + optimizer state + "
+            "triple index + initial-table copies, ~50 MB each at 100 universes) used round robin; no flush" % N_SETS,
+            "pipelining": "steps are launched on %d streams without host synchronisation between them" % N_SETS}
+
+
+def sm_time_util(pu, launch, dev, steps):
+    """Sum over universes of the time their thread block ran / (SMs x device time of the region), for one
+    isolated launch and for a pipelined round of launches (pk_debug_universe_timer: %globaltimer per block)."""
+    import torch
+    lib = pu.lib
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    n = launch["n"]
+    out = {"sms": sms}
+    try:
+        bufs = [torch.zeros(2 * n, dtype=torch.int64, device=dev) for _ in range(N_SETS)]
+
+        def round_(k):
+            torch.cuda.synchronize()
+            evs = []
+            for i in range(k):
+                s = launch["sets"][i % N_SETS]
+                with torch.cuda.stream(s["stream"]):
+                    s["reset"]()
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(s["stream"])
+                    lib.pk_debug_universe_timer(bufs[i % N_SETS].data_ptr())
+                    s["run"]()
+                    b.record(s["stream"])
+                    evs.append((a, b))
+            torch.cuda.synchronize()
+            lib.pk_debug_universe_timer(None)
+            region = max(evs[0][0].elapsed_time(b) for _, b in evs)
+            busy = sum(float(bufs[i % N_SETS][1::2].sum().item()) for i in range(k)) / 1e6
+            return busy, region
+        busy, region = round_(1)
+        out["single_launch"] = busy / (sms * region)
+        out["slowest_universe_ms"] = float(bufs[0][1::2].max().item()) / 1e6
+        busy, region = round_(N_SETS)
+        out["pipelined_round_of_%d" % N_SETS] = busy / (sms * region)
+    except Exception as e:   # diagnostics only
+        out["error"] = "%s: %s" % (type(e).__name__, e)
+    return out
+
+
+def _child_json(cmd, timeout=900):
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+    lines = [l for l in out.stdout.strip().splitlines() if l.startswith("{")]
+    if not lines:
+        raise RuntimeError("no JSON line from %s: %s" % (" ".join(cmd[-6:]), out.stderr[-400:]))
+    return json.loads(lines[-1])
+
+
+def run_extras(args, path, dev):
+    """Other configurations BASELINE.json names, measured in the same run (N = 1): ten times the universes per
+    GPU, PuTransH / PuTransD (configs[2]), the single-space Trainer (configs[0]) and the FB15K-shaped graph
+    (configs[3]).  Each is guarded: a failing extra must not cost the headline line."""
+    import torch
+    ex = {}
+    try:   # 1000 universes per GPU through the public API, one call
+        p3 = make_pu(path)
+        p3.async_training = True
+        p3.train_parallel_universes(1000)
+        p3.synchronize()
+        pos0 = p3.positive_triples
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        p3.train_parallel_universes(1000)
+        p3.train_parallel_universes(1000)
+        p3.synchronize()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        ex["m2_1000_universes_per_call"] = {"e2e_value": (p3.positive_triples - pos0) / dt, "unit": "positive triples/s",
+                                            "calls": 2, "ms_per_call": dt / 2 * 1e3}
+        del p3
+    except Exception as e:
+        ex["m2_1000_universes_per_call"] = {"error": "%s: %s" % (type(e).__name__, e)}
+    me = [sys.executable, os.path.abspath(__file__), "--no-extras", "--no-s1", "--no-cpu-baseline", "--steps", "8", "--warmup", "3"]
+    for key, extra in (("putransh", ["--model", "transh", "--no-eval"]), ("putransd", ["--model", "transd", "--no-eval"]),
+                       ("m4_fb15k_shape_1000_universes", ["--workload", "m4", "--universes", "1000", "--steps", "3", "--e2e-steps", "3"])):
+        try:
+            d = _child_json(me + extra)
+            ex[key] = {"value": d["value"], "e2e_value": d["e2e"]["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"],
+                       "e2e_ms_per_step": d["e2e"]["ms_per_step"], "workload": d["config"]["workload"]}
+            if "eval" in d:
+                ex[key]["eval"] = d["eval"]
+        except Exception as e:
+            ex[key] = {"error": "%s: %s" % (type(e).__name__, e)}
+    try:
+        ex["c1_transe_wn18_trainer_run"] = _child_json([sys.executable, os.path.join(REPO, "tools", "bench_c1.py"), "30", "--json"])
+    except Exception as e:
+        ex["c1_transe_wn18_trainer_run"] = {"error": "%s: %s" % (type(e).__name__, e)}
+    return ex
 
 
 def s1_roofline(args):
@@ -326,10 +477,8 @@ def s1_roofline(args):
     every gathered row comes from DRAM.  Run as a child process (tools/bench_k1.py) so that its 1.5 GB
     of tables do not stay resident; its JSON line is embedded."""
     try:
-        out = subprocess.run([sys.executable, os.path.join(REPO, "tools", "bench_k1.py"), "--opt", "adagrad", "--steps", "100",
-                              "--reps", "3"], capture_output=True, text=True, timeout=600)
-        last = [l for l in out.stdout.strip().splitlines() if l.startswith("{")][-1]
-        d = json.loads(last)
+        d = _child_json([sys.executable, os.path.join(REPO, "tools", "bench_k1.py"), "--opt", "adagrad", "--steps", "100", "--reps", "3"],
+                        timeout=600)
         r = d["roofline"]
         r.update(workload=d["workload"], kernel="k1_prepare + k1_grad + k1_apply (whole step)", us_per_step=d["us_per_step"],
                  positive_triples_per_s=d["positive_triples_per_s"], algorithmic_bytes_per_positive=d["algorithmic_bytes_per_positive"])
@@ -338,16 +487,18 @@ def s1_roofline(args):
         return {"error": "%s: %s" % (type(e).__name__, e)}
 
 
-def prepare_resident_launch(pu, ids, dev):
-    """Everything _train_chunk does before the kernel, kept resident; returns closures that reset the
-    tables to their initial values and relaunch K2."""
+def prepare_resident_launch(pu, ids, dev, n_sets=1):
+    """Everything _train_chunk does before the kernel, kept resident in n_sets independent copies (own
+    tables, optimizer state, loss buffer, triple index and stream each); returns per set closures that reset
+    the tables to their initial values and relaunch K2."""
     import torch
     from openke import _native as N
-    ck = pu._train_piece(ids, None)     # first (untimed) training: leaves descriptors + inputs resident
-    d_by_head = ck.train_inputs[0]
-    pu._finish_piece(ck)
+    ck = pu._train_chunk(ids)           # first (untimed) training: samples the subgraphs, leaves the index resident
+    by_head0 = ck.train_inputs[0]
+    pu.synchronize()
     torch.cuda.synchronize()
-    # initial tables again (same seeds): rebuild them on the host exactly as _train_chunk does
+    by_head0 = by_head0.clone()
+    # initial tables again (same seeds): rebuild them on the host exactly as the reference does
     init = {}
     for name in ck.proto.table_names():
         init[name] = torch.empty_like(ck.tables[name])
@@ -360,10 +511,8 @@ def prepare_resident_launch(pu, ids, dev):
             init[name][o[i]:o[i + 1]].copy_(getattr(sp, name).weight.data)
     nb = pu.train_dataloader.nbatches
     n = len(ids)
-    desc = (N.UniverseDesc * n)()
     W = pu.train_dataloader.work_threads
     lib = pu.lib
-    loss_total = 0
     # re-derive the descriptors (the library call copied them; we need our own for replays)
     s = np.array(seeds, dtype=np.int64)
     tcs = np.array([pu.universe_hyper[u]["tc"] for u in ids], dtype=np.int64)
@@ -372,40 +521,55 @@ def prepare_resident_launch(pu, ids, dev):
     lcg = np.zeros((n, W), dtype=np.uint64)
     N.check(lib.pk_universes_export(h, None, None, None, None, None, None, None, N.addr(lcg)))
     lib.pk_universes_free(h)
-    positives = 0
-    for i, u in enumerate(ids):
-        hy = pu.universe_hyper[u]
-        dd = desc[i]
-        dd.tri_off, dd.ent_off, dd.rel_off = int(ck.toff[i]), int(ck.eoff[i]), int(ck.roff[i])
-        dd.n_tri, dd.n_ent, dd.n_rel = int(ck.nT[i]), int(ck.nE[i]), int(ck.nR[i])
-        dd.batch_size, dd.nbatches, dd.epochs = hy["batch_size"], nb, hy["epochs"]
-        dd.margin, dd.lr = float(hy["margin"]), float(hy["lr"])
-        dd.loss_off = loss_total
-        for w in range(W):
-            dd.lcg[w] = int(lcg[i, w])
-        loss_total += hy["epochs"] * nb
-        positives += hy["epochs"] * nb * hy["batch_size"]
-    d_loss = torch.zeros(loss_total, dtype=torch.float32, device=dev)
+    hy = [pu.universe_hyper[u] for u in ids]
+    epochs = np.array([h_["epochs"] for h_ in hy], dtype=np.int64)
+    Bs = np.array([h_["batch_size"] for h_ in hy], dtype=np.int64)
+    steps = epochs * nb
+    darr = np.zeros(n, dtype=N.UNIVERSE_DESC_DTYPE)
+    darr["tri_off"], darr["ent_off"], darr["rel_off"] = ck.toff[:n], ck.eoff[:n], ck.roff[:n]
+    darr["n_tri"], darr["n_ent"], darr["n_rel"] = ck.nT, ck.nE, ck.nR
+    darr["batch_size"], darr["nbatches"], darr["epochs"] = Bs, nb, epochs
+    darr["margin"] = np.array([h_["margin"] for h_ in hy], dtype=np.float32)
+    darr["lr"] = np.array([h_["lr"] for h_ in hy], dtype=np.float32)
+    darr["loss_off"] = np.cumsum(steps) - steps
+    darr["lcg"][:, :min(W, 8)] = lcg[:, :min(W, 8)]
+    desc = (N.UniverseDesc * n).from_buffer(darr)
+    loss_total, positives = int(steps.sum()), int((steps * Bs).sum())
     cfg = ck.proto.native_cfg(opt=N.PK_ADAGRAD, neg_ent=K_NEG, bern=0, filt=0, work_threads=W)
-    tab = pu._packed_tables(ck, with_state=True)
-    st = torch.cuda.current_stream(dev).cuda_stream
     state = {"launches": 0}
+    sets = []
+    for j in range(n_sets):
+        tables = {name: t.clone() for name, t in init.items()}
+        opt_state = {name: torch.zeros_like(t) for name, t in init.items()}
+        by_head = by_head0.clone()
+        d_loss = torch.zeros(loss_total, dtype=torch.float32, device=dev)
+        stream = torch.cuda.Stream(device=dev)
+        tab = N.Tables()
+        for i in range(2):
+            tab.ent[i] = tab.rel[i] = tab.ent_state[i] = tab.rel_state[i] = None
+        for i, name in enumerate(ck.proto._ent_tables):
+            tab.ent[i], tab.ent_state[i] = tables[name].data_ptr(), opt_state[name].data_ptr()
+        for i, name in enumerate(ck.proto._rel_tables):
+            tab.rel[i], tab.rel_state[i] = tables[name].data_ptr(), opt_state[name].data_ptr()
+        tab.n_ent, tab.n_rel = int(ck.eoff[-1]), int(ck.roff[-1])
 
-    def reset():
-        for name, t in ck.tables.items():
-            t.copy_(init[name])
-            ck.state[name].zero_()
+        def reset(tables=tables, opt_state=opt_state):
+            for name, t in tables.items():
+                t.copy_(init[name])
+                opt_state[name].zero_()
 
-    def run():
-        N.check(lib.pk_train_universes(ctypes.byref(cfg), ctypes.byref(tab), d_by_head.data_ptr(), None, None, None, desc, n,
-                                       d_loss.data_ptr(), st), "pk_train_universes")
-        state["launches"] = lib.pk_last_launch_count()
+        def run(tab=tab, by_head=by_head, d_loss=d_loss, stream=stream):
+            N.check(lib.pk_train_universes(ctypes.byref(cfg), ctypes.byref(tab), by_head.data_ptr(), None, None, None, desc, n,
+                                           d_loss.data_ptr(), stream.cuda_stream), "pk_train_universes")
+            state["launches"] = lib.pk_last_launch_count()
 
-    run_once = run
-    reset()
-    run_once()
+        sets.append({"reset": reset, "run": run, "loss": d_loss, "stream": stream, "tables": tables, "keep": (tab, by_head, opt_state)})
     torch.cuda.synchronize()
-    return {"reset": reset, "run": run, "launches": state["launches"], "positives": positives, "loss": d_loss}
+    with torch.cuda.stream(sets[0]["stream"]):
+        sets[0]["reset"]()
+        sets[0]["run"]()
+    torch.cuda.synchronize()
+    return {"sets": sets, "launches": state["launches"], "positives": positives, "n": n, "keep": (darr, desc, init)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -528,29 +692,73 @@ def cpu_reference_leg(path, budget_s=20.0, universes=None, max_epochs=None):
                                               cores, _TUNED["torch_threads"], _TUNED["sampler_threads"])}
 
 
+REF_PKG = os.path.join(REPO, "baseline", "_ref")
+
+
+def reference_arm(path, budget_s=0.0, steps=1, warmup=0, universes_per_step=1, soft_limit_s=0.0, raw=False):
+    """The reference ITSELF on this box's host cores: its unmodified Python package
+    (Parallel_Universe_Config.train_parallel_universes, reference :316-367, use_gpu False) on its own native core,
+    from baseline/_ref (installed by __graft_entry__.build(), git-ignored), in a child interpreter
+    (tools/ref_arm.py).  None when baseline/_ref is not there."""
+    if not os.path.exists(os.path.join(REF_PKG, "openke", "release", "Base.so")):
+        return None
+    cmd = [sys.executable, os.path.join(REPO, "tools", "ref_arm.py"), "--pkg", REF_PKG, "--data", path, "--model", MODEL,
+           "--nbatches", str(NBATCHES), "--universes", str(universes_per_step), "--steps", str(steps), "--warmup", str(warmup)]
+    if budget_s:
+        cmd += ["--budget-s", str(budget_s), "--steps", "1000"]
+    if soft_limit_s:
+        cmd += ["--soft-limit-s", str(soft_limit_s)]
+    env = dict(os.environ)
+    env.pop("PYTHONPATH", None)
+    out = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    lines = [l for l in out.stdout.strip().splitlines() if l.startswith("{")]
+    if not lines:
+        sys.stderr.write("reference arm failed: %s\n" % out.stderr[-2000:])
+        return None
+    d = json.loads(lines[-1])
+    if raw:
+        return d
+    us = [x["universes"] for x in d["per_step"]]
+    return {"value": d["value"], "unit": "positive triples/s", "cores": d["cores"], "kind": "reference",
+            "sample": "the unmodified reference package (baseline/_ref: its Python + its Base.so) on universes %d..%d of the same seed "
+                      "sequence at their drawn epochs: %d train steps, %d positive triples in %.1f s; torch %s with %d intra-op threads, "
+                      "8 sampler pthreads, host has %d cores%s" % (us[0][0], us[-1][1], d["train_steps"], d["positives"], d["seconds"],
+                                                                  d["torch"], d["torch_threads"], d["cores"],
+                                                                  "; %d late steps ran with epochs capped at 5" % d["steps_with_capped_epochs"]
+                                                                  if d["steps_with_capped_epochs"] else "")}
+
+
 def run_reference(args):
+    """`--impl reference`: one step = ONE universe of the workload trained by the unmodified reference at its drawn
+    epochs (8-27 s of host time); step i trains universe i of the same seed sequence as our arm."""
     rank, world, local = dist_env()
     if rank != 0:
         return
-    import tempfile
-    import util
-    path = util.materialize_wn18(tempfile.mkdtemp())
-    # one step = universe 0 of the workload with its epochs capped so that a step is a few seconds
-    res = []
-    for _ in range(args.warmup):
-        cpu_reference_leg(path, universes=1, max_epochs=args.ref_epochs)
+    path, data_text = workload_dataset(args.workload)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        res.append(cpu_reference_leg(path, universes=1, max_epochs=args.ref_epochs))
-    dt = time.perf_counter() - t0
-    v = float(np.mean([r["value"] for r in res]))
-    base = dict(res[-1])
-    base["value"] = v
+    d = reference_arm(path, steps=args.steps, warmup=args.warmup, universes_per_step=args.ref_universes, soft_limit_s=args.ref_soft_limit,
+                      raw=True)
+    if d is None:     # no baseline/_ref on this box: the CPU port (oracle/) of the same loop
+        res = [cpu_reference_leg(path, universes=args.ref_universes) for _ in range(args.steps)]
+        v = float(np.mean([r["value"] for r in res]))
+        base = dict(res[-1])
+        base["value"] = v
+        ms = (time.perf_counter() - t0) / args.steps * 1e3
+    else:
+        v = d["value"]
+        ms = d["seconds"] / max(1, d["steps_done"]) * 1e3
+        base = {"value": v, "unit": "positive triples/s", "cores": d["cores"], "kind": "reference",
+                "sample": "step i = universe i (seeds 4..) trained by the unmodified reference package from baseline/_ref "
+                          "(Parallel_Universe_Config.train_parallel_universes(%d), use_gpu False) at its drawn 50-199 epochs: %d train steps, "
+                          "%d positive triples in %.1f s; torch %s with %d intra-op threads + 8 sampler pthreads on %d host cores; warm-up "
+                          "steps are 2-epoch universes%s" % (args.ref_universes, d["train_steps"], d["positives"], d["seconds"], d["torch"],
+                                                             d["torch_threads"], d["cores"],
+                                                             "; %d late steps ran with epochs capped at 5 (soft time limit)" %
+                                                             d["steps_with_capped_epochs"] if d["steps_with_capped_epochs"] else "")}
     line = {"impl": "reference", "metric": "PuTransE positive triples/sec (all universes)", "value": v,
             "unit": "positive triples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "WN18 graph (repacked reference benchmark files)",
-            "config": {"workload": "m2: PuTransE static WN18 (bounded sample: universe 0, epochs capped at %d per step)" % args.ref_epochs},
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.workload == "m4" else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": data_text, "config": bench_config(args, world),
             "cpu_baseline": base,
             "e2e": {"value": v, "unit": "positive triples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     _OUT.emit(json.dumps(line))
@@ -586,9 +794,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--universes", type=int, default=100)
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--workload", default="m2", choices=sorted(WORKLOADS))
+    ap.add_argument("--e2e-steps", type=int, default=0, help="end-to-end steps (0 = as many as --steps, at least 20)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
-    ap.add_argument("--ref-epochs", type=int, default=40)
+    ap.add_argument("--ref-universes", type=int, default=1, help="reference arm: universes per step")
+    ap.add_argument("--ref-soft-limit", type=float, default=1200.0)
+    ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eval", action="store_true")
     ap.add_argument("--model", default="transe", choices=["transe", "transh", "transd"])

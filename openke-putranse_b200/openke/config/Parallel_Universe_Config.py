@@ -130,7 +130,7 @@ class Parallel_Universe_Config(Tester):
         # have already left (a launch is as long as its slowest universe, and 100 universes cover 100 of 148 SMs).
         # Nothing waits for a launch until its results are needed (evaluation, checkpoints, the reference's
         # containers, per-step losses) or its slot comes round again.
-        self.launch_slots = 3
+        self.launch_slots = 4
         # False: train_parallel_universes returns when its universes are trained (the reference's behaviour, and
         # what its "Time took for creation of embedding spaces" line measures).  True: it returns when they
         # are LAUNCHED, so a caller that trains chunk after chunk keeps several launches in flight; anything

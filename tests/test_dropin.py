@@ -140,10 +140,10 @@ def test_reference_call_sequence_through_the_cabi(wn18_dir, golden):
     V = L.getValidTotal()
     csr = []
     for side in (0, 1):   # known-true candidates per valid query (Corrupt.h:188-199 _find, as a list)
-        off, nc = np.zeros(V + 1, np.int64), np.zeros(1, np.int64)
-        N.check(N.lib().pk_filter_csr(1, side, N.addr(off), None, N.addr(nc)))   # same dlopen handle, same global state
-        cand = np.zeros(max(int(nc[0]), 1), np.int32)
-        N.check(N.lib().pk_filter_csr(1, side, N.addr(off), N.addr(cand), N.addr(nc)))
+        off, nc = np.zeros(V + 1, np.int64), ctypes.c_int64(0)
+        N.check(N.lib().pk_filter_csr(1, side, N.addr(off), None, ctypes.byref(nc)))   # same dlopen handle, same global state
+        cand = np.zeros(max(nc.value, 1), np.int32)
+        N.check(N.lib().pk_filter_csr(1, side, N.addr(off), N.addr(cand), ctypes.byref(nc)))
         csr.append((off, cand))
     hits = [0, 0]
 

@@ -15,7 +15,11 @@ import util  # noqa: E402
 
 
 def main():
-    epochs = int(sys.argv[1]) if len(sys.argv) > 1 else 50
+    epochs = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 50
+    as_json = "--json" in sys.argv
+    real_stdout = os.dup(1)
+    if as_json:
+        os.dup2(2, 1)
     from openke.config import Trainer, Tester
     from openke.data import TrainDataLoader, TestDataLoader
     from openke.module.loss import MarginLoss
@@ -42,7 +46,18 @@ def main():
     t0 = time.perf_counter()
     out = te.run_link_prediction()
     torch.cuda.synchronize()
-    print("Tester.run_link_prediction: %.3f s, filtered (mrr, mr, hit10, hit3, hit1) = %s" % (time.perf_counter() - t0, out))
+    ev_s = time.perf_counter() - t0
+    print("Tester.run_link_prediction: %.3f s, filtered (mrr, mr, hit10, hit3, hit1) = %s" % (ev_s, out))
+    if as_json:
+        import json
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps({
+            "workload": "c1: TransE on WN18, one embedding space, d=50 L1 margin 5 SGD lr 1.0, nbatches=100 (B=%d), k=1, Bernoulli + "
+                        "filtered negatives, Trainer.run (BASELINE.json configs[0])" % train.get_batch_size(),
+            "value": pos / dt, "unit": "positive triples/s", "epochs": epochs, "us_per_step": dt / (epochs * 100) * 1e6,
+            "first_loss": float(tr.losses[0][0]), "last_loss": float(tr.losses[-1][-1]),
+            "link_prediction_seconds": ev_s, "filtered": dict(zip(("mrr", "mr", "hits10", "hits3", "hits1"), (float(x) for x in out))),
+        }) + "\n").encode())
 
 
 if __name__ == "__main__":

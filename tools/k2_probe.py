@@ -23,7 +23,7 @@ def main():
     dev = torch.device("cuda", 0)
     ids = [int(x) for x in os.environ["K2_PROBE_IDS"].split(",")] if os.environ.get("K2_PROBE_IDS") else list(range(n))
     n = len(ids)
-    launch = bench.prepare_resident_launch(pu, ids, dev)
+    launch = bench.prepare_resident_launch(pu, ids, dev)["sets"][0]
     ts = []
     for _ in range(reps):
         launch["reset"]()

@@ -19,7 +19,7 @@ def main():
     path = util.materialize_wn18(tempfile.mkdtemp())
     pu = bench.make_pu(path)
     dev = torch.device("cuda", 0)
-    launch = bench.prepare_resident_launch(pu, list(range(n)), dev)
+    launch = bench.prepare_resident_launch(pu, list(range(n)), dev)["sets"][0]
     buf = torch.zeros(2 * n, dtype=torch.int64, device=dev)
     pu.lib.pk_debug_universe_timer(buf.data_ptr())
     best = None

@@ -1,0 +1,50 @@
+"""How much the SMs gain from keeping several universe launches in flight: train_parallel_universes(n)
+called `steps` times, synchronous (the reference's semantics) against asynchronous launch slots."""
+import os
+import sys
+import tempfile
+import time
+
+REPO = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+for p in (os.path.join(REPO, "openke-putranse_b200"), REPO, os.path.join(REPO, "tests")):
+    sys.path.insert(0, p)
+import torch  # noqa: E402
+import util  # noqa: E402
+import bench  # noqa: E402
+
+
+def run(path, n, steps, async_, slots, losses=True):
+    pu = bench.make_pu(path)
+    pu.record_losses = losses
+    pu.async_training = async_
+    pu.launch_slots = slots
+    pu.train_parallel_universes(n)
+    pu.train_parallel_universes(n)
+    pu.synchronize()
+    torch.cuda.synchronize()
+    pu.timings.clear()
+    p0 = pu.positive_triples
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        pu.train_parallel_universes(n)
+    pu.synchronize()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    pos = pu.positive_triples - p0
+    print("n=%4d steps=%2d async=%d slots=%d losses=%d: %.2f ms/step  %.1f M positives/s   host: %s" % (
+        n, steps, async_, slots, losses, dt / steps * 1e3, pos / dt / 1e6,
+        {k: round(v / steps * 1e3, 2) for k, v in pu.timings.items()}), flush=True)
+
+
+def main():
+    path = util.materialize_wn18(tempfile.mkdtemp())
+    import io, contextlib
+    for n, steps in ((100, 20), (1000, 3)):
+        for async_, slots in ((0, 1), (1, 2), (1, 3), (1, 4)):
+            with contextlib.redirect_stdout(io.StringIO()):
+                pass
+            run(path, n, steps, async_, slots)
+
+
+if __name__ == "__main__":
+    main()
