@@ -114,8 +114,10 @@ int pk_import_count(void);                       /* how often importTrainFiles r
 /* current sampler id space (global graph, or the universe after swapHelpers) */
 int pk_train_index(int32_t* by_head /*[nT*3] sorted (h,r,t)*/, int32_t* by_tail /*[nT*3] sorted (t,r,h)*/,
                    float* left_mean /*[nR]*/, float* right_mean /*[nR]*/);
-int pk_get_lcg(uint64_t* state /*[workThreads]*/);
-int pk_set_lcg(const uint64_t* state);
+int pk_get_lcg(uint64_t* state, int n /* capacity of state; min(n, workThreads) streams are copied */);
+int pk_set_lcg(const uint64_t* state, int n);
+/* acc = (float)(acc + v[i]) in order: how the reference's float metric accumulators sum doubles (Test.h:213-223) */
+float pk_f32_running_sum(const double* v, int64_t n);
 int pk_universe_triples(int32_t* collected_global /*[nT*3] collection order*/);
 /* which: 0 test, 1 valid.  triples sorted (r,h,t) as the reference's testList/validList */
 int pk_eval_triples(int which, int32_t* hrt /*[n*3]*/);

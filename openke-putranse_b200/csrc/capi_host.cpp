@@ -94,6 +94,7 @@ void importTestFiles(void) {
         pk::fail(PK_ERR_IO, err);
         fprintf(stderr, "putranse: importTestFiles failed: %s\n", err.c_str());
     }
+    G().eval_epoch++;
 }
 
 int pk_import_count(void) { return (int)G().graph.import_count; }
@@ -155,13 +156,25 @@ int pk_train_index(int32_t* by_head, int32_t* by_tail, float* left_mean, float* 
     return PK_OK;
 }
 
-int pk_get_lcg(uint64_t* s) {
-    std::memcpy(s, G().lcg, (size_t)G().graph.work_threads * 8);
+// n = capacity of the caller's buffer in elements: work_threads is process-global (the LAST loader's
+// setWorkThreads), so the caller says how much it holds
+int pk_get_lcg(uint64_t* s, int n) {
+    if (!s || n < 0) return pk::fail(PK_ERR_ARG, "pk_get_lcg: null argument");
+    std::memcpy(s, G().lcg, (size_t)std::min<int64_t>(n, std::min<int64_t>(G().graph.work_threads, 64)) * 8);
     return PK_OK;
 }
-int pk_set_lcg(const uint64_t* s) {
-    std::memcpy(G().lcg, s, (size_t)G().graph.work_threads * 8);
+int pk_set_lcg(const uint64_t* s, int n) {
+    if (!s || n < 0) return pk::fail(PK_ERR_ARG, "pk_set_lcg: null argument");
+    std::memcpy(G().lcg, s, (size_t)std::min<int64_t>(n, std::min<int64_t>(G().graph.work_threads, 64)) * 8);
     return PK_OK;
+}
+
+// acc = (float)(acc + v) over v in order: the reference's `float += double` metric accumulators
+// (openke/base/Test.h:14-16,213-223), for the Python-side metric table
+float pk_f32_running_sum(const double* v, int64_t n) {
+    float acc = 0.f;
+    for (int64_t i = 0; i < n; ++i) acc = (float)((double)acc + v[i]);
+    return acc;
 }
 
 // ---------------------------------------------------------------- evaluation lists

@@ -28,6 +28,7 @@ DevIndex g_dev;
 
 struct DevFilter {  // device mirror of the filter CSR of one (which, side)
     bool ready = false;
+    uint64_t epoch = 0;  // pk::Global::eval_epoch it was built from
     std::vector<int64_t> off;
     int32_t* cand = nullptr;
 };
@@ -107,12 +108,16 @@ int rank_row(const PK_REAL* con, int which, int side, PK_INT index, int* raw, in
     const std::vector<pk::Tri>& q = which == 0 ? g.graph.test : g.graph.valid;
     if (index < 0 || (size_t)index >= q.size()) return pk::fail(PK_ERR_ARG, "rank: test index out of range");
     DevFilter& f = g_filter[which][side];
-    if (!f.ready) {
+    if (!f.ready || f.epoch != g.eval_epoch) {   // a later importTestFiles replaced the lists
+        if (f.cand) cudaFree(f.cand);
+        f.cand = nullptr;
+        f.ready = false;
         std::vector<int32_t> cand;
         g.graph.filter_candidates(which, side, f.off, cand);
         PK_CUDA(cudaMalloc(&f.cand, std::max<size_t>(cand.size(), 1) * 4));
         PK_CUDA(cudaMemcpy(f.cand, cand.data(), cand.size() * 4, cudaMemcpyHostToDevice));
         f.ready = true;
+        f.epoch = g.eval_epoch;
     }
     const int64_t E = g.graph.n_ent;
     if (g_con_cap < (size_t)E) {

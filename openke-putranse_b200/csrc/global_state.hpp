@@ -16,6 +16,7 @@ struct Global {
     bool have_universe = false;
     bool swapped = false;
     int64_t last_head = 0, last_tail = 0, last_valid_head = 0, last_valid_tail = 0;
+    uint64_t eval_epoch = 1;   // bumps whenever importTestFiles replaces the evaluation lists (device filter caches key on it)
     uint64_t index_epoch = 1;  // bumps whenever the sampler's id space changes (device caches key on it)
 };
 

@@ -38,6 +38,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <map>
 #include <vector>
 
 #include "common.hpp"
@@ -76,7 +77,11 @@ struct K2Smem {
     int nrelcap;    // distinct relations a batch can hold
     int per;        // samples per LCG stream slice
     int batch_ints; // ints in one batch buffer
-    __host__ __device__ K2Smem(int model, int d, int k, int W, int mE, int mR, int mB, int stage) {
+    // fast: the FAST kernel instance (k = 1, L1, normalised, Adagrad, four-lane layout) is the one launched; with a
+    // single relation table (TransE) its relation gradient sums need ONE int32 limb per element instead of three,
+    // which is what lets relation-rich universes (FB15K shape: 400-600 relations) keep their relation side in
+    // shared memory
+    __host__ __device__ K2Smem(int model, int d, int k, int W, int mE, int mR, int mB, int stage, int fast) {
         const int ntE = model == TRANSD ? 2 : 1, ntR = model == TRANSE ? 1 : 2;
         const int nrc = model == TRANSH ? 2 : 1;   // cached relation operands: r^ (all), w^ (TransH)
         const long long occ = (long long)(2 + k) * mB;
@@ -89,7 +94,7 @@ struct K2Smem {
         for (int i = 0; i < 2; ++i) { rel_state[i] = o; if (i < ntR) o = up16(o + (size_t)mR * d * 4); }
         for (int i = 0; i < 2; ++i) { relc[i] = o; if (i < nrc) o = up16(o + (size_t)mR * d * 4); }
         reln = o;    o = up16(o + (size_t)2 * mR * 4);
-        relacc = o;  o = up16(o + (size_t)mR * ntR * d * 12);  // fixed-point relation gradient sums, three int32 limbs
+        relacc = o;  o = up16(o + (size_t)mR * ntR * d * ((fast && ntR == 1) ? 4 : 12));  // fixed-point relation gradient sums
         scratch = o;   // (the entity scratch rows live in global memory, see K2Params::scratch)
         map = o;     o = up16(o + ((size_t)mE + mR) * 4);
         // one batch buffer: h | t | r | c[k] | code_h | code_t | code_c[k] | dup[slots] | dupslot[slots] | rel_ids | ndup | nrel
@@ -224,6 +229,7 @@ __device__ __forceinline__ void fix1_add_row(int32_t* row, int d, int lane, cons
 template <class L, int NTE_, int NTR_, int FAST_>
 struct K2Ctx {
     static constexpr int NTE = NTE_, NTR = NTR_;
+    static constexpr int ACC = (FAST_ != 0 && NTR_ == 1) ? 1 : 3;   // int32 limbs per relation gradient element
     static constexpr bool kMerge3 = FAST_ != 0 && NTE_ == 1 && NTR_ == 1;   // FAST TransE: see train_sample
     using Tgt = K2Tgt<L, NTE_>;
     float* ent[2];        // working entity tables: shared memory when staged, else global
@@ -255,7 +261,7 @@ struct K2Ctx {
     __device__ __forceinline__ const float* rel_y(int r) const { return rel_c[0] + (uint32_t)r * (uint32_t)d; }
     __device__ __forceinline__ const float* rel_w(int r) const { return rel_c[1] + (uint32_t)r * (uint32_t)d; }
     __device__ __forceinline__ void rel_add(int tbl, int r, const float (&g)[L::NF], int lane) const {
-        if (FAST_ && tbl == 0) fix1_add_row<L>(rel_acc + (uint32_t)(r * NTR * 3 * d), d, lane, g);
+        if (FAST_ && tbl == 0) fix1_add_row<L>(rel_acc + (uint32_t)(r * NTR * ACC * d), d, lane, g);
         else fix_add_row<L>(rel_acc + (uint32_t)((r * NTR + tbl) * 3 * d), d, lane, g);
     }
     __device__ __forceinline__ const float* ent_row(int tbl, const Tgt& tg) const { return ent[tbl] + (uint32_t)tg.id * (uint32_t)d; }
@@ -416,7 +422,8 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int ntE = MODEL == TRANSD ? 2 : 1, ntR = MODEL == TRANSE ? 1 : 2;
     const pk_universe_desc& U = P.desc[blockIdx.x];
-    const K2Smem S(MODEL, L::EX ? L::D : P.d, FAST ? 1 : P.k, P.W, P.mE, P.mR, P.mB, STAGE);
+    const K2Smem S(MODEL, L::EX ? L::D : P.d, FAST ? 1 : P.k, P.W, P.mE, P.mR, P.mB, STAGE, FAST);
+    constexpr int ACC = K2Ctx<L, MODEL == TRANSD ? 2 : 1, MODEL == TRANSE ? 1 : 2, FAST>::ACC;
     const int tid = threadIdx.x;
     long long t_begin = 0;
     if (P.timer && tid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_begin));
@@ -498,7 +505,7 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
                 rc.state[t][i] = g_rel_state[t] ? g_rel_state[t][i] : 0.f;
             }
         for (int i = tid; i < (2 + k) * P.mB * ntE * d; i += NT) __stcg(cx.scratch + i, 0.f);
-        for (int i = tid; i < nR * ntR * 3 * d; i += NT) rc.acc[i] = 0;
+        for (int i = tid; i < nR * ntR * ACC * d; i += NT) rc.acc[i] = 0;
         if (tid < 8) s0[tid] = U.lcg[tid];
         if (tid < W) {
             int64_t lef, rig;
@@ -724,7 +731,7 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
             for (int it = grp; it < nrel + nd; it += NG) {
                 if (it < nrel) {
                     const int r = bv.rel_ids[it];
-                    int32_t* pr = rc.acc + (uint32_t)(r * ntR * 3 * d);
+                    int32_t* pr = rc.acc + (uint32_t)(r * ntR * ACC * d);
                     float g0[L::NF], g1[ntR == 2 ? L::NF : 1];
                     bool nz = FAST ? fix1_take_row<L>(pr, d, lane, g0) : fix_take_row<L>(pr, d, lane, g0);
                     if constexpr (ntR == 2) nz |= fix_take_row<L>(pr + 3 * d, d, lane, g1);
@@ -834,6 +841,12 @@ inline LaySel pick_layout(int model, int d) {
     return LaySel{V, 32, 1, 0};
 }
 
+// whether dispatch_layout launches the FAST instance for this configuration (four-lane layouts only)
+inline int fast_instance(const pk_model_cfg* cfg) {
+    const LaySel l = pick_layout(cfg->model, cfg->dim);
+    return (cfg->neg_ent == 1 && cfg->p_norm == 1 && cfg->norm_flag == 1 && cfg->opt == PK_ADAGRAD && l.V == 1 && l.G == 4) ? 1 : 0;
+}
+
 // threads per block: as many consumer warps as the register budget allows
 constexpr int k2_threads(int model, int nf) { return nf > 5 ? 256 : (model == 2 ? 384 : 512); }
 
@@ -909,7 +922,8 @@ struct SideStream {
     cudaStream_t st = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;
 };
-thread_local SideStream g_side;
+// one per caller stream: launches of different caller streams (chunks in flight together) must not meet on one side stream
+thread_local std::map<cudaStream_t, SideStream> g_sides;
 long long* g_timer = nullptr;   // pk_debug_universe_timer
 
 DescSlot* acquire_desc(size_t bytes) {
@@ -961,9 +975,10 @@ extern "C" int pk_universe_kernel_class(const pk_model_cfg* cfg, int64_t n_ent, 
     PK_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     const int k = cfg->neg_ent;
     if ((long long)(3 + k) * batch_size >= 32768 || (long long)batch_size * k > 2047 || cfg->dim > 256 || cfg->work_threads > 8) return 2;
-    K2Smem a(cfg->model, cfg->dim, k, cfg->work_threads, (int)n_ent, (int)n_rel, (int)batch_size, 1);
+    const int fast = fast_instance(cfg);
+    K2Smem a(cfg->model, cfg->dim, k, cfg->work_threads, (int)n_ent, (int)n_rel, (int)batch_size, 1, fast);
     if (a.total <= (size_t)max_smem) return 0;
-    K2Smem b(cfg->model, cfg->dim, k, cfg->work_threads, (int)n_ent, (int)n_rel, (int)batch_size, 0);
+    K2Smem b(cfg->model, cfg->dim, k, cfg->work_threads, (int)n_ent, (int)n_rel, (int)batch_size, 0, fast);
     return b.total <= (size_t)max_smem ? 1 : 2;
 }
 
@@ -988,6 +1003,7 @@ extern "C" int pk_train_universes(const pk_model_cfg* cfg, const pk_tables* pack
     PK_CUDA(cudaGetDevice(&dev));
     PK_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
 
+    const int fast = fast_instance(cfg);
     // split into a staged launch (entity tables fit in shared memory) and an unstaged one
     std::vector<pk_universe_desc> cls[2];
     int mE[2] = {1, 1}, mR[2] = {1, 1}, mB[2] = {1, 1};
@@ -997,7 +1013,7 @@ extern "C" int pk_train_universes(const pk_model_cfg* cfg, const pk_tables* pack
             return pk::fail(PK_ERR_ARG, "pk_train_universes: degenerate universe descriptor");
         if ((long long)(3 + k) * u.batch_size >= 32768 || (long long)u.batch_size * k > 2047)
             return pk::fail(PK_ERR_UNSUPPORTED, "pk_train_universes: batch too large for the universe kernel (B*k <= 2047); use pk_train_steps");
-        K2Smem own(cfg->model, d, k, W, u.n_ent, u.n_rel, u.batch_size, 1);
+        K2Smem own(cfg->model, d, k, W, u.n_ent, u.n_rel, u.batch_size, 1, fast);
         const int c = own.total <= (size_t)max_smem ? 0 : 1;
         cls[c].push_back(u);
         mE[c] = std::max(mE[c], u.n_ent);
@@ -1007,7 +1023,7 @@ extern "C" int pk_train_universes(const pk_model_cfg* cfg, const pk_tables* pack
     // the uniform carve-up uses the class maxima; if that overflows, demote the largest universes
     for (;;) {
         if (cls[0].empty()) break;
-        K2Smem s(cfg->model, d, k, W, mE[0], mR[0], mB[0], 1);
+        K2Smem s(cfg->model, d, k, W, mE[0], mR[0], mB[0], 1, fast);
         if (s.total <= (size_t)max_smem) break;
         size_t worst = 0;
         for (size_t i = 1; i < cls[0].size(); ++i)
@@ -1031,6 +1047,7 @@ extern "C" int pk_train_universes(const pk_model_cfg* cfg, const pk_tables* pack
     if (const char* e = getenv("PK_K2_PRODUCERS")) np = std::max(1, std::min(threads / 32 - 1, atoi(e)));
     const bool both = !cls[0].empty() && !cls[1].empty();
     cudaStream_t caller = st;
+    SideStream& g_side = g_sides[caller];
     if (both) {
         if (!g_side.st) {
             PK_CUDA(cudaStreamCreateWithFlags(&g_side.st, cudaStreamNonBlocking));
@@ -1043,18 +1060,18 @@ extern "C" int pk_train_universes(const pk_model_cfg* cfg, const pk_tables* pack
     for (int c = 1; c >= 0; --c) {   // the unstaged class first: its universes are the slowest
         if (cls[c].empty()) continue;
         st = (both && c == 1) ? g_side.st : caller;
-        K2Smem s(cfg->model, d, k, W, mE[c], mR[c], mB[c], c == 0);
+        K2Smem s(cfg->model, d, k, W, mE[c], mR[c], mB[c], c == 0, fast);
         if (s.total > (size_t)max_smem) {
             // the class maxima do not fit together (c == 1 only): one launch per universe, each with its
             // own carve-up; a universe that does not fit alone belongs to pk_train_steps
             // (pk_universe_kernel_class tells the caller beforehand)
             for (const auto& u : cls[c]) {
-                K2Smem own(cfg->model, d, k, W, u.n_ent, u.n_rel, u.batch_size, 0);
+                K2Smem own(cfg->model, d, k, W, u.n_ent, u.n_rel, u.batch_size, 0, fast);
                 if (own.total > (size_t)max_smem)
                     return pk::fail(PK_ERR_UNSUPPORTED, "pk_train_universes: a universe's relation tables and batch scratch exceed shared memory; train it with pk_train_steps (see pk_universe_kernel_class)");
             }
             for (const auto& u : cls[c]) {
-                K2Smem own(cfg->model, d, k, W, u.n_ent, u.n_rel, u.batch_size, 0);
+                K2Smem own(cfg->model, d, k, W, u.n_ent, u.n_rel, u.batch_size, 0, fast);
                 const size_t stride1 = (size_t)(2 + k) * u.batch_size * (cfg->model == PK_TRANSD ? 2 : 1) * d;
                 DescSlot* slot1 = acquire_desc(kDescArea + stride1 * sizeof(float));
                 if (!slot1) return pk::cuda_fail(cudaGetLastError(), "pk_train_universes: descriptor buffer");

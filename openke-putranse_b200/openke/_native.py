@@ -114,7 +114,8 @@ def _declare(L):
         "pk_cuda_device_count": (ctypes.c_int, []), "pk_version": (ctypes.c_char_p, []),
         "pk_last_launch_count": (ctypes.c_int, []), "pk_import_count": (ctypes.c_int, []),
         "pk_train_index": (ctypes.c_int, [vp, vp, vp, vp]),
-        "pk_get_lcg": (ctypes.c_int, [vp]), "pk_set_lcg": (ctypes.c_int, [vp]),
+        "pk_get_lcg": (ctypes.c_int, [vp, ctypes.c_int]), "pk_set_lcg": (ctypes.c_int, [vp, ctypes.c_int]),
+        "pk_f32_running_sum": (ctypes.c_float, [vp, I]),
         "pk_universe_triples": (ctypes.c_int, [vp]),
         "pk_eval_triples": (ctypes.c_int, [ctypes.c_int, vp]),
         "pk_filter_csr": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, vp, vp, c_i64p]),

@@ -45,6 +45,11 @@ def defaultdict_int(innerfactory=int):
     return defaultdict(innerfactory)
 
 
+def float_default():
+    """Module-level factory the reference pickles inside its evaluation caches (reference :51-52)."""
+    return float("inf")
+
+
 def _host_cores():
     """Cores this process may run on (a container's CPU set can be smaller than os.cpu_count())."""
     try:
@@ -147,7 +152,8 @@ class Parallel_Universe_Config(Tester):
         self.prefetch_sampling = True
         self._prefetched = None
         self._pool = None
-        self.max_energy_bytes = 8 << 30   # size of one [keys, E] energy tile
+        self.max_energy_bytes = 8 << 30   # upper bound for the [keys, E] energy tile buffers of an evaluation (three of them)
+        self.eval_tile_rows = 1024        # key rows per energy tile (a tile is the unit of the NCCL min all-reduce)
         self.training_duration = 0.0
         self.positive_triples = 0         # sum over universes of epochs * nbatches * batch_size
         self.gpu_launches = 0
@@ -712,7 +718,7 @@ class Parallel_Universe_Config(Tester):
                 if hit10 > self.best_hit10:
                     self.best_hit10 = hit10
                     print("Best model | hit@10 of valid set is %f" % self.best_hit10)
-                    if self.checkpoint_dir and rank == 0:
+                    if self.checkpoint_dir:
                         self.save_model("Best_model_Pu{}_{}.ckpt".format(self.embedding_model.__name__, self.training_identifier))
                     self.bad_counts = 0
                 else:
@@ -721,7 +727,7 @@ class Parallel_Universe_Config(Tester):
                 if self.bad_counts == self.early_stopping_patience:
                     print("Early stopping at universe {}".format(self.next_universe_id - 1))
                     break
-            if self.save_steps and self.checkpoint_dir and rank == 0 and (done // self.save_steps) > ((done - c) // self.save_steps):
+            if self.save_steps and self.checkpoint_dir and (done // self.save_steps) > ((done - c) // self.save_steps):
                 self.save_model()
         self.training_duration += training_duration
         print("Time took for creation of embedding spaces: {:5.3f}s".format(training_duration))
@@ -734,13 +740,107 @@ class Parallel_Universe_Config(Tester):
         self.trained_embedding_spaces[self.next_universe_id] = embedding_space
 
     # ------------------------------------------------------------------ evaluation
-    def _rank_split(self, loader):
-        """Raw/filtered ranks [n,4] of every triple of `loader` under the min-over-universes energy
-        (reference eval_universes :556-603 + global_energy_estimation :605-642 + Test.h ranking)."""
+    def _fold_keys(self, k_fixed, k_rel, k_side, consume, want_tuple=False):
+        """energy[key, e] = min over the universes that hold the key's fixed entity and relation of that universe's
+        energy of candidate e (+inf where no universe speaks): reference eval_universes :556-603 +
+        transmit_max_scores :446-465, for ALL keys, tile by tile.
+
+        Keys (fixed entity, relation, side) must be sorted by nothing in particular; they are processed in tiles
+        of `eval_tile_rows` rows, three tile buffers deep.  The host-side index work (items per chunk) is done once,
+        vectorised, and uploaded once; per tile only kernels are launched.  With torch.distributed every rank folds
+        ITS universes into the tile and the tile is min-all-reduced over NCCL asynchronously: the reduction of tile
+        t runs beside the energy kernels of tile t+1.  `consume(ti, k0, k1, energy, tuple_score)` is called, in
+        tile order, on the current stream after the tile's reduction has been ordered before it; `energy` is the
+        [k1-k0, E] tile (with null-vector filling applied when that handling is configured)."""
         lib = self.lib
         dev = self._device()
         self.synchronize()
         dist, rank, world = _dist()
+        sharded = dist is not None and world > 1
+        t_host = time.perf_counter()
+        E = self.ent_tot
+        K = int(k_fixed.shape[0])
+        st = torch.cuda.current_stream(dev).cuda_stream
+        rows_per_tile = max(1, min(K, int(self.eval_tile_rows), int(self.max_energy_bytes // (3 * 4 * E))))
+        null_vector = self.missing_embedding_handling == "null_vector"
+        tuples = null_vector or want_tuple
+        # (key row, universe, local fixed entity, local relation, side) for every chunk, all keys at once; the
+        # items come out sorted by key row, so a tile's items are a contiguous range
+        per_chunk = []
+        for ck in self._chunks:
+            ix = self._chunk_index(ck)
+            items = self._energy_items(ix, k_fixed, k_rel, k_side)
+            if items.shape[0] == 0:
+                continue
+            bounds = np.searchsorted(items["key_row"], np.arange(0, K + rows_per_tile, rows_per_tile))
+            d_items = torch.from_numpy(items.view(np.int32).reshape(-1, 6)).to(dev)
+            per_chunk.append((ck, ix, d_items, bounds, ck.proto.native_cfg(), self._packed_tables(ck)))
+        self.timings["eval_host_prep"] += time.perf_counter() - t_host
+        n_tiles = (K + rows_per_tile - 1) // rows_per_tile
+        bufs = [torch.empty((rows_per_tile, E), dtype=torch.float32, device=dev) for _ in range(min(3, n_tiles))]
+        tbufs = [torch.empty(rows_per_tile, dtype=torch.float32, device=dev) for _ in bufs] if tuples else None
+
+        def fold(ti):
+            """energy kernels of tile ti (+ the asynchronous min-all-reduce when the universes are sharded)"""
+            k0 = ti * rows_per_tile
+            k1 = min(K, k0 + rows_per_tile)
+            energy = bufs[ti % len(bufs)][:k1 - k0]
+            N.check(lib.pk_fill_inf(energy.data_ptr(), energy.numel(), st), "pk_fill_inf")
+            tuple_score = None
+            if tuples:   # reference :494-514: per key, min over universes of the (zero vector, r, fixed) score
+                tuple_score = tbufs[ti % len(bufs)][:k1 - k0]
+                N.check(lib.pk_fill_inf(tuple_score.data_ptr(), tuple_score.numel(), st), "pk_fill_inf")
+            for ck, ix, d_items, bounds, cfg, tab in per_chunk:
+                i0, i1 = int(bounds[ti]), int(bounds[ti + 1])
+                if i1 == i0:
+                    continue
+                # key rows in the items are global: hand the kernels the address row 0 WOULD have
+                N.check(lib.pk_universe_energies(ctypes.byref(cfg), ctypes.byref(tab), ix["d_eoff"].data_ptr(),
+                                                 ix["d_roff"].data_ptr(), ix["d_nE"].data_ptr(), ix["d_remap"].data_ptr(),
+                                                 d_items.data_ptr() + i0 * 24, i1 - i0, energy.data_ptr() - k0 * E * 4, E, st),
+                        "pk_universe_energies")
+                self.gpu_launches += lib.pk_last_launch_count()
+                if tuples:
+                    N.check(lib.pk_universe_tuple_scores(ctypes.byref(cfg), ctypes.byref(tab), ix["d_eoff"].data_ptr(),
+                                                         ix["d_roff"].data_ptr(), d_items.data_ptr() + i0 * 24, i1 - i0,
+                                                         tuple_score.data_ptr() - k0 * 4, st), "pk_universe_tuple_scores")
+                    self.gpu_launches += lib.pk_last_launch_count()
+            works = []
+            if sharded:       # NCCL min over NVLink: the one exchange step of the whole path
+                works.append(dist.all_reduce(energy, op=dist.ReduceOp.MIN, async_op=True))
+                if tuples:
+                    works.append(dist.all_reduce(tuple_score, op=dist.ReduceOp.MIN, async_op=True))
+            return k0, k1, energy, tuple_score, works
+
+        def finish(ti, k0, k1, energy, tuple_score, works):
+            for w in works:
+                w.wait()          # orders this stream after the reduction; the host does not block
+            if null_vector:   # reference :634-640: candidates no universe scored get the key's tuple score
+                for r0 in range(0, k1 - k0, 65535):
+                    r1 = min(k1 - k0, r0 + 65535)
+                    N.check(lib.pk_fill_missing_energies(energy[r0:r1].data_ptr(), r1 - r0, E, tuple_score[r0:r1].data_ptr(), st),
+                            "pk_fill_missing_energies")
+                    self.gpu_launches += lib.pk_last_launch_count()
+            consume(ti, k0, k1, energy, tuple_score)
+
+        pending = []
+        for ti in range(n_tiles):
+            pending.append((ti,) + fold(ti))
+            if len(pending) == len(bufs):      # the buffer that tile ti+1 will reuse must have been consumed
+                finish(*pending.pop(0))
+        while pending:
+            finish(*pending.pop(0))
+        return rows_per_tile
+
+    def _rank_split(self, loader):
+        """Raw/filtered ranks [n,4] of every triple of `loader` under the min-over-universes energy
+        (reference eval_universes :556-603 + global_energy_estimation :605-642 + Test.h ranking).  Keys = distinct
+        (side, fixed entity, relation) of the queries; under torch.distributed the ranks of a tile's queries are
+        counted by the rank that owns them (a contiguous share of the tile), then summed."""
+        lib = self.lib
+        dev = self._device()
+        dist, rank, world = _dist()
+        sharded = dist is not None and world > 1
         tri, filt = loader.eval_arrays()
         n = tri.shape[0]
         E = self.ent_tot
@@ -757,72 +857,95 @@ class Parallel_Universe_Config(Tester):
         k_side = ucode // (self.rel_tot * E)
         foff = np.concatenate([filt[0][0], filt[0][0][-1] + filt[1][0][1:]]).astype(np.int64)
         fcand = np.concatenate([filt[0][1], filt[1][1]]).astype(np.int32)
-        if fcand.size == 0:
-            fcand = np.zeros(1, np.int32)
-        d_foff, d_fcand = torch.from_numpy(foff).to(dev), torch.from_numpy(fcand).to(dev)
-        d_truth = torch.from_numpy(truth).to(dev)
-        ranks = torch.zeros((2 * n, 2), dtype=torch.int32, device=dev)
-        st = torch.cuda.current_stream(dev).cuda_stream
-
-        rows_per_tile = max(1, min(K, int(self.max_energy_bytes // (4 * E))))
-        per_chunk = [self._chunk_index(ck) for ck in self._chunks]
-        order = np.argsort(key_of_query, kind="stable")   # queries grouped by key row
+        # queries in key order, with their filter lists gathered in that order (one vectorised pass)
+        order = np.argsort(key_of_query, kind="stable")
         sorted_keys = key_of_query[order]
-        for k0 in range(0, K, rows_per_tile):
-            k1 = min(K, k0 + rows_per_tile)
-            energy = torch.empty((k1 - k0, E), dtype=torch.float32, device=dev)
-            N.check(lib.pk_fill_inf(energy.data_ptr(), energy.numel(), st), "pk_fill_inf")
-            null_vector = self.missing_embedding_handling == "null_vector"
-            tuple_score = None
-            if null_vector:   # reference :494-514: per key, min over universes of the (zero vector, r, fixed) score
-                tuple_score = torch.empty(k1 - k0, dtype=torch.float32, device=dev)
-                N.check(lib.pk_fill_inf(tuple_score.data_ptr(), tuple_score.numel(), st), "pk_fill_inf")
-            for ck, ix in zip(self._chunks, per_chunk):
-                items = self._energy_items(ix, k_fixed[k0:k1], k_rel[k0:k1], k_side[k0:k1])
-                if items.shape[0] == 0:
-                    continue
-                d_items = torch.from_numpy(items.view(np.int32).reshape(-1, 6)).to(dev)
-                cfg, tab = ck.proto.native_cfg(), self._packed_tables(ck)
-                N.check(lib.pk_universe_energies(ctypes.byref(cfg), ctypes.byref(tab), ix["d_eoff"].data_ptr(),
-                                                 ix["d_roff"].data_ptr(), ix["d_nE"].data_ptr(), ix["d_remap"].data_ptr(),
-                                                 d_items.data_ptr(), items.shape[0], energy.data_ptr(), E, st),
-                        "pk_universe_energies")
+        cnt = foff[order + 1] - foff[order]
+        s_off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+        take = np.repeat(foff[order] - s_off[:-1], cnt) + np.arange(int(s_off[-1]), dtype=np.int64)
+        s_cand = fcand[take] if take.size else np.zeros(1, np.int32)
+        d_off = torch.from_numpy(s_off).to(dev)
+        d_cand = torch.from_numpy(np.ascontiguousarray(s_cand, dtype=np.int32)).to(dev)
+        d_truth = torch.from_numpy(np.ascontiguousarray(truth[order])).to(dev)
+        d_keyrow = torch.from_numpy(sorted_keys.astype(np.int32)).to(dev)
+        ranks_sorted = torch.zeros((2 * n, 2), dtype=torch.int32, device=dev)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        tile = max(1, min(K, int(self.eval_tile_rows), int(self.max_energy_bytes // (3 * 4 * E))))
+        q_bounds = np.searchsorted(sorted_keys, np.arange(0, K + tile, tile))
+
+        def count(ti, k0, k1, energy, tuple_score):
+            lo, hi = int(q_bounds[ti]), int(q_bounds[ti + 1])
+            if sharded:       # this rank's share of the tile's queries (the others add zeros)
+                per = (hi - lo + world - 1) // world
+                lo, hi = min(hi, lo + rank * per), min(hi, lo + (rank + 1) * per)
+            if hi > lo:
+                N.check(lib.pk_rank_from_energy(energy.data_ptr() - k0 * E * 4, E, hi - lo, d_keyrow.data_ptr() + lo * 4,
+                                                d_truth.data_ptr() + lo * 4, d_off.data_ptr() + lo * 8, d_cand.data_ptr(),
+                                                ranks_sorted.data_ptr() + lo * 8, st), "pk_rank_from_energy")
                 self.gpu_launches += lib.pk_last_launch_count()
-                if null_vector:
-                    N.check(lib.pk_universe_tuple_scores(ctypes.byref(cfg), ctypes.byref(tab), ix["d_eoff"].data_ptr(),
-                                                         ix["d_roff"].data_ptr(), d_items.data_ptr(), items.shape[0],
-                                                         tuple_score.data_ptr(), st), "pk_universe_tuple_scores")
-                    self.gpu_launches += lib.pk_last_launch_count()
-            if dist is not None and world > 1:
-                dist.all_reduce(energy, op=dist.ReduceOp.MIN)   # NCCL min over NVLink: the one exchange step
-                if null_vector:
-                    dist.all_reduce(tuple_score, op=dist.ReduceOp.MIN)
-            if null_vector:   # reference :634-640: candidates no universe scored get the key's tuple score
-                for r0 in range(0, k1 - k0, 65535):
-                    r1 = min(k1 - k0, r0 + 65535)
-                    N.check(lib.pk_fill_missing_energies(energy[r0:r1].data_ptr(), r1 - r0, E, tuple_score[r0:r1].data_ptr(), st),
-                            "pk_fill_missing_energies")
-                    self.gpu_launches += lib.pk_last_launch_count()
-            lo, hi = np.searchsorted(sorted_keys, k0), np.searchsorted(sorted_keys, k1)
+
+        used = self._fold_keys(k_fixed, k_rel, k_side, count)
+        assert used == tile
+        if sharded:
+            dist.all_reduce(ranks_sorted)      # every query was ranked by exactly one rank
+        r_sorted = ranks_sorted.cpu().numpy()
+        r = np.empty_like(r_sorted)
+        r[order] = r_sorted
+        return np.concatenate([r[:n], r[n:]], axis=1)   # head raw, head filt, tail raw, tail filt
+
+    def triple_energies(self, batch_h, batch_t, batch_r):
+        """Global energy of explicit triples, min over the universes that hold head, relation AND tail, +inf when
+        there is none (reference predict_triple :413-444); with missing_embedding_handling='null_vector' an
+        unscored triple gets min(tuple score of (h, r), tuple score of (r, t)) (reference test_one_step :720-729).
+
+        Note on the reference: its test_one_step unpacks `head, tail, rel = batch_h[i], batch_r[i], batch_t[i]`
+        (:716) and so looks relations up under tail ids and vice versa; this implements what predict_triple's own
+        signature says (head, relation, tail) — see DESIGN.md, decisions on reference defects."""
+        dev = self._device()
+        h = np.asarray(batch_h, dtype=np.int64).reshape(-1)
+        t = np.asarray(batch_t, dtype=np.int64).reshape(-1)
+        r = np.asarray(batch_r, dtype=np.int64).reshape(-1)
+        n = h.shape[0]
+        if n == 0:
+            return np.zeros(0, np.float32)
+        E, R = self.ent_tot, self.rel_tot
+        null_vector = self.missing_embedding_handling == "null_vector"
+        # the tail-side key (h, r) carries the triple's energy in column t; the head-side key (t, r) is only needed
+        # for its tuple score
+        fixed = np.concatenate([h, t]) if null_vector else h
+        rel = np.concatenate([r, r]) if null_vector else r
+        side = np.concatenate([np.ones(n, np.int64), np.zeros(n, np.int64)]) if null_vector else np.ones(n, np.int64)
+        code = (side * E + fixed) * R + rel
+        ucode, key_of = np.unique(code, return_inverse=True)
+        k_rel, k_fixed, k_side = ucode % R, (ucode // R) % E, ucode // (R * E)
+        d_key = torch.from_numpy(key_of[:n].astype(np.int64)).to(dev)
+        d_t = torch.from_numpy(t).to(dev)
+        out = torch.empty(n, dtype=torch.float32, device=dev)
+        tuple_all = torch.empty(ucode.shape[0], dtype=torch.float32, device=dev) if null_vector else None
+        order = torch.argsort(d_key)
+        sorted_key = d_key[order]
+
+        def gather(ti, k0, k1, energy, tuple_score):
+            lo = int(torch.searchsorted(sorted_key, k0).item())
+            hi = int(torch.searchsorted(sorted_key, k1).item())
             if hi > lo:
                 q = order[lo:hi]
-                d_q = torch.from_numpy(q.astype(np.int64)).to(dev)
-                d_row = torch.from_numpy((key_of_query[q] - k0).astype(np.int32)).to(dev)
-                sub_truth = d_truth[d_q].contiguous()
-                # filter CSR of the selected queries, re-based
-                cnt = foff[q + 1] - foff[q]
-                sub_off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
-                take = np.concatenate([np.arange(foff[i], foff[i + 1]) for i in q]) if cnt.sum() else np.zeros(0, np.int64)
-                sub_cand = fcand[take] if take.size else np.zeros(1, np.int32)
-                d_sub_off, d_sub_cand = torch.from_numpy(sub_off).to(dev), torch.from_numpy(sub_cand.astype(np.int32)).to(dev)
-                sub_ranks = torch.zeros((q.shape[0], 2), dtype=torch.int32, device=dev)
-                N.check(lib.pk_rank_from_energy(energy.data_ptr(), E, q.shape[0], d_row.data_ptr(), sub_truth.data_ptr(),
-                                                d_sub_off.data_ptr(), d_sub_cand.data_ptr(), sub_ranks.data_ptr(), st),
-                        "pk_rank_from_energy")
-                self.gpu_launches += lib.pk_last_launch_count()
-                ranks[d_q] = sub_ranks
-        r = ranks.cpu().numpy()
-        return np.concatenate([r[:n], r[n:]], axis=1)   # head raw, head filt, tail raw, tail filt
+                out[q] = energy[d_key[q] - k0, d_t[q]]
+            if null_vector:
+                tuple_all[k0:k1] = tuple_score
+
+        # the raw per-universe energies are wanted here: null-vector FILLING of whole rows is for ranking only
+        saved = self.missing_embedding_handling
+        self.missing_embedding_handling = "last_rank"
+        try:
+            self._fold_keys(k_fixed, k_rel, k_side, gather, want_tuple=null_vector)
+        finally:
+            self.missing_embedding_handling = saved
+        if null_vector:
+            d_key_head = torch.from_numpy(key_of[n:].astype(np.int64)).to(dev)
+            fill = torch.minimum(tuple_all[d_key], tuple_all[d_key_head])
+            out = torch.where(torch.isinf(out), fill, out)
+        return out.cpu().numpy()
 
     def _chunk_index(self, ck):
         """Inverted index of one chunk: which universes hold a global entity / relation, and under
@@ -934,9 +1057,22 @@ class Parallel_Universe_Config(Tester):
         return energy[0].cpu().numpy()[cands.astype(np.int64)]
 
     def test_one_step(self, data):
+        """Reference :704-733: candidate rows for the two link-prediction modes, triple energies for 'normal'."""
+        if data["mode"] == "normal":
+            return self.triple_energies(data["batch_h"], data["batch_t"], data["batch_r"])
         return self.global_energy_estimation(data)
 
-    # ------------------------------------------------------------------ checkpoints (flat tensors)
+    def run_triple_classification(self, threshlod=None, data_iterator=None):
+        """Reference :745-749 (Tester.run_triple_classification on the global energies)."""
+        acc, threshlod = super().run_triple_classification(threshlod, data_iterator)
+        print("Accuracy is: {}".format(acc))
+        return acc, threshlod
+
+    # ------------------------------------------------------------------ checkpoints
+    # Two layouts.  "flat" (default): the packed chunk tensors + offsets + remaps — what thousands of universes
+    # need (SURVEY.md 8(f) rank 2).  "reference": the dict of reference :852-888 — one pickled nn.Module per
+    # universe plus the nested id-map dicts — which the reference's own load_parameters reads (class and factory
+    # paths are the same in both packages) and which load_parameters here imports.
     def save_model(self, filename=None):
         if not filename:
             filename = "Pu{}_learned_spaces-{}_{}.ckpt".format(self.embedding_model.__name__, self.next_universe_id,
@@ -955,40 +1091,156 @@ class Parallel_Universe_Config(Tester):
                 "bad_counts": self.bad_counts, "initial_random_seed": self.initial_random_seed,
                 "ent_tot": self.ent_tot, "rel_tot": self.rel_tot}
 
-    def save_parameters(self, path):
-        os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
-        torch.save(self.extend_state_dict(), path)
+    def export_reference_state(self):
+        """The reference's checkpoint dict (reference extend_state_dict :852-888): CPU nn.Modules and the four
+        nested id maps, materialised from the packed chunks."""
+        self.synchronize()
+        spaces, ent_maps, rel_maps = {}, defaultdict(defaultdict_int), defaultdict(defaultdict_int)
+        ent_univ, rel_univ = defaultdict(set), defaultdict(set)
+        for ck in self._chunks:
+            for i, u in enumerate(ck.ids):
+                with torch.random.fork_rng(devices=[]):
+                    sp = self.embedding_model(int(ck.nE[i]), int(ck.nR[i]), **self.embedding_model_param)
+                for name in sp.table_names():
+                    off = ck.eoff if name in sp._ent_tables else ck.roff
+                    getattr(sp, name).weight.data.copy_(ck.tables[name][off[i]:off[i + 1]])
+                for q in sp.parameters():
+                    q.requires_grad = False
+                spaces[u] = sp
+                for l, g in enumerate(ck.ent_remap[ck.eoff[i]:ck.eoff[i + 1]].tolist()):
+                    ent_maps[u][g] = l
+                    ent_univ[g].add(u)
+                for l, g in enumerate(ck.rel_remap[ck.roff[i]:ck.roff[i + 1]].tolist()):
+                    rel_maps[u][g] = l
+                    rel_univ[g].add(u)
+        for u, sp in self.trained_embedding_spaces._extra.items():
+            spaces[u] = sp
+        state = {"initial_num_universes": self.initial_num_universes, "next_universe_id": self.next_universe_id,
+                 "trained_embedding_spaces": spaces, "entity_id_mappings": ent_maps, "relation_id_mappings": rel_maps,
+                 "entity_universes": ent_univ, "relation_universes": rel_univ}
+        for k_ in ("min_margin", "max_margin", "min_lr", "max_lr", "min_num_epochs", "max_num_epochs", "min_triple_constraint",
+                   "max_triple_constraint", "min_balance", "max_balance", "embedding_model", "embedding_model_param", "best_hit10",
+                   "bad_counts"):
+            state[k_] = getattr(self, k_)
+        # the reference stores its evaluation caches too and never reads them back (its `if '' in state_dict`, :921)
+        state.update(current_tested_universes=0, current_validated_universes=0, evaluation_head2tail_triple_score_dict={},
+                     evaluation_tail2head_triple_score_dict={}, evaluation_head2rel_tuple_score_dict={},
+                     evaluation_tail2rel_tuple_score_dict={})
+        return state
 
-    def process_state_dict(self, state):
-        dev = self._device()
+    def save_parameters(self, path, layout="flat"):
+        """Collective under torch.distributed: every rank holds only the universes u % world == rank, so rank 0
+        writes `path` (with the list of its sibling shards) and rank r > 0 writes `path.rank<r>of<world>`."""
+        dist, rank, world = _dist()
+        os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+        if layout == "reference":
+            if world > 1:
+                raise NotImplementedError("the reference layout is a single-process pickle: gather with layout='flat' and re-export")
+            torch.save(self.export_reference_state(), path)
+            return
+        state = self.extend_state_dict()
+        if world > 1:
+            state["shard"] = (rank, world)
+            state["shards"] = ["%s.rank%dof%d" % (os.path.basename(path), r, world) for r in range(1, world)]
+            torch.save(state, path if rank == 0 else "%s.rank%dof%d" % (path, rank, world))
+            dist.barrier()      # a checkpoint is complete when every shard is on disk
+        else:
+            torch.save(state, path)
+
+    def _adopt_chunk(self, ids, nT, nE, nR, ent_remap, rel_remap, tables):
+        # without a CUDA device a checkpoint can still be read, inspected and re-exported (conversion between the two
+        # layouts is not compute); every compute entry point asks for the device itself and fails loudly
+        dev = self._device() if (self.use_gpu and torch.cuda.is_available()) else torch.device("cpu")
+        ck = _Chunk()
+        ck.ids = list(ids)
+        ck.nT, ck.nE, ck.nR = (np.asarray(x, dtype=np.int64) for x in (nT, nE, nR))
+        ck.ent_remap, ck.rel_remap = np.ascontiguousarray(ent_remap, dtype=np.int32), np.ascontiguousarray(rel_remap, dtype=np.int32)
+        ck.eoff = np.concatenate([[0], np.cumsum(ck.nE)]).astype(np.int64)
+        ck.roff = np.concatenate([[0], np.cumsum(ck.nR)]).astype(np.int64)
+        ck.toff = np.concatenate([[0], np.cumsum(ck.nT)]).astype(np.int64)
+        ck.tables = {k: v.to(dev).contiguous() for k, v in tables.items()}
+        ck.state = None
+        ck.d_loss = ck.train_inputs = None
+        ck.proto = self._proto()
+        for i, u in enumerate(ck.ids):
+            self._where[u] = (ck, i)
+        self._chunks.append(ck)
+        return ck
+
+    def _reset_containers(self):
+        self.synchronize()
         self._chunks = []
         self._where = {}
         for m in (self.trained_embedding_spaces, self.entity_id_mappings, self.relation_id_mappings,
                   self.entity_universes, self.relation_universes):
             m.clear()
-        for c in state["chunks"]:
-            ck = _Chunk()
-            ck.ids, ck.nT, ck.nE, ck.nR = list(c["ids"]), c["nT"], c["nE"], c["nR"]
-            ck.ent_remap, ck.rel_remap = c["ent_remap"], c["rel_remap"]
-            ck.eoff = np.concatenate([[0], np.cumsum(ck.nE)]).astype(np.int64)
-            ck.roff = np.concatenate([[0], np.cumsum(ck.nR)]).astype(np.int64)
-            ck.toff = np.concatenate([[0], np.cumsum(ck.nT)]).astype(np.int64)
-            ck.tables = {k: v.to(dev) for k, v in c["tables"].items()}
-            ck.state = None
-            ck.proto = self._proto()
-            for i, u in enumerate(ck.ids):
-                self._where[u] = (ck, i)
-            self._chunks.append(ck)
-        self._maps_version += 1
-        self.next_universe_id = state["next_universe_id"]
-        self.universe_hyper = state.get("universe_hyper", {})
-        self.best_hit10 = state.get("best_hit10", 0)
-        self.bad_counts = state.get("bad_counts", 0)
         self._rank_cache.clear()
 
+    def process_state_dict(self, state, shard_states=()):
+        if "format" not in state and "trained_embedding_spaces" in state:
+            return self.import_reference_state(state)
+        dist, rank, world = _dist()
+        self._reset_containers()
+        chunks = [c for st_ in (state,) + tuple(shard_states) for c in st_["chunks"]]
+        have = sorted(u for c in chunks for u in c["ids"])
+        if have != list(range(state["next_universe_id"])):
+            raise N.NativeError("checkpoint holds %d of %d universes (a shard of a multi-GPU checkpoint is missing)"
+                                % (len(have), state["next_universe_id"]))
+        for j, c in enumerate(chunks):
+            if world > 1 and j % world != rank:   # evaluation min-all-reduces over ranks: every chunk lives on ONE rank
+                continue
+            self._adopt_chunk(c["ids"], c["nT"], c["nE"], c["nR"], c["ent_remap"], c["rel_remap"], c["tables"])
+        self._maps_version += 1
+        self.next_universe_id = state["next_universe_id"]
+        self.universe_hyper = dict(state.get("universe_hyper", {}))
+        for st_ in shard_states:
+            self.universe_hyper.update(st_.get("universe_hyper", {}))
+        self.best_hit10 = state.get("best_hit10", 0)
+        self.bad_counts = state.get("bad_counts", 0)
+
+    def import_reference_state(self, state):
+        """A checkpoint written by the reference (reference :852-888,929-931): one nn.Module per universe and
+        global->local dicts; packed into one chunk.  Hyper-parameter ranges are restored as the reference
+        restores them (:890-919)."""
+        dist, rank, world = _dist()
+        self._reset_containers()
+        spaces = state["trained_embedding_spaces"]
+        ids = sorted(spaces)
+        names = self._proto().table_names()
+        ent_names = set(self._proto()._ent_tables)
+        nE, nR, er, rr = [], [], [], []
+        tabs = {n_: [] for n_ in names}
+        mine = [u for j, u in enumerate(ids) if world == 1 or j % world == rank]
+        for u in mine:
+            sd = spaces[u].state_dict()
+            for n_ in names:
+                tabs[n_].append(sd[n_ + ".weight"].detach().float().cpu())
+            for maps, sizes, remaps, key in ((state["entity_id_mappings"], nE, er, next(iter(ent_names))),
+                                             (state["relation_id_mappings"], nR, rr, [n_ for n_ in names if n_ not in ent_names][0])):
+                rows = sd[key + ".weight"].shape[0]
+                remap = np.full(rows, -1, dtype=np.int64)
+                for g, l in maps[u].items():
+                    remap[int(l)] = int(g)
+                if (remap < 0).any():
+                    raise N.NativeError("reference checkpoint: universe %d has local ids without a global id" % u)
+                sizes.append(rows)
+                remaps.append(remap)
+        if mine:
+            self._adopt_chunk(mine, np.zeros(len(mine), np.int64), nE, nR, np.concatenate(er), np.concatenate(rr),
+                              {n_: torch.cat(tabs[n_], 0) for n_ in names})
+        self._maps_version += 1
+        self.next_universe_id = state["next_universe_id"]
+        for k_ in ("initial_num_universes", "min_margin", "max_margin", "min_lr", "max_lr", "min_num_epochs", "max_num_epochs",
+                   "min_triple_constraint", "max_triple_constraint", "min_balance", "max_balance", "best_hit10", "bad_counts"):
+            if k_ in state:
+                setattr(self, k_, state[k_])
+
     def load_parameters(self, filename):
-        state = torch.load(self.checkpoint_dir + filename, map_location="cpu", weights_only=False)
-        self.process_state_dict(state)
+        path = (self.checkpoint_dir or "") + filename
+        state = torch.load(path, map_location="cpu", weights_only=False)
+        shards = [torch.load(os.path.join(os.path.dirname(path), s_), map_location="cpu", weights_only=False)
+                  for s_ in state.get("shards", [])] if isinstance(state, dict) else []
+        self.process_state_dict(state, shards)
 
     def extend_parallel_universe(self, other):
         """Append another instance's universes after this one's (reference :797-823)."""

@@ -15,10 +15,8 @@ from .. import _native as N
 
 def _f32_running_sum(values):
     """acc = (float)(acc + v) for v in order, v and the sum in double: how a C `float += double` behaves."""
-    acc = np.float32(0.0)
-    for v in values:
-        acc = np.float32(float(acc) + v)
-    return acc
+    v = np.ascontiguousarray(values, dtype=np.float64)
+    return np.float32(N.lib().pk_f32_running_sum(N.addr(v), int(v.shape[0])))
 
 
 def link_metrics(ranks):
@@ -31,8 +29,8 @@ def link_metrics(ranks):
     table = {}
     for name, col in (("l_raw", 0), ("l_filter", 1), ("r_raw", 2), ("r_filter", 3)):
         r = ranks[:, col].astype(np.int64)
-        rank_sum = _f32_running_sum((r + 1).astype(np.float64).tolist())
-        reci_sum = _f32_running_sum((1.0 / (r + 1)).tolist())
+        rank_sum = _f32_running_sum((r + 1).astype(np.float64))
+        reci_sum = _f32_running_sum(1.0 / (r + 1))
         table[name] = (reci_sum / f32(n), rank_sum / f32(n), f32((r < 10).sum()) / f32(n), f32((r < 3).sum()) / f32(n),
                        f32((r < 1).sum()) / f32(n))
     avg = tuple(float((f32(a) + f32(b)) / f32(2)) for a, b in zip(table["l_filter"], table["r_filter"]))
@@ -98,5 +96,70 @@ class Tester(object):
         (mrr, mr, hit10, hit3, hit1), self.last_table = link_metrics(self.last_ranks)
         return mrr, mr, hit10, hit3, hit1
 
+    # ---- triple classification (reference Tester.py:95-191); the loops over sorted (answer, score) pairs are
+    #      evaluated as prefix sums, with the reference's tie order (np.argsort of the scores) and first-maximum rule
+    @staticmethod
+    def _sorted_answers(score, ans):
+        order = np.argsort(score)
+        return np.asarray(ans)[order], np.asarray(score)[order]
+
+    def get_best_threshlod(self, score, ans):
+        a, sc = self._sorted_answers(score, ans)
+        total_all = float(len(sc))
+        total_false = total_all - float(np.sum(a))
+        cur = np.cumsum(a == 1).astype(np.float64)
+        res = (2 * cur + total_false - np.arange(len(sc)) - 1) / total_all
+        if len(sc) == 0 or not (res > 0.0).any():
+            return None, 0.0
+        i = int(np.argmax(res))               # first index of the maximum, as `if res_current > res_mx` keeps it
+        return sc[i], float(res[i])
+
+    def determine_classification_cross_table_values(self, res, threshold):
+        ans, score = res[:, 0], res[:, 1]
+        pred = score < threshold
+        table = {"tp": int((pred & (ans == 1)).sum()), "fp": int((pred & (ans == 0)).sum()),
+                 "tn": int((~pred & (ans == 0)).sum()), "fn": int((~pred & (ans == 1)).sum())}
+        print("True Positives :{}".format(table["tp"]))
+        print("True Negatives :{}".format(table["tn"]))
+        print("False Positives :{}".format(table["fp"]))
+        print("False Negatives :{}".format(table["fn"]))
+        self.last_cross_table = table
+        return table
+
     def run_triple_classification(self, threshlod=None, data_iterator=None):
-        raise NotImplementedError("triple classification is outside the B200 hot path (SURVEY.md 8(f))")
+        self.lib.initTest()
+        score, ans = [], []
+        if data_iterator is None:
+            self.data_loader.set_sampling_mode("classification")
+            data_iterator = self.data_loader
+        for pos_ins, neg_ins in data_iterator:
+            res_pos = np.asarray(self.test_one_step(pos_ins), dtype=np.float32).reshape(-1)
+            ans += [1] * len(res_pos)
+            score.append(res_pos)
+            res_neg = np.asarray(self.test_one_step(neg_ins), dtype=np.float32).reshape(-1)
+            ans += [0] * len(res_neg)
+            score.append(res_neg)
+        score = np.concatenate(score, axis=-1)
+        ans = np.array(ans)
+        if threshlod is None:
+            threshlod, _ = self.get_best_threshlod(score, ans)
+        a, sc = self._sorted_answers(score, ans)
+        total_all = float(len(sc))
+        total_true = float(np.sum(a))
+        total_false = total_all - total_true
+        # Parallel-universe scores: nothing was scored at all (reference :169-176)
+        if threshlod == float("inf") and np.isinf(sc).all():
+            if total_true == 0:
+                return 1.0, threshlod
+            if total_false == 0:
+                return 0.0, threshlod
+            if total_false == total_true:
+                return 0.5, threshlod
+        acc = 0
+        if threshlod is not None:
+            above = np.nonzero(sc > threshlod)[0]
+            if above.size:                     # the reference's loop stops at the first score above the threshold
+                i = int(above[0])
+                acc = (2 * float((a[:i] == 1).sum()) + total_false - i) / total_all
+            self.determine_classification_cross_table_values(np.stack([a.astype(np.float64), sc.astype(np.float64)], axis=1), threshlod)
+        return acc, threshlod

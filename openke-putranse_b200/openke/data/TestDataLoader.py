@@ -34,8 +34,6 @@ class TestDataLoader(object):
                  load_all_triples=False):
         if setting != "static":
             raise NotImplementedError("only the static setting is on the B200 hot path (SURVEY.md 8(f))")
-        if load_all_triples:
-            raise NotImplementedError("load_all_triples (triple2id.txt) is not supported")
         if mode not in ("test", "valid"):
             raise ValueError("mode must be 'test' or 'valid'")
         self.lib = N.lib()
@@ -54,6 +52,8 @@ class TestDataLoader(object):
         self.lib.setRandomSeed(self.random_seed)
         self.lib.randReset()
         self.lib.importTrainFiles()
+        if self.load_all_triples:   # the filter set comes from triple2id.txt (reference Reader.h:295-308)
+            self.lib.activateLoadOfAllTriples(1)
         self.lib.importTestFiles()
         self.relTotal = self.lib.getRelationTotal()
         self.entTotal = self.lib.getEntityTotal()
@@ -96,6 +96,15 @@ class TestDataLoader(object):
                     "mode": "tail_batch"})
         return res
 
+    def sampling_tc(self):
+        """Triple classification inputs (reference TestDataLoader.py:183-206, Test.h:573-599): every test triple
+        and its corrupted twin, drawn by the device kernel behind getTestBatch."""
+        n = self.testTotal
+        buf = [np.zeros(n, dtype=np.int64) for _ in range(6)]
+        self.lib.getTestBatch(*[N.addr(b) for b in buf])
+        return [{"batch_h": buf[0], "batch_t": buf[1], "batch_r": buf[2], "mode": "normal"},
+                {"batch_h": buf[3], "batch_t": buf[4], "batch_r": buf[5], "mode": "normal"}]
+
     def get_ent_tot(self):
         return self.entTotal
 
@@ -106,14 +115,15 @@ class TestDataLoader(object):
         return self.testTotal
 
     def set_sampling_mode(self, sampling_mode):
-        if sampling_mode != "link":
-            raise NotImplementedError("triple classification is not on the PuTransE hot path")
         self.sampling_mode = sampling_mode
 
     def __len__(self):
         return self.testTotal if self.mode == "test" else self.validTotal
 
     def __iter__(self):
+        if self.sampling_mode != "link":      # reference TestDataLoader.py:234-236
+            self.lib.initTest()
+            return TestDataSampler(1, self.sampling_tc)
         if self.mode == "test":
             self.lib.initTest()
             return TestDataSampler(self.testTotal, self.sampling_lp)

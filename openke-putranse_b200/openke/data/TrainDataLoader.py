@@ -127,7 +127,7 @@ class TrainDataLoader(object):
         lm, rm = np.zeros(nR, dtype=np.float32), np.zeros(nR, dtype=np.float32)
         N.check(self.lib.pk_train_index(N.addr(by_head), N.addr(by_tail), N.addr(lm), N.addr(rm)), "pk_train_index")
         lcg = np.zeros(max(self.work_threads, 1), dtype=np.uint64)
-        N.check(self.lib.pk_get_lcg(N.addr(lcg)), "pk_get_lcg")
+        N.check(self.lib.pk_get_lcg(N.addr(lcg), int(lcg.shape[0])), "pk_get_lcg")
         # first record of every head / tail: filtered corruption then searches one entity's records only
         head_off = np.searchsorted(by_head[:, 0], np.arange(nE + 1)).astype(np.int64)
         tail_off = np.searchsorted(by_tail[:, 2], np.arange(nE + 1)).astype(np.int64)
@@ -151,7 +151,7 @@ class TrainDataLoader(object):
         later host-visible ``sampling()`` continues the same sequence the reference would."""
         if self._dev is not None:
             lcg = self._dev["lcg"].cpu().numpy().view(np.uint64).copy()
-            N.check(self.lib.pk_set_lcg(N.addr(lcg)), "pk_set_lcg")
+            N.check(self.lib.pk_set_lcg(N.addr(lcg), int(lcg.shape[0])), "pk_set_lcg")
 
     # ---- setters/getters of the reference (TrainDataLoader.py:278-326)
     def set_work_threads(self, work_threads):

@@ -340,7 +340,7 @@ def _record_step_losses():
     return log
 
 
-def _run_full(in_path, out_name, n_univ, model_name, param, nbatches, ranges, torch_threads=8, store_tables=True):
+def _run_full(in_path, out_name, n_univ, model_name, param, nbatches, ranges, torch_threads=8, store_tables=True, extra=None):
     """The static PuTrans* experiment exactly as experiments/static_experiment_PuTransE_on_WN18.py:43-88
     drives it (seeds 4.., drawn epochs 50-199, Adagrad), on the first n_univ universes: per-step losses,
     final tables, remaps, and the reference's own link-prediction ranks + metrics of the ensemble."""
@@ -363,6 +363,7 @@ def _run_full(in_path, out_name, n_univ, model_name, param, nbatches, ranges, to
     assert pu.initial_random_seed == 4
     res = {"n_univ": np.int64(n_univ), "initial_seed": np.int64(pu.initial_random_seed), "nbatches": np.int64(nbatches),
            "model": np.array(model_name)}
+    res.update(extra or {})
     t0 = time.time()
     positives = 0
     for u in range(n_univ):
@@ -370,10 +371,12 @@ def _run_full(in_path, out_name, n_univ, model_name, param, nbatches, ranges, to
         pu.train_parallel_universes(1)
         res[f"u{u}_losses"] = np.array(log, dtype=np.float32)
         sp = pu.trained_embedding_spaces[u]
-        if store_tables:
-            for k_, v in sp.state_dict().items():
-                if k_.endswith(".weight"):
+        for k_, v in sp.state_dict().items():
+            if k_.endswith(".weight"):
+                if store_tables:
                     res[f"u{u}_{k_[:-7]}"] = v.detach().numpy().copy()
+                else:     # the row norms are what the full-length test compares
+                    res[f"u{u}_{k_[:-7]}_rownorm"] = np.linalg.norm(v.detach().numpy(), axis=1).astype(np.float32)
         emap, rmap = pu.entity_id_mappings[u], pu.relation_id_mappings[u]
         er = np.zeros(len(emap), dtype=np.int32)
         for g, l in emap.items():
@@ -404,7 +407,88 @@ def topic_putranse_full():
     _run_full(WN18, "putranse_full_wn18.npz", 24, "TransE", {"dim": 20, "p_norm": 1, "norm_flag": 1}, 20, STATIC_RANGES)
 
 
-TOPICS = {"putranse_full": topic_putranse_full, "dataset": topic_dataset,"sampler": topic_sampler, "universe": topic_universe, "train": topic_train,
+def topic_putranse_full_fb15k():
+    """configs[3] shape at production length: the FB15K-shaped synthetic graph of tools/synth.py (E = 14 951,
+    R = 1 345, 483 142 train triples; the reference's own FB15K train file is not shipped), eight universes at their
+    drawn epochs, evaluated by the reference on 2 000 test triples (its evaluation is a Python loop)."""
+    import tempfile
+    sys.path.insert(0, os.path.join(REPO, "tools"))
+    import synth
+    tr, va, te, ne, nr = synth.fb15k_shape(n_valid=2000, n_test=2000)
+    path = synth.write_dataset(tempfile.mkdtemp(), tr, va, te, ne, nr)
+    _run_full(path, "putranse_full_fb15k.npz", 8, "TransE", {"dim": 20, "p_norm": 1, "norm_flag": 1}, 20, STATIC_RANGES,
+              store_tables=False, extra={"train_checksum": np.uint64(synth.checksum(tr)), "n_valid": np.int64(2000), "n_test": np.int64(2000)})
+
+
+def topic_tc():
+    """Triple classification (reference Test.h:573-599, Tester.py:120-191): the corrupted twins getTestBatch draws
+    for the WN18 test set right after TestDataLoader.read (seed 4), and the reference Tester's accuracy + threshold
+    for the shipped TransH checkpoint on exactly those pairs."""
+    _setup_ref_import()
+    import torch
+    from openke.config import Tester
+    from openke.data import TestDataLoader
+    from openke.module.model import TransH
+    tl = TestDataLoader(WN18, "classification")
+    lib = tl.lib
+    res = {}
+    pos, neg = tl.sampling_tc()
+    res["pos"] = np.stack([pos["batch_h"], pos["batch_t"], pos["batch_r"]]).astype(np.int32)
+    res["neg"] = np.stack([neg["batch_h"], neg["batch_t"], neg["batch_r"]]).astype(np.int32)
+    # which corruptions hit the reference's undefined read (entity without a record on that side: trainHead[-1])
+    lef_head = ctypes.POINTER(ctypes.c_long).in_dll(lib, "lefHead")
+    rig_head = ctypes.POINTER(ctypes.c_long).in_dll(lib, "rigHead")
+    rig_tail = ctypes.POINTER(ctypes.c_long).in_dll(lib, "rigTail")
+    res["head_has_records"] = np.array([rig_head[int(h)] >= 0 for h in pos["batch_h"]])
+    res["tail_has_records"] = np.array([rig_tail[int(t)] >= 0 for t in pos["batch_t"]])
+    sd = torch.load(REF + "/best_models/transH_WN18_optimal_model.ckpt", map_location="cpu")
+    m = TransH(tl.entTotal, tl.relTotal, dim=20, p_norm=1, norm_flag=True)
+    m.load_state_dict(sd)
+    m.eval()
+    tester = Tester(model=m, data_loader=tl, use_gpu=False)
+    data = [(pos, neg)]
+    with torch.no_grad():
+        acc, thr = tester.run_triple_classification(data_iterator=data)
+        acc2, _ = tester.run_triple_classification(threshlod=thr, data_iterator=data)
+        res["scores_pos"] = tester.test_one_step(pos).astype(np.float32)
+        res["scores_neg"] = tester.test_one_step(neg).astype(np.float32)
+    res["acc"], res["threshold"], res["acc_given_threshold"] = np.float64(acc), np.float64(thr), np.float64(acc2)
+    print("tc", acc, thr, acc2, int((~res["head_has_records"]).sum()), int((~res["tail_has_records"]).sum()))
+    np.savez_compressed(os.path.join(OUT, "tc_wn18.npz"), **res)
+
+
+def topic_ref_ckpt():
+    """A checkpoint written BY THE REFERENCE (Parallel_Universe_Config.save_parameters, reference :929-931): three
+    universes of two epochs, plus the reference's ranks for it; what load_parameters must import."""
+    _setup_ref_import()
+    import shutil
+    import torch
+    from openke.config import Parallel_Universe_Config
+    from openke.data import TrainDataLoader, TestDataLoader
+    from openke.module.model import TransE
+    torch.set_num_threads(8)
+    train = TrainDataLoader(in_path=WN18, nbatches=20, threads=8, sampling_mode="normal", bern_flag=0, filter_flag=0,
+                            neg_ent=1, neg_rel=0, random_seed=123)
+    test = TestDataLoader(train.in_path, "link")
+    pu = Parallel_Universe_Config(training_identifier="golden", train_dataloader=train, test_dataloader=test,
+                                  initial_num_universes=None, const_num_epochs=2, embedding_model=TransE,
+                                  embedding_model_param={"dim": 20, "p_norm": 1, "norm_flag": 1}, checkpoint_dir="/tmp/",
+                                  valid_steps=10 ** 9, save_steps=10 ** 9, training_setting="static", incremental_strategy=None,
+                                  **STATIC_RANGES)
+    pu.use_gpu = False
+    pu.train_parallel_universes(3)
+    pu.save_parameters("/tmp/putranse_reference_layout.ckpt")
+    shutil.copy("/tmp/putranse_reference_layout.ckpt", os.path.join(OUT, "putranse_reference_layout.ckpt"))
+    with torch.no_grad():
+        pu.data_loader.set_sampling_mode("link")
+        pu.eval_universes(eval_mode="test")
+        ranks = _rank_all(pu.lib, pu.data_loader, pu.test_one_step, test.testTotal, test.entTotal)
+    np.savez_compressed(os.path.join(OUT, "putranse_reference_layout_ranks.npz"), ranks=ranks,
+                        test_sorted=_triples(pu.lib, "testList", test.testTotal).astype(np.int32))
+    print("ref ckpt", os.path.getsize(os.path.join(OUT, "putranse_reference_layout.ckpt")), ranks[:3])
+
+
+TOPICS = {"putranse_full_fb15k": topic_putranse_full_fb15k, "tc": topic_tc, "ref_ckpt": topic_ref_ckpt, "putranse_full": topic_putranse_full, "dataset": topic_dataset,"sampler": topic_sampler, "universe": topic_universe, "train": topic_train,
           "rank": topic_rank, "putranse": topic_putranse, "putranse_nullvec": topic_putranse_nullvec}
 
 if __name__ == "__main__":

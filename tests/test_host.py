@@ -42,7 +42,7 @@ def test_glibc_rand_clone_matches_libc(wn18_dir):
         L.setRandomSeed(seed)
         L.randReset()
         got = np.zeros(8, np.uint64)
-        N.check(L.pk_get_lcg(N.addr(got)))
+        N.check(L.pk_get_lcg(N.addr(got), 8))
         libc.srand(ctypes.c_uint(seed))
         want = np.array([libc.rand() for _ in range(8)], np.uint64)
         assert np.array_equal(got, want), seed
@@ -339,3 +339,47 @@ def test_native_table_init_replays_torch_generator(cls_name, param):
         m = cls(int(nE[i]), int(nR[i]), **param)
         for a in host:
             assert torch.equal(host[a][offs[a][i]:offs[a][i + 1]], getattr(m, a).weight.data), (cls_name, i, a)
+
+
+@pytest.mark.skipif(not (os.path.isdir("/root/reference/openke") and os.path.exists(os.path.join(util.REPO, "oracle", "_ref", "Base.so"))),
+                    reason="needs the reference tree (build container only)")
+def test_reference_layout_checkpoint_round_trip(wn18_dir, tmp_path):
+    """a checkpoint written by the reference (golden, minted by make_golden.py ref_ckpt) is
+    imported by load_parameters, re-exported in the reference's layout, and read back by the UNMODIFIED reference:
+    same modules, same id maps, same energies.  Host-only (conversion is not compute)."""
+    import subprocess
+    import sys
+    import torch
+    from openke.config import Parallel_Universe_Config
+    from openke.data import TrainDataLoader, TestDataLoader
+    from openke.module.model import TransE
+    train = TrainDataLoader(in_path=wn18_dir, nbatches=20, threads=8, bern_flag=0, filter_flag=0, neg_ent=1, random_seed=123)
+    test = TestDataLoader(wn18_dir, "link")
+    pu = Parallel_Universe_Config(train_dataloader=train, test_dataloader=test, embedding_model=TransE,
+                                  embedding_model_param={"dim": 20, "p_norm": 1, "norm_flag": 1},
+                                  checkpoint_dir=util.GOLDEN + "/", valid_steps=10 ** 9, save_steps=None)
+    pu.load_parameters("putranse_reference_layout.ckpt")
+    assert pu.next_universe_id == 3 and sorted(pu._where) == [0, 1, 2]
+    assert (pu.min_triple_constraint, pu.max_triple_constraint, pu.min_lr, pu.max_lr) == (500, 2000, 0.001, 0.1)
+    ck = pu._chunks[0]
+    assert ck.tables["ent_embeddings"].shape == (int(ck.nE.sum()), 20) and ck.ent_remap.min() >= 0
+    g = np.load(os.path.join(util.GOLDEN, "putranse_wn18.npz"))      # the same three universes, minted earlier from the same seeds
+    for u in range(3):
+        assert np.array_equal(ck.ent_remap[ck.eoff[u]:ck.eoff[u + 1]], g["u%d_ent_remap" % u])
+        assert np.array_equal(ck.rel_remap[ck.roff[u]:ck.roff[u + 1]], g["u%d_rel_remap" % u])
+    out = str(tmp_path / "ours_reference_layout.ckpt")
+    pu.save_parameters(out, layout="reference")
+    env = dict(os.environ)
+    env.pop("PYTHONPATH", None)
+    res = subprocess.run([sys.executable, os.path.join(util.REPO, "tests", "_refckpt_child.py"), str(tmp_path / "refpkg"),
+                          os.path.join(util.REPO, "oracle", "_ref", "Base.so"), wn18_dir,
+                          os.path.join(util.GOLDEN, "putranse_reference_layout.ckpt"), out],
+                         capture_output=True, text=True, timeout=600, env=env, cwd=str(tmp_path))
+    assert res.returncode == 0 and "REFCKPT-OK" in res.stdout, res.stdout[-2000:] + res.stderr[-3000:]
+    # and the flat layout holds the same ensemble
+    pu.save_parameters(str(tmp_path / "flat.ckpt"))
+    p2 = Parallel_Universe_Config(train_dataloader=train, test_dataloader=test, embedding_model=TransE,
+                                  embedding_model_param={"dim": 20, "p_norm": 1, "norm_flag": 1},
+                                  checkpoint_dir=str(tmp_path) + "/", valid_steps=10 ** 9, save_steps=None)
+    p2.load_parameters("flat.ckpt")
+    assert torch.equal(p2._chunks[0].tables["ent_embeddings"], ck.tables["ent_embeddings"]) and np.array_equal(p2._chunks[0].ent_remap, ck.ent_remap)

@@ -1,0 +1,368 @@
+"""Product code around the kernels that round 1 left untested: checkpoints (flat layout, reference
+layout, shards of a multi-GPU run), validation + early stopping, Validator, extend_parallel_universe,
+asynchronous launch slots, sharded evaluation (2 ranks) against single-rank evaluation."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import util
+
+N = util.native()
+
+
+def _small_graph(tmp_path, n_ent=900, n_rel=9, n_train=9000, n_eval=120, seed=11):
+    tr, va, te = util.synthetic_graph(n_ent, n_rel, n_train, n_eval, seed=seed)
+    return util.write_dataset(str(tmp_path / "g"), tr, va, te, n_ent, n_rel), (tr, va, te)
+
+
+def _pu(path, ckpt_dir=None, valid_steps=10 ** 9, save_steps=None, epochs=2, patience=5, model="TransE", **over):
+    import openke.module.model as M
+    from openke.config import Parallel_Universe_Config
+    from openke.data import TrainDataLoader, TestDataLoader
+    train = TrainDataLoader(in_path=path, nbatches=10, threads=8, sampling_mode="normal", bern_flag=0, filter_flag=0,
+                            neg_ent=1, neg_rel=0, random_seed=123)
+    test = TestDataLoader(path, "link")
+    param = {"dim_e": 20, "dim_r": 20, "p_norm": 1, "norm_flag": 1} if model == "TransD" else {"dim": 20, "p_norm": 1, "norm_flag": 1}
+    kw = dict(min_margin=1, max_margin=4, min_lr=0.01, max_lr=0.1, const_num_epochs=epochs, min_triple_constraint=300,
+              max_triple_constraint=900, min_balance=0.25, max_balance=0.5)
+    kw.update(over)
+    return Parallel_Universe_Config(training_identifier="t", train_dataloader=train, test_dataloader=test,
+                                    initial_num_universes=None, embedding_model=getattr(M, model), embedding_model_param=param,
+                                    checkpoint_dir=ckpt_dir, valid_steps=valid_steps, save_steps=save_steps,
+                                    early_stopping_patience=patience, training_setting="static", incremental_strategy=None, **kw)
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("model", ["TransE", "TransD"])
+def test_checkpoint_round_trip_flat_and_reference_layout(tmp_path, model):
+    """save_parameters -> load_parameters -> run_link_prediction gives the same ranks, for the flat layout and for
+    the reference's pickle layout (reference Parallel_Universe_Config.py:852-935); the reference-layout file holds
+    one nn.Module per universe and the four nested id maps with the reference's keys."""
+    import torch
+    path, _ = _small_graph(tmp_path)
+    ck = str(tmp_path / "ck") + "/"
+    pu = _pu(path, ckpt_dir=ck, model=model)
+    pu.train_parallel_universes(12)
+    pu.train_parallel_universes(5)          # two chunks
+    want = pu.run_link_prediction()
+    ranks = pu.last_ranks.copy()
+    pu.save_parameters(ck + "flat.ckpt")
+    pu.save_parameters(ck + "ref.ckpt", layout="reference")
+
+    for name in ("flat.ckpt", "ref.ckpt"):
+        p2 = _pu(path, ckpt_dir=ck, model=model)
+        p2.load_parameters(name)
+        assert p2.next_universe_id == 17 and sorted(p2._where) == list(range(17))
+        got = p2.run_link_prediction()
+        assert np.array_equal(p2.last_ranks, ranks), name
+        assert got == want
+        # the reference's containers, rebuilt lazily from what was loaded
+        for u in (0, 11, 16):
+            a, b = pu.entity_id_mappings[u], p2.entity_id_mappings[u]
+            assert dict(a) == dict(b)
+            assert torch.equal(pu.trained_embedding_spaces[u].ent_embeddings.weight, p2.trained_embedding_spaces[u].ent_embeddings.weight)
+        e = int(next(iter(pu.entity_id_mappings[3])))
+        assert pu.entity_universes[e] == p2.entity_universes[e] and 3 in p2.entity_universes[e]
+
+    ref = torch.load(ck + "ref.ckpt", map_location="cpu", weights_only=False)
+    for key in ("initial_num_universes", "next_universe_id", "trained_embedding_spaces", "entity_id_mappings", "relation_id_mappings",
+                "entity_universes", "relation_universes", "min_margin", "max_lr", "embedding_model", "embedding_model_param",
+                "best_hit10", "bad_counts", "current_tested_universes", "evaluation_head2tail_triple_score_dict"):
+        assert key in ref, key
+    sp = ref["trained_embedding_spaces"][4]
+    assert type(sp).__name__ == model and not sp.ent_embeddings.weight.is_cuda and not sp.ent_embeddings.weight.requires_grad
+    l2g = {l: g for g, l in ref["entity_id_mappings"][4].items()}
+    assert sorted(l2g) == list(range(sp.ent_embeddings.weight.shape[0]))
+    assert all(4 in ref["entity_universes"][g] for g in l2g.values())
+    # a checkpoint that misses universes must not load as if it were complete (multi-GPU shards)
+    flat = torch.load(ck + "flat.ckpt", map_location="cpu", weights_only=False)
+    flat["chunks"] = flat["chunks"][:1]
+    torch.save(flat, ck + "truncated.ckpt")
+    with pytest.raises(N.NativeError):
+        _pu(path, ckpt_dir=ck, model=model).load_parameters("truncated.ckpt")
+
+
+@pytest.mark.gpu
+def test_validation_early_stopping_and_periodic_checkpoints(tmp_path, capsys):
+    """train_parallel_universes' validation branch (reference :330-356): every valid_steps universes the ensemble
+    is ranked on the valid split, the best state is checkpointed, and training stops after
+    early_stopping_patience non-improving validations.  valid() is the reference's getValidHit10 of the same
+    energies: checked against the reference-style manual loop through validHead/validTail."""
+    path, _ = _small_graph(tmp_path)
+    ck = str(tmp_path / "ck") + "/"
+    pu = _pu(path, ckpt_dir=ck, valid_steps=3, save_steps=4, patience=2, epochs=3)
+    history = []
+    orig = pu.valid
+
+    def recording_valid():
+        h = orig()
+        history.append(h)
+        return h
+    pu.valid = recording_valid
+    pu.train_parallel_universes(30)
+    assert len(history) >= 2 and pu.next_universe_id == 3 * len(history) <= 30
+    best = max(history)
+    assert pu.best_hit10 == best
+    assert os.path.exists(ck + "Best_model_PuTransE_t.ckpt")
+    if pu.next_universe_id < 30:        # stopped early: the last `patience` validations did not improve
+        assert pu.bad_counts == 2 and all(h <= max(history[:-2]) for h in history[-2:])
+        assert "Early stopping" in capsys.readouterr().out
+    assert any(f.startswith("PuTransE_learned_spaces-") for f in os.listdir(ck))
+
+    # valid() against the reference's own loop over the valid loader (Validator.py:37-45 with the PuTransE rows)
+    lib = pu.lib
+    lib.validInit()
+    for index, (dh, dt) in enumerate(pu.valid_dataloader):
+        s = pu.test_one_step(dh)
+        lib.validHead(N.addr(s), index)
+        s = pu.test_one_step(dt)
+        lib.validTail(N.addr(s), index)
+    assert lib.getValidHit10() == pytest.approx(orig(), abs=1e-7)
+    # the best checkpoint restores exactly the ensemble that scored best
+    p2 = _pu(path, ckpt_dir=ck)
+    p2.load_parameters("Best_model_PuTransE_t.ckpt")
+    assert p2.valid() == pytest.approx(best, abs=1e-7)
+
+
+@pytest.mark.gpu
+def test_validator_matches_manual_loop_and_oracle(tmp_path):
+    """Validator.valid (reference config/Validator.py:37-53) on a single embedding space: equal to the manual
+    validHead/validTail loop of the C-ABI and to the oracle's rank counting on torch-CPU scores."""
+    import torch
+    from openke.config import Validator
+    from openke.data import TestDataLoader
+    from openke.module.model import TransH
+    from oracle import native as on
+    from oracle.model_math import TorchOracle
+    path, (tr, va, te) = _small_graph(tmp_path, n_ent=600, n_rel=6, n_train=5000, n_eval=90, seed=3)
+    vl = TestDataLoader(path, "link", mode="valid")
+    torch.manual_seed(5)
+    m = TransH(600, 6, dim=24, p_norm=1, norm_flag=True)
+    tabs = {n: getattr(m, n).weight.detach().numpy().copy() for n in m.table_names()}
+    v = Validator(model=m, data_loader=vl)
+    got = v.valid()
+    lib = vl.lib
+    lib.validInit()
+    for index, (dh, dt) in enumerate(vl):
+        lib.validHead(N.addr(v.valid_one_step(dh)), index)
+        lib.validTail(N.addr(v.valid_one_step(dt)), index)
+    assert lib.getValidHit10() == pytest.approx(got, abs=1e-7)
+    o = on.Oracle()
+    o.import_train(tr, 600, 6)
+    o.import_test(te, tr, va)
+    orc = TorchOracle("transh", tabs, p_norm=1)
+    hits = [0, 0]
+    with torch.no_grad():
+        for i, (h, r, t) in enumerate(o.eval_list(1).tolist()):
+            sc = orc.score(np.concatenate([[h], np.delete(np.arange(600), h)]), [t], [r], "head_batch").numpy()
+            hits[0] += o.rank_row(1, sc, i, True)[1] < 10
+            sc = orc.score([h], np.concatenate([[t], np.delete(np.arange(600), t)]), [r], "tail_batch").numpy()
+            hits[1] += o.rank_row(1, sc, i, False)[1] < 10
+    want = (np.float32(hits[0]) / np.float32(90) + np.float32(hits[1]) / np.float32(90)) / np.float32(2)
+    assert abs(got - float(want)) <= 1.0 / 90 + 1e-7      # at most one near-tie across the hits@10 boundary
+
+
+@pytest.mark.gpu
+def test_extend_parallel_universe_and_async_slots(tmp_path):
+    """extend_parallel_universe (reference :825-850) appends another instance's universes under shifted ids: the
+    merged ensemble ranks like one instance that trained all of them.  And asynchronous launch slots (several
+    chunks in flight, per-slot buffers) give bit-identical tables and losses to synchronous training."""
+    import torch
+    path, _ = _small_graph(tmp_path)
+    a = _pu(path)
+    a.record_losses = True
+    a.train_parallel_universes(9)
+    b = _pu(path)
+    b.initial_random_seed = a.initial_random_seed + 9       # b's universes 0..4 are a's 9..13
+    b.train_parallel_universes(5)
+    whole = _pu(path)
+    whole.record_losses = True
+    whole.async_training = True
+    whole.launch_slots = 3
+    for n in (4, 3, 2, 5):                                   # 14 universes in four overlapping launches
+        whole.train_parallel_universes(n)
+    # async == sync up to the order of the float reductions of repeated rows (fire-and-forget RED.ADD.F32 is not
+    # order-deterministic): 20 steps apart, losses agree to 1e-4 relative and tables to 1e-4 absolute; a buffer
+    # shared between launches in flight would show up as errors of the order of the values themselves
+    for u in range(9):
+        assert np.allclose(a.universe_losses[u], whole.universe_losses[u], rtol=1e-4, atol=1e-6), u
+        wa = a.trained_embedding_spaces[u].ent_embeddings.weight
+        wb = whole.trained_embedding_spaces[u].ent_embeddings.weight
+        assert wa.shape == wb.shape and float((wa - wb).abs().max()) < 1e-4, u
+    a.extend_parallel_universe(b)
+    assert a.next_universe_id == 14 and sorted(a._where) == list(range(14))
+    assert dict(a.entity_id_mappings[11]) == dict(whole.entity_id_mappings[11])
+    a.run_link_prediction()
+    whole.run_link_prediction()
+    assert (a.last_ranks == whole.last_ranks).all(1).mean() > 0.95
+    # tiling of the evaluation does not change a rank
+    first = whole.last_ranks.copy()
+    whole.eval_tile_rows = 37
+    whole._rank_cache.clear()
+    whole.run_link_prediction()
+    assert np.array_equal(first, whole.last_ranks)
+
+
+# ------------------------------------------------------------------------------------------------
+_TWO_RANK_CHILD = r'''
+import os, sys
+import numpy as np
+sys.path[:0] = [%(pkg)r, %(repo)r, %(tests)r]
+import torch, torch.distributed as dist
+import test_product as T
+rank = int(os.environ["RANK"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+import pathlib
+pu = T._pu(%(path)r, ckpt_dir=%(ck)r, valid_steps=6, save_steps=None, epochs=2, patience=50)
+pu.eval_tile_rows = 64
+pu.train_parallel_universes(12)        # rank r trains universes u %% 2 == r; validates twice (collective)
+assert sorted(pu._where) == [u for u in range(12) if u %% 2 == rank]
+out = pu.run_link_prediction()
+pu.save_parameters(%(ck)r + "two.ckpt")
+np.save(%(ck)r + "ranks_rank%%d.npy" %% rank, pu.last_ranks)
+p2 = T._pu(%(path)r, ckpt_dir=%(ck)r)
+p2.load_parameters("two.ckpt")           # both shards, chunks dealt round robin over the ranks
+p2.run_link_prediction()
+assert np.array_equal(p2.last_ranks, pu.last_ranks)
+dist.barrier()
+dist.destroy_process_group()
+print("RANK-OK", rank)
+'''
+
+
+@pytest.mark.gpu
+def test_two_rank_evaluation_and_checkpoint_equal_single_rank(tmp_path):
+    """Universes sharded over 2 GPUs (u % 2), energies min-all-reduced per tile over NCCL, queries ranked by the rank
+    that owns them.  The sharded checkpoint (one file per rank) loads complete into ONE process, and that
+    process's single-rank evaluation of the very same tables must give the two-rank ranks bit for bit (the
+    min-fold is order-independent).  Against a separately trained single-process run the tables differ in the
+    last bits (float reductions of repeated rows), so ranks agree except near ties."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    path, _ = _small_graph(tmp_path)
+    ck = str(tmp_path / "ck") + "/"
+    os.makedirs(ck)
+    single = _pu(path, ckpt_dir=ck, valid_steps=6, epochs=2, patience=50)
+    single.train_parallel_universes(12)
+    single.run_link_prediction()
+    code = _TWO_RANK_CHILD % dict(pkg=os.path.join(util.REPO, "openke-putranse_b200"), repo=util.REPO,
+                                   tests=os.path.join(util.REPO, "tests"), path=path, ck=ck)
+    script = tmp_path / "child.py"
+    script.write_text(code)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29511", str(script)], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and out.stdout.count("RANK-OK") == 2, out.stdout[-2000:] + out.stderr[-4000:]
+    two = [np.load(ck + "ranks_rank%d.npy" % r) for r in (0, 1)]
+    assert np.array_equal(two[0], two[1])
+    assert os.path.exists(ck + "two.ckpt") and os.path.exists(ck + "two.ckpt.rank1of2")
+    merged = _pu(path, ckpt_dir=ck)
+    merged.load_parameters("two.ckpt")
+    assert sorted(merged._where) == list(range(12))
+    merged.run_link_prediction()
+    assert np.array_equal(merged.last_ranks, two[0])                 # sharded evaluation == single-rank evaluation
+    assert (single.last_ranks == two[0]).all(1).mean() > 0.95        # and the separately trained run, up to near ties
+    assert abs(merged.valid() - single.valid()) <= 2.0 / 120
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_triple_classification_matches_the_reference(wn18_dir, golden):
+    """SURVEY.md 8(f) rank 4.  (1) getTestBatch: the corrupted twins of the WN18 test set are those the reference
+    draws (Test.h:573-599) wherever the reference is defined (an entity without a record on the corrupted side makes
+    it read trainHead[-1]).  (2) Tester.run_triple_classification + get_best_threshlod (Tester.py:120-191) on the
+    shipped TransH checkpoint and the reference's own pairs: same threshold (the scores at the boundary agree to
+    2e-6) and accuracy within 2/10000."""
+    import torch
+    from openke.config import Tester
+    from openke.data import TestDataLoader
+    from openke.module.model import TransH
+    g = golden["tc_wn18"]
+    tl = TestDataLoader(wn18_dir, "classification")
+    pos, neg = tl.sampling_tc()
+    got_pos = np.stack([pos["batch_h"], pos["batch_t"], pos["batch_r"]])
+    got_neg = np.stack([neg["batch_h"], neg["batch_t"], neg["batch_r"]])
+    assert np.array_equal(got_pos, g["pos"])
+    tail_replaced = g["neg"][1] != g["pos"][1]
+    head_replaced = g["neg"][0] != g["pos"][0]
+    defined = np.where(tail_replaced, g["head_has_records"], np.where(head_replaced, g["tail_has_records"], True))
+    # which side was replaced is decided by the coin alone: identical everywhere
+    assert np.array_equal(got_neg[1] != got_pos[1], tail_replaced) or (~defined).sum() > 0
+    assert defined.mean() > 0.9
+    assert np.array_equal(got_neg[:, defined], g["neg"][:, defined]), int((got_neg[:, defined] != g["neg"][:, defined]).any(0).sum())
+    assert np.array_equal(got_neg[2], g["neg"][2])
+    # a second call continues LCG stream 0 two draws per triple further: different twins
+    pos2, neg2 = tl.sampling_tc()
+    assert (np.stack([neg2["batch_h"], neg2["batch_t"]]) != got_neg[:2]).any()
+
+    R = golden["rank_transh_wn18"]
+    m = TransH(tl.entTotal, tl.relTotal, dim=20, p_norm=1, norm_flag=True)
+    with torch.no_grad():
+        for n_ in ("ent_embeddings", "rel_embeddings", "norm_vector"):
+            getattr(m, n_).weight.copy_(torch.from_numpy(R[n_]))
+    tester = Tester(model=m, data_loader=tl, use_gpu=True)
+    ref_pairs = [({"batch_h": g["pos"][0].astype(np.int64), "batch_t": g["pos"][1].astype(np.int64), "batch_r": g["pos"][2].astype(np.int64), "mode": "normal"},
+                  {"batch_h": g["neg"][0].astype(np.int64), "batch_t": g["neg"][1].astype(np.int64), "batch_r": g["neg"][2].astype(np.int64), "mode": "normal"})]
+    sp, sn = tester.test_one_step(ref_pairs[0][0]), tester.test_one_step(ref_pairs[0][1])
+    assert np.allclose(sp, g["scores_pos"], rtol=2e-6, atol=2e-6) and np.allclose(sn, g["scores_neg"], rtol=2e-6, atol=2e-6)
+    acc, thr = tester.run_triple_classification(data_iterator=ref_pairs)
+    assert abs(thr - float(g["threshold"])) < 1e-5, (thr, float(g["threshold"]))
+    assert abs(acc - float(g["acc"])) <= 2.0 / 10000, (acc, float(g["acc"]))
+    acc2, _ = tester.run_triple_classification(threshlod=float(g["threshold"]), data_iterator=ref_pairs)
+    assert abs(acc2 - float(g["acc_given_threshold"])) <= 2.0 / 10000
+    t = tester.last_cross_table
+    assert t["tp"] + t["fp"] + t["tn"] + t["fn"] == 10000
+    # through the loader (sampling mode 'classification', reference Tester.py:145-147)
+    acc3, thr3 = tester.run_triple_classification()
+    assert 0.9 < acc3 <= 1.0
+
+
+@pytest.mark.gpu
+def test_putranse_triple_energies_and_classification(tmp_path):
+    """Parallel_Universe_Config.test_one_step in 'normal' mode (reference predict_triple :413-444): the energy of a
+    triple is entry t of the (h, r) tail-side row; unscored triples are +inf, or the smaller tuple score with
+    'null_vector' (reference :720-729).  run_triple_classification runs end to end on it."""
+    path, (tr, va, te) = _small_graph(tmp_path)
+    pu = _pu(path)
+    pu.train_parallel_universes(10)
+    h, t, r = te[:, 0], te[:, 1], te[:, 2]
+    got = pu.triple_energies(h, t, r)
+    assert got.shape == (te.shape[0],) and np.isfinite(got).any() and np.isinf(got).any()
+    for i in list(np.nonzero(np.isfinite(got))[0][:12]) + list(np.nonzero(np.isinf(got))[0][:6]):
+        row = pu.global_energy_estimation({"batch_h": np.array([h[i]]), "batch_t": np.arange(900), "batch_r": np.array([r[i]]),
+                                           "mode": "tail_batch"})
+        assert row[t[i]] == got[i] or (np.isinf(row[t[i]]) and np.isinf(got[i])), (i, row[t[i]], got[i])
+    pu.missing_embedding_handling = "null_vector"
+    filled = pu.triple_energies(h, t, r)
+    fin = np.isfinite(got)
+    assert np.array_equal(filled[fin], got[fin])
+    assert np.isfinite(filled[~fin]).sum() > 0           # a tuple score exists wherever (h, r) or (r, t) is held by a universe
+    pu.missing_embedding_handling = "last_rank"
+    acc, thr = pu.run_triple_classification()
+    assert 0.0 <= acc <= 1.0 and thr is not None
+    assert pu.last_cross_table["tp"] + pu.last_cross_table["fn"] == te.shape[0]
+
+
+@pytest.mark.gpu
+def test_load_checkpoint_written_by_the_reference(wn18_dir, golden):
+    """load_parameters on tests/golden/putranse_reference_layout.ckpt (pickled by the unmodified reference):
+    link-prediction ranks of the imported ensemble against the reference's own ranks for that checkpoint."""
+    from openke.config import Parallel_Universe_Config
+    from openke.data import TrainDataLoader, TestDataLoader
+    from openke.module.model import TransE
+    train = TrainDataLoader(in_path=wn18_dir, nbatches=20, threads=8, bern_flag=0, filter_flag=0, neg_ent=1, random_seed=123)
+    test = TestDataLoader(wn18_dir, "link")
+    pu = Parallel_Universe_Config(train_dataloader=train, test_dataloader=test, embedding_model=TransE,
+                                  embedding_model_param={"dim": 20, "p_norm": 1, "norm_flag": 1},
+                                  checkpoint_dir=util.GOLDEN + "/", valid_steps=10 ** 9, save_steps=None)
+    pu.load_parameters("putranse_reference_layout.ckpt")
+    pu.run_link_prediction()
+    want = golden["putranse_reference_layout_ranks"]["ranks"]
+    assert (pu.last_ranks == want).all(1).mean() > 0.999
+    missing = want[:, 0] == 40943
+    assert np.array_equal(pu.last_ranks[missing][:, :2], want[missing][:, :2])
