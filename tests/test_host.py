@@ -383,3 +383,48 @@ def test_reference_layout_checkpoint_round_trip(wn18_dir, tmp_path):
                                   checkpoint_dir=str(tmp_path) + "/", valid_steps=10 ** 9, save_steps=None)
     p2.load_parameters("flat.ckpt")
     assert torch.equal(p2._chunks[0].tables["ent_embeddings"], ck.tables["ent_embeddings"]) and np.array_equal(p2._chunks[0].ent_remap, ck.ent_remap)
+
+
+def test_builder_at_scale_matches_oracle_on_power_law_graph(tmp_path):
+    """the universe builder on a large hub-dominated graph (the S1 generator of
+    tools/synth.py scaled to 200 000 entities / 2 M triples / 400 relations: relation entity sets of tens of
+    thousands, hubs with > 10^5 incident triples), bit-exact against the oracle's plain restatement of
+    UniverseConstructor.h — whose std::set copies and std::advance picks take seconds per universe here while the
+    builder takes about a millisecond."""
+    import sys
+    import time
+    sys.path.insert(0, os.path.join(util.REPO, "tools"))
+    import synth
+    from oracle import native as on
+    g = synth.power_law_graph(200_000, 400, 2_000_000 + 2000, seed=99)
+    tr, va, te = g[:2_000_000], g[2_000_000:2_001_000], g[2_001_000:]
+    path = synth.write_dataset(str(tmp_path / "big"), tr, va, te, 200_000, 400)
+    L = N.lib()
+    _load(L, path)
+    assert L.getTrainTotal() == 2_000_000
+    cases = [(31, 1999, 0.5), (32, 640, 0.25), (33, 1500, 0.37)]
+    n = len(cases)
+    seeds = np.array([c[0] for c in cases], np.int64)
+    tcs = np.array([c[1] for c in cases], np.int64)
+    bals = np.array([c[2] for c in cases], np.float32)
+    t0 = time.perf_counter()
+    h = L.pk_universes_build(n, N.addr(seeds), N.addr(tcs), N.addr(bals), 1)
+    dt = time.perf_counter() - t0
+    assert h, N.last_error()
+    nT, nE, nR, foc = (np.zeros(n, np.int64) for _ in range(4))
+    N.check(L.pk_universes_sizes(h, N.addr(nT), N.addr(nE), N.addr(nR), N.addr(foc)))
+    er, rr = np.zeros(nE.sum(), np.int32), np.zeros(nR.sum(), np.int32)
+    bg = np.zeros((nT.sum(), 3), np.int32)
+    N.check(L.pk_universes_export(h, None, None, N.addr(bg), N.addr(er), N.addr(rr), None, None, None))
+    L.pk_universes_free(h)
+    assert dt < 1.0, "three universes took %.3f s" % dt
+    o = on.Oracle(threads=8, bern=0)
+    o.import_train(tr, 200_000, 400)
+    eo, ro, to = (np.concatenate([[0], np.cumsum(x)]) for x in (nE, nR, nT))
+    for i, (seed, tc, bal) in enumerate(cases):
+        o.seed(seed)
+        tri, oer, orr = o.universe(tc, float(np.float32(bal)))
+        assert np.array_equal(bg[to[i]:to[i + 1]], tri), (i, seed)
+        assert np.array_equal(er[eo[i]:eo[i + 1]], oer) and np.array_equal(rr[ro[i]:ro[i + 1]], orr)
+    # leave the process-global state on a small graph again
+    _load(L, util.write_dataset(str(tmp_path / "tiny"), [[0, 1, 0], [1, 2, 0]], [[0, 2, 0]], [[2, 0, 0]], 3, 1))

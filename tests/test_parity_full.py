@@ -52,18 +52,23 @@ def _epoch_means(x, nb):
 def test_full_length_universes_follow_the_reference(wn18_dir, golden):
     """24 universes x (50..199 epochs x 20 batches), exactly the reference's run.
 
-    Integer work is bit-exact: subgraphs, id maps, steps per universe, the unscored (+inf) ranks.
-    Floating point: a universe's trajectory is a chaotic map (an L1 energy flips sign(s_i) when an element
-    crosses zero, a hinge term switches on or off), so two correct fp32 implementations separate after
-    some tens of steps and then stay statistically, not pointwise, equal.  Stated tolerances:
-      steps 0..9    per-step loss  rtol 2e-5           (same arithmetic, other summation order)
-      steps 0..39   per-step loss  rtol 2e-3
-      every epoch   mean loss of the epoch within 25 % + 0.02 of the reference's epoch mean
-      whole run     mean loss over the last 10 epochs within 12 % + 0.004 per universe,
-                    and within 3 % averaged over the 24 universes
-      ensemble      filtered MRR within 5 % rel., MR within 0.5 % rel., Hits@10/3/1 within 0.008 abs
-                    (reference Test.h:450-454 values), >= 60 % of the scored ranks within +-3 of the
-                    reference's rank.
+    Integer work is bit-exact: subgraphs, id maps, steps per universe, which test triples no universe can score,
+    and their ranks (the +inf branch of Test.h:181-206).
+    Floating point: a universe's trajectory is a chaotic map (an L1 energy flips sign(s_i) when an element crosses
+    zero, a hinge term switches on or off), so two correct fp32 implementations follow each other for a while and
+    then stay statistically, not pointwise, equal.  Measured on the B200 (tools/parity_probe.py,
+    profiles/r2_parity_probe.log): 18 of 24 universes never leave 1e-3 relative over their whole 1 000-4 000 steps,
+    the first 100 steps of 23 universes agree to 1.3e-6; the high-learning-rate universes 10 (lr 0.094) and 19
+    (lr 0.06, margin 1) separate after 178 and 15 steps.  Stated tolerances, as a function of the step s:
+      s < 10         per-step loss rtol 2e-6, every universe
+      s < 400        per-step loss rtol 1e-4 for at least 18 of the 24 universes (21 measured)
+      every epoch    |mean loss of the epoch - reference's| <= 0.015 + 0.05 * reference's (largest measured: 0.0092),
+                     and for at least 14 universes <= 1e-3 in every epoch (19 measured)
+      last 10 epochs |mean loss - reference's| <= 3 % + 0.001 per universe (largest measured: 2 %), <= 1 % on average
+      trained entity tables: median row norm within 3 % of the reference's
+      ensemble       filtered MRR within 3 % relative (measured 0.8 %), MR within 1e-4 relative (1.7e-5), Hits@10/3/1
+                     within 0.002 absolute (0.0007) of the reference Tester's values (Test.h:450-454); of the ranks
+                     some universe scores, >= 55 % identical (66 %) and >= 70 % within +-3 (80 %).
     """
     g = golden["putranse_full_wn18"]
     n_univ, nb = int(g["n_univ"]), int(g["nbatches"])
@@ -71,45 +76,45 @@ def test_full_length_universes_follow_the_reference(wn18_dir, golden):
     pu.record_losses = True
     assert pu.initial_random_seed == int(g["initial_seed"]) == 4
     pu.train_parallel_universes(n_univ)
-    tails, ref_tails = [], []
+    tails, ref_tails, close_400, close_epochs = [], [], 0, 0
     for u in range(n_univ):
         er = np.array(sorted(pu.entity_id_mappings[u], key=pu.entity_id_mappings[u].get))
         rr = np.array(sorted(pu.relation_id_mappings[u], key=pu.relation_id_mappings[u].get))
         assert np.array_equal(er, g["u%d_ent_remap" % u]) and np.array_equal(rr, g["u%d_rel_remap" % u]), u
         got, want = pu.universe_losses[u], g["u%d_losses" % u]
         assert len(got) == len(want) == pu.universe_hyper[u]["epochs"] * nb, u
-        assert np.allclose(got[:10], want[:10], rtol=2e-5), (u, got[:10], want[:10])
-        assert np.allclose(got[:40], want[:40], rtol=2e-3), (u, np.abs(got[:40] / want[:40] - 1).max())
+        assert np.allclose(got[:10], want[:10], rtol=2e-6), (u, got[:10], want[:10])
+        close_400 += bool(np.allclose(got[:400], want[:400], rtol=1e-4, atol=1e-7))
         ge, we = _epoch_means(got, nb), _epoch_means(want, nb)
-        assert np.all(np.abs(ge - we) <= 0.25 * we + 0.02), (u, np.abs(ge - we).max(), int(np.argmax(np.abs(ge - we))))
+        assert np.all(np.abs(ge - we) <= 0.015 + 0.05 * we), (u, np.abs(ge - we).max(), int(np.argmax(np.abs(ge - we))))
+        close_epochs += bool(np.all(np.abs(ge - we) <= 1e-3))
         gt, wt = ge[-10:].mean(), we[-10:].mean()
-        assert abs(gt - wt) <= 0.12 * wt + 0.004, (u, gt, wt)
+        assert abs(gt - wt) <= 0.03 * wt + 0.001, (u, gt, wt)
         tails.append(gt)
         ref_tails.append(wt)
         sp = pu.trained_embedding_spaces[u]
         ent = sp.ent_embeddings.weight.detach().cpu().numpy()
         assert ent.shape == g["u%d_ent_embeddings" % u].shape and np.isfinite(ent).all()
-        # same geometry: row norms of the trained entity table agree in distribution (median within 3 %)
         n_got, n_ref = np.linalg.norm(ent, axis=1), np.linalg.norm(g["u%d_ent_embeddings" % u], axis=1)
         assert abs(np.median(n_got) / np.median(n_ref) - 1) < 0.03, (u, np.median(n_got), np.median(n_ref))
-    assert abs(np.mean(tails) / np.mean(ref_tails) - 1) < 0.03, (np.mean(tails), np.mean(ref_tails))
+    assert close_400 >= 18, close_400
+    assert close_epochs >= 14, close_epochs
+    assert abs(np.mean(tails) / np.mean(ref_tails) - 1) < 0.01, (np.mean(tails), np.mean(ref_tails))
 
     mrr, mr, hit10, hit3, hit1 = pu.run_link_prediction()
     ranks, want = pu.last_ranks, g["ranks"]
     E = 40943
-    missing = want[:, 0] == E
-    assert np.array_equal(ranks[missing][:, [0, 1]], want[missing][:, [0, 1]])        # truth in no universe: integer logic
-    missing_t = want[:, 2] == E
-    assert np.array_equal(ranks[missing_t][:, [2, 3]], want[missing_t][:, [2, 3]])
+    missing, missing_t = want[:, 0] == E, want[:, 2] == E
     assert np.array_equal(ranks[:, 0] == E, missing) and np.array_equal(ranks[:, 2] == E, missing_t)
+    assert np.array_equal(ranks[missing][:, [0, 1]], want[missing][:, [0, 1]])        # truth in no universe: integer logic
+    assert np.array_equal(ranks[missing_t][:, [2, 3]], want[missing_t][:, [2, 3]])
     scored = np.concatenate([np.abs(ranks[~missing][:, 1] - want[~missing][:, 1]), np.abs(ranks[~missing_t][:, 3] - want[~missing_t][:, 3])])
-    assert (scored <= 3).mean() >= 0.60, (scored <= 3).mean()
+    assert (scored == 0).mean() >= 0.55 and (scored <= 3).mean() >= 0.70, ((scored == 0).mean(), (scored <= 3).mean())
     ref = g["metrics"]   # mrr, mr, hit10, hit3, hit1
-    print("full-length ensemble: ours", (mrr, mr, hit10, hit3, hit1), "reference", ref.tolist(), "ranks within 3:", (scored <= 3).mean())
-    assert abs(mrr - ref[0]) <= 0.05 * ref[0], (mrr, ref[0])
-    assert abs(mr - ref[1]) <= 0.005 * ref[1], (mr, ref[1])
+    assert abs(mrr - ref[0]) <= 0.03 * ref[0], (mrr, ref[0])
+    assert abs(mr - ref[1]) <= 1e-4 * ref[1], (mr, ref[1])
     for got_h, want_h in ((hit10, ref[2]), (hit3, ref[3]), (hit1, ref[4])):
-        assert abs(got_h - want_h) <= 0.008, (got_h, want_h)
+        assert abs(got_h - want_h) <= 0.002, (got_h, want_h)
 
 
 # ------------------------------------------------------------------------------------------------
