@@ -145,7 +145,10 @@ def dist_env():
     return rank, world, local
 
 
+STRONG = ("m4", "s1pu")      # workloads whose universes per step are a TOTAL sharded over the ranks
 WORKLOADS = {
+    "s1pu": "PuTransE on the synthetic 1M-entity / 10M-triple graph (BASELINE.json configs[4], SURVEY 8(d) S1-PU; E=1000000, R=1000, "
+            "tools/synth.py seed 1234): %(n)d universes per step IN TOTAL, sharded u %% n_gpus, %(model)s d=20 L1 Adagrad, nbatches=%(nb)d, k=1",
     "m2": "PuTransE static WN18 (BASELINE.json configs[1]): %(n)d universes per GPU per step (seeds 4..), %(model)s d=20 L1 Adagrad, "
           "nbatches=%(nb)d, k=1, tc in [500,2000), epochs in [50,200)",
     "m4": "PuTransE on an FB15K-shaped graph (BASELINE.json configs[3]; E=14951, R=1345, 483142 synthetic train triples, tools/synth.py "
@@ -157,12 +160,13 @@ def workload_dataset(name):
     """Materialise the workload's graph as the header-less files the loaders read; returns (path, data text)."""
     import tempfile
     import util
-    if name == "m4":
+    if name in ("m4", "s1pu"):
         sys.path.insert(0, os.path.join(REPO, "tools"))
         import synth
-        tr, va, te, ne, nr = synth.fb15k_shape()
+        tr, va, te, ne, nr = synth.fb15k_shape() if name == "m4" else synth.s1_shape()
         path = synth.write_dataset(tempfile.mkdtemp(), tr, va, te, ne, nr)
-        return path, "synthetic FB15K-shaped graph (tools/synth.py, seed 1234, checksum %d); universes sampled from it" % synth.checksum(tr)
+        return path, "synthetic %s graph (tools/synth.py, seed 1234, checksum %d); universes sampled from it" % (
+            "FB15K-shaped" if name == "m4" else "1M-entity / 10M-triple", synth.checksum(tr))
     return (util.materialize_wn18(tempfile.mkdtemp()),
             "WN18 graph (repacked reference benchmark files, tests/golden/wn18.npz); universes sampled from it")
 
@@ -201,7 +205,7 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     path, data_text = workload_dataset(args.workload)
-    strong = args.workload == "m4"
+    strong = args.workload in STRONG
     nU = args.universes
     # m2: every rank trains its own nU universes per step (weak scaling); m4: the step's nU universes are
     # sharded over the ranks (strong scaling)
@@ -757,7 +761,7 @@ def run_reference(args):
                                                              d["steps_with_capped_epochs"] if d["steps_with_capped_epochs"] else "")}
     line = {"impl": "reference", "metric": "PuTransE positive triples/sec (all universes)", "value": v,
             "unit": "positive triples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.workload == "m4" else "weak", "vs_baseline": None,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.workload in STRONG else "weak", "vs_baseline": None,
             "dtype": "f32", "data": data_text, "config": bench_config(args, world),
             "cpu_baseline": base,
             "e2e": {"value": v, "unit": "positive triples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
