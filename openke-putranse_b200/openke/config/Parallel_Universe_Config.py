@@ -392,6 +392,7 @@ class Parallel_Universe_Config(Tester):
         self.timings["table_init"] += t2 - t1
 
         ck = _Chunk()
+        ck.items_cache = {}
         ck.ids = list(universe_ids)
         ck.nT, ck.nE, ck.nR, ck.eoff, ck.roff, ck.toff = nT, nE, nR, eoff, roff, toff
         ck.ent_remap, ck.rel_remap = ent_remap, rel_remap
@@ -740,7 +741,7 @@ class Parallel_Universe_Config(Tester):
         self.trained_embedding_spaces[self.next_universe_id] = embedding_space
 
     # ------------------------------------------------------------------ evaluation
-    def _fold_keys(self, k_fixed, k_rel, k_side, consume, want_tuple=False):
+    def _fold_keys(self, k_fixed, k_rel, k_side, consume, want_tuple=False, keys_token=None):
         """energy[key, e] = min over the universes that hold the key's fixed entity and relation of that universe's
         energy of candidate e (+inf where no universe speaks): reference eval_universes :556-603 +
         transmit_max_scores :446-465, for ALL keys, tile by tile.
@@ -766,14 +767,22 @@ class Parallel_Universe_Config(Tester):
         tuples = null_vector or want_tuple
         # (key row, universe, local fixed entity, local relation, side) for every chunk, all keys at once; the
         # items come out sorted by key row, so a tile's items are a contiguous range
+        # (a key set that comes back — the valid split every valid_steps universes, the test split — finds the items
+        # of the chunks it has already seen cached on the chunk: `keys_token` names the key set)
         per_chunk = []
         for ck in self._chunks:
             ix = self._chunk_index(ck)
-            items = self._energy_items(ix, k_fixed, k_rel, k_side)
-            if items.shape[0] == 0:
+            cached = ck.items_cache.get((keys_token, rows_per_tile)) if keys_token is not None else None
+            if cached is None:
+                items = self._energy_items(ix, k_fixed, k_rel, k_side)
+                bounds = np.searchsorted(items["key_row"], np.arange(0, K + rows_per_tile, rows_per_tile))
+                d_items = torch.from_numpy(items.view(np.int32).reshape(-1, 6)).to(dev) if items.shape[0] else None
+                cached = (d_items, bounds)
+                if keys_token is not None:
+                    ck.items_cache[(keys_token, rows_per_tile)] = cached
+            d_items, bounds = cached
+            if d_items is None:
                 continue
-            bounds = np.searchsorted(items["key_row"], np.arange(0, K + rows_per_tile, rows_per_tile))
-            d_items = torch.from_numpy(items.view(np.int32).reshape(-1, 6)).to(dev)
             per_chunk.append((ck, ix, d_items, bounds, ck.proto.native_cfg(), self._packed_tables(ck)))
         self.timings["eval_host_prep"] += time.perf_counter() - t_host
         n_tiles = (K + rows_per_tile - 1) // rows_per_tile
@@ -841,33 +850,11 @@ class Parallel_Universe_Config(Tester):
         dev = self._device()
         dist, rank, world = _dist()
         sharded = dist is not None and world > 1
-        tri, filt = loader.eval_arrays()
-        n = tri.shape[0]
         E = self.ent_tot
-        # keys: head side fixes (t, r); tail side fixes (h, r)
-        fixed = np.concatenate([tri[:, 2], tri[:, 0]]).astype(np.int64)
-        rel = np.concatenate([tri[:, 1], tri[:, 1]]).astype(np.int64)
-        side = np.concatenate([np.zeros(n, np.int64), np.ones(n, np.int64)])
-        truth = np.concatenate([tri[:, 0], tri[:, 2]]).astype(np.int32)
-        code = (side * E + fixed) * self.rel_tot + rel
-        ucode, key_of_query = np.unique(code, return_inverse=True)
-        K = ucode.shape[0]
-        k_rel = ucode % self.rel_tot
-        k_fixed = (ucode // self.rel_tot) % E
-        k_side = ucode // (self.rel_tot * E)
-        foff = np.concatenate([filt[0][0], filt[0][0][-1] + filt[1][0][1:]]).astype(np.int64)
-        fcand = np.concatenate([filt[0][1], filt[1][1]]).astype(np.int32)
-        # queries in key order, with their filter lists gathered in that order (one vectorised pass)
-        order = np.argsort(key_of_query, kind="stable")
-        sorted_keys = key_of_query[order]
-        cnt = foff[order + 1] - foff[order]
-        s_off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
-        take = np.repeat(foff[order] - s_off[:-1], cnt) + np.arange(int(s_off[-1]), dtype=np.int64)
-        s_cand = fcand[take] if take.size else np.zeros(1, np.int32)
-        d_off = torch.from_numpy(s_off).to(dev)
-        d_cand = torch.from_numpy(np.ascontiguousarray(s_cand, dtype=np.int32)).to(dev)
-        d_truth = torch.from_numpy(np.ascontiguousarray(truth[order])).to(dev)
-        d_keyrow = torch.from_numpy(sorted_keys.astype(np.int32)).to(dev)
+        q = self._query_arrays(loader, dev)
+        n, K, order = q["n"], q["K"], q["order"]
+        k_fixed, k_rel, k_side, sorted_keys = q["k_fixed"], q["k_rel"], q["k_side"], q["sorted_keys"]
+        d_off, d_cand, d_truth, d_keyrow = q["d_off"], q["d_cand"], q["d_truth"], q["d_keyrow"]
         ranks_sorted = torch.zeros((2 * n, 2), dtype=torch.int32, device=dev)
         st = torch.cuda.current_stream(dev).cuda_stream
         tile = max(1, min(K, int(self.eval_tile_rows), int(self.max_energy_bytes // (3 * 4 * E))))
@@ -884,7 +871,7 @@ class Parallel_Universe_Config(Tester):
                                                 ranks_sorted.data_ptr() + lo * 8, st), "pk_rank_from_energy")
                 self.gpu_launches += lib.pk_last_launch_count()
 
-        used = self._fold_keys(k_fixed, k_rel, k_side, count)
+        used = self._fold_keys(k_fixed, k_rel, k_side, count, keys_token=q["token"])
         assert used == tile
         if sharded:
             dist.all_reduce(ranks_sorted)      # every query was ranked by exactly one rank
@@ -892,6 +879,44 @@ class Parallel_Universe_Config(Tester):
         r = np.empty_like(r_sorted)
         r[order] = r_sorted
         return np.concatenate([r[:n], r[n:]], axis=1)   # head raw, head filt, tail raw, tail filt
+
+    _TOKENS = [0]
+
+    def _query_arrays(self, loader, dev):
+        """Everything about a loader's queries that does not depend on the universes — keys, key order, the filter
+        lists gathered in key order — built once per loader (vectorised numpy) and kept on the device."""
+        q = getattr(loader, "_pu_query_arrays", None)
+        if q is not None and q["device"] == dev and q["E"] == self.ent_tot and q["arrays"] is loader.eval_arrays():
+            return q
+        arrays = loader.eval_arrays()
+        tri, filt = arrays
+        n = tri.shape[0]
+        E = self.ent_tot
+        # keys: head side fixes (t, r); tail side fixes (h, r)
+        fixed = np.concatenate([tri[:, 2], tri[:, 0]]).astype(np.int64)
+        rel = np.concatenate([tri[:, 1], tri[:, 1]]).astype(np.int64)
+        side = np.concatenate([np.zeros(n, np.int64), np.ones(n, np.int64)])
+        truth = np.concatenate([tri[:, 0], tri[:, 2]]).astype(np.int32)
+        code = (side * E + fixed) * self.rel_tot + rel
+        ucode, key_of_query = np.unique(code, return_inverse=True)
+        foff = np.concatenate([filt[0][0], filt[0][0][-1] + filt[1][0][1:]]).astype(np.int64)
+        fcand = np.concatenate([filt[0][1], filt[1][1]]).astype(np.int32)
+        # queries in key order, with their filter lists gathered in that order (one vectorised pass)
+        order = np.argsort(key_of_query, kind="stable")
+        sorted_keys = key_of_query[order]
+        cnt = foff[order + 1] - foff[order]
+        s_off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+        take = np.repeat(foff[order] - s_off[:-1], cnt) + np.arange(int(s_off[-1]), dtype=np.int64)
+        s_cand = fcand[take] if take.size else np.zeros(1, np.int32)
+        Parallel_Universe_Config._TOKENS[0] += 1
+        q = {"device": dev, "E": E, "arrays": arrays, "token": Parallel_Universe_Config._TOKENS[0], "n": n, "K": int(ucode.shape[0]),
+             "order": order, "sorted_keys": sorted_keys, "k_rel": ucode % self.rel_tot, "k_fixed": (ucode // self.rel_tot) % E,
+             "k_side": ucode // (self.rel_tot * E), "d_off": torch.from_numpy(s_off).to(dev),
+             "d_cand": torch.from_numpy(np.ascontiguousarray(s_cand, dtype=np.int32)).to(dev),
+             "d_truth": torch.from_numpy(np.ascontiguousarray(truth[order])).to(dev),
+             "d_keyrow": torch.from_numpy(sorted_keys.astype(np.int32)).to(dev)}
+        loader._pu_query_arrays = q
+        return q
 
     def triple_energies(self, batch_h, batch_t, batch_r):
         """Global energy of explicit triples, min over the universes that hold head, relation AND tail, +inf when
@@ -1152,6 +1177,7 @@ class Parallel_Universe_Config(Tester):
         # layouts is not compute); every compute entry point asks for the device itself and fails loudly
         dev = self._device() if (self.use_gpu and torch.cuda.is_available()) else torch.device("cpu")
         ck = _Chunk()
+        ck.items_cache = {}
         ck.ids = list(ids)
         ck.nT, ck.nE, ck.nR = (np.asarray(x, dtype=np.int64) for x in (nT, nE, nR))
         ck.ent_remap, ck.rel_remap = np.ascontiguousarray(ent_remap, dtype=np.int32), np.ascontiguousarray(rel_remap, dtype=np.int32)
@@ -1250,6 +1276,7 @@ class Parallel_Universe_Config(Tester):
         for ck in other._chunks:
             ck.ids = [u + shift for u in ck.ids]
             ck.index = None
+            ck.items_cache = {}
             for i, u in enumerate(ck.ids):
                 self._where[u] = (ck, i)
             self._chunks.append(ck)
