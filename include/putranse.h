@@ -106,6 +106,26 @@ void   activateLoadOfAllTriples(bool unused);            /* openke/base/Reader.h
 void   getNegTest(void);
 void   getTestBatch(PK_INT* ph, PK_INT* pt, PK_INT* pr, PK_INT* nh, PK_INT* nt, PK_INT* nr);
 
+/* Incremental setting (openke/base/Incremental.h; bound by openke/data/IncrementalTrainDataLoader.py:40-60 and
+ * IncrementalTestDataLoader.py:34-66).  <inPath>/incremental/{entity2id,relation2id}.txt give the global id space,
+ * <inPath>/incremental/<s>/train-op2id.txt the "h t r +|-" operations of snapshot s, .../global_triple2id.txt the
+ * snapshot's whole triple list (filter set + candidate entities), .../{test,valid}2id.txt its evaluation lists. */
+void   activateIncrementalSetting(void);          /* Incremental.h:45-48   */
+void   initializeIncrementalSetting(void);        /* :207-217              */
+void   setNumSnapshots(PK_INT n);                 /* :52-60                */
+PK_INT getNumSnapshots(void);
+void   setNumOperationsRate(PK_INT n);            /* :141-144              */
+void   readGlobalNumEntities(void);               /* :182-193              */
+void   readGlobalNumRelations(void);              /* :195-205              */
+void   initializeTrainingOperations(int snapshot);/* :299-321              */
+void   evolveTrainList(void);                     /* :798-846 : replay the operations, rebuild every training index */
+void   loadSnapshotTriples(int snapshot);         /* :891-924              */
+void   loadTestData(int snapshot);                /* :248-271              */
+void   loadValidData(int snapshot);               /* :273-296              */
+PK_INT getNumCurrentlyContainedEntities(void);    /* :134-138              */
+int    pk_incremental_reset(void);
+int64_t pk_incremental_list(int which, int32_t* out);
+
 /* ===================================================================================== (B)
  * host-side exports of the graph state (for uploading to the device); ids are int32, triples are
  * (h, r, t) records of 3 x int32
@@ -301,6 +321,11 @@ int pk_rank_from_energy(const float* d_energy, int64_t n_ent_global, int64_t n, 
 /* one HOST-ordered row in the reference's candidate order (slot 0 = truth, then every other entity
  * ascending; Test.h:61-68): the kernel behind testHead/testTail.  d_truth1: int32[1]; d_foff2:
  * int64[2] = {0, #known}; d_ranks2: int32[2] = raw, filtered. */
+/* pk_rank_from_energy restricted to the candidates mask[e] != 0 (incremental setting: the entities the snapshot
+ * currently contains, Test.h:181-206); an unscored truth ranks n_candidates */
+int pk_rank_from_energy_masked(const float* d_energy, int64_t n_ent_global, int64_t n, const int32_t* d_key_row,
+                               const int32_t* d_truth, const int64_t* d_foff, const int32_t* d_fcand, int32_t* d_ranks,
+                               const uint8_t* d_candidate_mask, int64_t n_candidates, void* stream);
 int pk_rank_candidate_row(const float* d_con, int64_t n_ent, const int32_t* d_truth1, const int64_t* d_foff2,
                           const int32_t* d_fcand, int32_t* d_ranks2, void* stream);
 /* Model.forward / Model.predict on int64 index batches (reference TransE.py:62-74,88-94 and the

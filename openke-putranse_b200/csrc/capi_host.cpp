@@ -10,6 +10,7 @@
 #include "graph_host.hpp"
 #include "global_state.hpp"
 #include <mutex>
+#include <shared_mutex>
 
 namespace pk {
 
@@ -37,6 +38,14 @@ uint64_t index_epoch() { return G().index_epoch; }
 }  // namespace pk
 
 using pk::G;
+
+// pk_universes_build runs on caller threads beside the thread that owns the loaders (the orchestrator samples the
+// next chunk's subgraphs in the background); it holds this lock shared, and whatever replaces the training graph
+// (importTrainFiles, evolveTrainList, the incremental reset) takes it exclusively.
+static std::shared_mutex& graph_mutex() {
+    static std::shared_mutex m;
+    return m;
+}
 
 extern "C" {
 
@@ -79,6 +88,7 @@ void randReset(void) {
 }
 
 void importTrainFiles(void) {
+    std::unique_lock<std::shared_mutex> lk(graph_mutex());
     std::string err;
     if (!G().graph.import_train(&err)) {
         pk::fail(PK_ERR_IO, err);
@@ -283,6 +293,77 @@ void getEntityRelations(PK_INT* out, PK_INT entity, bool entity_is_tail) {
 // importTestFiles() reads the filter set from triple2id.txt instead of test ∪ train ∪ valid.
 void activateLoadOfAllTriples(bool) { G().graph.load_all_triples = true; }
 
+// ---------------------------------------------------------------- incremental setting (openke/base/Incremental.h)
+// Bound by the reference's IncrementalTrainDataLoader / IncrementalTestDataLoader
+// (openke/data/IncrementalTrainDataLoader.py:40-60, IncrementalTestDataLoader.py:34-66).
+static void report(bool ok, const char* who, const std::string& err) {
+    if (ok) return;
+    pk::fail(PK_ERR_IO, err);
+    fprintf(stderr, "putranse: %s failed: %s\n", who, err.c_str());
+}
+void activateIncrementalSetting(void) { G().graph.incremental = true; }          // Incremental.h:45-48
+void initializeIncrementalSetting(void) {                                         // :207-217
+    std::string err;
+    G().graph.incremental = true;
+    report(G().graph.read_global_totals(&err), "initializeIncrementalSetting", err);
+}
+void setNumSnapshots(PK_INT n) { G().graph.num_snapshots = n; }
+PK_INT getNumSnapshots(void) { return G().graph.num_snapshots; }
+void setNumOperationsRate(PK_INT n) { G().graph.ops_rate = n; }
+void readGlobalNumEntities(void) { std::unique_lock<std::shared_mutex> lk(graph_mutex()); std::string err; report(G().graph.read_global_totals(&err), "readGlobalNumEntities", err); }
+void readGlobalNumRelations(void) { std::unique_lock<std::shared_mutex> lk(graph_mutex()); std::string err; report(G().graph.read_global_totals(&err), "readGlobalNumRelations", err); }
+void initializeTrainingOperations(int snapshot) {
+    std::string err;
+    report(G().graph.load_train_ops(snapshot, &err), "initializeTrainingOperations", err);
+}
+void evolveTrainList(void) {
+    std::unique_lock<std::shared_mutex> lk(graph_mutex());
+    std::string err;
+    const bool ok = G().graph.evolve_train(&err);
+    report(ok, "evolveTrainList", err);
+    if (ok) G().index_epoch++;
+}
+void loadSnapshotTriples(int snapshot) {
+    std::string err;
+    const bool ok = G().graph.load_snapshot_triples(snapshot, &err);
+    report(ok, "loadSnapshotTriples", err);
+    if (ok) G().eval_epoch++;
+}
+void loadTestData(int snapshot) {
+    std::string err;
+    const bool ok = G().graph.load_snapshot_eval(snapshot, 0, &err);
+    report(ok, "loadTestData", err);
+    if (ok) G().eval_epoch++;
+}
+void loadValidData(int snapshot) {
+    std::string err;
+    const bool ok = G().graph.load_snapshot_eval(snapshot, 1, &err);
+    report(ok, "loadValidData", err);
+    if (ok) G().eval_epoch++;
+}
+PK_INT getNumCurrentlyContainedEntities(void) { return (PK_INT)G().graph.contained_entities.size(); }
+// leave the incremental setting (the reference cannot: its flag is set once per process)
+int pk_incremental_reset(void) {
+    std::unique_lock<std::shared_mutex> lk(graph_mutex());
+    pk::Graph& g = G().graph;
+    g.incremental = false;
+    g.ops.clear(); g.next_op = 0; g.ops_rate = 0;
+    g.train_count.clear(); g.train_rel_count.clear();
+    g.train_rel_contained.clear(); g.train_rel_all.clear(); g.train_rel_deleted.clear();
+    g.contained_entities.clear(); g.contained_relations.clear();
+    return PK_OK;
+}
+// which: 0 currently contained train relations (the universe focus is drawn by position from this array),
+// 1 all, 2 deleted, 3 entities of the snapshot's triple list, 4 its relations.  out = NULL: count only.
+int64_t pk_incremental_list(int which, int32_t* out) {
+    const pk::Graph& g = G().graph;
+    const std::vector<int32_t>* v = which == 0 ? &g.train_rel_contained : which == 1 ? &g.train_rel_all : which == 2 ? &g.train_rel_deleted
+                                    : which == 3 ? &g.contained_entities : which == 4 ? &g.contained_relations : nullptr;
+    if (!v) return pk::fail(PK_ERR_ARG, "pk_incremental_list: bad selector");
+    if (out && !v->empty()) std::memcpy(out, v->data(), v->size() * 4);
+    return (int64_t)v->size();
+}
+
 // ---------------------------------------------------------------- many universes, many threads
 struct pk_universe_set {
     std::vector<pk::Universe> u;
@@ -298,6 +379,7 @@ pk_universe_set* pk_universes_build(int n, const int64_t* seeds, const int64_t* 
         pk::fail(PK_ERR_STATE, "pk_universes_build: importTrainFiles has not run");
         return nullptr;
     }
+    std::shared_lock<std::shared_mutex> graph_lk(graph_mutex());
     pk_universe_set* s = new pk_universe_set();
     s->u.resize((size_t)n);
     s->work_threads = (int)G().graph.work_threads;

@@ -164,6 +164,15 @@ bool Graph::import_train(std::string* err) {
     train.n_rel = nr;
     train.by_head = raw;
     sort_unique(train.by_head, less_hrt);
+    finish_train_index(same_shape, /*drift=*/true);
+    return true;
+}
+
+// Everything that is derived from the (h,r,t)-sorted training list `train.by_head` (with or without duplicate
+// records): the (t,r,h) order, per-entity and per-relation ranges, the per-relation entity lists the universes
+// start from, and the Bernoulli statistics.
+void Graph::finish_train_index(bool same_shape, bool drift) {
+    const int64_t nr = n_rel;
     train.by_tail = train.by_head;
     std::sort(train.by_tail.begin(), train.by_tail.end(), less_trh);
     train.build_ranges();
@@ -202,9 +211,22 @@ bool Graph::import_train(std::string* err) {
     for (size_t k = 0; k < train.by_tail.size(); ++k)
         tail_to_head[k] = (int32_t)(std::lower_bound(train.by_head.begin(), train.by_head.end(), train.by_tail[k], less_hrt) - train.by_head.begin());
 
-    // Bernoulli statistics with the reference's import-count drift.
-    import_count = same_shape ? import_count + 1 : 1;
-    if (!same_shape) {
+    // positions of by_head that hold the same triple share one id for the walk's collected-before test (the
+    // reference compares triple VALUES, UniverseConstructor.h:82-90); only the incremental list has duplicates
+    head_canon.clear();
+    for (size_t k = 1; k < train.by_head.size(); ++k)
+        if (train.by_head[k] == train.by_head[k - 1]) {
+            if (head_canon.empty()) {
+                head_canon.resize(train.by_head.size());
+                for (size_t j = 0; j < head_canon.size(); ++j) head_canon[j] = (int32_t)j;
+            }
+            head_canon[k] = head_canon[k - 1];
+        }
+
+    // Bernoulli statistics with the reference's import-count drift (static reader), or computed afresh
+    // (incremental: resetIncrementalHelpers frees the arrays, Incremental.h:679-697).
+    import_count = (drift && same_shape) ? import_count + 1 : 1;
+    if (!same_shape || !drift) {
         train.left_mean.assign((size_t)nr, 0.f);
         train.right_mean.assign((size_t)nr, 0.f);
     }
@@ -216,7 +238,6 @@ bool Graph::import_train(std::string* err) {
         train.left_mean[(size_t)r] = (float)f / bump(train.left_mean[(size_t)r], dh[(size_t)r]);
         train.right_mean[(size_t)r] = (float)f / bump(train.right_mean[(size_t)r], dt[(size_t)r]);
     }
-    return true;
 }
 
 bool Graph::import_test(std::string* err) {
@@ -327,7 +348,16 @@ bool Graph::walk_universe(GlibcRand& rng, int64_t tc, float balance, Universe* u
     u->balance = balance;
     int64_t draws = 0;
 
-    const int64_t focus = rng.range(0, n_rel);           // UniverseConstructor.h:341
+    int64_t focus;
+    if (incremental) {   // UniverseConstructor.h:336-339: a relation the evolving training list currently holds
+        if (train_rel_contained.empty()) {
+            *err = "build_universe: the incremental training list holds no relation (evolveTrainList has not run)";
+            return false;
+        }
+        focus = train_rel_contained[(size_t)rng.range(0, (int64_t)train_rel_contained.size())];
+    } else {
+        focus = rng.range(0, n_rel);                     // UniverseConstructor.h:341
+    }
     ++draws;
     u->focus = focus;
     const int64_t threshold = (int64_t)(balance * (float)tc);  // :345-346 (float product, truncated)
@@ -400,7 +430,7 @@ bool Graph::walk_universe(GlibcRand& rng, int64_t tc, float balance, Universe* u
                 ++draws;
                 x = g.by_head[(size_t)idx];
                 nxt = x.t;
-                tid = idx;
+                tid = head_canon.empty() ? idx : head_canon[(size_t)idx];
             } else if (side == 1) {
                 const int64_t idx = rng.range(er.lef_tail, (int64_t)er.rig_tail + 1);  // :48
                 ++draws;
@@ -510,6 +540,179 @@ bool Graph::walk_universe(GlibcRand& rng, int64_t tc, float balance, Universe* u
         L.left_mean[(size_t)r] = (float)freq[(size_t)r] / bump(0.f, dh[(size_t)r]);
         L.right_mean[(size_t)r] = (float)freq[(size_t)r] / bump(0.f, dt[(size_t)r]);
     }
+    return true;
+}
+
+}  // namespace pk
+
+// ------------------------------------------------------------------------------------------------
+// Incremental setting (reference openke/base/Incremental.h).  The reference keeps the evolving training list as
+// a C array that it appends to and shift-deletes from, and re-derives "is this relation still present" by linear
+// scans; here the list is a multiset keyed by the packed triple with a per-relation counter, which gives the same
+// list (the reference sorts it before use, Incremental.h:710) and the same ORDER of the three relation arrays the
+// universe focus is drawn from.
+namespace pk {
+
+bool Graph::read_global_totals(std::string* err) {   // Incremental.h:182-205
+    int64_t ne, nr;
+    if (!count_lines(in_path + "incremental/entity2id.txt", &ne, err)) return false;
+    if (!count_lines(in_path + "incremental/relation2id.txt", &nr, err)) return false;
+    if (ne != n_ent || nr != n_rel) {   // a different id space: nothing of the previous one survives
+        train = TripleIndex();
+        train_count.clear();
+        train_rel_contained.clear();
+        train_rel_all.clear();
+        train_rel_deleted.clear();
+        ops.clear();
+        next_op = 0;
+    }
+    n_ent = ne;
+    n_rel = nr;
+    train.n_ent = ne;
+    train.n_rel = nr;
+    train_rel_count.resize((size_t)nr, 0);
+    return true;
+}
+
+static bool read_ops(const std::string& path, int64_t ne, int64_t nr, std::vector<Graph::TripleOp>* out, std::string* err) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) {
+        *err = "cannot open " + path;
+        return false;
+    }
+    out->clear();
+    char line[256];
+    while (fgets(line, sizeof line, f)) {
+        long long h, t, r;
+        char op[8] = {0};
+        if (sscanf(line, "%lld %lld %lld %7s", &h, &t, &r, op) != 4) continue;   // the reference reads with fscanf per line count
+        if (h < 0 || t < 0 || r < 0 || h >= ne || t >= ne || r >= nr || (op[0] != '+' && op[0] != '-')) {
+            fclose(f);
+            *err = "malformed operation in " + path;
+            return false;
+        }
+        out->push_back(Graph::TripleOp{Tri{(int32_t)h, (int32_t)r, (int32_t)t}, op[0]});
+    }
+    fclose(f);
+    return true;
+}
+
+bool Graph::load_train_ops(int snapshot, std::string* err) {   // initializeTrainingOperations, Incremental.h:299-321
+    if (n_ent <= 0 || n_rel <= 0) {
+        *err = "initializeTrainingOperations: readGlobalNumEntities/Relations have not run";
+        return false;
+    }
+    if (!read_ops(in_path + "incremental/" + std::to_string(snapshot) + "/train-op2id.txt", n_ent, n_rel, &ops, err)) return false;
+    next_op = 0;
+    return true;
+}
+
+bool Graph::evolve_train(std::string* err) {   // evolveTrainList, Incremental.h:798-846
+    size_t todo = ops_rate > 0 ? (size_t)ops_rate : ops.size();   // numOperationsRate == 0: the whole snapshot
+    if (todo > ops.size() - next_op) todo = ops.size() - next_op;
+    train_rel_count.resize((size_t)n_rel, 0);
+    auto erase_value = [](std::vector<int32_t>& v, int32_t x) {
+        for (size_t i = 0; i < v.size(); ++i)
+            if (v[i] == x) { v.erase(v.begin() + (long)i); return true; }
+        return false;
+    };
+    auto contains = [](const std::vector<int32_t>& v, int32_t x) {
+        for (int32_t y : v) if (y == x) return true;
+        return false;
+    };
+    for (size_t k = 0; k < todo; ++k, ++next_op) {
+        const TripleOp& o = ops[next_op];
+        const int32_t r = o.t.r;
+        if (o.op == '+') {   // insertTrainTriple :562-573 with adjustTrainRelationSet :540-552
+            if (train_rel_count[(size_t)r] == 0) {
+                if (!contains(train_rel_all, r)) train_rel_all.push_back(r);
+                else erase_value(train_rel_deleted, r);
+                train_rel_contained.push_back(r);
+            }
+            ++train_count[tri_key(o.t)];
+            ++train_rel_count[(size_t)r];
+        } else {             // deleteTrainTriple :651-676: the first equal record goes; unknown triples are reported and skipped
+            auto it = train_count.find(tri_key(o.t));
+            if (it == train_count.end() || it->second == 0) continue;
+            if (--it->second == 0) train_count.erase(it);
+            if (--train_rel_count[(size_t)r] == 0) {   // trainRelationRemovalCheck :618-626
+                erase_value(train_rel_contained, r);
+                train_rel_deleted.push_back(r);
+            }
+        }
+    }
+    // resetSnapShot :219-230 is called at the end of evolveTrainList: operations that were not replayed are dropped
+    ops_rate = 0;
+    ops.clear();
+    next_op = 0;
+    std::vector<Tri> list;
+    size_t total = 0;
+    for (const auto& kv : train_count) total += (size_t)kv.second;
+    if (total == 0) {
+        *err = "evolveTrainList: the training list is empty";
+        return false;
+    }
+    list.reserve(total);
+    for (const auto& kv : train_count) {
+        uint64_t key = kv.first;
+        Tri x;
+        x.t = (int32_t)(key % (uint64_t)n_ent); key /= (uint64_t)n_ent;
+        x.r = (int32_t)(key % (uint64_t)n_rel); key /= (uint64_t)n_rel;
+        x.h = (int32_t)key;
+        for (int32_t c = 0; c < kv.second; ++c) list.push_back(x);
+    }
+    std::sort(list.begin(), list.end(), less_hrt);   // :710 (duplicates stay: the sampler indexes this list)
+    train.n_ent = n_ent;
+    train.n_rel = n_rel;
+    train.by_head.swap(list);
+    train_lines = (int64_t)train.by_head.size();
+    finish_train_index(/*same_shape=*/false, /*drift=*/false);
+    return true;
+}
+
+// loadSnapshotTriples (Incremental.h:891-924): the snapshot's whole triple list becomes the filter set, its
+// entities the candidate set.  (The reference then copies the RELATION ids over the first entries of
+// currently_contained_entities, :882-887 — a slip; the entity array is kept intact here.)
+bool Graph::load_snapshot_triples(int snapshot, std::string* err) {
+    std::vector<Tri> all;
+    int64_t lines = 0;
+    if (!read_triples(in_path + "incremental/" + std::to_string(snapshot) + "/global_triple2id.txt", &all, &lines, err)) return false;
+    std::vector<int32_t> ents, rels;
+    ents.reserve(all.size() * 2);
+    for (const Tri& x : all) {
+        if (x.h < 0 || x.t < 0 || x.r < 0 || x.h >= n_ent || x.t >= n_ent || x.r >= n_rel) {
+            *err = "triple id out of range in global_triple2id.txt of snapshot " + std::to_string(snapshot);
+            return false;
+        }
+        ents.push_back(x.h);
+        ents.push_back(x.t);
+        rels.push_back(x.r);
+    }
+    std::sort(ents.begin(), ents.end());
+    ents.erase(std::unique(ents.begin(), ents.end()), ents.end());
+    std::sort(rels.begin(), rels.end());
+    rels.erase(std::unique(rels.begin(), rels.end()), rels.end());
+    contained_entities.swap(ents);
+    contained_relations.swap(rels);
+    all_hrt.swap(all);
+    sort_unique(all_hrt, less_hrt);
+    all_trh = all_hrt;
+    std::sort(all_trh.begin(), all_trh.end(), less_trh);
+    return true;
+}
+
+// loadTestData / loadValidData (Incremental.h:248-296): the snapshot's list in FILE order (not re-sorted).
+bool Graph::load_snapshot_eval(int snapshot, int which, std::string* err) {
+    std::vector<Tri> q;
+    int64_t lines = 0;
+    const std::string name = which == 0 ? "/test2id.txt" : "/valid2id.txt";
+    if (!read_triples(in_path + "incremental/" + std::to_string(snapshot) + name, &q, &lines, err)) return false;
+    for (const Tri& x : q)
+        if (x.h < 0 || x.t < 0 || x.r < 0 || x.h >= n_ent || x.t >= n_ent || x.r >= n_rel) {
+            *err = "triple id out of range in " + name + " of snapshot " + std::to_string(snapshot);
+            return false;
+        }
+    (which == 0 ? test : valid).swap(q);
     return true;
 }
 

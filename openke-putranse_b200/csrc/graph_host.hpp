@@ -12,6 +12,7 @@
 #include <cstdint>
 #include <set>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 namespace pk {
@@ -105,6 +106,29 @@ struct Graph {
 
     bool import_train(std::string* err);
     bool import_test(std::string* err);
+    void finish_train_index(bool same_shape, bool drift);
+
+    // ---- incremental setting (reference openke/base/Incremental.h): the training list evolves snapshot by
+    //      snapshot by replaying "h t r +|-" operations; evaluation lists and the filter set are per snapshot
+    struct TripleOp { Tri t; char op; };
+    bool incremental = false;
+    int64_t num_snapshots = 0, ops_rate = 0;
+    std::vector<TripleOp> ops;                         // KnowledgeGraphOperations
+    size_t next_op = 0;
+    std::unordered_map<uint64_t, int32_t> train_count; // the current training list as a multiset (duplicates are kept)
+    std::vector<int64_t> train_rel_count;              // its triples per relation
+    // the reference's arrays, in ITS order (append on first or renewed appearance, erase-and-shift on removal): the
+    // universe focus is drawn by position from train_rel_contained (UniverseConstructor.h:336-339)
+    std::vector<int32_t> train_rel_contained, train_rel_all, train_rel_deleted;
+    std::vector<int32_t> head_canon;                   // by_head position -> first position of the same triple (empty: no duplicates)
+    std::vector<int32_t> contained_entities;           // entities of the snapshot's triple list, ascending (Incremental.h:850-870)
+    std::vector<int32_t> contained_relations;
+    uint64_t tri_key(const Tri& x) const { return ((uint64_t)x.h * (uint64_t)n_rel + (uint64_t)x.r) * (uint64_t)n_ent + (uint64_t)x.t; }
+    bool read_global_totals(std::string* err);                       // readGlobalNumEntities / readGlobalNumRelations
+    bool load_train_ops(int snapshot, std::string* err);             // initializeTrainingOperations
+    bool evolve_train(std::string* err);                             // evolveTrainList
+    bool load_snapshot_triples(int snapshot, std::string* err);      // loadSnapshotTriples
+    bool load_snapshot_eval(int snapshot, int which, std::string* err);  // loadTestData / loadValidData
     // Known-true candidates for query i of `which` (0 test, 1 valid) on `side` (0 head, 1 tail),
     // excluding the true entity itself; ascending.  Equivalent to the reference's per-candidate
     // _find() (openke/base/Corrupt.h:188-199) evaluated for every other entity.

@@ -19,7 +19,6 @@
 // round-to-nearest intrinsics, so equal inputs give bit-equal energies and `<` is self-consistent.
 #include <algorithm>
 #include <cmath>
-#include <cstdlib>
 
 #include "common.hpp"
 #include "kge_device.cuh"
@@ -33,26 +32,6 @@ constexpr int R_TE = 256;      // entities per tile (one per thread)
 constexpr int R_QC = 64;       // queries per block chunk
 constexpr int R_MAXD = 256;
 
-// Per-thread operand rows.  Every device function and kernel below is instantiated for a compile-time row
-// capacity DM (32, 64 or 256, chosen from the embedding dimension at launch): for DM <= 64 the loops over the
-// dimension have a constant trip count and are fully unrolled with a guard, so the rows live in REGISTERS (the
-// PuTrans* scripts use d = 20, the single-space configs d = 50); only d > 64 falls back to runtime loops over
-// local-memory rows.  The order of every floating-point operation is the same in all instantiations.
-#define PK_FOR_D(i) _Pragma("unroll") for (int i = 0; i < (DM <= 64 ? DM : d); ++i) if (DM > 64 || i < d)
-#define PK_DISPATCH_DM(dim, ...)                                  \
-    do {                                                          \
-        const int cap__ = row_capacity(dim);                      \
-        if (cap__ == 32) { constexpr int DM = 32; __VA_ARGS__; }  \
-        else if (cap__ == 64) { constexpr int DM = 64; __VA_ARGS__; } \
-        else { constexpr int DM = 256; __VA_ARGS__; }             \
-    } while (0)
-// PK_K3_ROWS=256 forces the local-memory instantiation (experiments)
-inline int row_capacity(int d) {
-    static const int forced = getenv("PK_K3_ROWS") ? atoi(getenv("PK_K3_ROWS")) : 0;
-    const int want = d <= 32 ? 32 : (d <= 64 ? 64 : 256);
-    return forced > want ? forced : want;
-}
-
 struct SpaceView {
     const float* ent[2];
     const float* rel[2];
@@ -60,78 +39,74 @@ struct SpaceView {
 };
 
 // y_r(e) for one entity, sequential over d.  `w` = w^ (H) or r_p (D), already prepared.
-template <int DM>
 __device__ __forceinline__ void ent_operand(const SpaceView& sp, const float* __restrict__ e, const float* __restrict__ ep,
                                             const float* w, float* y) {
     const int d = sp.d;
     if (sp.model == TRANSE) {
-        PK_FOR_D(i) y[i] = e[i];
+        for (int i = 0; i < d; ++i) y[i] = e[i];
     } else if (sp.model == TRANSH) {
         float a = 0.f;
-        PK_FOR_D(i) a = __fmaf_rn(e[i], w[i], a);
-        PK_FOR_D(i) y[i] = __fsub_rn(e[i], __fmul_rn(a, w[i]));
+        for (int i = 0; i < d; ++i) a = __fmaf_rn(e[i], w[i], a);
+        for (int i = 0; i < d; ++i) y[i] = __fsub_rn(e[i], __fmul_rn(a, w[i]));
     } else {
         float a = 0.f;
-        PK_FOR_D(i) a = __fmaf_rn(e[i], ep[i], a);
+        for (int i = 0; i < d; ++i) a = __fmaf_rn(e[i], ep[i], a);
         float ss = 0.f;
-        PK_FOR_D(i) {
+        for (int i = 0; i < d; ++i) {
             y[i] = __fadd_rn(e[i], __fmul_rn(a, w[i]));
             ss = __fmaf_rn(y[i], y[i], ss);
         }
         const float n = fmaxf(__fsqrt_rn(ss), kNormEps);
-        PK_FOR_D(i) y[i] = __fdiv_rn(y[i], n);
+        for (int i = 0; i < d; ++i) y[i] = __fdiv_rn(y[i], n);
     }
     if (sp.norm_flag) {
         float ss = 0.f;
-        PK_FOR_D(i) ss = __fmaf_rn(y[i], y[i], ss);
+        for (int i = 0; i < d; ++i) ss = __fmaf_rn(y[i], y[i], ss);
         const float n = fmaxf(__fsqrt_rn(ss), kNormEps);
-        PK_FOR_D(i) y[i] = __fdiv_rn(y[i], n);
+        for (int i = 0; i < d; ++i) y[i] = __fdiv_rn(y[i], n);
     }
 }
 
 // relation-side preparation: rh = r^ ; w = w^ (H) / r_p (D)
-template <int DM>
 __device__ __forceinline__ void rel_operand(const SpaceView& sp, int r, float* rh, float* w) {
     const int d = sp.d;
     const float* rr = sp.rel[0] + (size_t)r * d;
-    PK_FOR_D(i) rh[i] = rr[i];
+    for (int i = 0; i < d; ++i) rh[i] = rr[i];
     if (sp.norm_flag) {
         float ss = 0.f;
-        PK_FOR_D(i) ss = __fmaf_rn(rh[i], rh[i], ss);
+        for (int i = 0; i < d; ++i) ss = __fmaf_rn(rh[i], rh[i], ss);
         const float n = fmaxf(__fsqrt_rn(ss), kNormEps);
-        PK_FOR_D(i) rh[i] = __fdiv_rn(rh[i], n);
+        for (int i = 0; i < d; ++i) rh[i] = __fdiv_rn(rh[i], n);
     }
     if (sp.model == TRANSH) {
         const float* ww = sp.rel[1] + (size_t)r * d;
         float ss = 0.f;
-        PK_FOR_D(i) { w[i] = ww[i]; ss = __fmaf_rn(w[i], w[i], ss); }
+        for (int i = 0; i < d; ++i) { w[i] = ww[i]; ss = __fmaf_rn(w[i], w[i], ss); }
         const float n = fmaxf(__fsqrt_rn(ss), kNormEps);
-        PK_FOR_D(i) w[i] = __fdiv_rn(w[i], n);
+        for (int i = 0; i < d; ++i) w[i] = __fdiv_rn(w[i], n);
     } else if (sp.model == TRANSD) {
         const float* ww = sp.rel[1] + (size_t)r * d;
-        PK_FOR_D(i) w[i] = ww[i];
+        for (int i = 0; i < d; ++i) w[i] = ww[i];
     }
 }
 
 // the query vector: head side q = r^ - y(t);  tail side q = y(h) + r^
-template <int DM>
 __device__ __forceinline__ void query_vector(int d, int side, const float* rh, const float* yfix, float* q) {
-    if (side == 0) PK_FOR_D(i) q[i] = __fsub_rn(rh[i], yfix[i]);
-    else           PK_FOR_D(i) q[i] = __fadd_rn(yfix[i], rh[i]);
+    if (side == 0) for (int i = 0; i < d; ++i) q[i] = __fsub_rn(rh[i], yfix[i]);
+    else           for (int i = 0; i < d; ++i) q[i] = __fadd_rn(yfix[i], rh[i]);
 }
 
 // energy of a candidate operand y (strided access so that tiles can be stored transposed)
-template <int DM>
 __device__ __forceinline__ float energy(int d, int p_norm, int side, const float* q, const float* y, int ystride) {
     float acc = 0.f;
     if (p_norm == 1) {
-        PK_FOR_D(i) {
+        for (int i = 0; i < d; ++i) {
             const float s = side == 0 ? __fadd_rn(y[(size_t)i * ystride], q[i]) : __fsub_rn(q[i], y[(size_t)i * ystride]);
             acc = __fadd_rn(acc, fabsf(s));
         }
         return acc;
     }
-    PK_FOR_D(i) {
+    for (int i = 0; i < d; ++i) {
         const float s = side == 0 ? __fadd_rn(y[(size_t)i * ystride], q[i]) : __fsub_rn(q[i], y[(size_t)i * ystride]);
         acc = __fmaf_rn(s, s, acc);
     }
@@ -152,7 +127,6 @@ struct RankParams {
     const int32_t* fcand[2];
 };
 
-template <int DM>
 __global__ void __launch_bounds__(128) k3_targets(const __grid_constant__ RankParams P) {
     const int64_t idx = (int64_t)blockIdx.x * 128 + threadIdx.x;  // query*2 + side
     if (idx >= P.n * 2) return;
@@ -160,14 +134,14 @@ __global__ void __launch_bounds__(128) k3_targets(const __grid_constant__ RankPa
     const int side = (int)(idx & 1);
     const int d = P.sp.d;
     const int32_t h = P.triples[qi * 3], r = P.triples[qi * 3 + 1], t = P.triples[qi * 3 + 2];
-    float rh[DM], w[DM], y[DM];
-    rel_operand<DM>(P.sp, r, rh, w);
+    float rh[R_MAXD], w[R_MAXD], y[R_MAXD];
+    rel_operand(P.sp, r, rh, w);
     const int32_t fix = side == 0 ? t : h, truth = side == 0 ? h : t;
-    ent_operand<DM>(P.sp, P.sp.ent[0] + (size_t)fix * d, P.sp.ent[1] ? P.sp.ent[1] + (size_t)fix * d : nullptr, w, y);
+    ent_operand(P.sp, P.sp.ent[0] + (size_t)fix * d, P.sp.ent[1] ? P.sp.ent[1] + (size_t)fix * d : nullptr, w, y);
     float* q = P.qvec + idx * d;
-    query_vector<DM>(d, side, rh, y, q);
-    ent_operand<DM>(P.sp, P.sp.ent[0] + (size_t)truth * d, P.sp.ent[1] ? P.sp.ent[1] + (size_t)truth * d : nullptr, w, y);
-    P.target[idx] = energy<DM>(d, P.sp.p_norm, side, q, y, 1);
+    query_vector(d, side, rh, y, q);
+    ent_operand(P.sp, P.sp.ent[0] + (size_t)truth * d, P.sp.ent[1] ? P.sp.ent[1] + (size_t)truth * d : nullptr, w, y);
+    P.target[idx] = energy(d, P.sp.p_norm, side, q, y, 1);
     P.ranks[qi * 4 + side * 2 + 0] = 0;
     P.ranks[qi * 4 + side * 2 + 1] = 0;
 }
@@ -176,7 +150,6 @@ __global__ void __launch_bounds__(128) k3_targets(const __grid_constant__ RankPa
 // sorted by relation (reference testList order, Reader.h:311), so a chunk is a few relation runs;
 // for each run the tile's operands y_r(e) are built once in shared memory (transposed: [d][R_TE])
 // and every query of the run is scored against them.
-template <int DM>
 __global__ void __launch_bounds__(R_THREADS) k3_raw(const __grid_constant__ RankParams P) {
     extern __shared__ __align__(16) float sm[];
     const int d = P.sp.d;
@@ -196,16 +169,16 @@ __global__ void __launch_bounds__(R_THREADS) k3_raw(const __grid_constant__ Rank
             if (P.sp.model != TRANSE) {
                 // every thread needs w; thread 0 prepares it once
                 if (tid == 0) {
-                    float rh[DM];
-                    rel_operand<DM>(P.sp, r, rh, wbuf);
+                    float rh[R_MAXD];
+                    rel_operand(P.sp, r, rh, wbuf);
                 }
                 __syncthreads();
             }
             if (live) {
-                float y[DM], w[DM];
-                if (P.sp.model != TRANSE) PK_FOR_D(i) w[i] = wbuf[i];
-                ent_operand<DM>(P.sp, P.sp.ent[0] + (size_t)e * d, P.sp.ent[1] ? P.sp.ent[1] + (size_t)e * d : nullptr, w, y);
-                PK_FOR_D(i) ytile[(size_t)i * R_TE + tid] = y[i];
+                float y[R_MAXD], w[R_MAXD];
+                if (P.sp.model != TRANSE) for (int i = 0; i < d; ++i) w[i] = wbuf[i];
+                ent_operand(P.sp, P.sp.ent[0] + (size_t)e * d, P.sp.ent[1] ? P.sp.ent[1] + (size_t)e * d : nullptr, w, y);
+                for (int i = 0; i < d; ++i) ytile[(size_t)i * R_TE + tid] = y[i];
             }
             cur_rel = r;
         }
@@ -217,7 +190,7 @@ __global__ void __launch_bounds__(R_THREADS) k3_raw(const __grid_constant__ Rank
         for (int side = 0; side < 2; ++side) {
             bool better = false;
             if (live) {
-                const float en = energy<DM>(d, P.sp.p_norm, side, qbuf + side * d, ytile + tid, R_TE);
+                const float en = energy(d, P.sp.p_norm, side, qbuf + side * d, ytile + tid, R_TE);
                 better = en < P.target[qi * 2 + side];
             }
             const unsigned m = __ballot_sync(0xffffffffu, better);
@@ -229,7 +202,6 @@ __global__ void __launch_bounds__(R_THREADS) k3_raw(const __grid_constant__ Rank
 }
 
 // pass 3: filtered rank = raw rank - #(known-true candidates that also beat the truth)
-template <int DM>
 __global__ void __launch_bounds__(128) k3_filter(const __grid_constant__ RankParams P) {
     const int64_t idx = (int64_t)blockIdx.x * 128 + threadIdx.x;  // query*2 + side
     if (idx >= P.n * 2) return;
@@ -240,14 +212,14 @@ __global__ void __launch_bounds__(128) k3_filter(const __grid_constant__ RankPar
     const int64_t lo = P.foff[side][qi], hi = P.foff[side][qi + 1];
     int sub = 0;
     if (hi > lo) {
-        float rh[DM], w[DM], y[DM];
-        rel_operand<DM>(P.sp, r, rh, w);
+        float rh[R_MAXD], w[R_MAXD], y[R_MAXD];
+        rel_operand(P.sp, r, rh, w);
         const float* q = P.qvec + idx * d;
         const float tgt = P.target[idx];
         for (int64_t c = lo; c < hi; ++c) {
             const int32_t ce = P.fcand[side][c];
-            ent_operand<DM>(P.sp, P.sp.ent[0] + (size_t)ce * d, P.sp.ent[1] ? P.sp.ent[1] + (size_t)ce * d : nullptr, w, y);
-            if (energy<DM>(d, P.sp.p_norm, side, q, y, 1) < tgt) ++sub;
+            ent_operand(P.sp, P.sp.ent[0] + (size_t)ce * d, P.sp.ent[1] ? P.sp.ent[1] + (size_t)ce * d : nullptr, w, y);
+            if (energy(d, P.sp.p_norm, side, q, y, 1) < tgt) ++sub;
         }
     }
     // raw count is final (previous kernel finished); derive the filtered one
@@ -268,7 +240,6 @@ struct EnergyParams {
     int64_t E;
 };
 
-template <int DM>
 __global__ void __launch_bounds__(R_THREADS) k3u_energies(const __grid_constant__ EnergyParams P) {
     extern __shared__ __align__(16) float sm[];
     const int d = P.sp.d;
@@ -283,19 +254,19 @@ __global__ void __launch_bounds__(R_THREADS) k3u_energies(const __grid_constant_
         if (sp.rel[i]) sp.rel[i] += (size_t)ro * d;
     }
     if (threadIdx.x == 0) {
-        float rh[DM], y[DM];
-        rel_operand<DM>(sp, it.rel_local, rh, w);
-        ent_operand<DM>(sp, sp.ent[0] + (size_t)it.fixed_local * d, sp.ent[1] ? sp.ent[1] + (size_t)it.fixed_local * d : nullptr, w, y);
-        query_vector<DM>(d, it.side, rh, y, q);
+        float rh[R_MAXD], y[R_MAXD];
+        rel_operand(sp, it.rel_local, rh, w);
+        ent_operand(sp, sp.ent[0] + (size_t)it.fixed_local * d, sp.ent[1] ? sp.ent[1] + (size_t)it.fixed_local * d : nullptr, w, y);
+        query_vector(d, it.side, rh, y, q);
     }
     __syncthreads();
     unsigned int* row = reinterpret_cast<unsigned int*>(P.energy + (size_t)it.key_row * P.E);
     const int32_t* remap = P.ent_remap + eo;
     for (int e = threadIdx.x; e < nE; e += R_THREADS) {
-        float y[DM], wl[DM];
-        if (sp.model != TRANSE) PK_FOR_D(i) wl[i] = w[i];
-        ent_operand<DM>(sp, sp.ent[0] + (size_t)e * d, sp.ent[1] ? sp.ent[1] + (size_t)e * d : nullptr, wl, y);
-        const float en = energy<DM>(d, sp.p_norm, it.side, q, y, 1);
+        float y[R_MAXD], wl[R_MAXD];
+        if (sp.model != TRANSE) for (int i = 0; i < d; ++i) wl[i] = w[i];
+        ent_operand(sp, sp.ent[0] + (size_t)e * d, sp.ent[1] ? sp.ent[1] + (size_t)e * d : nullptr, wl, y);
+        const float en = energy(d, sp.p_norm, it.side, q, y, 1);
         // energies are >= 0, so their bit patterns order like unsigned integers; +inf = 0x7f800000
         atomicMin(row + remap[e], __float_as_uint(en));
     }
@@ -306,7 +277,6 @@ __global__ void __launch_bounds__(R_THREADS) k3u_energies(const __grid_constant_
 // vector and WITHOUT the TransH / TransD projection (the reference calls _calc on the raw embedding
 // rows):  head batch ||0 + (r^ - e^)||_p ,  tail batch ||(e^ + r^) - 0||_p ,  e^ = normalize(e_fixed).
 // One thread per work item; min over universes with atomicMin on the bit pattern (scores >= 0).
-template <int DM>
 __global__ void __launch_bounds__(128) k3u_tuple_scores(const __grid_constant__ EnergyParams P, float* tuple) {
     const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
     if (i >= P.n_items) return;
@@ -317,12 +287,12 @@ __global__ void __launch_bounds__(128) k3u_tuple_scores(const __grid_constant__ 
     float ne = 1.f, nr = 1.f;
     if (P.sp.norm_flag) {
         float se = 0.f, sr = 0.f;
-        PK_FOR_D(j) { se = __fmaf_rn(e[j], e[j], se); sr = __fmaf_rn(r[j], r[j], sr); }
+        for (int j = 0; j < d; ++j) { se = __fmaf_rn(e[j], e[j], se); sr = __fmaf_rn(r[j], r[j], sr); }
         ne = fmaxf(__fsqrt_rn(se), kNormEps);
         nr = fmaxf(__fsqrt_rn(sr), kNormEps);
     }
     float acc = 0.f;
-    PK_FOR_D(j) {
+    for (int j = 0; j < d; ++j) {
         const float eh = __fdiv_rn(e[j], ne), rh = __fdiv_rn(r[j], nr);
         const float s = it.side == 0 ? __fadd_rn(0.f, __fsub_rn(rh, eh)) : __fsub_rn(__fadd_rn(eh, rh), 0.f);
         acc = P.sp.p_norm == 1 ? __fadd_rn(acc, fabsf(s)) : __fmaf_rn(s, s, acc);
@@ -350,6 +320,10 @@ struct FromEnergyParams {
     const int32_t* fcand;
     int32_t* ranks;  // [n*2]
     int layout;      // 0: row indexed by entity id; 1: reference candidate order (slot 0 = truth)
+    // incremental setting (Test.h:181-206 incremental branch): only entities the snapshot currently contains are
+    // candidates (mask[e] != 0) and an unscored truth ranks behind all n_candidates of them; nullptr: every entity
+    const uint8_t* mask;
+    int64_t n_candidates;
 };
 
 __device__ __forceinline__ float row_at(const float* row, int layout, int32_t truth, int64_t c) {
@@ -369,7 +343,9 @@ __global__ void __launch_bounds__(R_THREADS) k3_rank_rows(const __grid_constant_
     const bool missing = isinf(tgt) && tgt > 0.f;
     int raw = 0, sub = 0;
     if (!missing) {
-        if (P.layout == 0) {
+        if (P.layout == 0 && P.mask) {
+            for (int64_t c = threadIdx.x; c < P.E; c += R_THREADS) raw += (P.mask[c] != 0 && row[c] < tgt);
+        } else if (P.layout == 0) {
             for (int64_t c = threadIdx.x; c < P.E; c += R_THREADS) raw += (row[c] < tgt);
         } else {
             for (int64_t c = 1 + threadIdx.x; c < P.E; c += R_THREADS) raw += (row[c] < tgt);
@@ -378,6 +354,7 @@ __global__ void __launch_bounds__(R_THREADS) k3_rank_rows(const __grid_constant_
     const int64_t lo = P.foff ? P.foff[qi] : 0, hi = P.foff ? P.foff[qi + 1] : 0;
     for (int64_t c = lo + threadIdx.x; c < hi; c += R_THREADS) {
         const int32_t ce = P.fcand[c];
+        if (P.mask && P.mask[ce] == 0) continue;      // a known triple whose entity has left the graph is no candidate
         if (missing) sub += 1;
         else sub += (row_at(row, P.layout, truth, ce) < tgt);
     }
@@ -386,7 +363,7 @@ __global__ void __launch_bounds__(R_THREADS) k3_rank_rows(const __grid_constant_
     if ((threadIdx.x & 31) == 0) { atomicAdd(&s_raw, raw); atomicAdd(&s_sub, sub); }
     __syncthreads();
     if (threadIdx.x == 0) {
-        const int r = missing ? (int)P.E : s_raw;
+        const int r = missing ? (int)(P.mask ? P.n_candidates : P.E) : s_raw;
         P.ranks[qi * 2 + 0] = r;
         P.ranks[qi * 2 + 1] = r - s_sub;
     }
@@ -410,21 +387,20 @@ struct ScoreParams {
     int* bad;
 };
 
-template <int DM>
 __global__ void __launch_bounds__(128) k_score_batch(const __grid_constant__ ScoreParams P) {
     const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
     if (i >= P.n) return;
     const int d = P.sp.d;
     const int64_t h = P.h[i % P.nh], t = P.t[i % P.nt], r = P.r[i % P.nr];
     if (h < 0 || h >= P.n_ent || t < 0 || t >= P.n_ent || r < 0 || r >= P.n_rel) { *P.bad = 1; P.out[i] = nanf(""); return; }
-    float rh[DM], w[DM], y[DM], q[DM];
-    rel_operand<DM>(P.sp, (int)r, rh, w);
+    float rh[R_MAXD], w[R_MAXD], y[R_MAXD], q[R_MAXD];
+    rel_operand(P.sp, (int)r, rh, w);
     const int side = P.head_batch ? 0 : 1;
     const int64_t fix = side == 0 ? t : h, var = side == 0 ? h : t;
-    ent_operand<DM>(P.sp, P.sp.ent[0] + (size_t)fix * d, P.sp.ent[1] ? P.sp.ent[1] + (size_t)fix * d : nullptr, w, y);
-    query_vector<DM>(d, side, rh, y, q);
-    ent_operand<DM>(P.sp, P.sp.ent[0] + (size_t)var * d, P.sp.ent[1] ? P.sp.ent[1] + (size_t)var * d : nullptr, w, y);
-    P.out[i] = energy<DM>(d, P.sp.p_norm, side, q, y, 1);
+    ent_operand(P.sp, P.sp.ent[0] + (size_t)fix * d, P.sp.ent[1] ? P.sp.ent[1] + (size_t)fix * d : nullptr, w, y);
+    query_vector(d, side, rh, y, q);
+    ent_operand(P.sp, P.sp.ent[0] + (size_t)var * d, P.sp.ent[1] ? P.sp.ent[1] + (size_t)var * d : nullptr, w, y);
+    P.out[i] = energy(d, P.sp.p_norm, side, q, y, 1);
 }
 
 struct Scratch {  // query vectors + targets, grown on demand, per thread
@@ -474,15 +450,15 @@ extern "C" int pk_rank_space(const pk_model_cfg* cfg, const pk_tables* tab, int6
     P.ranks = d_ranks;
     P.foff[0] = d_foff_head; P.fcand[0] = d_fcand_head; P.foff[1] = d_foff_tail; P.fcand[1] = d_fcand_tail;
     const unsigned qb = (unsigned)((n * 2 + 127) / 128);
-    PK_DISPATCH_DM(d, (k3_targets<DM><<<qb, 128, 0, st>>>(P)));
+    k3_targets<<<qb, 128, 0, st>>>(P);
     PK_LAUNCHED("k3_targets");
     const size_t smem = ((size_t)d * R_TE + 3 * (size_t)d) * sizeof(float);
     if (smem > 227 * 1024) return pk::fail(PK_ERR_UNSUPPORTED, "pk_rank_space: dim too large for the ranking tile (d <= 220)");
-    PK_DISPATCH_DM(d, PK_CUDA(cudaFuncSetAttribute(k3_raw<DM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+    PK_CUDA(cudaFuncSetAttribute(k3_raw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((tab->n_ent + R_TE - 1) / R_TE), (unsigned)((n + R_QC - 1) / R_QC));
-    PK_DISPATCH_DM(d, (k3_raw<DM><<<grid, R_THREADS, smem, st>>>(P)));
+    k3_raw<<<grid, R_THREADS, smem, st>>>(P);
     PK_LAUNCHED("k3_raw");
-    PK_DISPATCH_DM(d, (k3_filter<DM><<<qb, 128, 0, st>>>(P)));
+    k3_filter<<<qb, 128, 0, st>>>(P);
     PK_LAUNCHED("k3_filter");
     return PK_OK;
 }
@@ -501,7 +477,7 @@ extern "C" int pk_universe_energies(const pk_model_cfg* cfg, const pk_tables* pa
     P.ent_off = d_ent_off; P.rel_off = d_rel_off; P.n_ent = d_n_ent; P.ent_remap = d_ent_remap;
     P.items = d_items; P.n_items = n_items; P.energy = d_energy; P.E = n_ent_global;
     const size_t smem = 2 * (size_t)cfg->dim * sizeof(float);
-    PK_DISPATCH_DM(cfg->dim, (k3u_energies<DM><<<(unsigned)n_items, R_THREADS, smem, (cudaStream_t)stream>>>(P)));
+    k3u_energies<<<(unsigned)n_items, R_THREADS, smem, (cudaStream_t)stream>>>(P);
     PK_LAUNCHED("k3u_energies");
     return PK_OK;
 }
@@ -517,7 +493,7 @@ extern "C" int pk_universe_tuple_scores(const pk_model_cfg* cfg, const pk_tables
     if (n_items == 0) return PK_OK;
     P.ent_off = d_ent_off; P.rel_off = d_rel_off; P.n_ent = nullptr; P.ent_remap = nullptr;
     P.items = d_items; P.n_items = n_items; P.energy = nullptr; P.E = 0;
-    PK_DISPATCH_DM(cfg->dim, (k3u_tuple_scores<DM><<<(unsigned)((n_items + 127) / 128), 128, 0, (cudaStream_t)stream>>>(P, d_tuple)));
+    k3u_tuple_scores<<<(unsigned)((n_items + 127) / 128), 128, 0, (cudaStream_t)stream>>>(P, d_tuple);
     PK_LAUNCHED("k3u_tuple_scores");
     return PK_OK;
 }
@@ -542,6 +518,23 @@ extern "C" int pk_rank_from_energy(const float* d_energy, int64_t n_ent_global, 
     FromEnergyParams P;
     P.energy = d_energy; P.E = n_ent_global; P.n = n; P.key_row = d_key_row; P.truth = d_truth;
     P.foff = d_foff; P.fcand = d_fcand; P.ranks = d_ranks; P.layout = 0;
+    P.mask = nullptr; P.n_candidates = n_ent_global;
+    k3_rank_rows<<<(unsigned)n, R_THREADS, 0, (cudaStream_t)stream>>>(P);
+    PK_LAUNCHED("k3_rank_rows");
+    return PK_OK;
+}
+
+// the same with a candidate mask: the incremental setting ranks among the entities the snapshot currently holds
+extern "C" int pk_rank_from_energy_masked(const float* d_energy, int64_t n_ent_global, int64_t n, const int32_t* d_key_row,
+                                          const int32_t* d_truth, const int64_t* d_foff, const int32_t* d_fcand, int32_t* d_ranks,
+                                          const uint8_t* d_candidate_mask, int64_t n_candidates, void* stream) {
+    pk::launch_counter() = 0;
+    if (!d_energy || !d_truth || !d_ranks || !d_candidate_mask || n < 0) return pk::fail(PK_ERR_ARG, "pk_rank_from_energy_masked: null argument");
+    if (n == 0) return PK_OK;
+    FromEnergyParams P;
+    P.energy = d_energy; P.E = n_ent_global; P.n = n; P.key_row = d_key_row; P.truth = d_truth;
+    P.foff = d_foff; P.fcand = d_fcand; P.ranks = d_ranks; P.layout = 0;
+    P.mask = d_candidate_mask; P.n_candidates = n_candidates;
     k3_rank_rows<<<(unsigned)n, R_THREADS, 0, (cudaStream_t)stream>>>(P);
     PK_LAUNCHED("k3_rank_rows");
     return PK_OK;
@@ -555,6 +548,7 @@ extern "C" int pk_rank_candidate_row(const float* d_con, int64_t n_ent, const in
     FromEnergyParams P;
     P.energy = d_con; P.E = n_ent; P.n = 1; P.key_row = nullptr; P.truth = d_truth1;
     P.foff = d_foff2; P.fcand = d_fcand; P.ranks = d_ranks2; P.layout = 1;
+    P.mask = nullptr; P.n_candidates = n_ent;
     k3_rank_rows<<<1, R_THREADS, 0, (cudaStream_t)stream>>>(P);
     PK_LAUNCHED("k3_rank_rows");
     return PK_OK;
@@ -572,7 +566,7 @@ extern "C" int pk_score_batch(const pk_model_cfg* cfg, const pk_tables* tab, con
     P.h = d_h; P.t = d_t; P.r = d_r; P.nh = nh; P.nt = nt; P.nr = nr;
     P.n = std::max(nh, std::max(nt, nr));
     P.head_batch = head_batch; P.out = d_out; P.n_ent = tab->n_ent; P.n_rel = tab->n_rel; P.bad = d_bad_flag;
-    PK_DISPATCH_DM(cfg->dim, (k_score_batch<DM><<<(unsigned)((P.n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(P)));
+    k_score_batch<<<(unsigned)((P.n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(P);
     PK_LAUNCHED("k_score_batch");
     return PK_OK;
 }

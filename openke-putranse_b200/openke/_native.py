@@ -108,6 +108,12 @@ def _declare(L):
         "getNumOfNegatives": (I, [I, I, B]), "getNumOfPositives": (I, [I, I, B]),
         "getNegativeEntities": (None, [vp, I, I, B]), "getPositiveEntities": (None, [vp, I, I, B]),
         "getNumOfEntityRelations": (I, [I, B]), "getEntityRelations": (None, [vp, I, B]),
+        "activateIncrementalSetting": (None, []), "initializeIncrementalSetting": (None, []), "setNumSnapshots": (None, [I]),
+        "getNumSnapshots": (I, []), "setNumOperationsRate": (None, [I]), "readGlobalNumEntities": (None, []),
+        "readGlobalNumRelations": (None, []), "initializeTrainingOperations": (None, [ctypes.c_int]), "evolveTrainList": (None, []),
+        "loadSnapshotTriples": (None, [ctypes.c_int]), "loadTestData": (None, [ctypes.c_int]), "loadValidData": (None, [ctypes.c_int]),
+        "getNumCurrentlyContainedEntities": (I, []), "pk_incremental_reset": (ctypes.c_int, []),
+        "pk_incremental_list": (I, [ctypes.c_int, vp]),
         "activateLoadOfAllTriples": (None, [B]), "getNegTest": (None, []), "getTestBatch": (None, [vp] * 6),
         # pk_* host
         "pk_last_error": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
@@ -139,6 +145,7 @@ def _declare(L):
         "pk_universe_tuple_scores": (ctypes.c_int, [ctypes.POINTER(ModelCfg), ctypes.POINTER(Tables), vp, vp, vp, I, vp, vp]),
         "pk_fill_missing_energies": (ctypes.c_int, [vp, I, I, vp, vp]),
         "pk_rank_from_energy": (ctypes.c_int, [vp, I, I, vp, vp, vp, vp, vp, vp]),
+        "pk_rank_from_energy_masked": (ctypes.c_int, [vp, I, I, vp, vp, vp, vp, vp, vp, I, vp]),
         "pk_rank_candidate_row": (ctypes.c_int, [vp, I, vp, vp, vp, vp, vp]),
         "pk_score_batch": (ctypes.c_int, [ctypes.POINTER(ModelCfg), ctypes.POINTER(Tables), vp, I, vp, I, vp, I, ctypes.c_int, vp, vp, vp]),
         "pk_fill_inf": (ctypes.c_int, [vp, I, vp]),

@@ -78,8 +78,8 @@ class Parallel_Universe_Config(Tester):
                  missing_embedding_handling="last_rank", save_steps=5, checkpoint_dir="./checkpoint/", valid_steps=5,
                  early_stopping_patience=5, training_setting="static", incremental_strategy="normal"):
         super().__init__(data_loader=test_dataloader, use_gpu=torch.cuda.is_available())
-        if training_setting != "static":
-            raise NotImplementedError("incremental PuTransE is outside the B200 hot path (SURVEY.md 8(f))")
+        if training_setting not in ("static", "incremental"):
+            raise ValueError("training_setting must be 'static' or 'incremental'")
         if missing_embedding_handling not in ("last_rank", "null_vector"):
             raise ValueError("missing_embedding_handling must be 'last_rank' or 'null_vector'")
         self.train_dataloader = train_dataloader
@@ -112,6 +112,9 @@ class Parallel_Universe_Config(Tester):
         self.save_steps, self.checkpoint_dir = save_steps, checkpoint_dir
         self.missing_embedding_handling = missing_embedding_handling
 
+        if valid_dataloader is None and training_setting == "incremental":
+            raise ValueError("the incremental setting needs an explicit valid_dataloader (IncrementalTestDataLoader, mode='valid'): "
+                             "the static default would re-import train2id.txt over the evolving training list")
         self.valid_dataloader = valid_dataloader if valid_dataloader is not None else TestDataLoader(
             train_dataloader.in_path, sampling_mode="link", mode="valid")
         self.valid_steps = valid_steps
@@ -121,7 +124,9 @@ class Parallel_Universe_Config(Tester):
         self.best_hit10 = 0
         self.best_state = None
         self.training_setting = training_setting
-        self.incremental_strategy = incremental_strategy
+        self.incremental_strategy = incremental_strategy      # "normal" | "deprecate" (reference :146-148)
+        self.deprecated_embeddingspaces = set()
+        self._deprecated_version = 0
 
         # B200 build state
         self.universe_hyper = {}          # universe id -> dict(tc, balance, margin, epochs, lr, nT, nE, nR, focus)
@@ -294,7 +299,7 @@ class Parallel_Universe_Config(Tester):
         return (tuple(universe_ids), self.initial_random_seed, self.min_triple_constraint, self.max_triple_constraint,
                 self.min_balance, self.max_balance, self.min_margin, self.max_margin, self.min_lr, self.max_lr,
                 self.min_num_epochs, self.max_num_epochs, self.const_num_epochs, dl.work_threads, bool(dl.filter),
-                self.lib.pk_import_count())
+                self.lib.pk_import_count(), self.lib.getTrainTotal(), getattr(dl, "tripleTotal", 0))
 
     def _sample_universes(self, universe_ids, threads=None):
         """Hyper-parameter draws + subgraphs of a set of universes (host only; pk_universes_build is
@@ -759,6 +764,8 @@ class Parallel_Universe_Config(Tester):
         dist, rank, world = _dist()
         sharded = dist is not None and world > 1
         t_host = time.perf_counter()
+        if self.incremental_strategy == "deprecate":
+            self.determine_deprecated_embedding_spaces()
         E = self.ent_tot
         K = int(k_fixed.shape[0])
         st = torch.cuda.current_stream(dev).cuda_stream
@@ -772,14 +779,19 @@ class Parallel_Universe_Config(Tester):
         per_chunk = []
         for ck in self._chunks:
             ix = self._chunk_index(ck)
-            cached = ck.items_cache.get((keys_token, rows_per_tile)) if keys_token is not None else None
+            dep = self._deprecated_version if self.incremental_strategy == "deprecate" else 0
+            cached = ck.items_cache.get((keys_token, rows_per_tile, dep)) if keys_token is not None else None
             if cached is None:
                 items = self._energy_items(ix, k_fixed, k_rel, k_side)
+                if dep and self.deprecated_embeddingspaces:   # reference :568-571: deprecated universes do not speak
+                    gone = np.isin(np.asarray(ck.ids, dtype=np.int64)[items["universe"]],
+                                   np.fromiter(self.deprecated_embeddingspaces, dtype=np.int64))
+                    items = items[~gone]
                 bounds = np.searchsorted(items["key_row"], np.arange(0, K + rows_per_tile, rows_per_tile))
                 d_items = torch.from_numpy(items.view(np.int32).reshape(-1, 6)).to(dev) if items.shape[0] else None
                 cached = (d_items, bounds)
                 if keys_token is not None:
-                    ck.items_cache[(keys_token, rows_per_tile)] = cached
+                    ck.items_cache[(keys_token, rows_per_tile, dep)] = cached
             d_items, bounds = cached
             if d_items is None:
                 continue
@@ -860,12 +872,24 @@ class Parallel_Universe_Config(Tester):
         tile = max(1, min(K, int(self.eval_tile_rows), int(self.max_energy_bytes // (3 * 4 * E))))
         q_bounds = np.searchsorted(sorted_keys, np.arange(0, K + tile, tile))
 
+        # incremental setting: the candidates are the entities the snapshot currently contains (Test.h:181-206)
+        d_mask, n_cand = None, 0
+        if hasattr(loader, "candidate_mask"):
+            mask = loader.candidate_mask()
+            d_mask, n_cand = torch.from_numpy(mask).to(dev), int(mask.sum())
+
         def count(ti, k0, k1, energy, tuple_score):
             lo, hi = int(q_bounds[ti]), int(q_bounds[ti + 1])
             if sharded:       # this rank's share of the tile's queries (the others add zeros)
                 per = (hi - lo + world - 1) // world
                 lo, hi = min(hi, lo + rank * per), min(hi, lo + (rank + 1) * per)
-            if hi > lo:
+            if hi > lo and d_mask is not None:
+                N.check(lib.pk_rank_from_energy_masked(energy.data_ptr() - k0 * E * 4, E, hi - lo, d_keyrow.data_ptr() + lo * 4,
+                                                       d_truth.data_ptr() + lo * 4, d_off.data_ptr() + lo * 8, d_cand.data_ptr(),
+                                                       ranks_sorted.data_ptr() + lo * 8, d_mask.data_ptr(), n_cand, st),
+                        "pk_rank_from_energy_masked")
+                self.gpu_launches += lib.pk_last_launch_count()
+            elif hi > lo:
                 N.check(lib.pk_rank_from_energy(energy.data_ptr() - k0 * E * 4, E, hi - lo, d_keyrow.data_ptr() + lo * 4,
                                                 d_truth.data_ptr() + lo * 4, d_off.data_ptr() + lo * 8, d_cand.data_ptr(),
                                                 ranks_sorted.data_ptr() + lo * 8, st), "pk_rank_from_energy")
@@ -1019,13 +1043,102 @@ class Parallel_Universe_Config(Tester):
         items["side"] = k_side[key_row][keep]
         return items
 
+    def _rank_state(self, eval_mode):
+        loader = self.data_loader if eval_mode == "test" else self.valid_dataloader
+        return (self.next_universe_id, self.incremental_strategy, self.missing_embedding_handling, id(loader.eval_arrays()),
+                len(getattr(self.train_dataloader, "deleted_triple_set", ())))
+
     def eval_universes(self, eval_mode):
         loader = self.data_loader if eval_mode == "test" else self.valid_dataloader
-        self._rank_cache[eval_mode] = (self.next_universe_id, self._rank_split(loader))
+        self._rank_cache[eval_mode] = (self._rank_state(eval_mode), self._rank_split(loader))
+
+    def reset_evaluation_helpers(self):
+        """Reference :545-554."""
+        self._rank_cache.clear()
+        self.incremental_strategy = "normal"
+
+    # ---- incremental setting: universes that hold a since-deleted triple (reference :817-823)
+    def _universes_holding(self, h, t, r):
+        """Ids of the universes that contain head, relation AND tail of at least one of the given triples."""
+        out = []
+        h, t, r = (np.asarray(x, dtype=np.int64) for x in (h, t, r))
+        for ck in self._chunks:
+            ix = self._chunk_index(ck)
+            lo = np.searchsorted(ix["ent_sorted"], h, side="left")
+            hi = np.searchsorted(ix["ent_sorted"], h, side="right")
+            cnt = hi - lo
+            tot = int(cnt.sum())
+            if tot == 0:
+                continue
+            tri = np.repeat(np.arange(h.shape[0], dtype=np.int64), cnt)
+            pos = np.arange(tot, dtype=np.int64) - np.repeat(np.cumsum(cnt) - cnt, cnt) + np.repeat(lo, cnt)
+            u = ix["ent_univ"][pos].astype(np.int64)
+            keep = ix["rel_local"][r[tri], u] >= 0
+            tri, u = tri[keep], u[keep]
+            # (universe, tail) membership through the sorted (entity, universe) pairs
+            pair = ix.get("pair_code")
+            if pair is None:
+                pair = np.sort(ix["ent_sorted"].astype(np.int64) * len(ck.ids) + ix["ent_univ"].astype(np.int64))
+                ix["pair_code"] = pair
+            want = t[tri] * len(ck.ids) + u
+            at = np.searchsorted(pair, want)
+            at[at >= pair.shape[0]] = pair.shape[0] - 1
+            hit = pair[at] == want
+            out.append(np.asarray(ck.ids, dtype=np.int64)[np.unique(u[hit])])
+        return np.unique(np.concatenate(out)) if out else np.zeros(0, np.int64)
+
+    def determine_deprecated_embedding_spaces(self):
+        deleted = getattr(self.train_dataloader, "deleted_triple_set", None) or ()
+        old = set(self.deprecated_embeddingspaces)
+        self.deprecated_embeddingspaces.clear()
+        if deleted:
+            arr = np.array([[int(a), int(b), int(c)] for a, b, c in deleted], dtype=np.int64)   # (head, tail, relation)
+            self.deprecated_embeddingspaces.update(int(u) for u in self._universes_holding(arr[:, 0], arr[:, 1], arr[:, 2]))
+        if old != self.deprecated_embeddingspaces or self._deprecated_version == 0:
+            self._deprecated_version += 1
+
+    def load_triple_classification_file(self, file):
+        """Reference :767-789: lines "head tail relation truth"."""
+        cols = [[], [], [], [], [], []]
+        with open(str(file), mode="rt", encoding="UTF-8") as f:
+            for line in f:
+                head, tail, rel, truth_value = line.split()
+                o = 0 if truth_value == "1" else 3
+                cols[o].append(int(head)); cols[o + 1].append(int(tail)); cols[o + 2].append(int(rel))
+        return tuple(cols)
+
+    def tc_datastructure_adapter(self, pos_h, pos_t, pos_r, neg_h, neg_t, neg_r):
+        """Reference :751-765."""
+        a = lambda x: np.asarray(x, dtype=np.int64) if len(x) else np.empty(0, dtype=np.int64)
+        return [({"batch_h": a(pos_h), "batch_t": a(pos_t), "batch_r": a(pos_r), "mode": "normal"},
+                 {"batch_h": a(neg_h), "batch_t": a(neg_t), "batch_r": a(neg_r), "mode": "normal"})]
+
+    def run_classification_of_deleted_triples(self, snapshot_idx, threshlod):
+        """Reference :791-800: every tc_* file of the snapshot, classified with the given threshold."""
+        folder = os.path.join(self.data_loader.in_path, "incremental", str(snapshot_idx))
+        res = {}
+        for name in sorted(os.listdir(folder)):
+            if name.startswith("tc_"):
+                data = self.tc_datastructure_adapter(*self.load_triple_classification_file(os.path.join(folder, name)))
+                acc, _ = Tester.run_triple_classification(self, threshlod, data_iterator=data)
+                print("Accuracy for {} is: {}".format(name, acc))
+                res[name] = acc
+        return res
+
+    def run_triple_classification_from_files(self, snapshot):
+        """Reference :802-815."""
+        folder = os.path.join(self.data_loader.in_path, "incremental", str(snapshot))
+        name = "triple_classification_prepared_test_examples.txt"
+        data = self.tc_datastructure_adapter(*self.load_triple_classification_file(os.path.join(folder, name)))
+        acc, threshlod = Tester.run_triple_classification(self, data_iterator=data)
+        print("Accuracy for {} is: {}".format(name, acc))
+        print("Determined threshold: {}".format(threshlod))
+        print("Run negative triple classification...")
+        return acc, threshlod, self.run_classification_of_deleted_triples(snapshot, threshlod)
 
     def _ranks(self, eval_mode):
         c = self._rank_cache.get(eval_mode)
-        if c is None or c[0] != self.next_universe_id:
+        if c is None or c[0] != self._rank_state(eval_mode):
             self.eval_universes(eval_mode)
             c = self._rank_cache[eval_mode]
         return c[1]

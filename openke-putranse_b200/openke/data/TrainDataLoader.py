@@ -7,8 +7,9 @@ Differences that matter:
 * ``device_sampler()`` exposes the current id space (global graph, or the universe after
   ``swap_helpers()``) as device-resident index arrays, so ``Trainer.run`` can keep sampling on the
   GPU and never materialise a host batch.
-* cross sampling (``sampling_mode != 'normal'``), relation negatives and the incremental setting are
-  not on the PuTransE hot path and are refused.
+* cross sampling (``sampling_mode != 'normal'``) and relation negatives are not on the PuTransE hot path and
+  are refused.  ``incremental_setting=True`` (reference :129: no training files are imported; the list is evolved
+  by IncrementalTrainDataLoader.load_snapshot) is supported.
 """
 import ctypes
 
@@ -37,8 +38,6 @@ class TrainDataSampler(object):
 class TrainDataLoader(object):
     def __init__(self, in_path="./", batch_size=None, nbatches=None, threads=8, sampling_mode="normal", bern_flag=0,
                  filter_flag=1, neg_ent=1, neg_rel=0, random_seed=2, incremental_setting=False):
-        if incremental_setting:
-            raise NotImplementedError("the incremental setting is outside the B200 hot path (SURVEY.md 8(f))")
         if neg_rel != 0:
             raise NotImplementedError("relation negatives (neg_rel) are not on the PuTransE hot path")
         if sampling_mode != "normal":
@@ -65,6 +64,10 @@ class TrainDataLoader(object):
         self.lib.setWorkThreads(self.work_threads)
         self.lib.setRandomSeed(self.random_seed)
         self.lib.randReset()
+        if self.incremental_setting:     # reference :129: the training list starts empty and is evolved per snapshot
+            self.lib.pk_incremental_reset()
+            return
+        self.lib.pk_incremental_reset()
         self.lib.importTrainFiles()
         self.relTotal = self.lib.getRelationTotal()
         self.entTotal = self.lib.getEntityTotal()

@@ -420,6 +420,59 @@ def topic_putranse_full_fb15k():
               store_tables=False, extra={"train_checksum": np.uint64(synth.checksum(tr)), "n_valid": np.int64(2000), "n_test": np.int64(2000)})
 
 
+INCREMENTAL_UNIVERSES = [(41, 700, 0.3), (42, 1500, 0.5), (43, 400, 0.25), (44, 1100, 0.4)]
+
+
+def topic_incremental():
+    """The reference's incremental TRAINING path (openke/base/Incremental.h:798-846 evolveTrainList,
+    UniverseConstructor.h:336-339 focus from the currently contained relations) on the evolving graph of
+    tools/synth.py incremental_dataset: after every snapshot the training list, the ordered relation arrays, the
+    Bernoulli means, the loader's bookkeeping, and four universes sampled from the evolved graph."""
+    _setup_ref_import()
+    import tempfile
+    sys.path.insert(0, os.path.join(REPO, "tools"))
+    import synth
+    from openke.data import IncrementalTrainDataLoader
+    path = tempfile.mkdtemp() + "/"
+    synth.incremental_dataset(path)
+    dl = IncrementalTrainDataLoader(in_path=path, nbatches=20, threads=8, sampling_mode="normal", bern_flag=0, filter_flag=0,
+                                    neg_ent=1, neg_rel=0, random_seed=4, incremental_setting=True, num_snapshots=3)
+    lib = dl.lib
+    res = {"universe_cases": np.array(INCREMENTAL_UNIVERSES, dtype=np.float64), "ent_rel_total": np.array([dl.entTotal, dl.relTotal])}
+
+    def int_array(sym, count_sym):
+        n = ctypes.c_long.in_dll(lib, count_sym).value
+        ptr = ctypes.POINTER(ctypes.c_long).in_dll(lib, sym)
+        return np.array([ptr[i] for i in range(n)], dtype=np.int32)
+
+    for s_ in (1, 2, 3):
+        dl.load_snapshot(s_)
+        n = lib.getTrainTotal()
+        res[f"s{s_}_train"] = _triples(lib, "trainList", n).astype(np.int32)             # (h, r, t), sorted (h,r,t), duplicates kept
+        res[f"s{s_}_rel_contained"] = int_array("currently_contained_train_relations", "num_currently_contained_train_relations")
+        res[f"s{s_}_rel_all"] = int_array("all_train_relations", "num_all_train_relations")
+        res[f"s{s_}_rel_deleted"] = int_array("deleted_train_relations", "num_deleted_train_relations")
+        res[f"s{s_}_left_mean"] = _reals(lib, "left_mean", dl.relTotal)
+        res[f"s{s_}_right_mean"] = _reals(lib, "right_mean", dl.relTotal)
+        res[f"s{s_}_loader"] = np.array([dl.tripleTotal, dl.batch_size, dl.nbatches, len(dl.deleted_triple_set)], dtype=np.int64)
+        for i, (seed, tc, bal) in enumerate(INCREMENTAL_UNIVERSES):
+            lib.setRandomSeed(seed + 10 * s_)
+            lib.randReset()
+            dl.compile_universe_dataset(tc, bal)
+            nT, nE, nR = lib.getTrainTotalUniverse(), lib.getEntityTotalUniverse(), lib.getRelationTotalUniverse()
+            er, rr = dl.get_universe_mappings()
+            res[f"s{s_}_u{i}_sizes"] = np.array([nT, nE, nR], dtype=np.int64)
+            res[f"s{s_}_u{i}_ent_remap"] = er.astype(np.int32)
+            res[f"s{s_}_u{i}_rel_remap"] = rr.astype(np.int32)
+            res[f"s{s_}_u{i}_triples_global"] = _triples(lib, "trainListUniverse", nT).astype(np.int32)
+            dl.swap_helpers()
+            d = dl.sampling()
+            res[f"s{s_}_u{i}_batch"] = np.stack([d["batch_h"], d["batch_t"], d["batch_r"]]).astype(np.int32)
+            dl.reset_universe()
+        print("snapshot", s_, res[f"s{s_}_loader"].tolist(), res[f"s{s_}_rel_contained"].tolist(), res[f"s{s_}_rel_deleted"].tolist())
+    np.savez_compressed(os.path.join(OUT, "incremental.npz"), **res)
+
+
 def topic_tc():
     """Triple classification (reference Test.h:573-599, Tester.py:120-191): the corrupted twins getTestBatch draws
     for the WN18 test set right after TestDataLoader.read (seed 4), and the reference Tester's accuracy + threshold
@@ -488,7 +541,7 @@ def topic_ref_ckpt():
     print("ref ckpt", os.path.getsize(os.path.join(OUT, "putranse_reference_layout.ckpt")), ranks[:3])
 
 
-TOPICS = {"putranse_full_fb15k": topic_putranse_full_fb15k, "tc": topic_tc, "ref_ckpt": topic_ref_ckpt, "putranse_full": topic_putranse_full, "dataset": topic_dataset,"sampler": topic_sampler, "universe": topic_universe, "train": topic_train,
+TOPICS = {"incremental": topic_incremental, "putranse_full_fb15k": topic_putranse_full_fb15k, "tc": topic_tc, "ref_ckpt": topic_ref_ckpt, "putranse_full": topic_putranse_full, "dataset": topic_dataset,"sampler": topic_sampler, "universe": topic_universe, "train": topic_train,
           "rank": topic_rank, "putranse": topic_putranse, "putranse_nullvec": topic_putranse_nullvec}
 
 if __name__ == "__main__":

@@ -428,3 +428,80 @@ def test_builder_at_scale_matches_oracle_on_power_law_graph(tmp_path):
         assert np.array_equal(er[eo[i]:eo[i + 1]], oer) and np.array_equal(rr[ro[i]:ro[i + 1]], orr)
     # leave the process-global state on a small graph again
     _load(L, util.write_dataset(str(tmp_path / "tiny"), [[0, 1, 0], [1, 2, 0]], [[0, 2, 0]], [[2, 0, 0]], 3, 1))
+
+
+def _incremental_dataset(tmp_path):
+    import sys
+    sys.path.insert(0, os.path.join(util.REPO, "tools"))
+    import synth
+    path = str(tmp_path / "evolve") + "/"
+    states = synth.incremental_dataset(path)
+    return path, states
+
+
+def test_incremental_training_list_and_universes_bit_exact_with_reference(tmp_path, golden):
+    """SURVEY.md 8(f) rank 3, training side.  IncrementalTrainDataLoader.load_snapshot (reference
+    IncrementalTrainDataLoader.py:59-81 -> initializeTrainingOperations + evolveTrainList, Incremental.h:299-321,
+    798-846) on the evolving graph of tools/synth.py: the training list with its duplicate records, the ORDER of the
+    reference's three relation arrays (relations that vanish and come back move to the end), the freshly computed
+    Bernoulli means, the loader's batch bookkeeping and deleted-triple set, and universes whose focus is drawn from
+    the currently contained relations (UniverseConstructor.h:336-339) — all against vectors minted from the
+    unmodified reference (make_golden.py incremental)."""
+    from openke.data import IncrementalTrainDataLoader
+    g = golden["incremental"]
+    path, states = _incremental_dataset(tmp_path)
+    dl = IncrementalTrainDataLoader(in_path=path, nbatches=20, threads=8, sampling_mode="normal", bern_flag=0, filter_flag=0,
+                                    neg_ent=1, neg_rel=0, random_seed=4, incremental_setting=True, num_snapshots=3)
+    L = dl.lib
+    assert [dl.entTotal, dl.relTotal] == g["ent_rel_total"].tolist()
+
+    def listing(which):
+        n = L.pk_incremental_list(which, None)
+        out = np.zeros(max(n, 1), np.int32)
+        L.pk_incremental_list(which, N.addr(out))
+        return out[:n]
+
+    for s_ in (1, 2, 3):
+        dl.load_snapshot(s_)
+        n = L.getTrainTotal()
+        by_head = np.zeros((n, 3), np.int32)
+        lm, rm = np.zeros(dl.relTotal, np.float32), np.zeros(dl.relTotal, np.float32)
+        N.check(L.pk_train_index(N.addr(by_head), None, N.addr(lm), N.addr(rm)))
+        assert np.array_equal(by_head, g["s%d_train" % s_]), s_
+        assert sorted(map(tuple, by_head[:, [0, 2, 1]].tolist())) == states[s_ - 1]          # and the generator's own replay
+        assert np.array_equal(listing(0), g["s%d_rel_contained" % s_]), (s_, listing(0))
+        assert np.array_equal(listing(1), g["s%d_rel_all" % s_])
+        assert np.array_equal(listing(2), g["s%d_rel_deleted" % s_])
+        present = np.unique(by_head[:, 1])
+        assert np.array_equal(lm[present], g["s%d_left_mean" % s_][present]) and np.array_equal(rm[present], g["s%d_right_mean" % s_][present])
+        assert [dl.tripleTotal, dl.batch_size, dl.nbatches, len(dl.deleted_triple_set)] == g["s%d_loader" % s_].tolist()
+        for i, (seed, tc, bal) in enumerate(g["universe_cases"]):
+            L.setRandomSeed(int(seed) + 10 * s_)
+            L.randReset()
+            dl.compile_universe_dataset(int(tc), float(bal))
+            assert (L.getTrainTotalUniverse(), L.getEntityTotalUniverse(), L.getRelationTotalUniverse()) == tuple(g["s%d_u%d_sizes" % (s_, i)])
+            er, rr = dl.get_universe_mappings()
+            tri = np.zeros((L.getTrainTotalUniverse(), 3), np.int32)
+            N.check(L.pk_universe_triples(N.addr(tri)))
+            assert np.array_equal(er, g["s%d_u%d_ent_remap" % (s_, i)]) and np.array_equal(rr, g["s%d_u%d_rel_remap" % (s_, i)])
+            assert np.array_equal(tri, g["s%d_u%d_triples_global" % (s_, i)])
+            dl.reset_universe()
+            assert dl.batch_size == g["s%d_loader" % s_][1]
+    assert len(np.unique(g["s3_train"], axis=0)) < len(g["s3_train"])      # the duplicate record is there
+    # the threaded builder sees the same incremental graph
+    cases = g["universe_cases"]
+    seeds = np.ascontiguousarray(cases[:, 0] + 30, np.int64)
+    tcs, bals = np.ascontiguousarray(cases[:, 1], np.int64), np.ascontiguousarray(cases[:, 2], np.float32)
+    h = L.pk_universes_build(len(cases), N.addr(seeds), N.addr(tcs), N.addr(bals), 3)
+    assert h, N.last_error()
+    nT, nE, nR, foc = (np.zeros(len(cases), np.int64) for _ in range(4))
+    N.check(L.pk_universes_sizes(h, N.addr(nT), N.addr(nE), N.addr(nR), N.addr(foc)))
+    er = np.zeros(nE.sum(), np.int32)
+    N.check(L.pk_universes_export(h, None, None, None, N.addr(er), None, None, None, None))
+    L.pk_universes_free(h)
+    assert np.array_equal(er, np.concatenate([g["s3_u%d_ent_remap" % i] for i in range(len(cases))]))
+    assert set(foc.tolist()) <= set(g["s3_rel_contained"].tolist())
+    # back to the static setting: the next static loader starts from a clean slate
+    L.pk_incremental_reset()
+    _load(L, util.write_dataset(str(tmp_path / "tiny"), [[0, 1, 0], [1, 2, 0]], [[0, 2, 0]], [[2, 0, 0]], 3, 1))
+    assert L.getTrainTotal() == 2

@@ -366,3 +366,116 @@ def test_load_checkpoint_written_by_the_reference(wn18_dir, golden):
     assert (pu.last_ranks == want).all(1).mean() > 0.999
     missing = want[:, 0] == 40943
     assert np.array_equal(pu.last_ranks[missing][:, :2], want[missing][:, :2])
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_incremental_putranse_over_three_snapshots(tmp_path, golden):
+    """SURVEY.md 8(f) rank 3 end to end (reference experiments/incremental_experiment_PuTransE_on_WikidataEvolve.py
+    :38-52,176-215): per snapshot evolve the training list, load the snapshot's triple list and evaluation lists,
+    train more universes on the evolved graph, evaluate with both incremental strategies.
+
+    * the device sampler inside universes of the evolved graph is bit-exact (reference batches, golden);
+    * universes trained on an earlier snapshot keep speaking; the 'deprecate' strategy silences exactly the universes
+      that hold head, relation and tail of a since-deleted triple (reference :817-823, brute force here);
+    * link-prediction ranks among the snapshot's currently contained entities equal the oracle's (numpy restatement of
+      eval_universes + the incremental branch of Test.h:181-206 in its evident meaning — the reference's own loops
+      skip every other candidate, Test.h:49-59) on torch-CPU energies of the trained tables."""
+    import sys
+    import torch
+    sys.path.insert(0, os.path.join(util.REPO, "tools"))
+    import synth
+    from openke.config import Parallel_Universe_Config
+    from openke.data import IncrementalTrainDataLoader, IncrementalTestDataLoader
+    from openke.module.model import TransE
+    from oracle import putranse_eval
+    g = golden["incremental"]
+    path = str(tmp_path / "evolve") + "/"
+    synth.incremental_dataset(path)
+    train = IncrementalTrainDataLoader(in_path=path, nbatches=20, threads=8, sampling_mode="normal", bern_flag=0, filter_flag=0,
+                                       neg_ent=1, neg_rel=0, random_seed=4, incremental_setting=True, num_snapshots=3)
+    valid = IncrementalTestDataLoader(in_path=path, sampling_mode="link", random_seed=4, mode="valid", setting="incremental", num_snapshots=3)
+    test = IncrementalTestDataLoader(in_path=path, sampling_mode="link", random_seed=4, mode="test", setting="incremental", num_snapshots=3)
+    pu = Parallel_Universe_Config(training_identifier="inc", train_dataloader=train, valid_dataloader=valid, test_dataloader=test,
+                                  min_margin=1, max_margin=5, min_lr=0.001, max_lr=0.1, const_num_epochs=2,
+                                  min_triple_constraint=500, max_triple_constraint=1500, min_balance=0.25, max_balance=0.5,
+                                  embedding_model=TransE, embedding_model_param={"dim": 20, "p_norm": 1, "norm_flag": 1},
+                                  checkpoint_dir=None, valid_steps=10 ** 9, early_stopping_patience=5, save_steps=None,
+                                  training_setting="incremental", missing_embedding_handling="last_rank")
+    L = train.lib
+    E = train.entTotal
+    for s_ in (1, 2, 3):
+        # (1) evolve the KG, as evolve_KG does
+        train.load_snapshot(s_)
+        pu.data_loader.evolveTripleList2(s_)
+        pu.valid_dataloader.load_snapshot(s_)
+        pu.data_loader.load_snapshot(s_)
+        assert [train.tripleTotal, train.batch_size, train.nbatches, len(train.deleted_triple_set)] == g["s%d_loader" % s_].tolist()
+        # device sampler inside a universe of the evolved graph, against the reference's batch
+        seed, tc, bal = g["universe_cases"][1]
+        L.setRandomSeed(int(seed) + 10 * s_)
+        L.randReset()
+        train.compile_universe_dataset(int(tc), float(bal))
+        train.swap_helpers()
+        d = train.sampling()
+        assert np.array_equal(np.stack([d["batch_h"], d["batch_t"], d["batch_r"]]), g["s%d_u1_batch" % s_]), s_
+        train.reset_universe()
+        # (2) train 5 more universes on the evolved graph
+        pu.train_parallel_universes(5)
+        assert pu.next_universe_id == 5 * s_
+        contained = set(g["s%d_rel_contained" % s_].tolist())
+        assert all(pu.universe_hyper[u]["focus"] in contained for u in range(5 * (s_ - 1), 5 * s_))
+        # (3) evaluate: both strategies
+        pu.incremental_strategy = "normal"
+        pu.run_link_prediction()
+        normal = pu.last_ranks.copy()
+        cand = test.contained_entities
+        assert test.currently_contained_entTotal == cand.shape[0] < E
+        tri, filt = test.eval_arrays()
+        spaces = []
+        for u in range(pu.next_universe_id):
+            sp = pu.trained_embedding_spaces[u]
+            er = np.array(sorted(pu.entity_id_mappings[u], key=pu.entity_id_mappings[u].get))
+            rr = np.array(sorted(pu.relation_id_mappings[u], key=pu.relation_id_mappings[u].get))
+            spaces.append(dict(tables={"ent_embeddings": sp.ent_embeddings.weight.detach().cpu().numpy(),
+                                       "rel_embeddings": sp.rel_embeddings.weight.detach().cpu().numpy()}, ent_remap=er, rel_remap=rr, id=u))
+        mask = np.zeros(E, bool)
+        mask[cand] = True
+
+        def oracle_ranks(use):
+            out = np.zeros((40, 4), np.int64)
+            for i in range(40):
+                h, r, t = (int(x) for x in tri[i])
+                for side, fixed, truth in ((0, t, h), (1, h, t)):
+                    en = putranse_eval.universe_energies(use, E, fixed, r, side)
+                    known = filt[side][1][filt[side][0][i]:filt[side][0][i + 1]]
+                    known = known[mask[known]]
+                    if np.isinf(en[truth]):
+                        raw, fil = cand.shape[0], cand.shape[0] - len(known)
+                    else:
+                        better = (en < en[truth]) & mask
+                        raw, fil = int(better.sum()), int(better.sum()) - int(better[known].sum())
+                    out[i, 2 * side:2 * side + 2] = (raw, fil)
+            return out
+        want = oracle_ranks(spaces)
+        assert (normal[:40] == want).all(1).mean() >= 0.9 and np.abs(normal[:40] - want).max() <= 3, (s_, normal[:5], want[:5])
+        unscored = want[:, 0] == cand.shape[0]
+        assert np.array_equal(normal[:40][unscored][:, :2], want[unscored][:, :2])
+        if s_ > 1:
+            pu.incremental_strategy = "deprecate"
+            pu.run_link_prediction()
+            brute = set()
+            for (a, b, c) in train.deleted_triple_set:       # (head, tail, relation) strings
+                for u in range(pu.next_universe_id):
+                    if int(a) in pu.entity_id_mappings[u] and int(b) in pu.entity_id_mappings[u] and int(c) in pu.relation_id_mappings[u]:
+                        brute.add(u)
+            assert pu.deprecated_embeddingspaces == brute and 0 < len(brute) < pu.next_universe_id, (len(brute), pu.next_universe_id)
+            want_d = oracle_ranks([sp for sp in spaces if sp["id"] not in brute])
+            assert (pu.last_ranks[:40] == want_d).all(1).mean() >= 0.9 and np.abs(pu.last_ranks[:40] - want_d).max() <= 3
+            assert (pu.last_ranks != normal).any()
+            acc, thr, per_file = pu.run_triple_classification_from_files(s_)
+            assert 0.0 <= acc <= 1.0 and "tc_negative_deleted_test_triples.txt" in per_file
+        pu.reset_evaluation_helpers()
+        assert pu.incremental_strategy == "normal"
+        assert 0.0 <= pu.valid() <= 1.0
+    L.pk_incremental_reset()

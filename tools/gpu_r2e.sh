@@ -2,6 +2,7 @@
 # round 2 evidence visit: full bench (both arms), s1pu workload, ncu launch list, full captures of K2 (100 and 1000 universes) and K3
 tag=${1:-r2e}
 mkdir -p gpurun_out
+python -m pytest tests -m gpu -q > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/${tag}_pytest.log; tail -5 gpurun_out/${tag}_pytest.log
 python bench.py --steps 20 --warmup 5 > gpurun_out/${tag}_bench.log 2> gpurun_out/${tag}_bench.err; echo "bench exit $?"
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${tag}_bench_ref.log 2> gpurun_out/${tag}_bench_ref.err; echo "ref exit $?"
 python bench.py --workload s1pu --universes 1000 --steps 3 --e2e-steps 3 --no-extras --no-s1 --no-cpu-baseline > gpurun_out/${tag}_s1pu.log 2> gpurun_out/${tag}_s1pu.err; echo "s1pu exit $?"; cut -c1-200 gpurun_out/${tag}_s1pu.log
