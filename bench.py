@@ -77,6 +77,14 @@ def k2_traffic(model):
         return None
 
 
+def k1_traffic(opt, degree):
+    try:
+        d = json.load(open(os.path.join(REPO, "profiles", "r2_k1_traffic.json")))
+        return float(d["%s_%s" % (opt, degree)]["traffic_bytes"])
+    except Exception:
+        return None
+
+
 def measured_peaks():
     try:
         with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
@@ -468,6 +476,9 @@ def run_extras(args, path, dev):
                 ex[key]["eval"] = d["eval"]
         except Exception as e:
             ex[key] = {"error": "%s: %s" % (type(e).__name__, e)}
+    for key, degree, opt in (("s1_uniform_degree_adagrad", "uniform", "adagrad"), ("s1_uniform_degree_sgd", "uniform", "sgd"),
+                             ("s1_power_law_sgd", "power", "sgd")):
+        ex[key] = s1_roofline(args, degree=degree, opt=opt)
     try:
         ex["c1_transe_wn18_trainer_run"] = _child_json([sys.executable, os.path.join(REPO, "tools", "bench_c1.py"), "30", "--json"])
     except Exception as e:
@@ -475,15 +486,18 @@ def run_extras(args, path, dev):
     return ex
 
 
-def s1_roofline(args):
+def s1_roofline(args, degree="power", opt="adagrad"):
     """The HBM-bound configuration of the same train step (SURVEY.md 8(d) "S1"): one embedding space
     with 1 M entities / 10 M triples, TransE d=64, k=1, B=100 000, Adagrad — tables far beyond L2, so
     every gathered row comes from DRAM.  Run as a child process (tools/bench_k1.py) so that its 1.5 GB
     of tables do not stay resident; its JSON line is embedded."""
     try:
-        d = _child_json([sys.executable, os.path.join(REPO, "tools", "bench_k1.py"), "--opt", "adagrad", "--steps", "100", "--reps", "3"],
-                        timeout=600)
+        d = _child_json([sys.executable, os.path.join(REPO, "tools", "bench_k1.py"), "--opt", opt, "--steps", "100", "--reps", "3",
+                         "--degree", degree], timeout=600)
         r = d["roofline"]
+        tr = k1_traffic(opt, degree)
+        if tr is not None:    # dram__bytes_read + dram__bytes_write of k1_grad from the committed ncu capture, per launch
+            r["traffic"] = tr
         r.update(workload=d["workload"], kernel="k1_prepare + k1_grad + k1_apply (whole step)", us_per_step=d["us_per_step"],
                  positive_triples_per_s=d["positive_triples_per_s"], algorithmic_bytes_per_positive=d["algorithmic_bytes_per_positive"])
         return r

@@ -117,6 +117,62 @@ def test_full_length_universes_follow_the_reference(wn18_dir, golden):
         assert abs(got_h - want_h) <= 0.002, (got_h, want_h)
 
 
+def _fb15k_shape_dir(tmp_path):
+    import sys
+    sys.path.insert(0, os.path.join(util.REPO, "tools"))
+    import synth
+    tr, va, te, ne, nr = synth.fb15k_shape(n_valid=2000, n_test=2000)
+    return synth.write_dataset(str(tmp_path / "fb15k_shape"), tr, va, te, ne, nr), synth.checksum(tr)
+
+
+@pytest.mark.gpu
+def test_full_length_fb15k_shape_follows_the_reference(tmp_path, golden):
+    """BASELINE.json configs[3] shape at production length: eight universes of the FB15K-shaped synthetic graph
+    (E = 14 951, R = 1 345; universes hold 360-550 relations, so the relation side of the batched kernel is what is
+    exercised) at their drawn epochs, against the unmodified reference (make_golden.py putranse_full_fb15k).
+    Same statement of tolerances as the WN18 test; measured values in profiles/r2_parity_probe_fb15k.log."""
+    g = golden["putranse_full_fb15k"]
+    path, checksum = _fb15k_shape_dir(tmp_path)
+    assert checksum == int(g["train_checksum"]), "tools/synth.py generated a different graph than the one the reference was run on"
+    n_univ, nb = int(g["n_univ"]), int(g["nbatches"])
+    pu = _static_putranse(path)
+    pu.record_losses = True
+    pu.train_parallel_universes(n_univ)
+    assert pu.universes_on_single_space_path == 0        # all of them fit the batched-universe kernel
+    tails, ref_tails, close_400 = [], [], 0
+    for u in range(n_univ):
+        er = np.array(sorted(pu.entity_id_mappings[u], key=pu.entity_id_mappings[u].get))
+        rr = np.array(sorted(pu.relation_id_mappings[u], key=pu.relation_id_mappings[u].get))
+        assert np.array_equal(er, g["u%d_ent_remap" % u]) and np.array_equal(rr, g["u%d_rel_remap" % u]), u
+        got, want = pu.universe_losses[u], g["u%d_losses" % u]
+        assert len(got) == len(want), u
+        assert np.allclose(got[:10], want[:10], rtol=2e-6), (u, got[:10], want[:10])
+        close_400 += bool(np.allclose(got[:400], want[:400], rtol=1e-4, atol=1e-7))
+        ge, we = _epoch_means(got, nb), _epoch_means(want, nb)
+        assert np.all(np.abs(ge - we) <= 0.015 + 0.05 * we), (u, np.abs(ge - we).max(), int(np.argmax(np.abs(ge - we))))
+        gt, wt = ge[-10:].mean(), we[-10:].mean()
+        assert abs(gt - wt) <= 0.03 * wt + 0.001, (u, gt, wt)
+        tails.append(gt)
+        ref_tails.append(wt)
+        ent = pu.trained_embedding_spaces[u].ent_embeddings.weight.detach().cpu().numpy()
+        n_got, n_ref = np.linalg.norm(ent, axis=1), g["u%d_ent_embeddings_rownorm" % u]
+        assert n_got.shape == n_ref.shape and abs(np.median(n_got) / np.median(n_ref) - 1) < 0.03, u
+    assert close_400 >= 5, close_400
+    assert abs(np.mean(tails) / np.mean(ref_tails) - 1) < 0.01
+    mrr, mr, hit10, hit3, hit1 = pu.run_link_prediction()
+    ranks, want = pu.last_ranks, g["ranks"]
+    E = 14951
+    missing, missing_t = want[:, 0] == E, want[:, 2] == E
+    assert np.array_equal(ranks[:, 0] == E, missing) and np.array_equal(ranks[:, 2] == E, missing_t)
+    assert np.array_equal(ranks[missing][:, [0, 1]], want[missing][:, [0, 1]]) and np.array_equal(ranks[missing_t][:, [2, 3]], want[missing_t][:, [2, 3]])
+    scored = np.concatenate([np.abs(ranks[~missing][:, 1] - want[~missing][:, 1]), np.abs(ranks[~missing_t][:, 3] - want[~missing_t][:, 3])])
+    assert (scored <= 3).mean() >= 0.5, (scored <= 3).mean()
+    ref = g["metrics"]
+    assert abs(mrr - ref[0]) <= 0.05 * ref[0] and abs(mr - ref[1]) <= 1e-3 * ref[1], (mrr, mr, ref)
+    for got_h, want_h in ((hit10, ref[2]), (hit3, ref[3]), (hit1, ref[4])):
+        assert abs(got_h - want_h) <= 0.002, (got_h, want_h)
+
+
 # ------------------------------------------------------------------------------------------------
 def _one_universe_launch(wn18_dir, model_name, param, seed, tc, bal, B, steps, lr, margin):
     """`steps` steps of pk_train_universes on ONE universe with a hand-made descriptor (epochs = 1,

@@ -21,8 +21,9 @@ for p in (os.path.join(REPO, "openke-putranse_b200"), REPO, os.path.join(REPO, "
     sys.path.insert(0, p)
 
 
-def synthetic_graph(E, R, T, seed=1234):
-    """Distinct (h,r,t): relation ~ Zipf(1.0) over R, entity ~ power law (alpha ~ 2) over E."""
+def synthetic_graph(E, R, T, seed=1234, degree="power"):
+    """Distinct (h,r,t): relation ~ Zipf(1.0) over R, entity ~ power law (alpha ~ 2) over E, or uniform entity
+    degrees (degree="uniform": no hub rows for the L2 to hold, every gathered row is a DRAM access)."""
     rng = np.random.default_rng(seed)
     pr = 1.0 / np.arange(1, R + 1)
     pr /= pr.sum()
@@ -30,7 +31,7 @@ def synthetic_graph(E, R, T, seed=1234):
     while keys.shape[0] < T:
         m = int((T - keys.shape[0]) * 1.3) + 1000
         u = rng.random((m, 2))
-        ent = np.minimum((E * (u ** 2.0)).astype(np.int64), E - 1)      # density ~ x^-1/2: heavy head, long tail
+        ent = np.minimum((E * (u ** (2.0 if degree == "power" else 1.0))).astype(np.int64), E - 1)   # power: density ~ x^-1/2
         ent = (ent * 2654435761) % E                                      # scatter the popular ids over the table
         rel = rng.choice(R, size=m, p=pr)
         ok = ent[:, 0] != ent[:, 1]
@@ -55,6 +56,7 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--filter", type=int, default=0)
     ap.add_argument("--bern", type=int, default=0)
+    ap.add_argument("--degree", default="power", choices=["power", "uniform"])
     args = ap.parse_args()
     import torch
     import bench
@@ -64,7 +66,7 @@ def main():
     dev = torch.device("cuda", 0)
     E, R, T, d, k = args.entities, args.relations, args.triples, args.dim, 1
     t0 = time.time()
-    tri = synthetic_graph(E, R, T)
+    tri = synthetic_graph(E, R, T, degree=args.degree)
     by_head = tri.astype(np.int32)
     order = np.argsort((tri[:, 2] * R + tri[:, 1]) * E + tri[:, 0], kind="stable")
     by_tail = by_head[order]
@@ -122,8 +124,8 @@ def main():
     bpp = bench.algorithmic_bytes_per_positive(args.model, d, k, args.opt)
     peak, src = bench.measured_peaks()
     gbs = pos * bpp / (best * 1e-3) / 1e9
-    print(json.dumps({"workload": "s1: single space %s d=%d k=1 %s, E=%d R=%d T=%d, B=%d, %d steps/call" %
-                      (args.model, d, args.opt, E, R, tri.shape[0], B, args.steps),
+    print(json.dumps({"workload": "s1: single space %s d=%d k=1 %s, E=%d R=%d T=%d (%s entity degrees), B=%d, %d steps/call" %
+                      (args.model, d, args.opt, E, R, tri.shape[0], args.degree, B, args.steps),
                       "positive_triples_per_s": pos / (best * 1e-3), "ms_per_call": ms, "us_per_step": best * 1e3 / args.steps,
                       "launches_per_call": launches, "algorithmic_bytes_per_positive": bpp,
                       "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "peak_source": src},

@@ -14,8 +14,13 @@ import test_parity_full as T  # noqa: E402
 
 
 def main():
-    g = np.load(os.path.join(util.GOLDEN, "putranse_full_wn18.npz"))
-    path = util.materialize_wn18(tempfile.mkdtemp())
+    fb = len(sys.argv) > 1 and sys.argv[1] == "fb15k"
+    g = np.load(os.path.join(util.GOLDEN, "putranse_full_fb15k.npz" if fb else "putranse_full_wn18.npz"))
+    if fb:
+        import pathlib
+        path, _ = T._fb15k_shape_dir(pathlib.Path(tempfile.mkdtemp()))
+    else:
+        path = util.materialize_wn18(tempfile.mkdtemp())
     pu = T._static_putranse(path)
     pu.record_losses = True
     n, nb = int(g["n_univ"]), int(g["nbatches"])
@@ -32,7 +37,7 @@ def main():
             (np.abs(ge - we) / we).max(), np.abs(ge - we).max(), ge[-10:].mean(), we[-10:].mean()))
     out = pu.run_link_prediction()
     ranks, want = pu.last_ranks, g["ranks"]
-    E = 40943
+    E = 14951 if fb else 40943
     mh, mt = want[:, 0] == E, want[:, 2] == E
     d = np.concatenate([np.abs(ranks[~mh][:, 1] - want[~mh][:, 1]), np.abs(ranks[~mt][:, 3] - want[~mt][:, 3])])
     print("ours", out)
