@@ -150,6 +150,9 @@ int pk_filter_csr(int which, int side, int64_t* offsets /*[n+1]*/, int32_t* cand
 typedef struct pk_universe_set pk_universe_set;
 pk_universe_set* pk_universes_build(int n, const int64_t* seeds, const int64_t* tcs, const float* balances,
                                     int nthreads);
+/* without the (t,r,h) order, per-entity ranges and Bernoulli means (enough for filter_flag = 0, bern_flag = 0) */
+pk_universe_set* pk_universes_build_lean(int n, const int64_t* seeds, const int64_t* tcs, const float* balances,
+                                         int nthreads);
 void pk_universes_free(pk_universe_set* s);
 int  pk_universes_count(const pk_universe_set* s);
 int  pk_universes_sizes(const pk_universe_set* s, int64_t* n_tri, int64_t* n_ent, int64_t* n_rel, int64_t* focus);

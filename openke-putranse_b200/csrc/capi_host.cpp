@@ -370,7 +370,16 @@ struct pk_universe_set {
     int work_threads = 1;
 };
 
+static pk_universe_set* universes_build(int n, const int64_t* seeds, const int64_t* tcs, const float* balances, int nthreads, bool helpers);
 pk_universe_set* pk_universes_build(int n, const int64_t* seeds, const int64_t* tcs, const float* balances, int nthreads) {
+    return universes_build(n, seeds, tcs, balances, nthreads, true);
+}
+// the same without the (t,r,h) order, per-entity ranges and Bernoulli means of every universe: what training with
+// filter_flag = 0 and bern_flag = 0 (every PuTrans* script) reads is the (h,r,t) list and the remaps
+pk_universe_set* pk_universes_build_lean(int n, const int64_t* seeds, const int64_t* tcs, const float* balances, int nthreads) {
+    return universes_build(n, seeds, tcs, balances, nthreads, false);
+}
+static pk_universe_set* universes_build(int n, const int64_t* seeds, const int64_t* tcs, const float* balances, int nthreads, bool helpers) {
     if (n < 0 || !seeds || !tcs || !balances) {
         pk::fail(PK_ERR_ARG, "pk_universes_build: null argument");
         return nullptr;
@@ -395,7 +404,7 @@ pk_universe_set* pk_universes_build(int n, const int64_t* seeds, const int64_t* 
             const int i = next.fetch_add(1);
             if (i >= n) break;
             std::string err;
-            if (!g.build_universe(seeds[i], tcs[i], balances[i], &s->u[(size_t)i], &err)) {
+            if (!g.build_universe(seeds[i], tcs[i], balances[i], &s->u[(size_t)i], &err, helpers)) {
                 std::lock_guard<std::mutex> lk(*mu);
                 if (!failed.exchange(true)) first_err = "universe " + std::to_string(i) + ": " + err;
             }
@@ -432,6 +441,9 @@ int pk_universes_export(const pk_universe_set* s, int32_t* tri_by_head, int32_t*
                         int32_t* ent_remap, int32_t* rel_remap, float* left_mean, float* right_mean, uint64_t* lcg) {
     if (!s) return pk::fail(PK_ERR_ARG, "pk_universes_export: null set");
     size_t to = 0, eo = 0, ro = 0;
+    for (size_t i = 0; i < s->u.size(); ++i)
+        if (!s->u[i].has_helpers && (tri_by_tail || left_mean || right_mean))
+            return pk::fail(PK_ERR_STATE, "pk_universes_export: the set was built lean (no (t,r,h) order / Bernoulli means)");
     for (size_t i = 0; i < s->u.size(); ++i) {
         const pk::Universe& u = s->u[i];
         const size_t nt = (size_t)u.local.n_tri(), ne = (size_t)u.local.n_ent, nr = (size_t)u.local.n_rel;

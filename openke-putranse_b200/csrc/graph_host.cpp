@@ -324,18 +324,18 @@ struct Fenwick {
 
 }  // namespace
 
-bool Graph::build_universe(int64_t seed, int64_t tc, float balance, Universe* u, std::string* err) const {
+bool Graph::build_universe(int64_t seed, int64_t tc, float balance, Universe* u, std::string* err, bool helpers) const {
     GlibcRand rng((uint32_t)seed);                       // setRandomSeed -> srand   (Random.h:38-45)
     std::memset(u->lcg, 0, sizeof u->lcg);
     const int64_t wt = std::min<int64_t>(work_threads, 64);
     for (int64_t i = 0; i < wt; ++i) u->lcg[i] = (uint64_t)(int64_t)rng.next();  // randReset (Random.h:11-15)
     u->seed = seed;
-    const bool ok = walk_universe(rng, tc, balance, u, err);
+    const bool ok = walk_universe(rng, tc, balance, u, err, helpers);
     u->draws += wt;
     return ok;
 }
 
-bool Graph::walk_universe(GlibcRand& rng, int64_t tc, float balance, Universe* u, std::string* err) const {
+bool Graph::walk_universe(GlibcRand& rng, int64_t tc, float balance, Universe* u, std::string* err, bool helpers) const {
     if (train.n_tri() == 0) {
         *err = "build_universe: no training graph imported";
         return false;
@@ -504,6 +504,28 @@ bool Graph::walk_universe(GlibcRand& rng, int64_t tc, float balance, Universe* u
     for (int32_t r : u->rel_remap) rmap[(size_t)r] = -1;
     L.n_ent = (int64_t)u->ent_remap.size();
     L.n_rel = (int64_t)u->rel_remap.size();
+    u->has_helpers = helpers;
+    if (!helpers) {   // training without filter / Bernoulli reads the (h,r,t) list only
+        L.by_tail.clear();
+        L.lef_head.clear(); L.rig_head.clear(); L.lef_tail.clear(); L.rig_tail.clear();
+        L.left_mean.clear(); L.right_mean.clear();
+        if (L.n_ent < (1 << 21) && L.n_rel < (1 << 21)) {
+            static thread_local std::vector<uint64_t> keys1;
+            keys1.resize(got.size());
+            for (size_t k = 0; k < got.size(); ++k) {
+                const Tri& x = L.by_head[k];
+                keys1[k] = ((uint64_t)x.h << 42) | ((uint64_t)x.r << 21) | (uint64_t)x.t;
+            }
+            std::sort(keys1.begin(), keys1.end());
+            for (size_t k = 0; k < got.size(); ++k) {
+                const uint64_t v = keys1[k];
+                L.by_head[k] = Tri{(int32_t)(v >> 42), (int32_t)((v >> 21) & 0x1fffff), (int32_t)(v & 0x1fffff)};
+            }
+        } else {
+            std::sort(L.by_head.begin(), L.by_head.end(), less_hrt);
+        }
+        return true;
+    }
     L.by_tail.resize(got.size());
     if (L.n_ent < (1 << 21) && L.n_rel < (1 << 21)) {
         // the two orders (:236) as sorts of packed 63-bit keys

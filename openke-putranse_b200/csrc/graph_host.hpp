@@ -78,6 +78,7 @@ struct Universe {
     std::vector<int32_t> ent_remap;  // local -> global
     std::vector<int32_t> rel_remap;
     TripleIndex local;               // local ids (trainListUniverseEnum + helpers)
+    bool has_helpers = true;         // by_tail / ranges / means were built
     uint64_t lcg[64];                // sampler streams as randReset() leaves them (first work_threads used)
     int64_t draws = 0;               // libc-equivalent rand() calls consumed (diagnostic)
 };
@@ -135,11 +136,13 @@ struct Graph {
     void filter_candidates(int which, int side, std::vector<int64_t>& offsets, std::vector<int32_t>& cand) const;
     // reference getParallelUniverse (openke/base/UniverseConstructor.h:327-397) continuing the given
     // generator, as the reference continues libc's after setRandomSeed()+randReset().
-    bool walk_universe(GlibcRand& rng, int64_t tc, float balance, Universe* out, std::string* err) const;
+    // helpers = false: only what unfiltered, non-Bernoulli training reads is built (the (h,r,t)-sorted local list and
+    // the remaps); the (t,r,h) order, the per-entity ranges and the Bernoulli means are skipped
+    bool walk_universe(GlibcRand& rng, int64_t tc, float balance, Universe* out, std::string* err, bool helpers = true) const;
     // srand(seed); randReset(); getParallelUniverse(tc, balance) in one re-entrant call: what
     // Parallel_Universe_Config.set_random_seed + compile_train_datset do per universe
     // (openke/config/Parallel_Universe_Config.py:157-161,209-226).
-    bool build_universe(int64_t seed, int64_t tc, float balance, Universe* out, std::string* err) const;
+    bool build_universe(int64_t seed, int64_t tc, float balance, Universe* out, std::string* err, bool helpers = true) const;
 };
 
 }  // namespace pk

@@ -126,6 +126,7 @@ def _declare(L):
         "pk_eval_triples": (ctypes.c_int, [ctypes.c_int, vp]),
         "pk_filter_csr": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, vp, vp, c_i64p]),
         "pk_universes_build": (vp, [ctypes.c_int, vp, vp, vp, ctypes.c_int]),
+        "pk_universes_build_lean": (vp, [ctypes.c_int, vp, vp, vp, ctypes.c_int]),
         "pk_universes_free": (None, [vp]), "pk_universes_count": (ctypes.c_int, [vp]),
         "pk_universes_sizes": (ctypes.c_int, [vp, vp, vp, vp, vp]),
         "pk_universes_export": (ctypes.c_int, [vp] * 9),

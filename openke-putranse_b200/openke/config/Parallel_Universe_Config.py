@@ -155,7 +155,8 @@ class Parallel_Universe_Config(Tester):
         # ids of the next call are predictable: they continue the sequence).  Measured on the B200 box:
         # 38.5 -> 27.5 ms per 100 universes end to end, i.e. host sampling disappears behind the kernel.
         self.prefetch_sampling = True
-        self._prefetched = None
+        self.prefetch_depth = 2           # chunks sampled ahead of the one being launched (the sampler thread never idles)
+        self._prefetched = {}             # sampling key -> future
         self._pool = None
         self.max_energy_bytes = 8 << 30   # upper bound for the [keys, E] energy tile buffers of an evaluation (three of them)
         self.eval_tile_rows = 1024        # key rows per energy tile (a tile is the unit of the NCCL min all-reduce)
@@ -314,7 +315,9 @@ class Parallel_Universe_Config(Tester):
         tcs = np.array([h["tc"] for h in hyper], dtype=np.int64)
         bals = np.array([h["balance"] for h in hyper], dtype=np.float32)
         # -- subgraphs: bit-identical to the reference's getParallelUniverse, on host threads
-        handle = lib.pk_universes_build(n, N.addr(seeds), N.addr(tcs), N.addr(bals), threads)
+        lean = not dl.filter and not dl.bern     # then training reads only the (h,r,t) list and the remaps
+        build = lib.pk_universes_build_lean if lean else lib.pk_universes_build
+        handle = build(n, N.addr(seeds), N.addr(tcs), N.addr(bals), threads)
         if not handle:
             raise N.NativeError("pk_universes_build: %s" % N.last_error())
         try:
@@ -328,7 +331,8 @@ class Parallel_Universe_Config(Tester):
             lm, rm = np.zeros(sR, dtype=np.float32), np.zeros(sR, dtype=np.float32)
             lcg = np.zeros((n, W), dtype=np.uint64)
             N.check(lib.pk_universes_export(handle, N.addr(by_head), N.addr(by_tail) if by_tail is not None else None, None,
-                                            N.addr(ent_remap), N.addr(rel_remap), N.addr(lm), N.addr(rm), N.addr(lcg)),
+                                            N.addr(ent_remap), N.addr(rel_remap), None if lean else N.addr(lm),
+                                            None if lean else N.addr(rm), N.addr(lcg)),
                     "pk_universes_export")
         finally:
             lib.pk_universes_free(handle)
@@ -344,13 +348,28 @@ class Parallel_Universe_Config(Tester):
         t0 = time.perf_counter()
         lib.setWorkThreads(dl.work_threads)
         # subgraphs of these universes may already have been sampled beside the previous launch
+        # queue the chunks after this one for the background sampler BEFORE waiting for this chunk's own sample: the
+        # sampler works through them while this thread prepares and launches
+        if prefetch_ids and self.prefetch_sampling:
+            if self._pool is None:
+                from concurrent.futures import ThreadPoolExecutor
+                self._pool = ThreadPoolExecutor(max_workers=1)
+            # this rank's share of the host's cores, minus one for the launching thread and the CUDA driver's threads
+            _, _, world_ = _dist()
+            bg_threads = int(self.sampler_threads) or max(2, _host_cores() // max(world_, 1) - 1)
+            step = prefetch_ids[0] - universe_ids[0]
+            for ahead in range(1, max(1, int(self.prefetch_depth)) + 1):
+                ids_next = [u + ahead * step for u in universe_ids]
+                key_next = self._sampling_key(ids_next)
+                if key_next not in self._prefetched:
+                    self._prefetched[key_next] = self._pool.submit(self._sample_universes, ids_next, bg_threads)
         smp = None
-        if self._prefetched is not None:
-            key, fut = self._prefetched
-            self._prefetched = None
-            res = fut.result()
-            if key == self._sampling_key(universe_ids):
-                smp = res
+        key = self._sampling_key(universe_ids)
+        fut = self._prefetched.pop(key, None)
+        for k_old in [k_ for k_ in self._prefetched if k_[0][0] <= universe_ids[0] or k_[1:] != key[1:]]:
+            self._prefetched.pop(k_old).cancel()       # samples nobody will ask for any more (passed, or of another graph/config)
+        if fut is not None:
+            smp = fut.result()
         if smp is None:
             smp = self._sample_universes(universe_ids)
         hyper, seeds, nT, nE, nR, focus = smp["hyper"], smp["seeds"], smp["nT"], smp["nE"], smp["nR"], smp["focus"]
@@ -474,17 +493,6 @@ class Parallel_Universe_Config(Tester):
         for i in big:
             self._train_single_space(ck, cfg, i, desc[i], d_by_head, d_by_tail, d_lm, d_rm, lcg[i], d_loss, st, dev)
         self.universes_on_single_space_path += len(big)
-        if prefetch_ids and self.prefetch_sampling:
-            # the GPU is busy with this launch: sample the subgraphs the next call will most likely ask for
-            if self._pool is None:
-                from concurrent.futures import ThreadPoolExecutor
-                self._pool = ThreadPoolExecutor(max_workers=1)
-            ids_next = list(prefetch_ids)
-            # this rank's share of the host's cores, minus one for the launching thread (which sleeps while the
-            # launch runs) and the CUDA driver's threads
-            _, _, world_ = _dist()
-            bg_threads = int(self.sampler_threads) or max(2, _host_cores() // max(world_, 1) - 1)
-            self._prefetched = (self._sampling_key(ids_next), self._pool.submit(self._sample_universes, ids_next, bg_threads))
         ck.train_inputs = (d_by_head, d_by_tail, d_lm, d_rm)  # keep alive until the stream is done
         self.h2d_bytes += sum(t.numel() * t.element_size() for t in ck.train_inputs if t is not None) + ctypes.sizeof(desc) \
             + n * (8 + len(ck.tables) * 20)   # + seeds / rows / offsets / bounds of the device initialiser
