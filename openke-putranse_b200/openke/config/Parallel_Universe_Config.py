@@ -237,7 +237,7 @@ class Parallel_Universe_Config(Tester):
             self.stream = torch.cuda.Stream(device=dev)
             self.done = torch.cuda.Event(blocking=True)   # waiting on it sleeps (the cores go to the sampler threads)
             self.busy = False
-            self.scratch, self.state = {}, {}
+            self.scratch, self.state, self.pinned = {}, {}, {}
             self.chunk = None
             self.host_loss = None
 
@@ -536,8 +536,15 @@ class Parallel_Universe_Config(Tester):
             slot.scratch[name] = buf
         view = buf[:numel]
         if host is not None:
+            # through the slot's own pinned staging buffer: a copy from pageable memory blocks the launching thread
+            # until the device has taken it, behind whatever the other slots have in flight
+            pin = slot.pinned.get(name)
+            if pin is None or pin.numel() < numel or pin.dtype != dtype:
+                pin = torch.empty(int(numel * 1.5) + 1024, dtype=dtype, pin_memory=True)
+                slot.pinned[name] = pin
+            pin[:numel].copy_(t.reshape(-1))
             view = view.view(t.shape)
-            view.copy_(t, non_blocking=True)
+            view.copy_(pin[:numel].view(t.shape), non_blocking=True)
         else:
             view.zero_()
         return view

@@ -469,10 +469,20 @@ def test_incremental_putranse_over_three_snapshots(tmp_path, golden):
                 for u in range(pu.next_universe_id):
                     if int(a) in pu.entity_id_mappings[u] and int(b) in pu.entity_id_mappings[u] and int(c) in pu.relation_id_mappings[u]:
                         brute.add(u)
-            assert pu.deprecated_embeddingspaces == brute and 0 < len(brute) < pu.next_universe_id, (len(brute), pu.next_universe_id)
+            assert pu.deprecated_embeddingspaces == brute and len(brute) > 0, (len(brute), pu.next_universe_id)
             want_d = oracle_ranks([sp for sp in spaces if sp["id"] not in brute])
             assert (pu.last_ranks[:40] == want_d).all(1).mean() >= 0.9 and np.abs(pu.last_ranks[:40] - want_d).max() <= 3
             assert (pu.last_ranks != normal).any()
+            # a handful of deleted triples: only some universes fall silent
+            saved = set(train.deleted_triple_set)
+            train.deleted_triple_set = set(sorted(saved)[:2])
+            pu.run_link_prediction()
+            few = {u for (a, b, c) in train.deleted_triple_set for u in range(pu.next_universe_id)
+                   if int(a) in pu.entity_id_mappings[u] and int(b) in pu.entity_id_mappings[u] and int(c) in pu.relation_id_mappings[u]}
+            assert pu.deprecated_embeddingspaces == few and len(few) < pu.next_universe_id
+            want_f = oracle_ranks([sp for sp in spaces if sp["id"] not in few])
+            assert (pu.last_ranks[:40] == want_f).all(1).mean() >= 0.9 and np.abs(pu.last_ranks[:40] - want_f).max() <= 3
+            train.deleted_triple_set = saved
             acc, thr, per_file = pu.run_triple_classification_from_files(s_)
             assert 0.0 <= acc <= 1.0 and "tc_negative_deleted_test_triples.txt" in per_file
         pu.reset_evaluation_helpers()
