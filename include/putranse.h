@@ -123,6 +123,8 @@ void   loadSnapshotTriples(int snapshot);         /* :891-924              */
 void   loadTestData(int snapshot);                /* :248-271              */
 void   loadValidData(int snapshot);               /* :273-296              */
 PK_INT getNumCurrentlyContainedEntities(void);    /* :134-138              */
+void   initializeTripleOperations(int snapshot);  /* :323-348 : bound by IncrementalTestDataLoader.py:38; refuses at call time */
+void   evolveTripleList(void);                    /* :926-949 : superseded by loadSnapshotTriples; refuses at call time */
 int    pk_incremental_reset(void);
 int64_t pk_incremental_list(int which, int32_t* out);
 

@@ -341,6 +341,18 @@ void loadValidData(int snapshot) {
     report(ok, "loadValidData", err);
     if (ok) G().eval_epoch++;
 }
+// The triple-operation replay of the FILTER list (Incremental.h:323-348,926-949) was superseded in the reference by
+// loadSnapshotTriples (experiments/incremental_experiment_PuTransE_on_WikidataEvolve.py:45-46).  The reference's
+// IncrementalTestDataLoader still binds the symbol at construction (IncrementalTestDataLoader.py:38), so both exist
+// and refuse at call time.
+void initializeTripleOperations(int) {
+    pk::fail(PK_ERR_UNSUPPORTED, "initializeTripleOperations: use loadSnapshotTriples (evolveTripleList2)");
+    fprintf(stderr, "putranse: %s\n", pk::last_error().c_str());
+}
+void evolveTripleList(void) {
+    pk::fail(PK_ERR_UNSUPPORTED, "evolveTripleList: use loadSnapshotTriples (evolveTripleList2)");
+    fprintf(stderr, "putranse: %s\n", pk::last_error().c_str());
+}
 PK_INT getNumCurrentlyContainedEntities(void) { return (PK_INT)G().graph.contained_entities.size(); }
 // leave the incremental setting (the reference cannot: its flag is set once per process)
 int pk_incremental_reset(void) {

@@ -112,7 +112,7 @@ def _declare(L):
         "getNumSnapshots": (I, []), "setNumOperationsRate": (None, [I]), "readGlobalNumEntities": (None, []),
         "readGlobalNumRelations": (None, []), "initializeTrainingOperations": (None, [ctypes.c_int]), "evolveTrainList": (None, []),
         "loadSnapshotTriples": (None, [ctypes.c_int]), "loadTestData": (None, [ctypes.c_int]), "loadValidData": (None, [ctypes.c_int]),
-        "getNumCurrentlyContainedEntities": (I, []), "pk_incremental_reset": (ctypes.c_int, []),
+        "getNumCurrentlyContainedEntities": (I, []), "initializeTripleOperations": (None, [ctypes.c_int]), "evolveTripleList": (None, []), "pk_incremental_reset": (ctypes.c_int, []),
         "pk_incremental_list": (I, [ctypes.c_int, vp]),
         "activateLoadOfAllTriples": (None, [B]), "getNegTest": (None, []), "getTestBatch": (None, [vp] * 6),
         # pk_* host

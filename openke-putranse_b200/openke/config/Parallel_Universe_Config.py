@@ -155,7 +155,8 @@ class Parallel_Universe_Config(Tester):
         # ids of the next call are predictable: they continue the sequence).  Measured on the B200 box:
         # 38.5 -> 27.5 ms per 100 universes end to end, i.e. host sampling disappears behind the kernel.
         self.prefetch_sampling = True
-        self.prefetch_depth = 2           # chunks sampled ahead of the one being launched (the sampler thread never idles)
+        self.prefetch_depth = 1           # chunks sampled ahead of the one being launched (deeper = the sampler's Python parts
+                                          # compete with the launching thread for the GIL: launch time 1.3 -> 13 ms per chunk)
         self._prefetched = {}             # sampling key -> future
         self._pool = None
         self.max_energy_bytes = 8 << 30   # upper bound for the [keys, E] energy tile buffers of an evaluation (three of them)
@@ -348,21 +349,6 @@ class Parallel_Universe_Config(Tester):
         t0 = time.perf_counter()
         lib.setWorkThreads(dl.work_threads)
         # subgraphs of these universes may already have been sampled beside the previous launch
-        # queue the chunks after this one for the background sampler BEFORE waiting for this chunk's own sample: the
-        # sampler works through them while this thread prepares and launches
-        if prefetch_ids and self.prefetch_sampling:
-            if self._pool is None:
-                from concurrent.futures import ThreadPoolExecutor
-                self._pool = ThreadPoolExecutor(max_workers=1)
-            # this rank's share of the host's cores, minus one for the launching thread and the CUDA driver's threads
-            _, _, world_ = _dist()
-            bg_threads = int(self.sampler_threads) or max(2, _host_cores() // max(world_, 1) - 1)
-            step = prefetch_ids[0] - universe_ids[0]
-            for ahead in range(1, max(1, int(self.prefetch_depth)) + 1):
-                ids_next = [u + ahead * step for u in universe_ids]
-                key_next = self._sampling_key(ids_next)
-                if key_next not in self._prefetched:
-                    self._prefetched[key_next] = self._pool.submit(self._sample_universes, ids_next, bg_threads)
         smp = None
         key = self._sampling_key(universe_ids)
         fut = self._prefetched.pop(key, None)
@@ -493,6 +479,7 @@ class Parallel_Universe_Config(Tester):
         for i in big:
             self._train_single_space(ck, cfg, i, desc[i], d_by_head, d_by_tail, d_lm, d_rm, lcg[i], d_loss, st, dev)
         self.universes_on_single_space_path += len(big)
+        self._queue_sampling(universe_ids, prefetch_ids)
         ck.train_inputs = (d_by_head, d_by_tail, d_lm, d_rm)  # keep alive until the stream is done
         self.h2d_bytes += sum(t.numel() * t.element_size() for t in ck.train_inputs if t is not None) + ctypes.sizeof(desc) \
             + n * (8 + len(ck.tables) * 20)   # + seeds / rows / offsets / bounds of the device initialiser
@@ -507,6 +494,26 @@ class Parallel_Universe_Config(Tester):
         self._chunks.append(ck)
         self._rank_cache.clear()
         return ck
+
+    def _queue_sampling(self, universe_ids, prefetch_ids):
+        """Queue the subgraphs of the chunks after this one for the background sampler.  Called AFTER this chunk's launch
+        has been issued: the sampler's Python parts (hyper-parameter draws, array allocation) hold the GIL, and the
+        launching thread must not compete for it while the GPU waits for its launch (measured: 1.3 ms -> 13 ms of
+        launch time per chunk when the sampler ran beside the launch)."""
+        if not (prefetch_ids and self.prefetch_sampling):
+            return
+        if self._pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+            self._pool = ThreadPoolExecutor(max_workers=1)
+        # this rank's share of the host's cores, minus one for the launching thread and the CUDA driver's threads
+        _, _, world_ = _dist()
+        bg_threads = int(self.sampler_threads) or max(2, _host_cores() // max(world_, 1) - 1)
+        step = prefetch_ids[0] - universe_ids[0]
+        for ahead in range(1, max(1, int(self.prefetch_depth)) + 1):
+            ids_next = [u + ahead * step for u in universe_ids]
+            key_next = self._sampling_key(ids_next)
+            if key_next not in self._prefetched:
+                self._prefetched[key_next] = self._pool.submit(self._sample_universes, ids_next, bg_threads)
 
     def _arena_rows(self, dev, rows, dim):
         """[rows, dim] fp32 device view carved from a slab.  The trained tables of every chunk stay
@@ -542,7 +549,7 @@ class Parallel_Universe_Config(Tester):
             if pin is None or pin.numel() < numel or pin.dtype != dtype:
                 pin = torch.empty(int(numel * 1.5) + 1024, dtype=dtype, pin_memory=True)
                 slot.pinned[name] = pin
-            pin[:numel].copy_(t.reshape(-1))
+            np.copyto(pin[:numel].numpy(), t.reshape(-1).numpy())   # one memcpy on this thread (torch's CPU copy_ wakes the intra-op pool)
             view = view.view(t.shape)
             view.copy_(pin[:numel].view(t.shape), non_blocking=True)
         else:

@@ -430,7 +430,7 @@ def test_incremental_putranse_over_three_snapshots(tmp_path, golden):
         pu.run_link_prediction()
         normal = pu.last_ranks.copy()
         cand = test.contained_entities
-        assert test.currently_contained_entTotal == cand.shape[0] < E
+        assert test.currently_contained_entTotal == cand.shape[0] == (2996, 2998, 3000)[s_ - 1] <= E   # the masked path matters for s_ < 3
         tri, filt = test.eval_arrays()
         spaces = []
         for u in range(pu.next_universe_id):
