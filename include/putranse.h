@@ -163,6 +163,27 @@ int  pk_universes_export(const pk_universe_set* s, int32_t* tri_by_head, int32_t
                          int32_t* tri_collected_global, int32_t* ent_remap, int32_t* rel_remap,
                          float* left_mean, float* right_mean, uint64_t* lcg /*[n*workThreads]*/);
 
+/* ---- the same universes built ON THE GPU, one warp per universe (csrc/walk_device.cu); replaces the host threads of
+ * pk_universes_build_lean for reference openke/base/UniverseConstructor.h:39-67,92-233,327-397 (getParallelUniverse,
+ * get_entity_subset, the bidirectional walk, enumerateTrainListUniverse) after Random.h:11-15,38-45 (srand + randReset).
+ * Bit-identical to the host builder (and through it to the reference).  Lean universes only: the local (h,r,t) list
+ * and the two remaps, which is what training with filter_flag = 0 and bern_flag = 0 reads.  Fixed strides per universe:
+ * PK_WALK_CAP triples, 2*PK_WALK_CAP entities, PK_WALK_CAP relations.  A universe the kernel does not handle reports a
+ * status != PK_WALK_OK in its sizes row and must be built by pk_universes_build_lean. */
+#define PK_WALK_CAP 2048
+enum { PK_WALK_OK = 0, PK_WALK_TOO_LARGE = 1 /* tc or starting points > PK_WALK_CAP */, PK_WALK_ISOLATED = 2 /* entity without triples */,
+       PK_WALK_EMPTY = 3 /* the walk collected nothing (the host builder reports the error) */ };
+int pk_walk_cap(void);
+int pk_walk_device_check(void);                      /* 0 = the current training graph can be walked on the device */
+int pk_walk_scratch_bytes(int n, int64_t* out3);     /* bytes of d_bitmaps, d_got, d_trees for n universes */
+/* h_lcg [n*workThreads] and h_focus [n] are HOST outputs, filled before the call returns; the d_* outputs are valid when
+ * `stream` reaches the end of the launch: d_tri [n][CAP][3] local ids sorted (h,r,t), d_ent_remap [n][2*CAP],
+ * d_rel_remap [n][CAP], d_sizes [n][8] = nT nE nR focus draws status rounds 0, d_got [n][CAP][3] collected triples in
+ * global ids (collection order).  d_bitmaps / d_trees are scratch (d_trees may be NULL when its size is 0). */
+int pk_universes_walk_device(int n, const int64_t* seeds, const int64_t* tcs, const float* balances, uint64_t* h_lcg,
+                             int64_t* h_focus, uint32_t* d_bitmaps, int32_t* d_got, uint32_t* d_trees, int32_t* d_tri,
+                             int32_t* d_ent_remap, int32_t* d_rel_remap, int32_t* d_sizes, void* stream);
+
 /* Initial tables of n embedding spaces on host threads, bit-identical to the reference's model
  * constructors after torch.manual_seed(seeds[i]) (reference openke/module/model/TransE.py:17-22,
  * TransH.py:17-24, TransD.py:18-27; Parallel_Universe_Config.py:157-161): every table first

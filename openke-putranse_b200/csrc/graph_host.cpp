@@ -4,6 +4,7 @@
 #include "graph_host.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <unordered_set>
@@ -172,6 +173,8 @@ bool Graph::import_train(std::string* err) {
 // records): the (t,r,h) order, per-entity and per-relation ranges, the per-relation entity lists the universes
 // start from, and the Bernoulli statistics.
 void Graph::finish_train_index(bool same_shape, bool drift) {
+    static std::atomic<uint64_t> next_version{1};
+    version = next_version.fetch_add(1);
     const int64_t nr = n_rel;
     train.by_tail = train.by_head;
     std::sort(train.by_tail.begin(), train.by_tail.end(), less_trh);

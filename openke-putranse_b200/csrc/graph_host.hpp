@@ -89,6 +89,7 @@ struct Graph {
     int64_t bern = 0;
     int64_t n_ent = 0, n_rel = 0;
     int64_t train_lines = 0;   // raw line count of train2id.txt
+    uint64_t version = 0;      // unique per rebuilt training index (device mirrors key on it)
     int64_t import_count = 0;  // how many times the training files were imported (bern drift)
     bool load_all_triples = false;  // activateLoadOfAllTriples (Reader.h:240-244): filter set = triple2id.txt
     TripleIndex train;

@@ -1,0 +1,115 @@
+"""Universe subgraphs built on the GPU (csrc/walk_device.cu) for the orchestrator.
+
+Replaces the host threads of ``pk_universes_build_lean`` for the reference's ``getParallelUniverse``
+(openke/base/UniverseConstructor.h:327-397, called through ``TrainDataLoader.compile_universe_dataset``,
+openke/data/TrainDataLoader.py:117-130) when training needs only the lean universe (no filter, no Bernoulli):
+one launch per chunk on its own high-priority stream, results copied into pinned memory behind it.
+The output buffers are strided (PK_WALK_CAP triples per universe) and stay on the device: the training kernel
+reads the local triple lists where the walk wrote them."""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+
+class WalkResult(object):
+    """One chunk's walk in flight.  ``wait()`` blocks until the sizes are on the host."""
+
+    def __init__(self, walker, bufs, n, seeds, tcs, bals, lcg, focus):
+        self.walker, self.bufs, self.n = walker, bufs, n
+        self.seeds, self.tcs, self.bals, self.lcg, self.focus = seeds, tcs, bals, lcg, focus
+        self.event = torch.cuda.Event(blocking=True)
+        self.sizes = None
+
+    def wait(self):
+        if self.sizes is None:
+            self.event.synchronize()
+            self.sizes = self.bufs["h_sizes"][:self.n].numpy().astype(np.int64)
+        return self.sizes
+
+    @property
+    def ok(self):
+        return bool((self.wait()[:, 5] == 0).all())
+
+    def packed_remaps(self):
+        """(ent_remap [sum nE], rel_remap [sum nR]) int32 numpy, universes back to back (what evaluation indexes)."""
+        s = self.wait()
+        cap = self.walker.cap
+        er = self.bufs["h_ent_remap"][:self.n].numpy()
+        rr = self.bufs["h_rel_remap"][:self.n].numpy()
+        nE, nR = s[:, 1], s[:, 2]
+        cols_e = np.arange(2 * cap)[None, :] < nE[:, None]
+        cols_r = np.arange(cap)[None, :] < nR[:, None]
+        return er[cols_e].copy(), rr[cols_r].copy()
+
+    def release(self):
+        """The training launch that read d_tri has finished: the buffers may carry another chunk."""
+        if self.bufs is not None:
+            self.walker._free.append(self.bufs)
+            self.bufs = None
+
+
+class DeviceWalker(object):
+    def __init__(self, lib, device):
+        self.lib, self.device = lib, device
+        self.cap = int(lib.pk_walk_cap())
+        lo, hi = torch.cuda.Stream.priority_range()
+        self.stream = torch.cuda.Stream(device=device, priority=hi)   # its few blocks go first when an SM frees up
+        self._free = []
+        self.launches = 0
+        self.d2h_bytes = 0
+
+    def usable(self):
+        return self.lib.pk_walk_device_check() == 0
+
+    def _buffers(self, n):
+        for i, b in enumerate(self._free):
+            if b["n"] >= n and b["graph"] == self._graph_key():
+                return self._free.pop(i)
+        cap, dev = self.cap, self.device
+        need = np.zeros(3, dtype=np.int64)
+        m = int(n * 1.25) + 8
+        N.check(self.lib.pk_walk_scratch_bytes(m, N.addr(need)), "pk_walk_scratch_bytes")
+        b = dict(n=m, graph=self._graph_key(),
+                 bitmaps=torch.empty(max(int(need[0]) // 4, 1), dtype=torch.int32, device=dev),
+                 got=torch.empty((m, cap, 3), dtype=torch.int32, device=dev),
+                 trees=torch.empty(max(int(need[2]) // 4, 1), dtype=torch.int32, device=dev) if need[2] else None,
+                 tri=torch.empty((m, cap, 3), dtype=torch.int32, device=dev),
+                 ent_remap=torch.empty((m, 2 * cap), dtype=torch.int32, device=dev),
+                 rel_remap=torch.empty((m, cap), dtype=torch.int32, device=dev),
+                 sizes=torch.empty((m, 8), dtype=torch.int32, device=dev),
+                 h_sizes=torch.empty((m, 8), dtype=torch.int32, pin_memory=True),
+                 h_ent_remap=torch.empty((m, 2 * cap), dtype=torch.int32, pin_memory=True),
+                 h_rel_remap=torch.empty((m, cap), dtype=torch.int32, pin_memory=True))
+        return b
+
+    def _graph_key(self):
+        return (int(self.lib.pk_import_count()), int(self.lib.getEntityTotal()), int(self.lib.getTrainTotal()))
+
+    def submit(self, seeds, tcs, bals, work_threads, copy_remaps=True):
+        """Launch the walk of len(seeds) universes; returns a WalkResult at once."""
+        n = len(seeds)
+        seeds = np.ascontiguousarray(seeds, dtype=np.int64)
+        tcs = np.ascontiguousarray(tcs, dtype=np.int64)
+        bals = np.ascontiguousarray(bals, dtype=np.float32)
+        lcg = np.zeros((n, int(work_threads)), dtype=np.uint64)
+        focus = np.zeros(n, dtype=np.int64)
+        b = self._buffers(n)
+        res = WalkResult(self, b, n, seeds, tcs, bals, lcg, focus)
+        with torch.cuda.stream(self.stream):
+            N.check(self.lib.pk_universes_walk_device(
+                n, N.addr(seeds), N.addr(tcs), N.addr(bals), N.addr(lcg), N.addr(focus),
+                b["bitmaps"].data_ptr(), b["got"].data_ptr(), b["trees"].data_ptr() if b["trees"] is not None else None,
+                b["tri"].data_ptr(), b["ent_remap"].data_ptr(), b["rel_remap"].data_ptr(), b["sizes"].data_ptr(),
+                ctypes.c_void_p(self.stream.cuda_stream)), "pk_universes_walk_device")
+            self.launches += self.lib.pk_last_launch_count()
+            b["h_sizes"][:n].copy_(b["sizes"][:n], non_blocking=True)
+            self.d2h_bytes += n * 32
+            if copy_remaps:
+                b["h_ent_remap"][:n].copy_(b["ent_remap"][:n], non_blocking=True)
+                b["h_rel_remap"][:n].copy_(b["rel_remap"][:n], non_blocking=True)
+                self.d2h_bytes += n * 3 * self.cap * 4
+            res.event.record(self.stream)
+        return res
