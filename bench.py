@@ -544,7 +544,7 @@ def prepare_resident_launch(pu, ids, dev, n_sets=1):
     Bs = np.array([h_["batch_size"] for h_ in hy], dtype=np.int64)
     steps = epochs * nb
     darr = np.zeros(n, dtype=N.UNIVERSE_DESC_DTYPE)
-    darr["tri_off"], darr["ent_off"], darr["rel_off"] = ck.toff[:n], ck.eoff[:n], ck.roff[:n]
+    darr["tri_off"], darr["ent_off"], darr["rel_off"] = ck.tri_off[:n], ck.eoff[:n], ck.roff[:n]
     darr["n_tri"], darr["n_ent"], darr["n_rel"] = ck.nT, ck.nE, ck.nR
     darr["batch_size"], darr["nbatches"], darr["epochs"] = Bs, nb, epochs
     darr["margin"] = np.array([h_["margin"] for h_ in hy], dtype=np.float32)

@@ -163,6 +163,16 @@ int  pk_universes_export(const pk_universe_set* s, int32_t* tri_by_head, int32_t
                          int32_t* tri_collected_global, int32_t* ent_remap, int32_t* rel_remap,
                          float* left_mean, float* right_mean, uint64_t* lcg /*[n*workThreads]*/);
 
+/* Hyper-parameters of n universes as the reference draws them from Python's `random` after random.seed(seeds[i])
+ * (openke/config/Parallel_Universe_Config.py:157-161,211-212,232,237-240): tc = randrange(tc_lo, tc_hi); balance =
+ * round(uniform(bal_lo, bal_hi), 2); margin = randrange(..); epochs = randrange(..) if draw_epochs else epochs_lo;
+ * lr = round(uniform(lr_lo, lr_hi), lr_digits).  CPython's generator restated; PK_ERR_UNSUPPORTED for ranges it does not
+ * cover (the caller then uses random.Random). */
+int pk_python_hyper_draws(int n, const int64_t* seeds, int64_t tc_lo, int64_t tc_hi, double bal_lo, double bal_hi,
+                          int64_t margin_lo, int64_t margin_hi, int64_t epochs_lo, int64_t epochs_hi, int draw_epochs,
+                          double lr_lo, double lr_hi, int lr_digits, int64_t* tc, double* balance, int64_t* margin,
+                          int64_t* epochs, double* lr);
+
 /* ---- the same universes built ON THE GPU, one warp per universe (csrc/walk_device.cu); replaces the host threads of
  * pk_universes_build_lean for reference openke/base/UniverseConstructor.h:39-67,92-233,327-397 (getParallelUniverse,
  * get_entity_subset, the bidirectional walk, enumerateTrainListUniverse) after Random.h:11-15,38-45 (srand + randReset).
@@ -183,6 +193,10 @@ int pk_walk_scratch_bytes(int n, int64_t* out3);     /* bytes of d_bitmaps, d_go
 int pk_universes_walk_device(int n, const int64_t* seeds, const int64_t* tcs, const float* balances, uint64_t* h_lcg,
                              int64_t* h_focus, uint32_t* d_bitmaps, int32_t* d_got, uint32_t* d_trees, int32_t* d_tri,
                              int32_t* d_ent_remap, int32_t* d_rel_remap, int32_t* d_sizes, void* stream);
+/* the strided remaps of universes 0..n-1 back to back: d_ent_packed [sum nE], d_rel_packed [sum nR] (what the
+ * evaluation indexes; the caller knows the sums from the sizes rows) */
+int pk_walk_pack_remaps(int n, const int32_t* d_sizes, const int32_t* d_ent_remap, const int32_t* d_rel_remap,
+                        int32_t* d_ent_packed, int32_t* d_rel_packed, void* stream);
 
 /* Initial tables of n embedding spaces on host threads, bit-identical to the reference's model
  * constructors after torch.manual_seed(seeds[i]) (reference openke/module/model/TransE.py:17-22,

@@ -4,6 +4,7 @@
 // universe owns one MT19937 state in shared memory; the 624-word twist is done cooperatively in the
 // three dependency-free segments of the recurrence, outputs are tempered in parallel and written
 // coalesced.  This removes the host RNG time and the H2D copy of the tables from the end-to-end path.
+#include <algorithm>
 #include <vector>
 
 #include "common.hpp"
@@ -93,11 +94,18 @@ __global__ void __launch_bounds__(INIT_THREADS) k_init_tables(const __grid_const
     }
 }
 
-struct DevScratch {
-    void* p = nullptr;
-    size_t cap = 0;
+// Kernel arguments travel through a ring of (pinned host, device) buffer pairs: launches of different launch slots are
+// in flight together and must not share one scratch, and a copy from pageable memory beyond 64 KB makes the launching
+// thread wait for the stream.  A pair is reused only after the launch that read it has finished (event).
+struct ArgRing {
+    static constexpr int N = 8;
+    void* h[N] = {};
+    void* d[N] = {};
+    size_t cap[N] = {};
+    cudaEvent_t ev[N] = {};
+    int next = 0;
 };
-thread_local DevScratch g_init_scratch;
+thread_local ArgRing g_args;
 
 }  // namespace
 
@@ -112,26 +120,35 @@ extern "C" int pk_init_tables_device(int n, const int64_t* seeds, int n_tables, 
         if (rows[i] * dims[i % n_tables] < 16)
             return pk::fail(PK_ERR_UNSUPPORTED, "pk_init_tables_device: a table has fewer than 16 elements (torch takes another path there)");
     // host arguments -> one device buffer: seeds | rows | row_off | bounds(float)
-    std::vector<unsigned char> host(8 * n + 16 * nt + 4 * nt);
-    int64_t* hs = reinterpret_cast<int64_t*>(host.data());
+    const size_t bytes = 8 * (size_t)n + 16 * nt + 4 * nt;
+    const int slot = g_args.next;
+    g_args.next = (g_args.next + 1) % ArgRing::N;
+    if (!g_args.ev[slot]) PK_CUDA(cudaEventCreateWithFlags(&g_args.ev[slot], cudaEventDisableTiming));
+    else PK_CUDA(cudaEventSynchronize(g_args.ev[slot]));
+    if (g_args.cap[slot] < bytes) {   // all pairs at once: an allocation waits for the launches in flight
+        const size_t want = std::max<size_t>(bytes * 2, 256 << 10);
+        for (int r = 0; r < ArgRing::N; ++r) {
+            if (g_args.cap[r] >= want) continue;
+            if (g_args.ev[r]) PK_CUDA(cudaEventSynchronize(g_args.ev[r]));
+            if (g_args.h[r]) cudaFreeHost(g_args.h[r]);
+            if (g_args.d[r]) cudaFree(g_args.d[r]);
+            g_args.h[r] = g_args.d[r] = nullptr;
+            g_args.cap[r] = 0;
+            PK_CUDA(cudaHostAlloc(&g_args.h[r], want, cudaHostAllocDefault));
+            PK_CUDA(cudaMalloc(&g_args.d[r], want));
+            g_args.cap[r] = want;
+        }
+    }
+    int64_t* hs = reinterpret_cast<int64_t*>(g_args.h[slot]);
     int64_t* hr = hs + n;
     int64_t* ho = hr + nt;
     float* hb = reinterpret_cast<float*>(ho + nt);
     for (int i = 0; i < n; ++i) hs[i] = seeds[i];
     for (size_t i = 0; i < nt; ++i) { hr[i] = rows[i]; ho[i] = row_off[i]; hb[i] = (float)bounds[i]; }
     cudaStream_t st = (cudaStream_t)stream;
-    if (g_init_scratch.cap < host.size()) {
-        if (g_init_scratch.p) cudaFree(g_init_scratch.p);
-        g_init_scratch.p = nullptr;
-        g_init_scratch.cap = 0;
-        PK_CUDA(cudaMalloc(&g_init_scratch.p, host.size() * 2));
-        g_init_scratch.cap = host.size() * 2;
-    }
-    // the previous call's kernel may still read the scratch: same-stream ordering covers the usual
-    // case; a copy from pageable memory is staged before cudaMemcpyAsync returns
-    PK_CUDA(cudaMemcpyAsync(g_init_scratch.p, host.data(), host.size(), cudaMemcpyHostToDevice, st));
+    PK_CUDA(cudaMemcpyAsync(g_args.d[slot], g_args.h[slot], bytes, cudaMemcpyHostToDevice, st));
     InitParams P;
-    unsigned char* d = static_cast<unsigned char*>(g_init_scratch.p);
+    unsigned char* d = static_cast<unsigned char*>(g_args.d[slot]);
     P.seeds = reinterpret_cast<const int64_t*>(d);
     P.rows = P.seeds + n;
     P.row_off = P.rows + nt;
@@ -141,5 +158,6 @@ extern "C" int pk_init_tables_device(int n, const int64_t* seeds, int n_tables, 
     P.fused = fused;
     k_init_tables<<<n, INIT_THREADS, 0, st>>>(P);
     PK_LAUNCHED("k_init_tables");
+    PK_CUDA(cudaEventRecord(g_args.ev[slot], st));
     return PK_OK;
 }

@@ -38,6 +38,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <vector>
 
@@ -910,6 +911,22 @@ int launch_model2(const LaySel& l, const K2Params& P, int stage, int n, size_t s
 struct DescSlot {
     pk_universe_desc* d = nullptr;
     size_t cap = 0;
+    // pinned staging for the descriptors: a copy from pageable memory beyond 64 KB (a few hundred universes) makes the
+    // launching thread wait for the stream, i.e. for the launches ahead of this one
+    pk_universe_desc* h = nullptr;
+    size_t hcap = 0;
+    pk_universe_desc* stage(const pk_universe_desc* src, size_t bytes) {
+        if (hcap < bytes) {
+            if (h) cudaFreeHost(h);
+            h = nullptr;
+            hcap = 0;
+            const size_t want = bytes + bytes / 2 + 4096;
+            if (cudaHostAlloc(&h, want, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+            hcap = want;
+        }
+        std::memcpy(h, src, bytes);
+        return h;
+    }
     cudaEvent_t done = nullptr;
     bool busy = false;
 };
@@ -1075,7 +1092,9 @@ extern "C" int pk_train_universes(const pk_model_cfg* cfg, const pk_tables* pack
                 const size_t stride1 = (size_t)(2 + k) * u.batch_size * (cfg->model == PK_TRANSD ? 2 : 1) * d;
                 DescSlot* slot1 = acquire_desc(kDescArea + stride1 * sizeof(float));
                 if (!slot1) return pk::cuda_fail(cudaGetLastError(), "pk_train_universes: descriptor buffer");
-                PK_CUDA(cudaMemcpyAsync(slot1->d, &u, sizeof(pk_universe_desc), cudaMemcpyHostToDevice, st));
+                const pk_universe_desc* staged1 = slot1->stage(&u, sizeof(pk_universe_desc));
+                if (!staged1) return pk::cuda_fail(cudaGetLastError(), "pk_train_universes: pinned descriptor staging");
+                PK_CUDA(cudaMemcpyAsync(slot1->d, staged1, sizeof(pk_universe_desc), cudaMemcpyHostToDevice, st));
                 K2Params P1;
                 P1.desc = slot1->d;
                 for (int i = 0; i < 2; ++i) {
@@ -1110,7 +1129,9 @@ extern "C" int pk_train_universes(const pk_model_cfg* cfg, const pk_tables* pack
         DescSlot* slot = acquire_desc(desc_area + cls[c].size() * stride * sizeof(float));
         if (!slot) return pk::cuda_fail(cudaGetLastError(), "pk_train_universes: descriptor buffer");
         pk_universe_desc* d_desc = slot->d;
-        PK_CUDA(cudaMemcpyAsync(d_desc, cls[c].data(), bytes, cudaMemcpyHostToDevice, st));
+        const pk_universe_desc* staged = slot->stage(cls[c].data(), bytes);
+        if (!staged) return pk::cuda_fail(cudaGetLastError(), "pk_train_universes: pinned descriptor staging");
+        PK_CUDA(cudaMemcpyAsync(d_desc, staged, bytes, cudaMemcpyHostToDevice, st));
         K2Params P;
         P.desc = d_desc;
         for (int i = 0; i < 2; ++i) {
@@ -1126,8 +1147,7 @@ extern "C" int pk_train_universes(const pk_model_cfg* cfg, const pk_tables* pack
         P.timer = g_timer; P.timer_base = c == 1 ? (int)cls[0].size() : 0;
         P.scratch = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(slot->d) + desc_area);
         P.scratch_stride = stride;
-        // descriptors were copied from pageable host memory owned by this call: the copy has
-        // completed (or been staged) when cudaMemcpyAsync returns, so cls[c] may go out of scope
+        // the slot (device buffer + pinned staging) is handed out again only after this launch's `done` event
         int rc = PK_OK;
         const int nblk = (int)cls[c].size();
         if (cfg->model == PK_TRANSE) rc = launch_model0(lay, P, c == 0, nblk, s.total, st);

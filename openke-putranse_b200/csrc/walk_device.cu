@@ -37,16 +37,19 @@ namespace {
 constexpr int CAP = PK_WALK_CAP;          // triples per universe (2048)
 constexpr int HASH_SLOTS = 2 * CAP;       // collected-before set, open addressing, load <= 0.5
 constexpr int MAX_LEVELS = 7;
-// shared memory of one warp (= one block = one universe)
-constexpr int SM_SORT_BYTES = 2 * CAP * 8;            // phase D: 2*CAP 64-bit keys; phases B/C: X list + hash or tree
-constexpr int SM_X_BYTES = CAP * 4;                   // starting points of the current round
-constexpr int SM_TREE_BYTES = SM_SORT_BYTES - SM_X_BYTES;
+// Two kernels, one warp (= one block) per universe each.  The walk (phases A-C) is one lane chasing L2 latency for a
+// millisecond, so its blocks are kept small (24 KB: nine per SM) — every SM they sit on is lost to the training kernel,
+// whose blocks fill an SM's shared memory.  The numbering (phase D) is short and needs the sort buffer.
+constexpr int SM_X_BYTES = CAP * 4;                   // walk: starting points of the current round
+constexpr int SM_TREE_BYTES = HASH_SLOTS * 4;         // walk: pick tree, then the collected-before hash set
+constexpr int SM_RNG = SM_X_BYTES + SM_TREE_BYTES;    // walk: uint32 [32] generator state
+constexpr int SM_WALK_TOTAL = SM_RNG + 32 * 4;
+constexpr int SM_SORT_BYTES = 2 * CAP * 8;            // numbering: 2*CAP 64-bit keys
 constexpr int SM_LOC = SM_SORT_BYTES;                 // uint16 [2*CAP] local entity id per occurrence
 constexpr int SM_RLOC = SM_LOC + 2 * CAP * 2;         // uint16 [CAP]   local relation id per triple
 constexpr int SM_FLAGS = SM_RLOC + CAP * 2;           // uint32 [2*CAP/32] first-appearance flags
 constexpr int SM_PRE = SM_FLAGS + (2 * CAP / 32) * 4; // uint32 [2*CAP/32] flags before each word
-constexpr int SM_RNG = SM_PRE + (2 * CAP / 32) * 4;   // uint32 [32] generator state
-constexpr int SM_TOTAL = SM_RNG + 32 * 4;
+constexpr int SM_NUMBER_TOTAL = SM_PRE + (2 * CAP / 32) * 4;
 
 struct UniIn {            // per universe, filled by the host
     uint32_t seed;
@@ -210,11 +213,6 @@ __global__ void __launch_bounds__(32) k_walk_universes(WalkArgs A) {
     const UniIn in = A.in[u];
     int32_t* X = reinterpret_cast<int32_t*>(smem);                              // [CAP]
     int32_t* hash = reinterpret_cast<int32_t*>(smem + SM_X_BYTES);              // [HASH_SLOTS] (after the tree is done)
-    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem);     // phase D
-    unsigned short* LOC = reinterpret_cast<unsigned short*>(smem + SM_LOC);
-    unsigned short* RLOC = reinterpret_cast<unsigned short*>(smem + SM_RLOC);
-    uint32_t* flags = reinterpret_cast<uint32_t*>(smem + SM_FLAGS);
-    uint32_t* pre = reinterpret_cast<uint32_t*>(smem + SM_PRE);
     Rng rng{reinterpret_cast<uint32_t*>(smem + SM_RNG), 3, 0};
     int32_t* sizes = A.sizes + (size_t)u * 8;
     int draws = 0, status = PK_WALK_OK;
@@ -377,12 +375,24 @@ __global__ void __launch_bounds__(32) k_walk_universes(WalkArgs A) {
     }
     draws = __shfl_sync(0xffffffffu, draws, 0);
     if (status == PK_WALK_OK && ngot == 0) status = PK_WALK_EMPTY;
-    if (status != PK_WALK_OK) {
-        if (lane == 0) { sizes[0] = 0; sizes[1] = 0; sizes[2] = 0; sizes[3] = in.focus; sizes[4] = draws; sizes[5] = status; sizes[6] = rounds; sizes[7] = 0; }
-        return;
-    }
+    if (status != PK_WALK_OK) ngot = 0;
+    if (lane == 0) { sizes[0] = ngot; sizes[1] = 0; sizes[2] = 0; sizes[3] = in.focus; sizes[4] = draws; sizes[5] = status; sizes[6] = rounds; sizes[7] = 0; }
+}
 
-    // ---- phase D: local ids by first appearance, entities (h then t of every triple in collection order)
+// ---- phase D: local ids by first appearance, entities (h then t of every triple in collection order), relations, and
+//      the (h,r,t) order of the local list
+__global__ void __launch_bounds__(32) k_number_universes(WalkArgs A) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int u = blockIdx.x, lane = threadIdx.x;
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem);
+    unsigned short* LOC = reinterpret_cast<unsigned short*>(smem + SM_LOC);
+    unsigned short* RLOC = reinterpret_cast<unsigned short*>(smem + SM_RLOC);
+    uint32_t* flags = reinterpret_cast<uint32_t*>(smem + SM_FLAGS);
+    uint32_t* pre = reinterpret_cast<uint32_t*>(smem + SM_PRE);
+    int32_t* sizes = A.sizes + (size_t)u * 8;
+    const int ngot = sizes[0];
+    if (sizes[5] != PK_WALK_OK || ngot <= 0) return;
+    const int32_t* got = A.got + (size_t)u * CAP * 3;
     const int nocc = 2 * ngot;
     int M = 2;
     while (M < nocc) M <<= 1;
@@ -414,7 +424,28 @@ __global__ void __launch_bounds__(32) k_walk_universes(WalkArgs A) {
         tri[3 * p + 1] = (int32_t)((v >> 21) & 0x1fffff);
         tri[3 * p + 2] = (int32_t)(v & 0x1fffff);
     }
-    if (lane == 0) { sizes[0] = ngot; sizes[1] = nE; sizes[2] = nR; sizes[3] = in.focus; sizes[4] = draws; sizes[5] = PK_WALK_OK; sizes[6] = rounds; sizes[7] = 0; }
+    if (lane == 0) { sizes[1] = nE; sizes[2] = nR; }
+}
+
+// ---- the two remaps of a chunk back to back (what evaluation indexes), universes in order; block u finds its offsets
+//      by summing the sizes of the universes before it
+__global__ void __launch_bounds__(128) k_pack_remaps(int n, const int32_t* sizes, const int32_t* ent_remap, const int32_t* rel_remap,
+                                                      int32_t* ent_out, int32_t* rel_out) {
+    __shared__ long long part[2][4];
+    const int u = blockIdx.x, tid = threadIdx.x;
+    long long eo = 0, ro = 0;
+    for (int v = tid; v < u; v += 128) { eo += sizes[v * 8 + 1]; ro += sizes[v * 8 + 2]; }
+    for (int d = 16; d > 0; d >>= 1) {
+        eo += __shfl_down_sync(0xffffffffu, eo, d);
+        ro += __shfl_down_sync(0xffffffffu, ro, d);
+    }
+    if ((tid & 31) == 0) { part[0][tid >> 5] = eo; part[1][tid >> 5] = ro; }
+    __syncthreads();
+    eo = part[0][0] + part[0][1] + part[0][2] + part[0][3];
+    ro = part[1][0] + part[1][1] + part[1][2] + part[1][3];
+    const int nE = sizes[u * 8 + 1], nR = sizes[u * 8 + 2];
+    for (int i = tid; i < nE; i += 128) ent_out[eo + i] = ent_remap[(size_t)u * 2 * CAP + i];
+    for (int i = tid; i < nR; i += 128) rel_out[ro + i] = rel_remap[(size_t)u * CAP + i];
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -523,7 +554,8 @@ int pk_universes_walk_device(int n, const int64_t* seeds, const int64_t* tcs, co
     if (int rc = upload_graph(st)) return rc;
     static bool attr_done = false;
     if (!attr_done) {
-        PK_CUDA(cudaFuncSetAttribute(k_walk_universes, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+        PK_CUDA(cudaFuncSetAttribute(k_walk_universes, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_WALK_TOTAL));
+        PK_CUDA(cudaFuncSetAttribute(k_number_universes, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_NUMBER_TOTAL));
         attr_done = true;
     }
     const int slot = g_ring.next;
@@ -582,9 +614,22 @@ int pk_universes_walk_device(int n, const int64_t* seeds, const int64_t* tcs, co
     A.in = g_ring.d[slot];
     A.q = d_bitmaps; A.qwords = (int32_t)qwords;
     A.tree = d_trees; A.got = d_got; A.tri = d_tri; A.ent_remap = d_ent_remap; A.rel_remap = d_rel_remap; A.sizes = d_sizes;
-    k_walk_universes<<<n, 32, SM_TOTAL, st>>>(A);
+    k_walk_universes<<<n, 32, SM_WALK_TOTAL, st>>>(A);
     PK_LAUNCHED("k_walk_universes");
+    k_number_universes<<<n, 32, SM_NUMBER_TOTAL, st>>>(A);
+    PK_LAUNCHED("k_number_universes");
     PK_CUDA(cudaEventRecord(g_ring.ev[slot], st));
+    return PK_OK;
+}
+
+// d_ent_packed [sum nE], d_rel_packed [sum nR]: the remaps of universes 0..n-1 back to back (sizes from d_sizes).
+int pk_walk_pack_remaps(int n, const int32_t* d_sizes, const int32_t* d_ent_remap, const int32_t* d_rel_remap, int32_t* d_ent_packed,
+                        int32_t* d_rel_packed, void* stream) {
+    pk::launch_counter() = 0;
+    if (n <= 0 || !d_sizes || !d_ent_remap || !d_rel_remap || !d_ent_packed || !d_rel_packed)
+        return pk::fail(PK_ERR_ARG, "pk_walk_pack_remaps: null argument");
+    k_pack_remaps<<<n, 128, 0, (cudaStream_t)stream>>>(n, d_sizes, d_ent_remap, d_rel_remap, d_ent_packed, d_rel_packed);
+    PK_LAUNCHED("k_pack_remaps");
     return PK_OK;
 }
 

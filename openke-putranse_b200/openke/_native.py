@@ -130,9 +130,12 @@ def _declare(L):
         "pk_universes_free": (None, [vp]), "pk_universes_count": (ctypes.c_int, [vp]),
         "pk_universes_sizes": (ctypes.c_int, [vp, vp, vp, vp, vp]),
         "pk_universes_export": (ctypes.c_int, [vp] * 9),
+        "pk_python_hyper_draws": (ctypes.c_int, [ctypes.c_int, vp, I, I, ctypes.c_double, ctypes.c_double, I, I, I, I, ctypes.c_int,
+                                                 ctypes.c_double, ctypes.c_double, ctypes.c_int, vp, vp, vp, vp, vp]),
         "pk_walk_cap": (ctypes.c_int, []), "pk_walk_device_check": (ctypes.c_int, []),
         "pk_walk_scratch_bytes": (ctypes.c_int, [ctypes.c_int, vp]),
         "pk_universes_walk_device": (ctypes.c_int, [ctypes.c_int] + [vp] * 13),
+        "pk_walk_pack_remaps": (ctypes.c_int, [ctypes.c_int] + [vp] * 6),
         "pk_torch_init_tables": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_int, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int]),
         "pk_init_tables_device": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_int, vp, vp, vp, vp, vp, ctypes.c_int, vp]),
         # pk_* device

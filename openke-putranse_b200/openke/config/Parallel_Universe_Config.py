@@ -67,7 +67,30 @@ def _dist():
 
 class _Chunk(object):
     """One pk_train_universes launch worth of universes: packed device tables + host-side maps."""
-    pass
+    d_ent_remap = d_rel_remap = None      # device copies of the packed remaps (device-built universes)
+    _ent_remap = _rel_remap = None
+
+    # local -> global ids of all universes of the chunk, back to back; universes built on the GPU leave them on the
+    # device (evaluation reads them there) and the host copy is fetched when something first asks for it
+    @property
+    def ent_remap(self):
+        if self._ent_remap is None and self.d_ent_remap is not None:
+            self._ent_remap = self.d_ent_remap.cpu().numpy()
+        return self._ent_remap
+
+    @ent_remap.setter
+    def ent_remap(self, v):
+        self._ent_remap = v
+
+    @property
+    def rel_remap(self):
+        if self._rel_remap is None and self.d_rel_remap is not None:
+            self._rel_remap = self.d_rel_remap.cpu().numpy()
+        return self._rel_remap
+
+    @rel_remap.setter
+    def rel_remap(self, v):
+        self._rel_remap = v
 
 
 class Parallel_Universe_Config(Tester):
@@ -151,14 +174,23 @@ class Parallel_Universe_Config(Tester):
         self._pinned = {}
         self._pinned_busy = None
         self._arena, self._arena_used = None, 0
+        # trained tables are carved from slabs (a cudaMalloc waits for the launches in flight: tens of ms when four are);
+        # 1 GiB = the tables of ~80 chunks of 100 WN18 universes.  Untouched slab memory costs address space only.
+        self.arena_slab_floats = 256 << 20
         # sample the next chunk's subgraphs on a host thread while the GPU trains this one (the universe
         # ids of the next call are predictable: they continue the sequence).  Measured on the B200 box:
         # 38.5 -> 27.5 ms per 100 universes end to end, i.e. host sampling disappears behind the kernel.
         self.prefetch_sampling = True
         self.prefetch_depth = 1           # chunks sampled ahead of the one being launched (deeper = the sampler's Python parts
                                           # compete with the launching thread for the GIL: launch time 1.3 -> 13 ms per chunk)
-        self._prefetched = {}             # sampling key -> future
+        self._prefetched = {}             # sampling key -> sample in flight (("host", future) or ("device", hyper, WalkResult))
         self._pool = None
+        # Subgraphs on the GPU (csrc/walk_device.cu, openke/universe_walk.py) whenever training reads only the lean
+        # universe (no filter, no Bernoulli): no host cores, no H2D copy of the triple index; bit-identical to the host
+        # builder.  The walks of the next `device_walk_depth` chunks run beside the training launches.
+        self.device_walk = True
+        self.device_walk_depth = 2
+        self._walker = None
         self.max_energy_bytes = 8 << 30   # upper bound for the [keys, E] energy tile buffers of an evaluation (three of them)
         self.eval_tile_rows = 1024        # key rows per energy tile (a tile is the unit of the NCCL min all-reduce)
         self.training_duration = 0.0
@@ -224,6 +256,32 @@ class Parallel_Universe_Config(Tester):
         lr = round(rnd.uniform(self.min_lr, self.max_lr), len(str(self.min_lr).split(".")[1]))
         return dict(tc=tc, balance=balance, margin=margin, epochs=epochs, lr=lr)
 
+    def draw_hyper_batch(self, seeds):
+        """draw_universe_hyper for many universes in one native call (CPython's generator restated in
+        csrc/pyrandom_host.cpp: the interpreter needs 8-17 us per universe on the launching thread); ranges the
+        native generator does not cover go through random.Random."""
+        n = len(seeds)
+        try:
+            ints = [int(v) for v in (self.min_triple_constraint, self.max_triple_constraint, self.min_margin, self.max_margin)]
+            exact = all(a == b for a, b in zip(ints, (self.min_triple_constraint, self.max_triple_constraint, self.min_margin, self.max_margin)))
+            const = self.const_num_epochs is not None
+            ep = (int(self.const_num_epochs), int(self.const_num_epochs)) if const else (int(self.min_num_epochs), int(self.max_num_epochs))
+            digits = len(str(self.min_lr).split(".")[1])
+            s64 = np.ascontiguousarray(seeds, dtype=np.int64)
+            tc, margin, epochs = (np.zeros(n, dtype=np.int64) for _ in range(3))
+            bal, lr = np.zeros(n, dtype=np.float64), np.zeros(n, dtype=np.float64)
+            rc = -1 if not exact else self.lib.pk_python_hyper_draws(
+                n, N.addr(s64), ints[0], ints[1], float(self.min_balance), float(self.max_balance), ints[2], ints[3], ep[0], ep[1],
+                0 if const else 1, float(self.min_lr), float(self.max_lr), digits, N.addr(tc), N.addr(bal), N.addr(margin),
+                N.addr(epochs), N.addr(lr))
+        except (TypeError, ValueError, IndexError, OverflowError):
+            rc = -1
+        if rc != 0:
+            return [self.draw_universe_hyper(int(s_)) for s_ in seeds]
+        ep_out = [self.const_num_epochs] * n if const else epochs.tolist()
+        return [dict(tc=a, balance=b, margin=c, epochs=d, lr=e)
+                for a, b, c, d, e in zip(tc.tolist(), bal.tolist(), margin.tolist(), ep_out, lr.tolist())]
+
     # ------------------------------------------------------------------ training
     def _device(self):
         if not self.use_gpu:
@@ -280,6 +338,9 @@ class Parallel_Universe_Config(Tester):
                 o += steps
             ck.d_loss = None
         ck.train_inputs = None
+        if getattr(ck, "walk", None) is not None:
+            ck.walk.release()
+            ck.walk = None
 
     @property
     def universe_losses(self):
@@ -311,8 +372,8 @@ class Parallel_Universe_Config(Tester):
         t_begin = time.perf_counter()
         threads = int(self.sampler_threads) if threads is None else int(threads)
         n = len(universe_ids)
-        hyper = [self.draw_universe_hyper(self.initial_random_seed + u) for u in universe_ids]
         seeds = np.array([self.initial_random_seed + u for u in universe_ids], dtype=np.int64)
+        hyper = self.draw_hyper_batch(seeds)
         tcs = np.array([h["tc"] for h in hyper], dtype=np.int64)
         bals = np.array([h["balance"] for h in hyper], dtype=np.float32)
         # -- subgraphs: bit-identical to the reference's getParallelUniverse, on host threads
@@ -349,15 +410,14 @@ class Parallel_Universe_Config(Tester):
         t0 = time.perf_counter()
         lib.setWorkThreads(dl.work_threads)
         # subgraphs of these universes may already have been sampled beside the previous launch
-        smp = None
         key = self._sampling_key(universe_ids)
-        fut = self._prefetched.pop(key, None)
+        entry = self._prefetched.pop(key, None)
         for k_old in [k_ for k_ in self._prefetched if k_[0][0] <= universe_ids[0] or k_[1:] != key[1:]]:
-            self._prefetched.pop(k_old).cancel()       # samples nobody will ask for any more (passed, or of another graph/config)
-        if fut is not None:
-            smp = fut.result()
-        if smp is None:
-            smp = self._sample_universes(universe_ids)
+            self._drop_sample(self._prefetched.pop(k_old))   # samples nobody will ask for any more (passed, or of another graph/config)
+        if entry is None:
+            entry = self._submit_sample(universe_ids, background=False)
+        smp = self._resolve_sample(entry, universe_ids)
+        walk = smp.get("walk")
         hyper, seeds, nT, nE, nR, focus = smp["hyper"], smp["seeds"], smp["nT"], smp["nE"], smp["nR"], smp["focus"]
         by_head, by_tail, ent_remap, rel_remap, lm, rm, lcg = (smp[k_] for k_ in ("by_head", "by_tail", "ent_remap", "rel_remap",
                                                                                    "lm", "rm", "lcg"))
@@ -415,7 +475,18 @@ class Parallel_Universe_Config(Tester):
         ck.tables = tables
         adagrad = True  # reference :241-242 hard-codes opt_method='Adagrad' for universes
         ck.state = {name: self._state_rows(slot, name, t) for name, t in ck.tables.items()} if adagrad else None
-        d_by_head = self._dev_scratch(slot, "by_head", dev, by_head)
+        if walk is not None:      # the walk wrote the local triple lists where the training kernel reads them
+            slot.stream.wait_event(walk.event)
+            ck.d_ent_remap = torch.empty(max(sE, 1), dtype=torch.int32, device=dev)[:sE]
+            ck.d_rel_remap = torch.empty(max(sR, 1), dtype=torch.int32, device=dev)[:sR]
+            N.check(lib.pk_walk_pack_remaps(n, walk.bufs["sizes"].data_ptr(), walk.bufs["ent_remap"].data_ptr(),
+                                            walk.bufs["rel_remap"].data_ptr(), ck.d_ent_remap.data_ptr(), ck.d_rel_remap.data_ptr(),
+                                            slot.stream.cuda_stream), "pk_walk_pack_remaps")
+            d_by_head = walk.bufs["tri"].view(-1, 3)
+            tri_off = np.arange(n, dtype=np.int64) * self._walker.cap
+        else:
+            d_by_head = self._dev_scratch(slot, "by_head", dev, by_head)
+            tri_off = toff[:n]
         d_by_tail = self._dev_scratch(slot, "by_tail", dev, by_tail) if by_tail is not None else None
         d_lm = self._dev_scratch(slot, "lm", dev, lm) if dl.bern else None
         d_rm = self._dev_scratch(slot, "rm", dev, rm) if dl.bern else None
@@ -430,7 +501,7 @@ class Parallel_Universe_Config(Tester):
         # the descriptor array column by column (a Python loop over ctypes fields costs ~1 ms per 100 universes,
         # all of it with the GPU idle)
         darr = np.zeros(n, dtype=N.UNIVERSE_DESC_DTYPE)
-        darr["tri_off"], darr["ent_off"], darr["rel_off"] = toff[:n], eoff[:n], roff[:n]
+        darr["tri_off"], darr["ent_off"], darr["rel_off"] = tri_off, eoff[:n], roff[:n]
         darr["n_tri"], darr["n_ent"], darr["n_rel"] = nT, nE, nR
         darr["batch_size"], darr["nbatches"], darr["epochs"] = Bs, nb, epochs
         darr["margin"] = np.array([h["margin"] for h in hyper], dtype=np.float32)
@@ -481,8 +552,15 @@ class Parallel_Universe_Config(Tester):
         self.universes_on_single_space_path += len(big)
         self._queue_sampling(universe_ids, prefetch_ids)
         ck.train_inputs = (d_by_head, d_by_tail, d_lm, d_rm)  # keep alive until the stream is done
-        self.h2d_bytes += sum(t.numel() * t.element_size() for t in ck.train_inputs if t is not None) + ctypes.sizeof(desc) \
-            + n * (8 + len(ck.tables) * 20)   # + seeds / rows / offsets / bounds of the device initialiser
+        ck.walk = walk
+        ck.tri_off = np.asarray(tri_off, dtype=np.int64)   # row offsets of the universes' triple lists inside train_inputs[0]
+        if walk is not None:   # walk inputs (40 B per universe) in, sizes + remaps out; the triple index never leaves the device
+            self.h2d_bytes += n * 40 + ctypes.sizeof(desc) + n * (8 + len(ck.tables) * 20)
+            self.d2h_bytes += n * 32
+            self.gpu_launches += 3
+        else:
+            self.h2d_bytes += sum(t.numel() * t.element_size() for t in ck.train_inputs if t is not None) + ctypes.sizeof(desc) \
+                + n * (8 + len(ck.tables) * 20)   # + seeds / rows / offsets / bounds of the device initialiser
         ck.d_loss = d_loss
         t3 = time.perf_counter()
         self.timings["launch"] += t3 - t2
@@ -495,25 +573,80 @@ class Parallel_Universe_Config(Tester):
         self._rank_cache.clear()
         return ck
 
-    def _queue_sampling(self, universe_ids, prefetch_ids):
-        """Queue the subgraphs of the chunks after this one for the background sampler.  Called AFTER this chunk's launch
-        has been issued: the sampler's Python parts (hyper-parameter draws, array allocation) hold the GIL, and the
-        launching thread must not compete for it while the GPU waits for its launch (measured: 1.3 ms -> 13 ms of
-        launch time per chunk when the sampler ran beside the launch)."""
-        if not (prefetch_ids and self.prefetch_sampling):
-            return
+    def _use_device_walk(self):
+        dl = self.train_dataloader
+        if not self.device_walk or dl.filter or dl.bern:
+            return False
+        if self._walker is None:
+            from ..universe_walk import DeviceWalker
+            self._walker = DeviceWalker(self.lib, self._device())
+        cap = self._walker.cap
+        tc_max = int(self.max_triple_constraint) - 1
+        if tc_max > cap or int(np.float32(self.max_balance) * np.float32(tc_max)) > cap:
+            return False
+        return self._walker.usable()
+
+    def _submit_sample(self, universe_ids, background):
+        """Start sampling the subgraphs of `universe_ids`: a walk launch on the GPU, or the host builder (on the sampler
+        thread when `background`)."""
+        self.lib.setWorkThreads(self.train_dataloader.work_threads)
+        if self._use_device_walk():
+            t0 = time.perf_counter()
+            seeds = np.array([self.initial_random_seed + u for u in universe_ids], dtype=np.int64)
+            hyper = self.draw_hyper_batch(seeds)
+            tcs = np.array([h["tc"] for h in hyper], dtype=np.int64)
+            bals = np.array([h["balance"] for h in hyper], dtype=np.float32)
+            t1 = time.perf_counter()
+            res = self._walker.submit(seeds, tcs, bals, self.train_dataloader.work_threads, copy_remaps=False)
+            self.timings["hyper_draws"] += t1 - t0
+            self.timings["walk_submit"] += time.perf_counter() - t1
+            return ("device", hyper, res)
+        if not background:
+            return ("host", self._sample_universes(universe_ids))
         if self._pool is None:
             from concurrent.futures import ThreadPoolExecutor
             self._pool = ThreadPoolExecutor(max_workers=1)
         # this rank's share of the host's cores, minus one for the launching thread and the CUDA driver's threads
         _, _, world_ = _dist()
         bg_threads = int(self.sampler_threads) or max(2, _host_cores() // max(world_, 1) - 1)
+        return ("host", self._pool.submit(self._sample_universes, universe_ids, bg_threads))
+
+    def _resolve_sample(self, entry, universe_ids):
+        if entry[0] == "host":
+            return entry[1] if isinstance(entry[1], dict) else entry[1].result()
+        _, hyper, res = entry
+        t0 = time.perf_counter()
+        sizes = res.wait()
+        self.timings["wait_for_walk"] += time.perf_counter() - t0
+        if not res.ok:      # beyond the kernel (capacity, isolated entity, empty walk): the host builder decides
+            res.release()
+            return self._sample_universes(universe_ids)
+        return dict(hyper=hyper, seeds=res.seeds, nT=sizes[:, 0].copy(), nE=sizes[:, 1].copy(), nR=sizes[:, 2].copy(),
+                    focus=sizes[:, 3].copy(), by_head=None, by_tail=None, ent_remap=None, rel_remap=None, lm=None, rm=None,
+                    lcg=res.lcg, walk=res)
+
+    def _drop_sample(self, entry):
+        if entry[0] == "host":
+            if not isinstance(entry[1], dict):
+                entry[1].cancel()
+        else:
+            entry[2].event.synchronize()
+            entry[2].release()
+
+    def _queue_sampling(self, universe_ids, prefetch_ids):
+        """Queue the subgraphs of the chunks after this one.  Called AFTER this chunk's launch has been issued.  Host
+        builder: its Python parts (hyper-parameter draws, array allocation) hold the GIL, and the launching thread must
+        not compete for it while the GPU waits for its launch (measured: 1.3 ms -> 13 ms of launch time per chunk when
+        the sampler ran beside the launch), so it works one chunk ahead.  Device walk: launches on the walk stream."""
+        if not (prefetch_ids and self.prefetch_sampling):
+            return
         step = prefetch_ids[0] - universe_ids[0]
-        for ahead in range(1, max(1, int(self.prefetch_depth)) + 1):
+        depth = int(self.device_walk_depth) if self._use_device_walk() else int(self.prefetch_depth)
+        for ahead in range(1, max(1, depth) + 1):
             ids_next = [u + ahead * step for u in universe_ids]
             key_next = self._sampling_key(ids_next)
             if key_next not in self._prefetched:
-                self._prefetched[key_next] = self._pool.submit(self._sample_universes, ids_next, bg_threads)
+                self._prefetched[key_next] = self._submit_sample(ids_next, background=True)
 
     def _arena_rows(self, dev, rows, dim):
         """[rows, dim] fp32 device view carved from a slab.  The trained tables of every chunk stay
@@ -522,7 +655,7 @@ class Parallel_Universe_Config(Tester):
         need = rows * dim
         need_al = (need + 63) // 64 * 64
         if self._arena is None or self._arena_used + need_al > self._arena.numel():
-            self._arena = torch.empty(max(need_al, 64 << 20), dtype=torch.float32, device=dev)   # 256 MB slabs
+            self._arena = torch.empty(max(need_al, int(self.arena_slab_floats)), dtype=torch.float32, device=dev)
             self._arena_used = 0
         view = self._arena[self._arena_used:self._arena_used + need].view(rows, dim)
         self._arena_used += need_al
@@ -1037,7 +1170,7 @@ class Parallel_Universe_Config(Tester):
         ix["d_eoff"] = torch.from_numpy(ck.eoff[:-1].copy()).to(dev)
         ix["d_roff"] = torch.from_numpy(ck.roff[:-1].copy()).to(dev)
         ix["d_nE"] = torch.from_numpy(ck.nE.astype(np.int32)).to(dev)
-        ix["d_remap"] = torch.from_numpy(ck.ent_remap).to(dev)
+        ix["d_remap"] = ck.d_ent_remap if ck.d_ent_remap is not None else torch.from_numpy(ck.ent_remap).to(dev)
         ck.index = ix
         return ix
 

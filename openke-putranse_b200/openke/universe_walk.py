@@ -36,13 +36,10 @@ class WalkResult(object):
     def packed_remaps(self):
         """(ent_remap [sum nE], rel_remap [sum nR]) int32 numpy, universes back to back (what evaluation indexes)."""
         s = self.wait()
-        cap = self.walker.cap
         er = self.bufs["h_ent_remap"][:self.n].numpy()
         rr = self.bufs["h_rel_remap"][:self.n].numpy()
-        nE, nR = s[:, 1], s[:, 2]
-        cols_e = np.arange(2 * cap)[None, :] < nE[:, None]
-        cols_r = np.arange(cap)[None, :] < nR[:, None]
-        return er[cols_e].copy(), rr[cols_r].copy()
+        nE, nR = s[:, 1].tolist(), s[:, 2].tolist()
+        return (np.concatenate([er[i, :nE[i]] for i in range(self.n)]), np.concatenate([rr[i, :nR[i]] for i in range(self.n)]))
 
     def release(self):
         """The training launch that read d_tri has finished: the buffers may carry another chunk."""

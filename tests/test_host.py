@@ -273,6 +273,37 @@ def test_hyper_draws_match_static_script(wn18_dir):
         assert (h["tc"], h["epochs"], h["lr"], h["margin"]) == w
 
 
+def test_native_hyper_draws_equal_python_random():
+    """csrc/pyrandom_host.cpp restates CPython's random.seed(int) / randrange / uniform / round for the draws of
+    Parallel_Universe_Config.py:211-212,232,237-240; the orchestrator uses it for whole chunks.  Every value must be
+    the very object Python computes: 30 000 seeds (small, around 2^31/2^32, 2^40+, negative) x four range configurations
+    (static WN18 script, WikidataEvolve script, constant epochs, wide ranges with more lr digits)."""
+    from openke.config import Parallel_Universe_Config
+    from openke import _native as N
+    pu = Parallel_Universe_Config.__new__(Parallel_Universe_Config)
+    pu.lib = N.lib()
+    seeds = np.concatenate([np.arange(0, 20000), np.arange(2 ** 31 - 1000, 2 ** 31 + 1000), np.arange(2 ** 32 - 1000, 2 ** 32 + 1000),
+                            2 ** 40 + np.arange(3000) * 7919, -np.arange(1, 3001)]).astype(np.int64)
+    configs = [dict(tc=(500, 2000), bal=(0.25, 0.5), margin=(1, 4), const=None, ep=(50, 200), lr=(0.001, 0.1)),
+               dict(tc=(500, 1500), bal=(0.25, 0.5), margin=(1, 5), const=None, ep=(50, 200), lr=(0.001, 0.1)),
+               dict(tc=(1000, 1001), bal=(0.1, 0.9), margin=(2, 3), const=7, ep=(50, 200), lr=(0.01, 0.1)),
+               dict(tc=(1, 100000), bal=(0.0, 1.0), margin=(1, 1000), const=None, ep=(1, 3), lr=(0.0001, 2.5))]
+    for c in configs:
+        pu.min_triple_constraint, pu.max_triple_constraint = c["tc"]
+        pu.min_balance, pu.max_balance = c["bal"]
+        pu.min_margin, pu.max_margin = c["margin"]
+        pu.const_num_epochs, (pu.min_num_epochs, pu.max_num_epochs) = c["const"], c["ep"]
+        pu.min_lr, pu.max_lr = c["lr"]
+        got = pu.draw_hyper_batch(seeds)
+        want = [pu.draw_universe_hyper(int(s_)) for s_ in seeds]
+        assert got == want, next((s_, g, w) for s_, g, w in zip(seeds, got, want) if g != w)
+        assert all(type(g[k]) is type(w[k]) for g, w in zip(got[:50], want[:50]) for k in w)
+    # ranges the native generator refuses fall back to the interpreter (same values, same errors)
+    pu.min_triple_constraint, pu.max_triple_constraint = 5, 5
+    with pytest.raises(ValueError):
+        pu.draw_hyper_batch(seeds[:3])
+
+
 def test_link_metrics_accumulate_like_the_reference(golden):
     from openke.config.Tester import link_metrics
     g = golden["rank_transh_wn18"]
