@@ -282,8 +282,9 @@ def run_ours(args):
 
     # ---- end-to-end leg through the public API: one Parallel_Universe_Config (loaders built once,
     # as a user would), every step = train_parallel_universes(...) on the NEXT universes of the seed
-    # sequence: host subgraph sampling + table init + H2D of the triple index and descriptors + K2 + D2H of the
-    # per-step losses into pinned memory.  async_training: a call returns when its launch is queued, so
+    # sequence: subgraph sampling (bit-exact walk on the GPU, launched two chunks ahead; host threads + H2D of the triple
+    # index when filter/Bernoulli sampling needs the full universe helpers) + table init + descriptors + K2 + D2H of the
+    # universe sizes and of the per-step losses into pinned memory.  async_training: a call returns when its launch is queued, so
     # consecutive chunks overlap on the device exactly like the resident leg; the final synchronize() is
     # inside the timed region.
     e2e_steps = args.e2e_steps if args.e2e_steps > 0 else max(20, args.steps)
@@ -334,9 +335,31 @@ def run_ours(args):
         mrr, mr, hit10, hit3, hit1 = p2.run_link_prediction()
         torch.cuda.synchronize()
         ev_s = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        p2.run_link_prediction()                  # what a validation loop pays: index and work items are cached per chunk
+        torch.cuda.synchronize()
+        ev_s2 = time.perf_counter() - t0
         ev = {"universes": int(p2.next_universe_id), "test_triples": int(p2.last_ranks.shape[0]), "seconds": ev_s,
-              "test_triples_per_s": p2.last_ranks.shape[0] / ev_s, "filtered": {"mrr": float(mrr), "mr": float(mr), "hits10": float(hit10),
-                                                                                 "hits3": float(hit3), "hits1": float(hit1)}}
+              "test_triples_per_s": p2.last_ranks.shape[0] / ev_s, "repeat_seconds": ev_s2,
+              "repeat_test_triples_per_s": p2.last_ranks.shape[0] / ev_s2,
+              "filtered": {"mrr": float(mrr), "mr": float(mr), "hits10": float(hit10), "hits3": float(hit3), "hits1": float(hit1)}}
+        if args.workload == "m2" and not strong:  # the ensemble size VERDICT r1 quoted: 400 universes in total
+            p4 = make_pu(path)
+            p4.train_parallel_universes(400)
+            p4.synchronize()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            m4_ = p4.run_link_prediction()
+            torch.cuda.synchronize()
+            e1 = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            p4.run_link_prediction()
+            torch.cuda.synchronize()
+            e2 = time.perf_counter() - t0
+            ev["ensemble_of_400"] = {"universes": 400, "seconds": e1, "test_triples_per_s": p4.last_ranks.shape[0] / e1, "repeat_seconds": e2,
+                                     "repeat_test_triples_per_s": p4.last_ranks.shape[0] / e2, "filtered_mrr": float(m4_[0]),
+                                     "filtered_hits10": float(m4_[2])}
+            del p4
 
     if dist:
         dist.barrier()
@@ -359,7 +382,9 @@ def run_ours(args):
                 "host_breakdown_s_per_step": {k: v for k, v in timings.items()},
                 "mean_final_loss_last_universes": loss_check,
                 "host": {"cores": len(os.sched_getaffinity(0)), "ranks_on_host": world,
-                         "note": "the next chunk's subgraphs are sampled on host threads beside the launch (bit-exact glibc rand() walk)"}},
+                         "universes_built_on": "gpu" if getattr(p2, "_walker", None) is not None and p2._walker.launches else "host threads",
+                         "note": "subgraphs of the next chunks are sampled beside the launch (bit-exact glibc rand() walk): on the GPU "
+                                 "(k_walk_universes) for unfiltered non-Bernoulli training, else on host threads"}},
         "gpu_launches": launches,
         "positive_triples_per_step_per_gpu": positives, "final_loss_last_universe": final_loss,
         "launch_ms": {"alone_on_the_gpu": float(np.median(single_ms)), "inside_the_pipelined_region": float(np.mean(launch_ms)),
