@@ -73,7 +73,7 @@ __host__ __device__ inline size_t up16(size_t x) { return (x + 15) & ~(size_t)15
 
 // shared-memory carve-up, identical on host (sizing) and device (pointers)
 struct K2Smem {
-    size_t ent[2], rel[2], rel_state[2], relc[2], reln, relacc, scratch, map, batch[2], lossv, lcg, total;
+    size_t ent[2], rel[2], rel_state[2], relc[2], reln, relacc, scratch, map, batch[2], lossv, lcg, bar, total;
     int slots;      // entity scratch rows: a multiply-occurring entity needs >= 2 of the (2+k)B occurrences
     int nrelcap;    // distinct relations a batch can hold
     int per;        // samples per LCG stream slice
@@ -104,6 +104,7 @@ struct K2Smem {
         lossv = o;   o = up16(o + (size_t)2 * mB * 4);   // per-sample loss terms, double-buffered
         // s0[8] | Aadv[8] | Cadv[8] | A[per] | C[per]
         lcg = o;     o = up16(o + (size_t)(24 + 2 * per) * 8);
+        bar = o;     o = up16(o + 16);   // mbarrier of the bulk (TMA) copy that stages the entity tables
         total = o;
     }
     __host__ __device__ static long long min_(long long a, long long b) { return a < b ? a : b; }
@@ -140,6 +141,41 @@ __device__ __forceinline__ void lcg_affine(uint64_t n, uint64_t& A, uint64_t& C)
     }
     A = ra;
     C = rc;
+}
+
+// ---- bulk asynchronous copies (TMA, 1-D): the staged entity tables of a universe travel global <-> shared memory as a
+//      few cp.async.bulk transfers issued by ONE thread (SASS: UBLKCP) instead of a float4 loop through the registers
+//      of all 512; completion of the load is counted in bytes on an mbarrier, of the store by the bulk async-group
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t arrivals) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+constexpr uint32_t kBulkChunk = 32768;   // bytes per transfer (a multiple of 16)
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    for (uint32_t o = 0; o < bytes; o += kBulkChunk) {
+        const uint32_t n = min(kBulkChunk, bytes - o);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(static_cast<unsigned char*>(smem_dst) + o)), "l"(static_cast<const unsigned char*>(gmem_src) + o),
+                       "r"(n), "r"(smem_u32(bar)) : "memory");
+    }
+}
+__device__ __forceinline__ void bulk_store(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+    for (uint32_t o = 0; o < bytes; o += kBulkChunk) {
+        const uint32_t n = min(kBulkChunk, bytes - o);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     ::"l"(static_cast<unsigned char*>(gmem_dst) + o), "r"(smem_u32(static_cast<const unsigned char*>(smem_src) + o)), "r"(n) : "memory");
+    }
 }
 
 __device__ __forceinline__ void named_barrier(int id, int nthreads) {
@@ -468,6 +504,11 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
     uint64_t* Aj = Cadv + 8;
     uint64_t* Cj = Aj + S.per;
     const int per = (B % W == 0) ? B / W : B / W + 1;   // Base.cpp:199-207
+    uint64_t* stage_bar = reinterpret_cast<uint64_t*>(smem + S.bar);
+    const uint32_t table_bytes = (uint32_t)nE * (uint32_t)d * 4u;
+    // bulk copies move multiples of 16 bytes between 16-byte aligned addresses: rows of d % 4 == 0 floats at a row offset
+    // of the packed table (whose base the allocator aligns to 256 bytes)
+    const bool bulk = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(g_ent[0]) | (ntE > 1 ? reinterpret_cast<uintptr_t>(g_ent[1]) : 0)) & 15) == 0;
     const size_t batch_stride = S.batch[1] - S.batch[0];
 
     // refresh the cached operands of relation r from the working tables (group-masked shuffles:
@@ -490,15 +531,15 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
 
     // ---- stage tables, clear scratch, build the LCG jump tables
     {
-        const bool vec = (d % 4 == 0);
-        for (int t = 0; t < ntE && STAGE; ++t) {
-            if (vec) {
-                const float4* src = reinterpret_cast<const float4*>(g_ent[t]);
-                float4* dst = reinterpret_cast<float4*>(cx.ent[t]);
-                for (int i = tid; i < nE * d / 4; i += NT) dst[i] = src[i];
-            } else {
-                for (int i = tid; i < nE * d; i += NT) cx.ent[t][i] = g_ent[t][i];
+        if (STAGE && bulk) {
+            if (tid == 0) {
+                mbar_init(stage_bar, 1);
+                mbar_expect_tx(stage_bar, (uint32_t)ntE * table_bytes);
+                for (int t = 0; t < ntE; ++t) bulk_load(cx.ent[t], g_ent[t], table_bytes, stage_bar);
             }
+        } else {
+            for (int t = 0; t < ntE && STAGE; ++t)
+                for (int i = tid; i < nE * d; i += NT) cx.ent[t][i] = g_ent[t][i];
         }
         for (int t = 0; t < ntR; ++t)
             for (int i = tid; i < nR * d; i += NT) {
@@ -516,6 +557,7 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
         for (int j = tid; j < per; j += NT) lcg_affine((uint64_t)j * (uint64_t)(1 + 2 * k), Aj[j], Cj[j]);
     }
     __syncthreads();
+    if (STAGE && bulk) mbar_wait(stage_bar, 0);   // the staged tables have landed (and are visible to whoever waited)
     for (int r = grp; r < nR; r += NT / L::G) recache(r);
 
     const long long steps = (long long)U.epochs * U.nbatches;
@@ -786,15 +828,17 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
 
     // ---- write staged tables back
     {
-        const bool vec = (d % 4 == 0);
-        for (int t = 0; t < ntE && STAGE; ++t) {
-            if (vec) {
-                const float4* src = reinterpret_cast<const float4*>(cx.ent[t]);
-                float4* dst = reinterpret_cast<float4*>(g_ent[t]);
-                for (int i = tid; i < nE * d / 4; i += NT) dst[i] = src[i];
-            } else {
-                for (int i = tid; i < nE * d; i += NT) g_ent[t][i] = cx.ent[t][i];
+        if (STAGE && bulk) {
+            // shared-memory writes of the generic proxy (the updates) must be ordered before the async proxy reads them
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (tid == 0) {
+                for (int t = 0; t < ntE; ++t) bulk_store(g_ent[t], cx.ent[t], table_bytes);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
+        } else {
+            for (int t = 0; t < ntE && STAGE; ++t)
+                for (int i = tid; i < nE * d; i += NT) g_ent[t][i] = cx.ent[t][i];
         }
         for (int t = 0; t < ntR; ++t)
             for (int i = tid; i < nR * d; i += NT) {
@@ -802,6 +846,7 @@ __global__ void __launch_bounds__(NT) k2_train_universes(const __grid_constant__
                 if (g_rel_state[t]) g_rel_state[t][i] = rc.state[t][i];
             }
     }
+    if (STAGE && bulk && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the block must not retire before its stores
     if (P.timer && tid == 0) {
         long long t_end;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_end));

@@ -329,12 +329,12 @@ class Parallel_Universe_Config(Tester):
         self.timings["wait_for_launch"] += time.perf_counter() - t0
         ck, slot.busy, slot.chunk = slot.chunk, False, None
         if ck.d_loss is not None:
-            host = slot.host_loss[:ck.d_loss.numel()].numpy()
+            host = slot.host_loss[:ck.d_loss.numel()].numpy().copy()   # one copy out of the pinned buffer; universes get views
             self.d2h_bytes += host.nbytes
             o = 0
             for u in ck.ids:
                 steps = self.universe_hyper[u]["epochs"] * self.universe_hyper[u]["nbatches"]
-                self._universe_losses[u] = host[o:o + steps].copy()
+                self._universe_losses[u] = host[o:o + steps]
                 o += steps
             ck.d_loss = None
         ck.train_inputs = None
@@ -477,8 +477,9 @@ class Parallel_Universe_Config(Tester):
         ck.state = {name: self._state_rows(slot, name, t) for name, t in ck.tables.items()} if adagrad else None
         if walk is not None:      # the walk wrote the local triple lists where the training kernel reads them
             slot.stream.wait_event(walk.event)
-            ck.d_ent_remap = torch.empty(max(sE, 1), dtype=torch.int32, device=dev)[:sE]
-            ck.d_rel_remap = torch.empty(max(sR, 1), dtype=torch.int32, device=dev)[:sR]
+            # from the table slab (a fresh allocation per chunk costs a cudaMalloc every few chunks, with launches in flight)
+            ck.d_ent_remap = self._arena_rows(dev, max(sE, 1), 1).view(torch.int32).view(-1)[:sE]
+            ck.d_rel_remap = self._arena_rows(dev, max(sR, 1), 1).view(torch.int32).view(-1)[:sR]
             N.check(lib.pk_walk_pack_remaps(n, walk.bufs["sizes"].data_ptr(), walk.bufs["ent_remap"].data_ptr(),
                                             walk.bufs["rel_remap"].data_ptr(), ck.d_ent_remap.data_ptr(), ck.d_rel_remap.data_ptr(),
                                             slot.stream.cuda_stream), "pk_walk_pack_remaps")

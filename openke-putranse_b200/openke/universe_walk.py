@@ -78,8 +78,7 @@ class DeviceWalker(object):
                  rel_remap=torch.empty((m, cap), dtype=torch.int32, device=dev),
                  sizes=torch.empty((m, 8), dtype=torch.int32, device=dev),
                  h_sizes=torch.empty((m, 8), dtype=torch.int32, pin_memory=True),
-                 h_ent_remap=torch.empty((m, 2 * cap), dtype=torch.int32, pin_memory=True),
-                 h_rel_remap=torch.empty((m, cap), dtype=torch.int32, pin_memory=True))
+                 h_ent_remap=None, h_rel_remap=None)     # pinned copies of the strided remaps: only on request
         return b
 
     def _graph_key(self):
@@ -105,6 +104,9 @@ class DeviceWalker(object):
             b["h_sizes"][:n].copy_(b["sizes"][:n], non_blocking=True)
             self.d2h_bytes += n * 32
             if copy_remaps:
+                if b["h_ent_remap"] is None:
+                    b["h_ent_remap"] = torch.empty((b["n"], 2 * self.cap), dtype=torch.int32, pin_memory=True)
+                    b["h_rel_remap"] = torch.empty((b["n"], self.cap), dtype=torch.int32, pin_memory=True)
                 b["h_ent_remap"][:n].copy_(b["ent_remap"][:n], non_blocking=True)
                 b["h_rel_remap"][:n].copy_(b["rel_remap"][:n], non_blocking=True)
                 self.d2h_bytes += n * 3 * self.cap * 4

@@ -123,3 +123,47 @@ def test_device_walk_equals_host_builder_on_relation_rich_and_large_graphs(tmp_p
     assert need[2] > 0, "this graph was meant to need the global-memory pick tree"
     seeds, tcs, bals = _hyper(64, 11, 500, 2000)
     _compare(dl.lib, walker, seeds, tcs, bals, 8)
+
+
+def test_orchestrator_trains_the_same_ensemble_with_device_and_host_universes(tmp_path):
+    """Parallel_Universe_Config with universes built on the GPU (default) against the same configuration with the host
+    builder: identical subgraphs (sizes, focus relations, local id maps), the same sampler streams and therefore the same
+    training — losses and tables agree up to the order of the float reductions of repeated rows, the evaluation ranks
+    the same.  Requests the kernel does not cover take the host path; an impossible request raises the host builder's
+    error either way."""
+    import torch
+    import test_product as T
+    path, _ = T._small_graph(tmp_path)
+    dev_pu, host_pu = T._pu(path), T._pu(path)
+    host_pu.device_walk = False
+    for pu in (dev_pu, host_pu):
+        pu.record_losses = True
+        pu.async_training = True
+        for n in (5, 4, 6):
+            pu.train_parallel_universes(n)
+        pu.synchronize()
+    assert dev_pu._walker is not None and dev_pu._walker.launches >= 3 and host_pu._walker is None
+    for u in range(15):
+        a, b = dev_pu.universe_hyper[u], host_pu.universe_hyper[u]
+        assert a == b, (u, a, b)
+        assert dict(dev_pu.entity_id_mappings[u]) == dict(host_pu.entity_id_mappings[u])
+        assert dict(dev_pu.relation_id_mappings[u]) == dict(host_pu.relation_id_mappings[u])
+        assert np.allclose(dev_pu.universe_losses[u], host_pu.universe_losses[u], rtol=1e-4, atol=1e-6), u
+        wa = dev_pu.trained_embedding_spaces[u].ent_embeddings.weight
+        wb = host_pu.trained_embedding_spaces[u].ent_embeddings.weight
+        assert wa.shape == wb.shape and float((wa - wb).abs().max()) < 1e-4, u
+    dev_pu.run_link_prediction()
+    host_pu.run_link_prediction()
+    assert (dev_pu.last_ranks == host_pu.last_ranks).all(1).mean() > 0.95
+    # beyond the kernel's capacity: the host builder is used from the start
+    big = T._pu(path, min_triple_constraint=2500, max_triple_constraint=2600)
+    big.train_parallel_universes(2)
+    big.synchronize()
+    assert (big._walker is None or big._walker.launches == 0) and big.universe_hyper[0]["nT"] >= 1
+    # no starting points (balance 0): the walk collects nothing; both builders end in the same error
+    for flag in (True, False):
+        none = T._pu(path, min_balance=0.0, max_balance=0.0)
+        none.device_walk = flag
+        with pytest.raises(N.NativeError, match="collected no triples"):
+            none.train_parallel_universes(2)
+            none.synchronize()
