@@ -381,6 +381,9 @@ int pk_score_batch(const pk_model_cfg* cfg, const pk_tables* tab, const int64_t*
 int pk_selftest_arith(int64_t n, uint32_t seed, int64_t* mismatches3);
 /* fill with +inf */
 int pk_fill_inf(float* d, int64_t n, void* stream);
+/* d_out[r] = d_in[r] / max(||d_in[r]||_2, eps), the ranking kernels' own normalisation (reference TransE.py:52-55
+ * F.normalize): PuTransE evaluation normalises a TransE universe's tables once instead of once per (key, universe) */
+int pk_normalise_rows(const float* d_in, float* d_out, int64_t rows, int d, void* stream);
 
 #ifdef __cplusplus
 }

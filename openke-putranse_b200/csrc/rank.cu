@@ -571,6 +571,29 @@ extern "C" int pk_score_batch(const pk_model_cfg* cfg, const pk_tables* tab, con
     return PK_OK;
 }
 
+// x / max(||x||, eps) per row with the ranking kernels' own sequence of operations (ent_operand / rel_operand above), so
+// that a space whose tables were normalised ONCE scores bit-identically with norm_flag = 0 (TransE: the operand of a
+// candidate is its normalised row, whatever the key; the evaluation of an ensemble visits every universe once per key)
+__global__ void __launch_bounds__(128) k_normalise_rows(const float* __restrict__ in, float* __restrict__ out, int64_t rows, int d) {
+    const int64_t r = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (r >= rows) return;
+    const float* x = in + r * d;
+    float* y = out + r * d;
+    float ss = 0.f;
+    for (int i = 0; i < d; ++i) ss = __fmaf_rn(x[i], x[i], ss);
+    const float n = fmaxf(__fsqrt_rn(ss), kNormEps);
+    for (int i = 0; i < d; ++i) y[i] = __fdiv_rn(x[i], n);
+}
+
+extern "C" int pk_normalise_rows(const float* d_in, float* d_out, int64_t rows, int d, void* stream) {
+    pk::launch_counter() = 0;
+    if (!d_in || !d_out || rows < 0 || d < 1) return pk::fail(PK_ERR_ARG, "pk_normalise_rows: bad argument");
+    if (rows == 0) return PK_OK;
+    k_normalise_rows<<<(unsigned)((rows + 127) / 128), 128, 0, (cudaStream_t)stream>>>(d_in, d_out, rows, d);
+    PK_LAUNCHED("k_normalise_rows");
+    return PK_OK;
+}
+
 extern "C" int pk_fill_inf(float* d, int64_t n, void* stream) {
     pk::launch_counter() = 0;
     if (!d || n < 0) return pk::fail(PK_ERR_ARG, "pk_fill_inf: null argument");

@@ -156,6 +156,7 @@ def _declare(L):
         "pk_rank_candidate_row": (ctypes.c_int, [vp, I, vp, vp, vp, vp, vp]),
         "pk_score_batch": (ctypes.c_int, [ctypes.POINTER(ModelCfg), ctypes.POINTER(Tables), vp, I, vp, I, vp, I, ctypes.c_int, vp, vp, vp]),
         "pk_fill_inf": (ctypes.c_int, [vp, I, vp]),
+        "pk_normalise_rows": (ctypes.c_int, [vp, vp, I, ctypes.c_int, vp]),
         "pk_selftest_arith": (ctypes.c_int, [I, ctypes.c_uint32, vp]),
     }
     for name, (res, args) in sig.items():

@@ -951,7 +951,8 @@ class Parallel_Universe_Config(Tester):
             d_items, bounds = cached
             if d_items is None:
                 continue
-            per_chunk.append((ck, ix, d_items, bounds, ck.proto.native_cfg(), self._packed_tables(ck)))
+            cfg_e, tab_e = self._eval_operands(ck, dev)
+            per_chunk.append((ck, ix, d_items, bounds, cfg_e, tab_e))
         self.timings["eval_host_prep"] += time.perf_counter() - t_host
         n_tiles = (K + rows_per_tile - 1) // rows_per_tile
         bufs = [torch.empty((rows_per_tile, E), dtype=torch.float32, device=dev) for _ in range(min(3, n_tiles))]
@@ -1008,6 +1009,35 @@ class Parallel_Universe_Config(Tester):
         while pending:
             finish(*pending.pop(0))
         return rows_per_tile
+
+    def _eval_operands(self, ck, dev):
+        """(model configuration, tables) the energy kernels score a chunk with.  TransE with norm_flag: the operand of a
+        candidate is its normalised row whatever the key, and an ensemble evaluation visits a universe once per key that
+        it can answer — the chunk's tables are normalised ONCE (same operations, same order: bit-identical energies) and
+        scored with norm_flag = 0; 45 % of the energy kernel's instructions were that division."""
+        cfg = ck.proto.native_cfg()
+        if ck.proto._pk_model != N.PK_TRANSE or not cfg.norm_flag:
+            return cfg, self._packed_tables(ck)
+        cache = getattr(ck, "norm_tables", None)
+        if cache is None:
+            st = torch.cuda.current_stream(dev).cuda_stream
+            cache = {}
+            for name, t in ck.tables.items():
+                out = torch.empty_like(t)
+                N.check(self.lib.pk_normalise_rows(t.data_ptr(), out.data_ptr(), t.shape[0], t.shape[1], st), "pk_normalise_rows")
+                self.gpu_launches += self.lib.pk_last_launch_count()
+                cache[name] = out
+            ck.norm_tables = cache
+        cfg.norm_flag = 0
+        t = N.Tables()
+        for i in range(2):
+            t.ent[i] = t.rel[i] = t.ent_state[i] = t.rel_state[i] = None
+        for i, name in enumerate(ck.proto._ent_tables):
+            t.ent[i] = cache[name].data_ptr()
+        for i, name in enumerate(ck.proto._rel_tables):
+            t.rel[i] = cache[name].data_ptr()
+        t.n_ent, t.n_rel = int(ck.eoff[-1]), int(ck.roff[-1])
+        return cfg, t
 
     def _rank_split(self, loader):
         """Raw/filtered ranks [n,4] of every triple of `loader` under the min-over-universes energy

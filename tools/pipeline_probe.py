@@ -18,8 +18,8 @@ def run(path, n, steps, async_, slots, losses=True):
     pu.record_losses = losses
     pu.async_training = async_
     pu.launch_slots = slots
-    pu.train_parallel_universes(n)
-    pu.train_parallel_universes(n)
+    for _ in range(slots + 5):       # every slot's buffers exist before the timed loop
+        pu.train_parallel_universes(n)
     pu.synchronize()
     torch.cuda.synchronize()
     pu.timings.clear()
@@ -39,10 +39,13 @@ def run(path, n, steps, async_, slots, losses=True):
 def main():
     path = util.materialize_wn18(tempfile.mkdtemp())
     import io, contextlib
-    for n, steps in ((100, 20), (1000, 3)):
-        for async_, slots in ((0, 1), (1, 2), (1, 3), (1, 4)):
-            with contextlib.redirect_stdout(io.StringIO()):
-                pass
+    combos = ((0, 1), (1, 2), (1, 3), (1, 4))
+    if len(sys.argv) > 1:   # e.g. "4,6,8": asynchronous slot counts only, longer runs
+        combos = tuple((1, int(x)) for x in sys.argv[1].split(","))
+    for n, steps in ((100, 40 if len(sys.argv) > 1 else 20), (1000, 3)):
+        if len(sys.argv) > 1 and n != 100:
+            continue
+        for async_, slots in combos:
             run(path, n, steps, async_, slots)
 
 
