@@ -192,7 +192,7 @@ class Parallel_Universe_Config(Tester):
         self.device_walk_depth = 2
         self._walker = None
         self.max_energy_bytes = 8 << 30   # upper bound for the [keys, E] energy tile buffers of an evaluation (three of them)
-        self.eval_tile_rows = 1024        # key rows per energy tile (a tile is the unit of the NCCL min all-reduce)
+        self.eval_tile_rows = 4096        # key rows per energy tile (a tile is the unit of the NCCL min all-reduce); 671 MB on WN18
         self.training_duration = 0.0
         self.positive_triples = 0         # sum over universes of epochs * nbatches * batch_size
         self.gpu_launches = 0
