@@ -16,7 +16,8 @@
 //            shared-memory hash set keyed by the triple's position in the (h,r,t) order.  The reference's two
 //            std::sets of starting points are two bitmaps over the entities that swap roles every round: next
 //            round's starting points and the skipped ("resurface a round later") ones are OR-ed in fire-and-forget,
-//            and a round starts by enumerating + clearing its bitmap (ascending order, duplicates gone, no sort).
+//            and a round starts by enumerating + clearing its bitmap (ascending order, duplicates gone, no sort); one
+//            summary bit per bitmap word keeps a round with three starting points from scanning the whole bitmap.
 //   phase D  local ids by first appearance (:193-233) without a map over all entities: sort (id, position) keys,
 //            flag the first position of every id, local id = number of flags before it.  Then the (h,r,t) order
 //            of the local triples as one sort of packed keys (:236).
@@ -62,8 +63,8 @@ struct UniIn {            // per universe, filled by the host
 struct WalkArgs {
     const int4* ent_range; const int2* head_rt; const int4* tail_rht; const int32_t* rel_ent;
     const UniIn* in;
-    uint32_t* q;          // [n][2][qwords] starting-point bitmaps (zero on entry)
-    int32_t qwords;
+    uint32_t* q;          // [n][2][qwords + swords] starting-point bitmaps + one summary bit per word (zero on entry)
+    int32_t qwords, swords;
     uint32_t* tree;       // scratch for pick trees that do not fit shared memory
     int32_t* got;         // [n][CAP][3] collected triples, global ids, collection order
     int32_t* tri;         // [n][CAP][3] local ids sorted (h,r,t)
@@ -153,6 +154,48 @@ __device__ int enumerate_clear(uint32_t* q, int words, int32_t* out, int cap, co
                 m &= m - 1;
                 const int idx = w * 32 + j;
                 out[o++] = value ? value[idx] : idx;
+            }
+        }
+    }
+    __syncwarp();
+    return base;
+}
+
+// A starting-point set: bitmap over the entities [qwords] followed by a summary [swords] with one bit per bitmap word, so
+// that a round with a handful of starting points (relation-rich graphs: a focus relation with three entities walks in
+// hundreds of rounds) does not scan the whole bitmap.
+__device__ __forceinline__ void set_insert(uint32_t* q, int qwords, int e) {
+    const int w = e >> 5;
+    atomicOr(&q[w], 1u << (e & 31));
+    atomicOr(&q[qwords + (w >> 5)], 1u << (w & 31));
+}
+// members in ascending order -> out[], set emptied; returns the count (<= cap, else -1)
+__device__ int set_enumerate_clear(uint32_t* q, int qwords, int swords, int32_t* out, int cap, int lane) {
+    uint32_t* S = q + qwords;
+    int base = 0;
+    for (int s0 = 0; s0 < swords; s0 += 32) {
+        const int si = s0 + lane;
+        const uint32_t sv = si < swords ? ld_cg(S + si) : 0u;
+        uint32_t nz = __ballot_sync(0xffffffffu, sv != 0);
+        if (sv) S[si] = 0;
+        while (nz) {
+            const int sl = __ffs(nz) - 1;
+            nz &= nz - 1;
+            const uint32_t group = __shfl_sync(0xffffffffu, sv, sl);   // the non-empty words among the 32 this summary word covers
+            const int w = (s0 + sl) * 32 + lane;
+            uint32_t m = ((group >> lane) & 1u) ? ld_cg(q + w) : 0u;
+            const int c = __popc(m);
+            const int incl = warp_incl_scan(c, lane);
+            int o = base + incl - c;
+            base += __shfl_sync(0xffffffffu, incl, 31);
+            if (base > cap) return -1;
+            if (m) {
+                q[w] = 0;
+                while (m) {
+                    const int j = __ffs(m) - 1;
+                    m &= m - 1;
+                    out[o++] = w * 32 + j;
+                }
             }
         }
     }
@@ -295,13 +338,14 @@ __global__ void __launch_bounds__(32) k_walk_universes(WalkArgs A) {
     // ---- phase C: the walk
     for (int i = lane; i < HASH_SLOTS; i += 32) hash[i] = -1;
     __syncwarp();
-    uint32_t* Q0 = A.q + (size_t)u * 2 * A.qwords;
+    const int qstride = A.qwords + A.swords;
+    uint32_t* Q0 = A.q + (size_t)u * 2 * qstride;
     int32_t* got = A.got + (size_t)u * CAP * 3;
     int ngot = 0, target = in.tc, rounds = 0;
     int last_dup = -1, dup_tol = 5, stall_tol = 20, last_size = 0;
     while (status == PK_WALK_OK && ngot < target) {
-        uint32_t* Qnext = Q0 + (size_t)((rounds + 1) & 1) * A.qwords;   // next round's starting points
-        uint32_t* Qlate = Q0 + (size_t)(rounds & 1) * A.qwords;         // skipped ones: the round after next
+        uint32_t* Qnext = Q0 + (size_t)((rounds + 1) & 1) * qstride;   // next round's starting points
+        uint32_t* Qlate = Q0 + (size_t)(rounds & 1) * qstride;         // skipped ones: the round after next
         int i = 0;
         if (lane == 0) {
             int4 er = fsz > 0 ? A.ent_range[X[0]] : make_int4(0, -1, 0, -1);
@@ -341,7 +385,7 @@ __global__ void __launch_bounds__(32) k_walk_universes(WalkArgs A) {
                         if (last_dup == e) --dup_tol; else last_dup = e;
                         if (dup_tol == 0) {
                             dup_tol = 5;
-                            atomicOr(&Qlate[e >> 5], 1u << (e & 31));
+                            set_insert(Qlate, A.qwords, e);
                             advance = true;
                         }
                         continue;
@@ -349,7 +393,7 @@ __global__ void __launch_bounds__(32) k_walk_universes(WalkArgs A) {
                     hash[s] = tid;
                     got[3 * ngot + 0] = h; got[3 * ngot + 1] = r; got[3 * ngot + 2] = t;
                     ++ngot;
-                    atomicOr(&Qnext[nxt >> 5], 1u << (nxt & 31));
+                    set_insert(Qnext, A.qwords, nxt);
                     advance = true;
                 }
                 if (status != PK_WALK_OK) break;
@@ -363,10 +407,10 @@ __global__ void __launch_bounds__(32) k_walk_universes(WalkArgs A) {
         status = __shfl_sync(0xffffffffu, status, 0);
         if (status != PK_WALK_OK) break;
         // the starting points this round did not reach stay for the round after next (:112-113,170)
-        for (int k2 = i + lane; k2 < fsz; k2 += 32) atomicOr(&Qlate[X[k2] >> 5], 1u << (X[k2] & 31));
+        for (int k2 = i + lane; k2 < fsz; k2 += 32) set_insert(Qlate, A.qwords, X[k2]);
         __threadfence();
         __syncwarp();
-        fsz = enumerate_clear(Qnext, A.qwords, X, CAP, nullptr, true, lane);
+        fsz = set_enumerate_clear(Qnext, A.qwords, A.swords, X, CAP, lane);
         if (fsz < 0) { status = PK_WALK_TOO_LARGE; break; }
         ++rounds;
         if (ngot == last_size) --stall_tol;
@@ -524,13 +568,13 @@ int pk_walk_device_check(void) {
 int pk_walk_scratch_bytes(int n, int64_t* out3) {
     if (!out3 || n < 0) return pk::fail(PK_ERR_ARG, "pk_walk_scratch_bytes: bad argument");
     const pk::Graph& g = pk::G().graph;
-    const int64_t qwords = (g.n_ent + 31) / 32;
+    const int64_t qwords = (g.n_ent + 31) / 32, swords = (qwords + 31) / 32;
     int64_t worst = 0;
     for (int64_t r = 0; r < g.n_rel; ++r) {
         const int64_t nf = g.rel_ent_off[(size_t)r + 1] - g.rel_ent_off[(size_t)r];
         if (tree_words(nf) * 4 > SM_TREE_BYTES) worst = std::max(worst, tree_words(nf));
     }
-    out3[0] = (int64_t)n * 2 * qwords * 4;
+    out3[0] = (int64_t)n * 2 * (qwords + swords) * 4;
     out3[1] = (int64_t)n * CAP * 3 * 4;
     out3[2] = (int64_t)n * worst * 4;
     return PK_OK;
@@ -607,12 +651,12 @@ int pk_universes_walk_device(int n, const int64_t* seeds, const int64_t* tcs, co
         }
     }
     PK_CUDA(cudaMemcpyAsync(g_ring.d[slot], in, (size_t)n * sizeof(UniIn), cudaMemcpyHostToDevice, st));
-    const int64_t qwords = (g.n_ent + 31) / 32;
-    PK_CUDA(cudaMemsetAsync(d_bitmaps, 0, (size_t)n * 2 * (size_t)qwords * 4, st));
+    const int64_t qwords = (g.n_ent + 31) / 32, swords = (qwords + 31) / 32;
+    PK_CUDA(cudaMemsetAsync(d_bitmaps, 0, (size_t)n * 2 * (size_t)(qwords + swords) * 4, st));
     WalkArgs A;
     A.ent_range = g_graph.ent_range; A.head_rt = g_graph.head_rt; A.tail_rht = g_graph.tail_rht; A.rel_ent = g_graph.rel_ent;
     A.in = g_ring.d[slot];
-    A.q = d_bitmaps; A.qwords = (int32_t)qwords;
+    A.q = d_bitmaps; A.qwords = (int32_t)qwords; A.swords = (int32_t)swords;
     A.tree = d_trees; A.got = d_got; A.tri = d_tri; A.ent_remap = d_ent_remap; A.rel_remap = d_rel_remap; A.sizes = d_sizes;
     k_walk_universes<<<n, 32, SM_WALK_TOTAL, st>>>(A);
     PK_LAUNCHED("k_walk_universes");

@@ -10,11 +10,14 @@ from openke import _native as N
 from openke.data import TrainDataLoader
 from openke.universe_walk import DeviceWalker
 
-path = util.materialize_wn18(tempfile.mkdtemp())
+import bench
+wl = sys.argv[1] if len(sys.argv) > 1 else "m2"
+path = bench.workload_dataset(wl)[0] if wl != "m2" else util.materialize_wn18(tempfile.mkdtemp())
+print("workload", wl)
 dl = TrainDataLoader(in_path=path, nbatches=20, threads=8, bern_flag=0, filter_flag=0, neg_ent=1, random_seed=4)
 L = dl.lib
 w = DeviceWalker(L, torch.device("cuda", 0))
-for n in (1, 100, 1000):
+for n in (1, 100, 125, 1000):
     seeds = np.arange(4, 4 + n, dtype=np.int64)
     tcs, bals = np.zeros(n, dtype=np.int64), np.zeros(n, dtype=np.float32)
     for i in range(n):
@@ -32,8 +35,8 @@ for n in (1, 100, 1000):
         torch.cuda.synchronize()
         t2 = time.perf_counter()
         res.release()
-    print("n=%5d device walk %.3f ms (submit call %.3f ms, until sizes on host %.3f ms); rounds max %d, statuses %s" % (
-        n, e0.elapsed_time(e1), (t1 - t0) * 1e3, (t2 - t0) * 1e3, int(s[:, 6].max()), np.unique(s[:, 5]).tolist()))
+    print("n=%5d device walk %.3f ms (submit call %.3f ms, until sizes on host %.3f ms); rounds max %d mean %.1f, draws mean %.0f, nT mean %.0f, statuses %s" % (
+        n, e0.elapsed_time(e1), (t1 - t0) * 1e3, (t2 - t0) * 1e3, int(s[:, 6].max()), s[:, 6].mean(), s[:, 4].mean(), s[:, 0].mean(), np.unique(s[:, 5]).tolist()))
     t0 = time.perf_counter()
     h = L.pk_universes_build_lean(n, N.addr(seeds), N.addr(tcs), N.addr(bals), 8)
     t1 = time.perf_counter()
