@@ -62,8 +62,10 @@ class DeviceWalker(object):
         return self.lib.pk_walk_device_check() == 0
 
     def _buffers(self, n):
+        key = self._graph_key()
+        self._free = [b for b in self._free if b["graph"] == key]    # buffers sized for a graph that is gone
         for i, b in enumerate(self._free):
-            if b["n"] >= n and b["graph"] == self._graph_key():
+            if b["n"] >= n:
                 return self._free.pop(i)
         cap, dev = self.cap, self.device
         need = np.zeros(3, dtype=np.int64)
