@@ -22,6 +22,7 @@ class WalkResult(object):
         self.seeds, self.tcs, self.bals, self.lcg, self.focus = seeds, tcs, bals, lcg, focus
         self.event = torch.cuda.Event(blocking=True)
         self.sizes = None
+        self.copied_remaps = False
 
     def wait(self):
         if self.sizes is None:
@@ -36,8 +37,12 @@ class WalkResult(object):
     def packed_remaps(self):
         """(ent_remap [sum nE], rel_remap [sum nR]) int32 numpy, universes back to back (what evaluation indexes)."""
         s = self.wait()
-        er = self.bufs["h_ent_remap"][:self.n].numpy()
-        rr = self.bufs["h_rel_remap"][:self.n].numpy()
+        if self.bufs["h_ent_remap"] is not None and self.copied_remaps:
+            er = self.bufs["h_ent_remap"][:self.n].numpy()
+            rr = self.bufs["h_rel_remap"][:self.n].numpy()
+        else:       # not copied behind the launch: fetch them now
+            er = self.bufs["ent_remap"][:self.n].cpu().numpy()
+            rr = self.bufs["rel_remap"][:self.n].cpu().numpy()
         nE, nR = s[:, 1].tolist(), s[:, 2].tolist()
         return (np.concatenate([er[i, :nE[i]] for i in range(self.n)]), np.concatenate([rr[i, :nR[i]] for i in range(self.n)]))
 
@@ -112,5 +117,6 @@ class DeviceWalker(object):
                 b["h_ent_remap"][:n].copy_(b["ent_remap"][:n], non_blocking=True)
                 b["h_rel_remap"][:n].copy_(b["rel_remap"][:n], non_blocking=True)
                 self.d2h_bytes += n * 3 * self.cap * 4
+                res.copied_remaps = True
             res.event.record(self.stream)
         return res
