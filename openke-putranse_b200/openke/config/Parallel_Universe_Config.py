@@ -191,6 +191,13 @@ class Parallel_Universe_Config(Tester):
         self.device_walk = True
         self.device_walk_depth = 2
         self._walker = None
+        # Validation every `valid_steps` universes re-evaluates an ensemble that only GROWS: the [keys, E] min-energy matrix of
+        # a key set (valid split, test split) stays resident on the device and an evaluation folds in only the chunks trained
+        # since the previous one (min is associative and idempotent, so the ranks are those of a full evaluation).  1.6 GB
+        # for a WN18 split; key sets above the budget are evaluated tile by tile from scratch as before.
+        self.energy_cache = True
+        self.energy_cache_bytes = 24 << 30
+        self._energy_cache = {}
         self.max_energy_bytes = 8 << 30   # upper bound for the [keys, E] energy tile buffers of an evaluation (three of them)
         self.eval_tile_rows = 4096        # key rows per energy tile (a tile is the unit of the NCCL min all-reduce); 671 MB on WN18
         self.training_duration = 0.0
@@ -932,8 +939,23 @@ class Parallel_Universe_Config(Tester):
         # items come out sorted by key row, so a tile's items are a contiguous range
         # (a key set that comes back — the valid split every valid_steps universes, the test split — finds the items
         # of the chunks it has already seen cached on the chunk: `keys_token` names the key set)
+        cache = None
+        if (self.energy_cache and keys_token is not None and not tuples and self.incremental_strategy != "deprecate"
+                and K * E * 4 <= int(self.energy_cache_bytes)):
+            ckey = (keys_token, K, E, dev)
+            cache = self._energy_cache.get(ckey)
+            if cache is None:
+                for old_key in [k_ for k_ in self._energy_cache if k_[0] == keys_token]:
+                    del self._energy_cache[old_key]
+                while len(self._energy_cache) >= 3:          # key sets that went away (snapshots of the incremental setting)
+                    del self._energy_cache[next(iter(self._energy_cache))]
+                energy_all = torch.empty((K, E), dtype=torch.float32, device=dev)
+                N.check(lib.pk_fill_inf(energy_all.data_ptr(), energy_all.numel(), st), "pk_fill_inf")
+                cache = self._energy_cache[ckey] = {"energy": energy_all, "folded": set()}
         per_chunk = []
         for ck in self._chunks:
+            if cache is not None and id(ck) in cache["folded"]:
+                continue                   # its universes have spoken in this matrix already
             ix = self._chunk_index(ck)
             dep = self._deprecated_version if self.incremental_strategy == "deprecate" else 0
             cached = ck.items_cache.get((keys_token, rows_per_tile, dep)) if keys_token is not None else None
@@ -955,6 +977,29 @@ class Parallel_Universe_Config(Tester):
             per_chunk.append((ck, ix, d_items, bounds, cfg_e, tab_e))
         self.timings["eval_host_prep"] += time.perf_counter() - t_host
         n_tiles = (K + rows_per_tile - 1) // rows_per_tile
+        if cache is not None:
+            # resident matrix: fold the new chunks in, tile by tile (a tile is still the unit of the all-reduce and of the
+            # rank counting), then hand every tile to the consumer
+            for ti in range(n_tiles):
+                k0 = ti * rows_per_tile
+                k1 = min(K, k0 + rows_per_tile)
+                energy = cache["energy"][k0:k1]
+                for ck, ix, d_items, bounds, cfg, tab in per_chunk:
+                    i0, i1 = int(bounds[ti]), int(bounds[ti + 1])
+                    if i1 == i0:
+                        continue
+                    N.check(lib.pk_universe_energies(ctypes.byref(cfg), ctypes.byref(tab), ix["d_eoff"].data_ptr(),
+                                                     ix["d_roff"].data_ptr(), ix["d_nE"].data_ptr(), ix["d_remap"].data_ptr(),
+                                                     d_items.data_ptr() + i0 * 24, i1 - i0, energy.data_ptr() - k0 * E * 4, E, st),
+                            "pk_universe_energies")
+                    self.gpu_launches += lib.pk_last_launch_count()
+                if sharded:    # in place: the minimum over the ranks is as good a starting point for later folds as the local one
+                    dist.all_reduce(energy, op=dist.ReduceOp.MIN)
+                consume(ti, k0, k1, energy, None)
+            for ck in self._chunks:
+                cache["folded"].add(id(ck))
+            cache["chunks"] = list(self._chunks)      # keeps the ids alive and unique
+            return rows_per_tile
         bufs = [torch.empty((rows_per_tile, E), dtype=torch.float32, device=dev) for _ in range(min(3, n_tiles))]
         tbufs = [torch.empty(rows_per_tile, dtype=torch.float32, device=dev) for _ in bufs] if tuples else None
 
@@ -1241,6 +1286,7 @@ class Parallel_Universe_Config(Tester):
     def reset_evaluation_helpers(self):
         """Reference :545-554."""
         self._rank_cache.clear()
+        self._energy_cache.clear()
         self.incremental_strategy = "normal"
 
     # ---- incremental setting: universes that hold a since-deleted triple (reference :817-823)
@@ -1500,6 +1546,7 @@ class Parallel_Universe_Config(Tester):
                   self.entity_universes, self.relation_universes):
             m.clear()
         self._rank_cache.clear()
+        self._energy_cache.clear()
 
     def process_state_dict(self, state, shard_states=()):
         if "format" not in state and "trained_embedding_spaces" in state:

@@ -489,3 +489,37 @@ def test_incremental_putranse_over_three_snapshots(tmp_path, golden):
         assert pu.incremental_strategy == "normal"
         assert 0.0 <= pu.valid() <= 1.0
     L.pk_incremental_reset()
+
+
+@pytest.mark.gpu
+def test_resident_energy_matrix_gives_the_ranks_of_a_full_evaluation(tmp_path):
+    """Validation re-evaluates an ensemble that only grows: the min-energy matrix of a key set stays on the device and
+    an evaluation folds in only the chunks trained since the previous one.  After every training call the ranks must be
+    EXACTLY those of an evaluation from scratch (min is associative and idempotent), for both splits, and a chunk must be
+    folded once."""
+    path, _ = _small_graph(tmp_path)
+    pu = _pu(path)
+    launches = []
+    for n in (4, 3, 5):
+        pu.train_parallel_universes(n)
+        g0 = pu.gpu_launches
+        pu.run_link_prediction()
+        test_inc = pu.last_ranks.copy()
+        hit10_inc = pu.valid()
+        launches.append(pu.gpu_launches - g0)
+        assert len(pu._energy_cache) == 2 and all(len(c["folded"]) == len(pu._chunks) for c in pu._energy_cache.values())
+        pu.energy_cache = False
+        pu._rank_cache.clear()
+        pu.run_link_prediction()
+        assert np.array_equal(test_inc, pu.last_ranks), n
+        assert pu.valid() == hit10_inc
+        pu.energy_cache = True
+        pu._rank_cache.clear()
+        pu.run_link_prediction()                      # nothing new to fold: ranking only, same ranks
+        assert np.array_equal(test_inc, pu.last_ranks)
+    # a replaced ensemble starts from an empty matrix
+    pu.save_parameters(str(tmp_path / "e.ckpt"))
+    pu.load_parameters(str(tmp_path / "e.ckpt"))
+    assert not pu._energy_cache
+    pu.run_link_prediction()
+    assert np.array_equal(test_inc, pu.last_ranks)
