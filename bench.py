@@ -495,6 +495,28 @@ def run_extras(args, path, dev):
         del p3
     except Exception as e:
         ex["m2_1000_universes_per_call"] = {"error": "%s: %s" % (type(e).__name__, e)}
+    try:   # the static WN18 experiment as its script runs it (experiments/static_experiment_PuTransE_on_WN18.py:43-110), 1/3 length:
+        # 2 000 universes, validation on the valid split every 100 universes (early stopping off), then the test evaluation
+        import contextlib
+        import io
+        p5 = make_pu(path)
+        p5.valid_steps, p5.early_stopping_patience = 100, 10 ** 9
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):
+            p5.train_parallel_universes(2000)
+            t1 = time.perf_counter()
+            m5 = p5.run_link_prediction()
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        ex["static_experiment_2000_universes_valid_every_100"] = {
+            "seconds_training_with_20_validations": t1 - t0, "seconds_test_evaluation": t2 - t1, "positive_triples": int(p5.positive_triples),
+            "positive_triples_per_s_including_validation": p5.positive_triples / (t1 - t0), "best_valid_hits10": float(p5.best_hit10),
+            "test_filtered": {"mrr": float(m5[0]), "mr": float(m5[1]), "hits10": float(m5[2])},
+            "note": "validation folds only the 100 new universes into the resident min-energy matrix of the valid split"}
+        del p5
+    except Exception as e:
+        ex["static_experiment_2000_universes_valid_every_100"] = {"error": "%s: %s" % (type(e).__name__, e)}
     me = [sys.executable, os.path.abspath(__file__), "--no-extras", "--no-s1", "--no-cpu-baseline", "--steps", "8", "--warmup", "3"]
     for key, extra in (("putransh", ["--model", "transh", "--no-eval"]), ("putransd", ["--model", "transd", "--no-eval"]),
                        ("m4_fb15k_shape_1000_universes", ["--workload", "m4", "--universes", "1000", "--steps", "3", "--e2e-steps", "6"])):

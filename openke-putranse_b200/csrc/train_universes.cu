@@ -976,6 +976,8 @@ struct DescSlot {
     bool busy = false;
 };
 thread_local std::vector<DescSlot> g_desc_pool;
+thread_local size_t g_desc_next_wait = 0;
+constexpr size_t kMaxDescSlots = 8;
 constexpr size_t kDescArea = 256;   // one descriptor (128 B), padded
 
 // The unstaged class (universes whose tables do not fit in shared memory) runs beside the staged one
@@ -1000,6 +1002,17 @@ DescSlot* acquire_desc(size_t bytes) {
         else if (!grow || s.cap > grow->cap) grow = &s;
     }
     if (fit) return fit;
+    // A caller that queues launches faster than they finish (twenty steps issued back to back) would grow the pool by one
+    // buffer per launch, and every allocation (cudaMalloc + cudaHostAlloc) stalls behind the launches in flight: beyond
+    // kMaxDescSlots buffers the launching thread waits for the oldest launch instead.
+    if (!grow && g_desc_pool.size() >= kMaxDescSlots) {
+        DescSlot* oldest = &g_desc_pool[g_desc_next_wait % g_desc_pool.size()];
+        ++g_desc_next_wait;
+        cudaEventSynchronize(oldest->done);
+        oldest->busy = false;
+        if (oldest->cap >= bytes) return oldest;
+        grow = oldest;
+    }
     const size_t want = bytes + bytes / 2 + (1u << 20);
     if (grow) {
         if (grow->d) cudaFree(grow->d);
