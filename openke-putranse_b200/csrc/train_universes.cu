@@ -974,10 +974,11 @@ struct DescSlot {
     }
     cudaEvent_t done = nullptr;
     bool busy = false;
+    uint64_t seq = 0;      // launch order (the oldest busy buffer is the one to wait for)
 };
 thread_local std::vector<DescSlot> g_desc_pool;
-thread_local size_t g_desc_next_wait = 0;
-constexpr size_t kMaxDescSlots = 8;
+thread_local uint64_t g_desc_seq = 0;
+constexpr size_t kMaxDescSlots = 16;
 constexpr size_t kDescArea = 256;   // one descriptor (128 B), padded
 
 // The unstaged class (universes whose tables do not fit in shared memory) runs beside the staged one
@@ -1006,8 +1007,9 @@ DescSlot* acquire_desc(size_t bytes) {
     // buffer per launch, and every allocation (cudaMalloc + cudaHostAlloc) stalls behind the launches in flight: beyond
     // kMaxDescSlots buffers the launching thread waits for the oldest launch instead.
     if (!grow && g_desc_pool.size() >= kMaxDescSlots) {
-        DescSlot* oldest = &g_desc_pool[g_desc_next_wait % g_desc_pool.size()];
-        ++g_desc_next_wait;
+        DescSlot* oldest = &g_desc_pool[0];
+        for (auto& s : g_desc_pool)
+            if (s.seq < oldest->seq) oldest = &s;
         cudaEventSynchronize(oldest->done);
         oldest->busy = false;
         if (oldest->cap >= bytes) return oldest;
@@ -1172,6 +1174,7 @@ extern "C" int pk_train_universes(const pk_model_cfg* cfg, const pk_tables* pack
                           : (cfg->model == PK_TRANSH ? launch_model1(lay, P1, 0, 1, own.total, st) : launch_model2(lay, P1, 0, 1, own.total, st));
                 if (rc1 != PK_OK) return rc1;
                 slot1->busy = true;
+                slot1->seq = ++g_desc_seq;
                 PK_CUDA(cudaEventRecord(slot1->done, st));
             }
             continue;
@@ -1213,6 +1216,7 @@ extern "C" int pk_train_universes(const pk_model_cfg* cfg, const pk_tables* pack
         else rc = launch_model2(lay, P, c == 0, nblk, s.total, st);
         if (rc != PK_OK) return rc;
         slot->busy = true;
+        slot->seq = ++g_desc_seq;
         PK_CUDA(cudaEventRecord(slot->done, st));
     }
     if (both) {
