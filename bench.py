@@ -794,8 +794,9 @@ def reference_arm(path, budget_s=0.0, steps=1, warmup=0, universes_per_step=1, s
     return {"value": d["value"], "unit": "positive triples/s", "cores": d["cores"], "kind": "reference",
             "sample": "the unmodified reference package (baseline/_ref: its Python + its Base.so) on universes %d..%d of the same seed "
                       "sequence at their drawn epochs: %d train steps, %d positive triples in %.1f s; torch %s with %d intra-op threads, "
-                      "8 sampler pthreads, host has %d cores%s" % (us[0][0], us[-1][1], d["train_steps"], d["positives"], d["seconds"],
-                                                                  d["torch"], d["torch_threads"], d["cores"],
+                      "8 sampler pthreads, host has %d cores (the faster of all-threads / one thread on a 4-epoch universe: %s s)%s" % (
+                          us[0][0], us[-1][1], d["train_steps"], d["positives"], d["seconds"], d["torch"], d["torch_threads"], d["cores"],
+                          d.get("thread_calibration_s"),
                                                                   "; %d late steps ran with epochs capped at 5" % d["steps_with_capped_epochs"]
                                                                   if d["steps_with_capped_epochs"] else "")}
 
@@ -822,9 +823,10 @@ def run_reference(args):
         base = {"value": v, "unit": "positive triples/s", "cores": d["cores"], "kind": "reference",
                 "sample": "step i = universe i (seeds 4..) trained by the unmodified reference package from baseline/_ref "
                           "(Parallel_Universe_Config.train_parallel_universes(%d), use_gpu False) at its drawn 50-199 epochs: %d train steps, "
-                          "%d positive triples in %.1f s; torch %s with %d intra-op threads + 8 sampler pthreads on %d host cores; warm-up "
+                          "%d positive triples in %.1f s; torch %s with %d intra-op threads (the faster of all-threads / one thread on a "
+                          "4-epoch universe: %s s) + 8 sampler pthreads on %d host cores; warm-up "
                           "steps are 2-epoch universes%s" % (args.ref_universes, d["train_steps"], d["positives"], d["seconds"], d["torch"],
-                                                             d["torch_threads"], d["cores"],
+                                                             d["torch_threads"], d.get("thread_calibration_s"), d["cores"],
                                                              "; %d late steps ran with epochs capped at 5 (soft time limit)" %
                                                              d["steps_with_capped_epochs"] if d["steps_with_capped_epochs"] else "")}
     line = {"impl": "reference", "metric": "PuTransE positive triples/sec (all universes)", "value": v,

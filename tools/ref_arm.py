@@ -79,6 +79,19 @@ def main():
     pu.const_num_epochs = 2
     for _ in range(args.warmup):
         pu.train_parallel_universes(args.universes)
+    # the reference's tensors are tiny (a batch of 25-99 rows of 20 floats): torch's intra-op pool usually costs more than
+    # it gives.  Unless told otherwise, time the same 4-epoch universe with all threads and with one and keep the faster
+    # setting, so that the baseline is the reference at its best on this host.
+    calibration = {}
+    if not args.torch_threads:
+        pu.const_num_epochs = 4
+        for t_ in sorted({cores, torch.get_num_threads(), 1}, reverse=True):
+            torch.set_num_threads(t_)
+            pu.next_universe_id = 10 ** 6 + 500
+            t0 = time.perf_counter()
+            pu.train_parallel_universes(1)
+            calibration[t_] = time.perf_counter() - t0
+        torch.set_num_threads(min(calibration, key=calibration.get))
     pu.const_num_epochs = args.max_epochs or None
     pu.next_universe_id = args.first_universe
     counter["positives"] = counter["steps"] = 0
@@ -101,7 +114,8 @@ def main():
     out = {"kind": "reference", "cores": cores, "torch_threads": torch.get_num_threads(), "sampler_threads": 8,
            "torch": torch.__version__, "positives": counter["positives"], "train_steps": counter["steps"], "seconds": seconds,
            "value": counter["positives"] / seconds, "per_step": per_step, "max_epochs": args.max_epochs,
-           "steps_with_capped_epochs": int(capped), "steps_done": len(per_step)}
+           "steps_with_capped_epochs": int(capped), "steps_done": len(per_step),
+           "thread_calibration_s": {str(k): round(v, 3) for k, v in calibration.items()}}
     if args.eval:
         if args.eval_triples:
             pu.data_loader.testTotal = min(pu.data_loader.testTotal, args.eval_triples)
