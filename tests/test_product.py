@@ -148,8 +148,10 @@ def test_validator_matches_manual_loop_and_oracle(tmp_path):
     lib = vl.lib
     lib.validInit()
     for index, (dh, dt) in enumerate(vl):
-        lib.validHead(N.addr(v.valid_one_step(dh)), index)
-        lib.validTail(N.addr(v.valid_one_step(dt)), index)
+        s_h = v.valid_one_step(dh)            # keep the arrays alive across the calls: N.addr() is a bare address
+        lib.validHead(N.addr(s_h), index)
+        s_t = v.valid_one_step(dt)
+        lib.validTail(N.addr(s_t), index)
     assert lib.getValidHit10() == pytest.approx(got, abs=1e-7)
     o = on.Oracle()
     o.import_train(tr, 600, 6)
