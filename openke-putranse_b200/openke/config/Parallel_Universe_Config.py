@@ -169,6 +169,12 @@ class Parallel_Universe_Config(Tester):
         # are LAUNCHED, so a caller that trains chunk after chunk keeps several launches in flight; anything
         # that reads results synchronises by itself (synchronize()).
         self.async_training = False
+        # A validation that cannot end the training (bad_counts + 1 < early_stopping_patience) is run BEHIND the launch of
+        # the next chunk, on the ensemble as it was when the validation fell due (`_view`): the GPU trains chunk i+1 while
+        # chunk i's universes are folded into the valid split's energy matrix and ranked.  Same validations, same order,
+        # same checkpoints; a validation that can stop the training runs before anything else is launched.
+        self.pipeline_validation = True
+        self._view = None                 # (chunks visible, next_universe_id) while a deferred validation runs
         self._slots = None
         self._launch_index = 0
         self._pinned = {}
@@ -354,14 +360,23 @@ class Parallel_Universe_Config(Tester):
         self.synchronize()
         return self._universe_losses
 
+    def _visible_chunks(self):
+        return self._chunks if self._view is None else self._chunks[:self._view[0]]
+
+    def _visible_next_id(self):
+        return self.next_universe_id if self._view is None else self._view[1]
+
     def synchronize(self):
         """Wait for every launch in flight (training is asynchronous between calls; everything that reads
-        trained tables goes through here first)."""
+        trained tables goes through here first).  Inside a deferred validation only the launches of the chunks
+        it looks at are waited for."""
         if self._slots:
-            for slot in self._slots:
+            seen = None if self._view is None else {id(ck) for ck in self._visible_chunks()}
+            slots = [s_ for s_ in self._slots if seen is None or s_.chunk is None or id(s_.chunk) in seen]
+            for slot in slots:
                 self._retire(slot)
             dev = self._device()
-            for slot in self._slots:   # later work on the caller's stream is ordered after the launches
+            for slot in slots:   # later work on the caller's stream is ordered after the launches
                 torch.cuda.current_stream(dev).wait_stream(slot.stream)
 
     def _sampling_key(self, universe_ids):
@@ -861,43 +876,77 @@ class Parallel_Universe_Config(Tester):
         t.n_ent, t.n_rel = int(ck.eoff[-1]), int(ck.roff[-1])
         return t
 
+    def _validate(self, view):
+        """The validation branch of reference :330-356 on the ensemble `view` = (chunks, next_universe_id) describes.
+        Returns True when early stopping ends the training."""
+        self._view = view
+        try:
+            print("Universe %d has finished, validating..." % (view[1] - 1))
+            self.eval_universes(eval_mode="valid")
+            hit10 = self.valid()
+            print("Current hit@10: {}".format(hit10))
+            if hit10 > self.best_hit10:
+                self.best_hit10 = hit10
+                print("Best model | hit@10 of valid set is %f" % self.best_hit10)
+                if self.checkpoint_dir:
+                    self.save_model("Best_model_Pu{}_{}.ckpt".format(self.embedding_model.__name__, self.training_identifier))
+                self.bad_counts = 0
+            else:
+                print("Hit@10 of valid set is %f | bad count is %d" % (hit10, self.bad_counts))
+                self.bad_counts += 1
+            if self.bad_counts == self.early_stopping_patience:
+                print("Early stopping at universe {}".format(view[1] - 1))
+                return True
+            return False
+        finally:
+            self._view = None
+
     def train_parallel_universes(self, num_of_embedding_spaces):
         """Reference :316-367.  Universes are trained in chunks that end where the reference would
-        validate (every ``valid_steps`` universes); with torch.distributed each rank trains its share."""
+        validate (every ``valid_steps`` universes); with torch.distributed each rank trains its share.
+        The chunks of one call are launched without waiting for each other; a validation that cannot end the
+        training runs behind the next chunk's launch (pipeline_validation)."""
         dist, rank, world = _dist()
-        training_duration = 0.0
+        t_call, t_valid = time.time(), 0.0
         done = 0
-        while done < num_of_embedding_spaces:
+        pending = None          # a validation deferred behind the next launch: (chunks visible, next_universe_id)
+        stop = False
+
+        def flush():
+            nonlocal pending, t_valid, stop
+            if pending is not None:
+                t0 = time.time()
+                stop = self._validate(pending) or stop
+                t_valid += time.time() - t0
+                pending = None
+
+        while done < num_of_embedding_spaces and not stop:
             c = min(num_of_embedding_spaces - done, self.valid_steps - (done % self.valid_steps), self.max_chunk * world)
-            start = time.time()
             ids = [self.next_universe_id + j for j in range(c)]
             mine = [u for u in ids if u % world == rank]
             if mine:
                 self._train_chunk(mine, prefetch_ids=[u + c for u in mine])
             self.next_universe_id += c
             done += c
-            if not self.async_training:
-                self.synchronize()
-            training_duration += time.time() - start
+            flush()             # the validation that fell due before this chunk (it could not stop the training)
             if done % self.valid_steps == 0:
-                print("Universe %d has finished, validating..." % (self.next_universe_id - 1))
-                self.eval_universes(eval_mode="valid")
-                hit10 = self.valid()
-                print("Current hit@10: {}".format(hit10))
-                if hit10 > self.best_hit10:
-                    self.best_hit10 = hit10
-                    print("Best model | hit@10 of valid set is %f" % self.best_hit10)
-                    if self.checkpoint_dir:
-                        self.save_model("Best_model_Pu{}_{}.ckpt".format(self.embedding_model.__name__, self.training_identifier))
-                    self.bad_counts = 0
+                view = (len(self._chunks), self.next_universe_id)
+                can_stop = self.bad_counts + 1 >= self.early_stopping_patience
+                if (self.pipeline_validation and not can_stop and done < num_of_embedding_spaces
+                        and self.training_setting == "static"):
+                    pending = view
                 else:
-                    print("Hit@10 of valid set is %f | bad count is %d" % (hit10, self.bad_counts))
-                    self.bad_counts += 1
-                if self.bad_counts == self.early_stopping_patience:
-                    print("Early stopping at universe {}".format(self.next_universe_id - 1))
-                    break
+                    t0 = time.time()
+                    stop = self._validate(view)
+                    t_valid += time.time() - t0
             if self.save_steps and self.checkpoint_dir and (done // self.save_steps) > ((done - c) // self.save_steps):
-                self.save_model()
+                flush()         # the checkpoint carries best_hit10 / bad_counts: nothing may be outstanding
+                if not stop:
+                    self.save_model()
+        flush()
+        if not self.async_training:
+            self.synchronize()
+        training_duration = time.time() - t_call - t_valid
         self.training_duration += training_duration
         print("Time took for creation of embedding spaces: {:5.3f}s".format(training_duration))
 
@@ -953,7 +1002,7 @@ class Parallel_Universe_Config(Tester):
                 N.check(lib.pk_fill_inf(energy_all.data_ptr(), energy_all.numel(), st), "pk_fill_inf")
                 cache = self._energy_cache[ckey] = {"energy": energy_all, "folded": set()}
         per_chunk = []
-        for ck in self._chunks:
+        for ck in self._visible_chunks():
             if cache is not None and id(ck) in cache["folded"]:
                 continue                   # its universes have spoken in this matrix already
             ix = self._chunk_index(ck)
@@ -996,7 +1045,7 @@ class Parallel_Universe_Config(Tester):
                 if sharded:    # in place: the minimum over the ranks is as good a starting point for later folds as the local one
                     dist.all_reduce(energy, op=dist.ReduceOp.MIN)
                 consume(ti, k0, k1, energy, None)
-            for ck in self._chunks:
+            for ck in self._visible_chunks():
                 cache["folded"].add(id(ck))
             cache["chunks"] = list(self._chunks)      # keeps the ids alive and unique
             return rows_per_tile
@@ -1276,7 +1325,7 @@ class Parallel_Universe_Config(Tester):
 
     def _rank_state(self, eval_mode):
         loader = self.data_loader if eval_mode == "test" else self.valid_dataloader
-        return (self.next_universe_id, self.incremental_strategy, self.missing_embedding_handling, id(loader.eval_arrays()),
+        return (self._visible_next_id(), self.incremental_strategy, self.missing_embedding_handling, id(loader.eval_arrays()),
                 len(getattr(self.train_dataloader, "deleted_triple_set", ())))
 
     def eval_universes(self, eval_mode):
@@ -1445,18 +1494,19 @@ class Parallel_Universe_Config(Tester):
     # paths are the same in both packages) and which load_parameters here imports.
     def save_model(self, filename=None):
         if not filename:
-            filename = "Pu{}_learned_spaces-{}_{}.ckpt".format(self.embedding_model.__name__, self.next_universe_id,
+            filename = "Pu{}_learned_spaces-{}_{}.ckpt".format(self.embedding_model.__name__, self._visible_next_id(),
                                                                self.training_identifier)
         self.save_parameters(os.path.join("{}{}".format(self.checkpoint_dir, filename)))
 
     def extend_state_dict(self):
         self.synchronize()
         chunks = []
-        for ck in self._chunks:
+        for ck in self._visible_chunks():
             chunks.append({"ids": ck.ids, "nT": ck.nT, "nE": ck.nE, "nR": ck.nR, "ent_remap": ck.ent_remap,
                            "rel_remap": ck.rel_remap, "tables": {k: v.cpu() for k, v in ck.tables.items()}})
-        return {"format": "putranse-b200/flat-1", "next_universe_id": self.next_universe_id, "chunks": chunks,
-                "universe_hyper": self.universe_hyper, "embedding_model": self.embedding_model.__name__,
+        upto = self._visible_next_id()
+        return {"format": "putranse-b200/flat-1", "next_universe_id": upto, "chunks": chunks,
+                "universe_hyper": {u: h for u, h in self.universe_hyper.items() if u < upto}, "embedding_model": self.embedding_model.__name__,
                 "embedding_model_param": self.embedding_model_param, "best_hit10": self.best_hit10,
                 "bad_counts": self.bad_counts, "initial_random_seed": self.initial_random_seed,
                 "ent_tot": self.ent_tot, "rel_tot": self.rel_tot}
@@ -1467,7 +1517,7 @@ class Parallel_Universe_Config(Tester):
         self.synchronize()
         spaces, ent_maps, rel_maps = {}, defaultdict(defaultdict_int), defaultdict(defaultdict_int)
         ent_univ, rel_univ = defaultdict(set), defaultdict(set)
-        for ck in self._chunks:
+        for ck in self._visible_chunks():
             for i, u in enumerate(ck.ids):
                 with torch.random.fork_rng(devices=[]):
                     sp = self.embedding_model(int(ck.nE[i]), int(ck.nR[i]), **self.embedding_model_param)
@@ -1485,7 +1535,7 @@ class Parallel_Universe_Config(Tester):
                     rel_univ[g].add(u)
         for u, sp in self.trained_embedding_spaces._extra.items():
             spaces[u] = sp
-        state = {"initial_num_universes": self.initial_num_universes, "next_universe_id": self.next_universe_id,
+        state = {"initial_num_universes": self.initial_num_universes, "next_universe_id": self._visible_next_id(),
                  "trained_embedding_spaces": spaces, "entity_id_mappings": ent_maps, "relation_id_mappings": rel_maps,
                  "entity_universes": ent_univ, "relation_universes": rel_univ}
         for k_ in ("min_margin", "max_margin", "min_lr", "max_lr", "min_num_epochs", "max_num_epochs", "min_triple_constraint",

@@ -525,3 +525,44 @@ def test_resident_energy_matrix_gives_the_ranks_of_a_full_evaluation(tmp_path):
     assert not pu._energy_cache
     pu.run_link_prediction()
     assert np.array_equal(test_inc, pu.last_ranks)
+
+
+@pytest.mark.gpu
+def test_validation_runs_behind_the_next_launch_on_the_ensemble_it_fell_due_for(tmp_path):
+    """pipeline_validation: a validation that cannot stop the training is run after the NEXT chunk has been launched,
+    on the ensemble as it was when the validation fell due.  The best checkpoint written by such a validation must hold
+    exactly that ensemble (its universes, its next_universe_id) and reproduce the validation's hits@10; the history is
+    the one synchronous validation gives (up to the float reduction order of training)."""
+    path, _ = _small_graph(tmp_path)
+    hist = {}
+    for flag in (True, False):
+        ck = str(tmp_path / ("ck%d" % flag)) + "/"
+        pu = _pu(path, ckpt_dir=ck, valid_steps=3, save_steps=None, patience=10 ** 6, epochs=3)
+        pu.pipeline_validation = flag
+        seen = []
+        orig = pu.valid
+
+        def recording_valid(pu=pu, orig=orig, seen=seen):
+            h = orig()
+            seen.append((pu._visible_next_id(), len(pu._visible_chunks()), len(pu._chunks), h))
+            return h
+        pu.valid = recording_valid
+        pu.train_parallel_universes(15)
+        assert [s_[0] for s_ in seen] == [3, 6, 9, 12, 15] and [s_[1] for s_ in seen] == [1, 2, 3, 4, 5]
+        if flag:     # every validation but the last ran with the next chunk already launched
+            assert [s_[2] for s_ in seen] == [2, 3, 4, 5, 5]
+        else:
+            assert [s_[2] for s_ in seen] == [1, 2, 3, 4, 5]
+        best_i = int(np.argmax([s_[3] for s_ in seen]))
+        assert pu.best_hit10 == seen[best_i][3] and pu.next_universe_id == 15
+        p2 = _pu(path, ckpt_dir=ck)
+        p2.load_parameters("Best_model_PuTransE_t.ckpt")
+        assert p2.next_universe_id == 3 * (best_i + 1) and sorted(p2._where) == list(range(3 * (best_i + 1)))
+        assert p2.valid() == pytest.approx(seen[best_i][3], abs=1e-7)
+        # the final state is the whole ensemble
+        pu.valid = orig
+        pu.energy_cache = False
+        pu._rank_cache.clear()
+        assert pu.valid() == pytest.approx(seen[-1][3], abs=1e-7)
+        hist[flag] = [s_[3] for s_ in seen]
+    assert np.allclose(hist[True], hist[False], atol=0.02)
