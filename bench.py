@@ -515,7 +515,8 @@ def run_extras(args, path, dev):
             "seconds_training_with_20_validations": t1 - t0, "seconds_test_evaluation": t2 - t1, "positive_triples": int(p5.positive_triples),
             "positive_triples_per_s_including_validation": p5.positive_triples / (t1 - t0), "best_valid_hits10": float(p5.best_hit10),
             "test_filtered": {"mrr": float(m5[0]), "mr": float(m5[1]), "hits10": float(m5[2])},
-            "note": "validation folds only the 100 new universes into the resident min-energy matrix of the valid split"}
+            "note": "a validation folds only the 100 new universes into the resident min-energy matrix of the valid split and runs behind "
+                    "the next chunk's launch; first use of a fresh object: includes slab / matrix allocation"}
         del p5
     except Exception as e:
         ex["static_experiment_2000_universes_valid_every_100"] = {"error": "%s: %s" % (type(e).__name__, e)}
