@@ -167,3 +167,59 @@ def test_orchestrator_trains_the_same_ensemble_with_device_and_host_universes(tm
         with pytest.raises(N.NativeError, match="collected no triples"):
             none.train_parallel_universes(2)
             none.synchronize()
+
+
+def test_device_walk_against_reference_goldens_and_the_oracle(wn18_dir, golden):
+    """The GPU builder pinned directly: (1) to the universes the UNMODIFIED reference built (tests/golden/universe.npz,
+    minted by getParallelUniverse through the reference's own Python: sizes, both remaps, the collected triples in global
+    ids, the local (h,r,t) list); (2) to the oracle's plain restatement of UniverseConstructor.h on 72 further universes
+    of the static script's ranges."""
+    import random
+    import torch
+    from openke.data import TrainDataLoader
+    from openke.universe_walk import DeviceWalker
+    from oracle import native as on
+    dl = TrainDataLoader(in_path=wn18_dir, nbatches=20, threads=8, bern_flag=0, filter_flag=0, neg_ent=1, random_seed=4)
+    walker = DeviceWalker(dl.lib, torch.device("cuda", 0))
+    cap = walker.cap
+    U = golden["universe"]
+    cases = [(int(s_), int(tc), float(b)) for s_, tc, b in U["cases"]]
+    keep = [i for i, c in enumerate(cases) if c[1] <= cap and int(np.float32(c[2]) * np.float32(c[1])) <= cap]
+    assert len(keep) >= 4
+    seeds = np.array([cases[i][0] for i in keep], np.int64)
+    tcs = np.array([cases[i][1] for i in keep], np.int64)
+    bals = np.array([cases[i][2] for i in keep], np.float32)
+    res = walker.submit(seeds, tcs, bals, 8)
+    s = res.wait()
+    torch.cuda.synchronize()
+    tri, got = res.bufs["tri"].cpu().numpy(), res.bufs["got"].cpu().numpy()
+    er, rr = res.bufs["ent_remap"].cpu().numpy(), res.bufs["rel_remap"].cpu().numpy()
+    for j, i in enumerate(keep):
+        assert s[j, 5] == 0 and tuple(s[j, :3]) == tuple(U["u%d_sizes" % i]), (i, s[j])
+        nT, nE, nR = (int(x) for x in s[j, :3])
+        assert np.array_equal(er[j, :nE], U["u%d_ent_remap" % i]) and np.array_equal(rr[j, :nR], U["u%d_rel_remap" % i])
+        assert np.array_equal(got[j, :nT], U["u%d_triples_global" % i])
+        assert np.array_equal(tri[j, :nT], U["u%d_triples_local" % i])
+    res.release()
+
+    w = np.load(os.path.join(util.GOLDEN, "wn18.npz"))
+    o = on.Oracle(threads=8, bern=0)
+    o.import_train(w["train"], 40943, 18)
+    rng = random.Random(7)
+    more = [(1000 + i, rng.randrange(500, 2000), rng.uniform(0.25, 0.5)) for i in range(72)]
+    more += [(5, 50, 0.02), (8, 700, 1.0), (10, 3, 0.5), (11, 2, 1.0)]
+    seeds = np.array([c[0] for c in more], np.int64)
+    tcs = np.array([c[1] for c in more], np.int64)
+    bals = np.array([c[2] for c in more], np.float32)
+    res = walker.submit(seeds, tcs, bals, 8)
+    s = res.wait()
+    torch.cuda.synchronize()
+    got = res.bufs["got"].cpu().numpy()
+    er, rr = res.bufs["ent_remap"].cpu().numpy(), res.bufs["rel_remap"].cpu().numpy()
+    for j, (seed, tc, bal) in enumerate(more):
+        o.seed(seed)
+        otri, oer, orr = o.universe(tc, float(np.float32(bal)))
+        assert s[j, 5] == 0, (j, seed, tc, bal, s[j])
+        assert np.array_equal(got[j, :s[j, 0]], otri), (j, seed, tc, bal)
+        assert np.array_equal(er[j, :s[j, 1]], oer) and np.array_equal(rr[j, :s[j, 2]], orr)
+    res.release()
