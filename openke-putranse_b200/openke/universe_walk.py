@@ -58,10 +58,17 @@ class DeviceWalker(object):
         self.lib, self.device = lib, device
         self.cap = int(lib.pk_walk_cap())
         lo, hi = torch.cuda.Stream.priority_range()
-        self.stream = torch.cuda.Stream(device=device, priority=hi)   # its few blocks go first when an SM frees up
+        # two streams, used alternately: under training load a walk takes 4.9 ms from queue to finish (its blocks wait for
+        # SMs the training kernel vacates) against 5.3 ms per training step — one stream would nearly be the bottleneck.
+        # High priority: its few blocks go first when an SM frees up.
+        self.streams = [torch.cuda.Stream(device=device, priority=hi) for _ in range(2)]
+        self.stream = self.streams[0]
+        self._next_stream = 0
         self._free = []
         self.launches = 0
         self.d2h_bytes = 0
+        self.time_walks = False       # profiling aid: CUDA events around every walk (queue-to-finish on the device)
+        self.walk_events = []
 
     def usable(self):
         return self.lib.pk_walk_device_check() == 0
@@ -101,7 +108,12 @@ class DeviceWalker(object):
         focus = np.zeros(n, dtype=np.int64)
         b = self._buffers(n)
         res = WalkResult(self, b, n, seeds, tcs, bals, lcg, focus)
+        self.stream = self.streams[self._next_stream % len(self.streams)]
+        self._next_stream += 1
         with torch.cuda.stream(self.stream):
+            if self.time_walks:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(self.stream)
             N.check(self.lib.pk_universes_walk_device(
                 n, N.addr(seeds), N.addr(tcs), N.addr(bals), N.addr(lcg), N.addr(focus),
                 b["bitmaps"].data_ptr(), b["got"].data_ptr(), b["trees"].data_ptr() if b["trees"] is not None else None,
@@ -119,4 +131,7 @@ class DeviceWalker(object):
                 self.d2h_bytes += n * 3 * self.cap * 4
                 res.copied_remaps = True
             res.event.record(self.stream)
+            if self.time_walks:
+                e1.record(self.stream)
+                self.walk_events.append((e0, e1))
         return res

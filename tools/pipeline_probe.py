@@ -23,6 +23,8 @@ def run(path, n, steps, async_, slots, losses=True):
     pu.synchronize()
     torch.cuda.synchronize()
     pu.timings.clear()
+    if pu._walker is not None:
+        pu._walker.time_walks = True
     p0 = pu.positive_triples
     t0 = time.perf_counter()
     for _ in range(steps):
@@ -31,6 +33,9 @@ def run(path, n, steps, async_, slots, losses=True):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     pos = pu.positive_triples - p0
+    if pu._walker is not None and pu._walker.walk_events:
+        w = [a.elapsed_time(b) for a, b in pu._walker.walk_events]
+        print("      walks on the device, queue to finish: mean %.2f ms, max %.2f ms (%d walks)" % (sum(w) / len(w), max(w), len(w)))
     print("n=%4d steps=%2d async=%d slots=%d losses=%d: %.2f ms/step  %.1f M positives/s   host: %s" % (
         n, steps, async_, slots, losses, dt / steps * 1e3, pos / dt / 1e6,
         {k: round(v / steps * 1e3, 2) for k, v in pu.timings.items()}), flush=True)

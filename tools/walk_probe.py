@@ -17,6 +17,7 @@ print("workload", wl)
 dl = TrainDataLoader(in_path=path, nbatches=20, threads=8, bern_flag=0, filter_flag=0, neg_ent=1, random_seed=4)
 L = dl.lib
 w = DeviceWalker(L, torch.device("cuda", 0))
+w.streams = w.streams[:1]      # one stream: the events below bracket the launch
 for n in (1, 100, 125, 1000):
     seeds = np.arange(4, 4 + n, dtype=np.int64)
     tcs, bals = np.zeros(n, dtype=np.int64), np.zeros(n, dtype=np.float32)
