@@ -174,6 +174,7 @@ class Parallel_Universe_Config(Tester):
         # chunk i's universes are folded into the valid split's energy matrix and ranked.  Same validations, same order,
         # same checkpoints; a validation that can stop the training runs before anything else is launched.
         self.pipeline_validation = True
+        self.validation_lag = 3           # chunks launched ahead of the oldest outstanding validation (at most launch_slots)
         self._view = None                 # (chunks visible, next_universe_id) while a deferred validation runs
         self._slots = None
         self._launch_index = 0
@@ -909,16 +910,15 @@ class Parallel_Universe_Config(Tester):
         dist, rank, world = _dist()
         t_call, t_valid = time.time(), 0.0
         done = 0
-        pending = None          # a validation deferred behind the next launch: (chunks visible, next_universe_id)
+        pending = []            # validations deferred behind later launches: (chunks visible, next_universe_id), oldest first
         stop = False
 
-        def flush():
-            nonlocal pending, t_valid, stop
-            if pending is not None:
+        def flush(keep=0):
+            nonlocal t_valid, stop
+            while len(pending) > keep:
                 t0 = time.time()
-                stop = self._validate(pending) or stop
+                stop = self._validate(pending.pop(0)) or stop
                 t_valid += time.time() - t0
-                pending = None
 
         while done < num_of_embedding_spaces and not stop:
             c = min(num_of_embedding_spaces - done, self.valid_steps - (done % self.valid_steps), self.max_chunk * world)
@@ -928,14 +928,17 @@ class Parallel_Universe_Config(Tester):
                 self._train_chunk(mine, prefetch_ids=[u + c for u in mine])
             self.next_universe_id += c
             done += c
-            flush()             # the validation that fell due before this chunk (it could not stop the training)
+            # validations that fell due `validation_lag` chunks ago (none of them can stop the training)
+            flush(max(0, min(int(self.validation_lag), int(self.launch_slots)) - 1))
             if done % self.valid_steps == 0:
                 view = (len(self._chunks), self.next_universe_id)
-                can_stop = self.bad_counts + 1 >= self.early_stopping_patience
-                if (self.pipeline_validation and not can_stop and done < num_of_embedding_spaces
+                # even if every outstanding validation and this one fail to improve, patience is not exhausted
+                harmless = self.bad_counts + len(pending) + 1 < self.early_stopping_patience
+                if (self.pipeline_validation and harmless and done < num_of_embedding_spaces
                         and self.training_setting == "static"):
-                    pending = view
+                    pending.append(view)
                 else:
+                    flush()
                     t0 = time.time()
                     stop = self._validate(view)
                     t_valid += time.time() - t0

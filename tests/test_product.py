@@ -535,10 +535,11 @@ def test_validation_runs_behind_the_next_launch_on_the_ensemble_it_fell_due_for(
     the one synchronous validation gives (up to the float reduction order of training)."""
     path, _ = _small_graph(tmp_path)
     hist = {}
-    for flag in (True, False):
+    for flag in (1, 3, 0):                 # chunks launched ahead of the oldest outstanding validation; 0 = synchronous
         ck = str(tmp_path / ("ck%d" % flag)) + "/"
         pu = _pu(path, ckpt_dir=ck, valid_steps=3, save_steps=None, patience=10 ** 6, epochs=3)
-        pu.pipeline_validation = flag
+        pu.pipeline_validation = bool(flag)
+        pu.validation_lag = max(flag, 1)
         seen = []
         orig = pu.valid
 
@@ -549,10 +550,8 @@ def test_validation_runs_behind_the_next_launch_on_the_ensemble_it_fell_due_for(
         pu.valid = recording_valid
         pu.train_parallel_universes(15)
         assert [s_[0] for s_ in seen] == [3, 6, 9, 12, 15] and [s_[1] for s_ in seen] == [1, 2, 3, 4, 5]
-        if flag:     # every validation but the last ran with the next chunk already launched
-            assert [s_[2] for s_ in seen] == [2, 3, 4, 5, 5]
-        else:
-            assert [s_[2] for s_ in seen] == [1, 2, 3, 4, 5]
+        # every validation but the last ran with `flag` more chunks already launched
+        assert [s_[2] for s_ in seen] == [min(k + flag, 5) for k in (1, 2, 3, 4)] + [5]
         best_i = int(np.argmax([s_[3] for s_ in seen]))
         assert pu.best_hit10 == seen[best_i][3] and pu.next_universe_id == 15
         p2 = _pu(path, ckpt_dir=ck)
@@ -565,4 +564,4 @@ def test_validation_runs_behind_the_next_launch_on_the_ensemble_it_fell_due_for(
         pu._rank_cache.clear()
         assert pu.valid() == pytest.approx(seen[-1][3], abs=1e-7)
         hist[flag] = [s_[3] for s_ in seen]
-    assert np.allclose(hist[True], hist[False], atol=0.02)
+    assert np.allclose(hist[1], hist[0], atol=0.02) and np.allclose(hist[3], hist[0], atol=0.02)
