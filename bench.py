@@ -68,10 +68,10 @@ def algorithmic_bytes_per_positive(model="transe", d=20, k=1, opt="adagrad"):
 
 def k2_traffic(model):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant (staged) K2 launch of THIS workload, from
-    the committed `ncu --set full` capture (profiles/r1_k2_traffic.json, written by tools/ncu_traffic.py);
+    the committed `ncu --set full` capture (profiles/r2_k2_traffic.json, from the raw page of the capture);
     None when no capture of this model's launch is committed."""
     try:
-        d = json.load(open(os.path.join(REPO, "profiles", "r1_k2_traffic.json")))
+        d = json.load(open(os.path.join(REPO, "profiles", "r2_k2_traffic.json")))
         return float(d["traffic_bytes"]) if model == "transe" else None
     except Exception:
         return None
@@ -81,6 +81,14 @@ def k1_traffic(opt, degree):
     try:
         d = json.load(open(os.path.join(REPO, "profiles", "r2_k1_traffic.json")))
         return float(d["%s_%s" % (opt, degree)]["traffic_bytes"])
+    except Exception:
+        return None
+
+
+def k1_step_traffic(opt, degree):
+    try:
+        d = json.load(open(os.path.join(REPO, "profiles", "r2_k1_traffic.json")))
+        return float(d["%s_%s" % (opt, degree)]["step_traffic_bytes_steady_state"])
     except Exception:
         return None
 
@@ -553,6 +561,10 @@ def s1_roofline(args, degree="power", opt="adagrad"):
         tr = k1_traffic(opt, degree)
         if tr is not None:    # dram__bytes_read + dram__bytes_write of k1_grad from the committed ncu capture, per launch
             r["traffic"] = tr
+        st_ = k1_step_traffic(opt, degree)
+        if st_ is not None:   # all kernels of a step, caches not flushed between them (profiles/r2_k1_steady_state_dram_*.csv)
+            r["traffic_whole_step_steady_state"] = st_
+            r["frac_measured_dram"] = st_ / (d["us_per_step"] * 1e-6) / 1e9 / r["peak"]
         r.update(workload=d["workload"], kernel="k1_prepare + k1_grad + k1_apply (whole step)", us_per_step=d["us_per_step"],
                  positive_triples_per_s=d["positive_triples_per_s"], algorithmic_bytes_per_positive=d["algorithmic_bytes_per_positive"])
         return r
