@@ -1,5 +1,5 @@
 // Universe subgraphs built ON THE GPU: the reference's getParallelUniverse (openke/base/UniverseConstructor.h:39-67,
-// 92-233,327-397) for a whole chunk of universes in one launch, bit-identical to the host builder
+// 92-233,327-397) for a whole chunk of universes at once (k_walk_universes: phases A-C, k_number_universes: phase D), bit-identical to the host builder
 // (graph_host.cpp Graph::build_universe, itself pinned to the reference) — subgraph sampling is integer work.
 //
 // Why: with the training kernel at ~5 ms per 100 universes, the bit-exact glibc-rand() walk on the host cores
